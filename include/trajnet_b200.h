@@ -1,0 +1,199 @@
+/*
+ * trajnet_b200.h -- C ABI of the B200-native TrajNet++ hot path (libtrajnet_b200.so).
+ *
+ * The reference (vita-epfl/trajnetplusplusbaselines) is pure Python and has no FFI; this
+ * header is the boundary a maintainer binds with ctypes.  Every entry
+ * point names the reference interface it replaces (paths relative to
+ * /root/reference/trajnetbaselines/).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types.  Return 0 on success, < 0 on error;
+ *     tb2_last_error() returns a thread-local message.  No exceptions cross the ABI.
+ *   - Buffers named *_dev are CALLER-OWNED device pointers (fp32 unless noted), borrowed for
+ *     the call.  The library allocates device memory only inside the opaque handles
+ *     (repacked weights, scene layout) created/destroyed explicitly.
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it (no hidden
+ *     synchronisation) unless documented otherwise.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef TRAJNET_B200_H
+#define TRAJNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB2_OK 0
+#define TB2_ERR_INVALID (-1)      /* bad argument / unsupported configuration */
+#define TB2_ERR_CUDA (-2)         /* CUDA runtime error (message holds cudaGetErrorString) */
+#define TB2_ERR_UNSUPPORTED (-3)  /* valid in the reference, not built here (fails loudly) */
+
+#define TB2_POOL_NONE 0           /* --type vanilla */
+#define TB2_POOL_OCCUPANCY 1      /* GridBasedPooling(type_='occupancy')   gridbased_pooling.py:112-116 */
+#define TB2_POOL_DIRECTIONAL 2    /* GridBasedPooling(type_='directional') gridbased_pooling.py:118-143 */
+#define TB2_POOL_SOCIAL 3         /* GridBasedPooling(type_='social')      gridbased_pooling.py:145-170 */
+
+#define TB2_PHASE_ENCODER 0
+#define TB2_PHASE_DECODER 1
+
+const char* tb2_last_error(void);
+int tb2_version(void);
+/* Number of library kernel launches issued by this process so far (bench "gpu_launches"). */
+uint64_t tb2_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Model configuration = constructor arguments of LSTM (lstm/lstm.py:46) and
+ * GridBasedPooling (lstm/gridbased_pooling.py:16-19).
+ * ------------------------------------------------------------------------------------- */
+typedef struct tb2_lstm_config {
+    int32_t hidden_dim;      /* LSTM hidden_dim (128)                              */
+    int32_t embedding_dim;   /* LSTM embedding_dim (64); Linear(2, E-2)+2 zero tags */
+    int32_t pool_type;       /* TB2_POOL_*                                         */
+    int32_t pool_to_input;   /* 1: concat pooled to LSTM input, 0: h += pooled     */
+    int32_t n;               /* grid cells per side                                */
+    float cell_side;         /* metres                                             */
+    int32_t pool_size;       /* must be 1 (CLI never sets it, trainer.py:483-487)  */
+    int32_t blur_size;       /* must be 1                                          */
+    int32_t front;           /* GridBasedPooling(front=...)                        */
+    float constant;          /* background value of the grid                       */
+    int32_t latent_dim;      /* social: hidden_dim_encoding out features (16)      */
+    int32_t num_layers;      /* grid-embedding MLP: 0 ('None'), 1, 2 or 3 layers   */
+    int32_t layer_dims[2];   /* hidden widths of the two/three_layer MLP           */
+    int32_t out_dim;         /* pool.out_dim                                       */
+} tb2_lstm_config;
+
+/* Device pointers to the parameters in the reference's state_dict layout (row-major
+ * [out_features, in_features]).  Unused entries may be NULL. */
+typedef struct tb2_lstm_weights {
+    const float* input_embedding_weight;  /* input_embedding.input_embeddings.0.weight [E-2, 2] */
+    const float* input_embedding_bias;    /* [E-2] */
+    const float* encoder_weight_ih;       /* [4H, E (+out_dim)] */
+    const float* encoder_weight_hh;       /* [4H, H] */
+    const float* encoder_bias_ih;         /* [4H] */
+    const float* encoder_bias_hh;         /* [4H] */
+    const float* decoder_weight_ih;
+    const float* decoder_weight_hh;
+    const float* decoder_bias_ih;
+    const float* decoder_bias_hh;
+    const float* hidden2normal_weight;    /* hidden2normal.linear.weight [5, H] */
+    const float* hidden2normal_bias;      /* [5] */
+    const float* pool_encoding_weight;    /* pool.hidden_dim_encoding.weight [latent, H] (social) */
+    const float* pool_encoding_bias;      /* [latent] */
+    const float* pool_embedding_weight[3];/* pool.embedding.{0,2,4}.weight */
+    const float* pool_embedding_bias[3];  /* pool.embedding.{0,2,4}.bias   */
+} tb2_lstm_weights;
+
+typedef struct tb2_lstm tb2_lstm;          /* opaque: config + repacked weights on the device */
+typedef struct tb2_layout tb2_layout;      /* opaque: scene partition (batch_split) on the device */
+
+/* Replaces LSTM.__init__ + GridBasedPooling.__init__ weight ownership (lstm.py:46-89,
+ * gridbased_pooling.py:16-92).  Allocates the repacked weight buffers; tb2_lstm_set_weights
+ * must be called before any compute (and again whenever the parameters change). */
+int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out);
+int tb2_lstm_destroy(tb2_lstm* model);
+/* Asynchronous device-side repack (transposes / cell-major slabs / fused biases). */
+int tb2_lstm_set_weights(tb2_lstm* model, const tb2_lstm_weights* w, void* stream);
+
+/* Replaces the `batch_split` argument of LSTM.forward (lstm.py:170,179-181): scene b owns
+ * tracks [scene_offsets[b], scene_offsets[b+1]); its first row is the primary.
+ * scene_offsets_host is a HOST pointer (int64, like the reference's LongTensor); the call
+ * copies it to the device (synchronous, tiny). */
+int tb2_layout_create(const int64_t* scene_offsets_host, int32_t num_scenes, tb2_layout** out);
+int tb2_layout_destroy(tb2_layout* layout);
+int32_t tb2_layout_num_tracks(const tb2_layout* layout);
+int32_t tb2_layout_max_scene(const tb2_layout* layout);
+
+/* Bytes of caller-provided scratch needed by the step / sequence / pool calls below. */
+size_t tb2_lstm_workspace_bytes(const tb2_lstm* model, const tb2_layout* layout);
+
+/* Debug export for the bit-exactness gate.  Replaces the index arithmetic of
+ * GridBasedPooling.occupancy (gridbased_pooling.py:248-249,257-263,273-287).
+ *   obs_dev      [M, 2]  positions (NaN = absent)
+ *   cell_out_dev [M, n_max-1] int32: flattened cell index oi of neighbour slot jj
+ *                (j = jj + (jj >= i) inside the scene padded to n_max); 0 when out of range
+ *   in_range_out_dev [M, n_max-1] uint8
+ * n_max = tb2_layout_max_scene(layout) (the reference pads every scene to the batch max). */
+int tb2_grid_indices(const tb2_lstm* model, const tb2_layout* layout, const float* obs_dev,
+                     int32_t* cell_out_dev, uint8_t* in_range_out_dev, void* stream);
+
+/* The pool plug: replaces GridBasedPooling.forward (gridbased_pooling.py:94-110) on the ragged
+ * layout.  hidden_dev [M, H], obs1_dev/obs2_dev [M, 2] -> pooled_out_dev [M, out_dim].
+ * Rows absent at obs2 still get a (discarded-by-the-caller) row, like the reference. */
+int tb2_pool_forward(const tb2_lstm* model, const tb2_layout* layout, const float* hidden_dev,
+                     const float* obs1_dev, const float* obs2_dev, float* pooled_out_dev,
+                     void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* One recurrence step: replaces LSTM.step (lstm.py:91-168).
+ *   phase            TB2_PHASE_ENCODER / TB2_PHASE_DECODER (which LSTMCell)
+ *   obs1_dev/obs2_dev [M, 2]
+ *   h_in/c_in -> h_out/c_out [M, H] (may alias); absent tracks keep their state
+ *   normal_out_dev   [M, 5]  (mu_x, mu_y, sigma_x, sigma_y, rho), NaN rows for absent tracks
+ *   pos_out_dev      [M, 2]  obs2 + mu (lstm.py:232,255), may be NULL */
+int tb2_lstm_step_forward(const tb2_lstm* model, const tb2_layout* layout, int32_t phase,
+                          const float* obs1_dev, const float* obs2_dev,
+                          const float* h_in_dev, const float* c_in_dev,
+                          float* h_out_dev, float* c_out_dev,
+                          float* normal_out_dev, float* pos_out_dev,
+                          void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Whole time loop: replaces LSTM.forward (lstm.py:170-264) including the decoder input rule
+ * (lstm.py:240-250).
+ *   observed_dev  [obs_length, M, 2]
+ *   truth_dev     [n_decode, M, 2] teacher-forcing positions (prediction_truth) or NULL for a
+ *                 free-running rollout (n_predict = n_decode + 1)
+ *   normals_out_dev   [S, M, 5],  S = obs_length - 1 + n_decode
+ *   positions_out_dev [S, M, 2]
+ *   h_dev, c_dev  [M, H] state buffers: zeroed by the call, hold the final state on return.
+ *   states_out_dev optional [S, 2, M, H] (h, c after every step; training) or NULL. */
+int tb2_lstm_forward_sequence(const tb2_lstm* model, const tb2_layout* layout,
+                              const float* observed_dev, int32_t obs_length,
+                              const float* truth_dev, int32_t n_decode,
+                              float* normals_out_dev, float* positions_out_dev,
+                              float* h_dev, float* c_dev, float* states_out_dev,
+                              void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Classical crowd simulators (classical/socialforce.py, classical/orca.py).  One simulator
+ * per scene, all scenes stepped in lockstep by one persistent kernel; no collective.
+ * State is SoA-free AoS fp32: scenes are contiguous ranges of agents (layout handle).
+ * ------------------------------------------------------------------------------------- */
+typedef struct tb2_sf_params {
+    float delta_t;      /* 1/fps = 0.05            socialforce.py:80,91 */
+    float tau;          /* sf_params[0] = 0.5      socialforce.py:92    */
+    float v0;           /* sf_params[1] = 2.1      socialforce.py:89    */
+    float sigma;        /* sf_params[2] = 0.3      socialforce.py:89    */
+    int32_t n_steps;    /* pred_length * sampling_rate = 96   socialforce.py:93 */
+    int32_t sample_every; /* sampling_rate = 8; sample kept when step_index % 8 == 0 (:95) */
+} tb2_sf_params;
+
+/* Replaces socialforce.Simulator(...).step() x n_steps (socialforce.py:91-95).
+ *   state_dev  [A, 6] (x, y, vx, vy, dx, dy) initial state, socialforce.py:15-55
+ *   out_dev    [n_samples, A, 2] sampled positions, n_samples = ceil(n_steps / sample_every) */
+int tb2_sf_simulate(const tb2_layout* layout, const tb2_sf_params* p, const float* state_dev,
+                    float* out_dev, void* stream);
+
+typedef struct tb2_orca_params {
+    float time_step;       /* 1/fps                         orca.py:90 */
+    float neighbor_dist;   /* orca_params[0] = 1.5                     */
+    int32_t max_neighbors; /* 10                                       */
+    float time_horizon;    /* orca_params[1] = 1.5                     */
+    float radius;          /* orca_params[2] = 0.4                     */
+    float end_range;       /* 0.05 (orca.py:97)                        */
+    int32_t n_steps;       /* sampling_rate * pred_length + 1 = 97 (orca.py:99) */
+    int32_t sample_every;  /* 8: sample when step_count % 8 == 0 (orca.py:107) */
+} tb2_orca_params;
+
+/* Replaces rvo2.PyRVOSimulator + the doStep/setAgentPrefVelocity loop (orca.py:90-119).
+ *   pos_dev [A,2], vel_dev [A,2], goal_dev [A,2], speed_dev [A] (initial speed; maxSpeed = 1.3x)
+ *   out_dev [n_samples, A, 2], n_samples = n_steps / sample_every */
+int tb2_orca_simulate(const tb2_layout* layout, const tb2_orca_params* p, const float* pos_dev,
+                      const float* vel_dev, const float* goal_dev, const float* speed_dev,
+                      float* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRAJNET_B200_H */

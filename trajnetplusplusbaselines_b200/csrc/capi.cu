@@ -1,0 +1,357 @@
+// extern "C" boundary of libtrajnet_b200 (see include/trajnet_b200.h).
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+namespace tb2 {
+
+static thread_local std::string g_error;
+std::atomic<uint64_t> g_launch_count{0};
+
+void set_error(const std::string& msg) { g_error = msg; }
+
+static int dev_alloc(std::vector<void*>& owned, void** out, size_t bytes) {
+    *out = nullptr;
+    if (bytes == 0) bytes = 16;
+    TB2_CHECK_CUDA(cudaMalloc(out, bytes));
+    owned.push_back(*out);
+    return TB2_OK;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+size_t carve_workspace(const tb2_lstm* m, const tb2_layout* l, void* base, Workspace* ws) {
+    const size_t M = (size_t)l->M;
+    const size_t nm1 = (size_t)(l->n_max > 1 ? l->n_max - 1 : 1);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return base ? (void*)((char*)base + o) : (void*)nullptr;
+    };
+    Workspace w;
+    w.obs1 = (float*)take(M * 2 * sizeof(float));
+    w.obs2 = (float*)take(M * 2 * sizeof(float));
+    w.lat = (float*)take(M * (size_t)std::max(m->C, 1) * sizeof(float));
+    w.win_count = (int*)take(M * sizeof(int));
+    w.win_ent = (uint32_t*)take(M * nm1 * sizeof(uint32_t));
+    w.win_val = (float*)take(M * nm1 * 2 * sizeof(float));
+    w.pair_cell = (int*)take(M * nm1 * sizeof(int));
+    w.pair_flag = (uint8_t*)take(M * nm1);
+    size_t wmax = 1;
+    for (int i = 1; i <= m->n_mlp; ++i) wmax = std::max(wmax, (size_t)m->mlp_dims[i]);
+    w.act[0] = (float*)take(M * wmax * sizeof(float));
+    w.act[1] = (float*)take(M * wmax * sizeof(float));
+    w.pooled = (float*)take(M * (size_t)std::max(m->pool_out, 1) * sizeof(float));
+    w.bytes = off;
+    if (ws) *ws = w;
+    return off;
+}
+
+}  // namespace tb2
+
+using namespace tb2;
+
+extern "C" {
+
+const char* tb2_last_error(void) { return g_error.c_str(); }
+int tb2_version(void) { return 100; }
+uint64_t tb2_launch_count(void) { return g_launch_count.load(); }
+
+int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
+    TB2_REQUIRE(cfg && out, "null argument");
+    *out = nullptr;
+    TB2_REQUIRE(cfg->hidden_dim == 128, "hidden_dim must be 128 (kernel specialisation)");
+    TB2_REQUIRE(cfg->embedding_dim >= 4 && cfg->embedding_dim <= 1024, "embedding_dim out of range");
+    TB2_REQUIRE(cfg->pool_type >= TB2_POOL_NONE && cfg->pool_type <= TB2_POOL_SOCIAL, "bad pool_type");
+    tb2_lstm* m = new (std::nothrow) tb2_lstm();
+    TB2_REQUIRE(m, "out of host memory");
+    m->cfg = *cfg;
+    m->H = cfg->hidden_dim;
+    m->E = cfg->embedding_dim;
+    m->weights_set = false;
+    m->C = 0; m->cells = 0; m->n_mlp = 0; m->P = 0; m->pool_out = 0;
+    m->We = m->be = m->Wn = m->bn = m->WencT = m->benc = m->Wt1 = m->base1 = nullptr;
+    for (int i = 0; i < 2; ++i) m->WgT[i] = m->bg[i] = nullptr;
+    for (int i = 0; i < kMaxMlpLayers; ++i) m->WT[i] = m->bl[i] = nullptr;
+    auto fail = [&](int rc) { tb2_lstm_destroy(m); return rc; };
+    if (cfg->pool_type != TB2_POOL_NONE) {
+        if (cfg->pool_size != 1 || cfg->blur_size != 1) {
+            set_error("pool_size / blur_size != 1 are not built (the reference CLI never sets them)");
+            return fail(TB2_ERR_UNSUPPORTED);
+        }
+        if (!(cfg->n >= 1 && cfg->n <= 64 && cfg->cell_side > 0.f)) { set_error("invalid argument: grid size"); return fail(TB2_ERR_INVALID); }
+        if (!(cfg->num_layers >= 0 && cfg->num_layers <= kMaxMlpLayers)) { set_error("invalid argument: num_layers"); return fail(TB2_ERR_INVALID); }
+        m->C = cfg->pool_type == TB2_POOL_OCCUPANCY ? 1 : cfg->pool_type == TB2_POOL_DIRECTIONAL ? 2 : cfg->latent_dim;
+        if (cfg->pool_type == TB2_POOL_SOCIAL && !(m->C == 4 || m->C == 8 || m->C == 16 || m->C == 32)) {
+            set_error("social latent_dim must be 4, 8, 16 or 32");
+            return fail(TB2_ERR_UNSUPPORTED);
+        }
+        m->cells = cfg->n * cfg->n;
+        m->n_mlp = cfg->num_layers;
+        m->mlp_dims[0] = m->C * m->cells;
+        for (int i = 1; i <= m->n_mlp; ++i)
+            m->mlp_dims[i] = (i == m->n_mlp) ? cfg->out_dim : cfg->layer_dims[i - 1];
+        m->pool_out = m->n_mlp == 0 ? m->mlp_dims[0] : cfg->out_dim;
+        for (int i = 1; i <= m->n_mlp; ++i)
+            if (m->mlp_dims[i] < 1) { set_error("invalid argument: MLP width"); return fail(TB2_ERR_INVALID); }
+        if (cfg->pool_to_input) m->P = m->pool_out;
+        else if (m->pool_out != m->H) { set_error("invalid argument: pool_to_input=0 needs out_dim == hidden_dim"); return fail(TB2_ERR_INVALID); }
+    }
+    m->K_gate = m->E + m->P + m->H;
+    m->K_gate_pad = (m->K_gate + kGateBK - 1) / kGateBK * kGateBK;
+    int rc;
+#define ALLOC(ptr, count) if ((rc = dev_alloc(m->owned, (void**)&(ptr), (size_t)(count) * sizeof(float)))) return fail(rc)
+    ALLOC(m->We, (m->E - 2) * 2);
+    ALLOC(m->be, m->E - 2);
+    ALLOC(m->Wn, 5 * m->H);
+    ALLOC(m->bn, 5);
+    for (int ph = 0; ph < 2; ++ph) {
+        ALLOC(m->WgT[ph], (size_t)m->K_gate_pad * 4 * m->H);
+        ALLOC(m->bg[ph], 4 * m->H);
+    }
+    if (cfg->pool_type == TB2_POOL_SOCIAL) {
+        ALLOC(m->WencT, m->H * m->C);
+        ALLOC(m->benc, m->C);
+    }
+    if (m->n_mlp >= 1) {
+        ALLOC(m->Wt1, (size_t)m->cells * m->C * m->mlp_dims[1]);
+        ALLOC(m->base1, m->mlp_dims[1]);
+        for (int layer = 1; layer < m->n_mlp; ++layer) {
+            ALLOC(m->WT[layer], (size_t)m->mlp_dims[layer] * m->mlp_dims[layer + 1]);
+            ALLOC(m->bl[layer], m->mlp_dims[layer + 1]);
+        }
+    }
+#undef ALLOC
+    *out = m;
+    return TB2_OK;
+}
+
+int tb2_lstm_destroy(tb2_lstm* m) {
+    if (!m) return TB2_OK;
+    for (void* p : m->owned) cudaFree(p);
+    delete m;
+    return TB2_OK;
+}
+
+int tb2_lstm_set_weights(tb2_lstm* m, const tb2_lstm_weights* w, void* stream) {
+    TB2_REQUIRE(m && w, "null argument");
+    return launch_repack(m, w, (cudaStream_t)stream);
+}
+
+int tb2_layout_create(const int64_t* off, int32_t B, tb2_layout** out) {
+    TB2_REQUIRE(off && out && B >= 1, "null / empty batch_split");
+    *out = nullptr;
+    TB2_REQUIRE(off[0] == 0, "batch_split must start at 0");
+    tb2_layout* l = new (std::nothrow) tb2_layout();
+    TB2_REQUIRE(l, "out of host memory");
+    l->B = B;
+    l->scene_off_host.resize(B + 1);
+    int n_max = 0;
+    for (int b = 0; b <= B; ++b) {
+        if (b > 0 && off[b] <= off[b - 1]) { delete l; set_error("invalid argument: batch_split must be strictly increasing"); return TB2_ERR_INVALID; }
+        if (off[b] > 0x7fffffff / 4) { delete l; set_error("invalid argument: too many tracks"); return TB2_ERR_INVALID; }
+        l->scene_off_host[b] = (int)off[b];
+        if (b > 0) n_max = std::max(n_max, (int)(off[b] - off[b - 1]));
+    }
+    l->M = (int)off[B];
+    l->n_max = n_max;
+    l->scene_off = l->row_scene = nullptr;
+    l->group_off[0] = l->group_off[1] = nullptr;
+    auto fail = [&](int rc) { tb2_layout_destroy(l); return rc; };
+    int rc;
+    if ((rc = dev_alloc(l->owned, (void**)&l->scene_off, (size_t)(B + 1) * sizeof(int)))) return fail(rc);
+    if ((rc = dev_alloc(l->owned, (void**)&l->row_scene, (size_t)l->M * sizeof(int)))) return fail(rc);
+    std::vector<int> row_scene(l->M);
+    for (int b = 0; b < B; ++b)
+        for (int r = l->scene_off_host[b]; r < l->scene_off_host[b + 1]; ++r) row_scene[r] = b;
+    if (cudaMemcpy(l->scene_off, l->scene_off_host.data(), (size_t)(B + 1) * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(l->row_scene, row_scene.data(), (size_t)l->M * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error(std::string("cudaMemcpy(layout): ") + cudaGetErrorString(cudaGetLastError()));
+        return fail(TB2_ERR_CUDA);
+    }
+    // scene groups for sparse_layer1_kernel: [0] large (wide layers), [1] small (narrow layers)
+    const int caps[2] = {160, 40};
+    for (int g = 0; g < 2; ++g) {
+        int cap = std::max(caps[g], n_max);
+        std::vector<int> go;
+        go.push_back(0);
+        int rows = 0;
+        for (int b = 0; b < B; ++b) {
+            int n_b = l->scene_off_host[b + 1] - l->scene_off_host[b];
+            if (rows + n_b > cap) { go.push_back(b); rows = 0; }
+            rows += n_b;
+        }
+        go.push_back(B);
+        l->group_cap[g] = cap;
+        l->num_groups[g] = (int)go.size() - 1;
+        if ((rc = dev_alloc(l->owned, (void**)&l->group_off[g], go.size() * sizeof(int)))) return fail(rc);
+        if (cudaMemcpy(l->group_off[g], go.data(), go.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+            set_error(std::string("cudaMemcpy(groups): ") + cudaGetErrorString(cudaGetLastError()));
+            return fail(TB2_ERR_CUDA);
+        }
+    }
+    *out = l;
+    return TB2_OK;
+}
+
+int tb2_layout_destroy(tb2_layout* l) {
+    if (!l) return TB2_OK;
+    for (void* p : l->owned) cudaFree(p);
+    delete l;
+    return TB2_OK;
+}
+
+int32_t tb2_layout_num_tracks(const tb2_layout* l) { return l ? l->M : -1; }
+int32_t tb2_layout_max_scene(const tb2_layout* l) { return l ? l->n_max : -1; }
+
+size_t tb2_lstm_workspace_bytes(const tb2_lstm* m, const tb2_layout* l) {
+    if (!m || !l) return 0;
+    return carve_workspace(m, l, nullptr, nullptr);
+}
+
+static int check_ready(const tb2_lstm* m, const tb2_layout* l, void* ws, size_t ws_bytes) {
+    TB2_REQUIRE(m && l, "null handle");
+    TB2_REQUIRE(m->weights_set, "tb2_lstm_set_weights has not been called");
+    TB2_REQUIRE(ws && ws_bytes >= carve_workspace(m, l, nullptr, nullptr), "workspace too small");
+    TB2_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+    return TB2_OK;
+}
+
+int tb2_grid_indices(const tb2_lstm* m, const tb2_layout* l, const float* obs, int32_t* cell_out,
+                     uint8_t* in_range_out, void* stream) {
+    TB2_REQUIRE(m && l && obs && cell_out && in_range_out, "null argument");
+    TB2_REQUIRE(m->cfg.pool_type != TB2_POOL_NONE, "model has no grid pooling");
+    // The pair tables are produced straight into the caller's buffers: no workspace needed.
+    Workspace ws;
+    std::memset(&ws, 0, sizeof(ws));
+    // pool_prepare writes winners too; give it scratch inside a temporary allocation
+    size_t bytes = carve_workspace(m, l, nullptr, nullptr);
+    void* tmp = nullptr;
+    TB2_CHECK_CUDA(cudaMalloc(&tmp, bytes));
+    carve_workspace(m, l, tmp, &ws);
+    cudaStream_t st = (cudaStream_t)stream;
+    // occupancy-style call: obs1 is irrelevant for the indices, pass obs for both
+    tb2_lstm tmp_model = *m;
+    tmp_model.owned.clear();
+    tmp_model.cfg.pool_type = TB2_POOL_OCCUPANCY;   // indices do not depend on the payload
+    int rc = launch_pool_prepare(&tmp_model, l, nullptr, obs, obs, 0, &ws, st);
+    if (rc == TB2_OK) rc = launch_grid_indices_copy(l, &ws, cell_out, in_range_out, st);
+    cudaError_t e = cudaStreamSynchronize(st);       // debug export: synchronous so tmp can be freed
+    cudaFree(tmp);
+    if (rc != TB2_OK) return rc;
+    TB2_CHECK_CUDA(e);
+    return TB2_OK;
+}
+
+int tb2_pool_forward(const tb2_lstm* m, const tb2_layout* l, const float* hidden, const float* obs1,
+                     const float* obs2, float* pooled_out, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+    int rc = check_ready(m, l, workspace, workspace_bytes);
+    if (rc) return rc;
+    TB2_REQUIRE(m->cfg.pool_type != TB2_POOL_NONE, "model has no grid pooling");
+    TB2_REQUIRE(obs1 && obs2 && pooled_out, "null argument");
+    TB2_REQUIRE(m->cfg.pool_type != TB2_POOL_SOCIAL || hidden, "social pooling needs hidden states");
+    Workspace ws;
+    carve_workspace(m, l, workspace, &ws);
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = launch_pool_prepare(m, l, hidden, obs1, obs2, 0, &ws, st))) return rc;
+    return launch_pool_mlp(m, l, &ws, pooled_out, st);
+}
+
+static int step_impl(const tb2_lstm* m, const tb2_layout* l, int phase, const float* obs1,
+                     const float* obs2, const float* h_in, const float* c_in, float* h_out,
+                     float* c_out, float* normal_out, float* pos_out, Workspace* ws, cudaStream_t st) {
+    int rc;
+    const float* pooled = nullptr;
+    if (m->cfg.pool_type != TB2_POOL_NONE) {
+        if ((rc = launch_pool_prepare(m, l, h_in, obs1, obs2, 1, ws, st))) return rc;
+        if ((rc = launch_pool_mlp(m, l, ws, ws->pooled, st))) return rc;
+        pooled = ws->pooled;
+    }
+    return launch_gates(m, l, phase, obs1, obs2, pooled, h_in, c_in, h_out, c_out, normal_out, pos_out, st);
+}
+
+int tb2_lstm_step_forward(const tb2_lstm* m, const tb2_layout* l, int32_t phase, const float* obs1,
+                          const float* obs2, const float* h_in, const float* c_in, float* h_out,
+                          float* c_out, float* normal_out, float* pos_out, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    int rc = check_ready(m, l, workspace, workspace_bytes);
+    if (rc) return rc;
+    TB2_REQUIRE(phase == TB2_PHASE_ENCODER || phase == TB2_PHASE_DECODER, "bad phase");
+    TB2_REQUIRE(obs1 && obs2 && h_in && c_in && h_out && c_out && normal_out, "null argument");
+    Workspace ws;
+    carve_workspace(m, l, workspace, &ws);
+    return step_impl(m, l, phase, obs1, obs2, h_in, c_in, h_out, c_out, normal_out, pos_out, &ws,
+                     (cudaStream_t)stream);
+}
+
+int tb2_lstm_forward_sequence(const tb2_lstm* m, const tb2_layout* l, const float* observed,
+                              int32_t obs_length, const float* truth, int32_t n_decode,
+                              float* normals_out, float* positions_out, float* h, float* c,
+                              float* states_out, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_ready(m, l, workspace, workspace_bytes);
+    if (rc) return rc;
+    TB2_REQUIRE(observed && normals_out && positions_out && h && c, "null argument");
+    TB2_REQUIRE(obs_length >= 2 && n_decode >= 0, "need obs_length >= 2 and n_decode >= 0");
+    Workspace ws;
+    carve_workspace(m, l, workspace, &ws);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t M = (size_t)l->M, H = (size_t)m->H;
+    const size_t frame = M * 2;
+    TB2_CHECK_CUDA(cudaMemsetAsync(h, 0, M * H * sizeof(float), st));     // lstm.py:207-210
+    TB2_CHECK_CUDA(cudaMemsetAsync(c, 0, M * H * sizeof(float), st));
+    const int S = obs_length - 1 + n_decode;
+    const float* h_prev = h;
+    const float* c_prev = c;
+    for (int s = 0; s < S; ++s) {
+        const float* o1;
+        const float* o2;
+        int phase;
+        if (s < obs_length - 1) {                                          // encoder, lstm.py:226-232
+            phase = TB2_PHASE_ENCODER;
+            o1 = observed + (size_t)s * frame;
+            o2 = observed + (size_t)(s + 1) * frame;
+        } else {                                                           // decoder, lstm.py:240-255
+            phase = TB2_PHASE_DECODER;
+            const int k = s - (obs_length - 1);
+            // positions[-1] = output of step s-1, positions[-2] = output of step s-2
+            // (or observed[-1] when obs_length == 2, lstm.py:222-223)
+            const float* pos_m1 = positions_out + (size_t)(s - 1) * frame;
+            const float* pos_m2 = (s >= 2) ? positions_out + (size_t)(s - 2) * frame
+                                           : observed + (size_t)(obs_length - 1) * frame;
+            // obs1 = seq[k]: seq[0] = observed[-1] (always a tensor -> primary rows only)
+            if (k == 0) {
+                if ((rc = launch_resolve_obs(l, observed + (size_t)(obs_length - 1) * frame, pos_m2, ws.obs1, st))) return rc;
+                o1 = ws.obs1;
+            } else if (truth) {
+                if ((rc = launch_resolve_obs(l, truth + (size_t)(k - 1) * frame, pos_m2, ws.obs1, st))) return rc;
+                o1 = ws.obs1;
+            } else {
+                o1 = pos_m2;                                               // :242 all rows predicted
+            }
+            if (truth) {
+                if ((rc = launch_resolve_obs(l, truth + (size_t)k * frame, pos_m1, ws.obs2, st))) return rc;
+                o2 = ws.obs2;
+            } else {
+                o2 = pos_m1;                                               // :247
+            }
+        }
+        float* h_next = states_out ? states_out + ((size_t)s * 2 + 0) * M * H : h;
+        float* c_next = states_out ? states_out + ((size_t)s * 2 + 1) * M * H : c;
+        if ((rc = step_impl(m, l, phase, o1, o2, h_prev, c_prev, h_next, c_next,
+                            normals_out + (size_t)s * M * 5, positions_out + (size_t)s * frame, &ws, st)))
+            return rc;
+        h_prev = h_next;
+        c_prev = c_next;
+    }
+    if (states_out && S > 0) {
+        TB2_CHECK_CUDA(cudaMemcpyAsync(h, h_prev, M * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        TB2_CHECK_CUDA(cudaMemcpyAsync(c, c_prev, M * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    return TB2_OK;
+}
+
+}  // extern "C"

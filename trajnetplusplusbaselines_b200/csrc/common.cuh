@@ -1,0 +1,114 @@
+// Shared host/device declarations of libtrajnet_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "trajnet_b200.h"
+
+namespace tb2 {
+
+void set_error(const std::string& msg);
+extern std::atomic<uint64_t> g_launch_count;
+
+#define TB2_CHECK_CUDA(expr)                                                              \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            ::tb2::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+            return TB2_ERR_CUDA;                                                          \
+        }                                                                                 \
+    } while (0)
+
+#define TB2_REQUIRE(cond, msg)                                                            \
+    do {                                                                                  \
+        if (!(cond)) {                                                                    \
+            ::tb2::set_error(std::string("invalid argument: ") + (msg));                  \
+            return TB2_ERR_INVALID;                                                       \
+        }                                                                                 \
+    } while (0)
+
+#define TB2_LAUNCH_CHECK()                                                                \
+    do {                                                                                  \
+        ::tb2::g_launch_count.fetch_add(1, std::memory_order_relaxed);                    \
+        TB2_CHECK_CUDA(cudaGetLastError());                                               \
+    } while (0)
+
+constexpr int kMaxMlpLayers = 3;
+constexpr int kGateBK = 16;        // K-chunk of the gate GEMM; weight rows are padded to it
+
+}  // namespace tb2
+
+// Opaque handle bodies ---------------------------------------------------------------------
+struct tb2_lstm {
+    tb2_lstm_config cfg;
+    int H, E, C, cells, n_mlp;
+    int P;                 // pooled width fed to the LSTM input (0 if none / pool_to_input == 0)
+    int pool_out;          // width of the pool output (grid width when n_mlp == 0)
+    int mlp_dims[tb2::kMaxMlpLayers + 1];  // [grid_dim, d1, ..]
+    int K_gate, K_gate_pad;
+    bool weights_set;
+    // device buffers (owned)
+    float* We;             // [E-2, 2]
+    float* be;             // [E-2]
+    float* WgT[2];         // [K_gate_pad, 4H]  rows: emb | pooled | h
+    float* bg[2];          // [4H] = b_ih + b_hh
+    float* Wn;             // [5, H]
+    float* bn;             // [5]
+    float* WencT;          // [H, C]
+    float* benc;           // [C]
+    float* Wt1;            // [cells, C, d1]  cell-major slabs of pool.embedding.0.weight
+    float* base1;          // [d1] = b1 + constant * rowsum(W1)
+    float* WT[tb2::kMaxMlpLayers];   // layers >= 2: [K, N] transposed
+    float* bl[tb2::kMaxMlpLayers];   // biases of layers >= 2
+    std::vector<void*> owned;
+};
+
+struct tb2_layout {
+    int B, M, n_max;
+    std::vector<int> scene_off_host;
+    int* scene_off;        // [B+1] device
+    int* row_scene;        // [M]   device
+    // scene groups for the sparse grid-MLP kernel: consecutive scenes, <= cap rows each
+    int group_cap[2];
+    int num_groups[2];
+    int* group_off[2];     // [G+1] scene indices, device
+    std::vector<void*> owned;
+};
+
+namespace tb2 {
+
+struct Workspace {
+    float* obs1;           // [M,2] resolved step inputs
+    float* obs2;           // [M,2]
+    float* lat;            // [M,C]
+    int* win_count;        // [M]
+    uint32_t* win_ent;     // [M, nm1]  cell << 16 | scene-local j
+    float* win_val;        // [M, nm1, 2]
+    int* pair_cell;        // [M, nm1]
+    uint8_t* pair_flag;    // [M, nm1]
+    float* act[2];         // ping-pong MLP activations [M, max width]
+    float* pooled;         // [M, pool_out]
+    size_t bytes;
+};
+size_t carve_workspace(const tb2_lstm* m, const tb2_layout* l, void* base, Workspace* ws);
+
+// kernels.cu launchers (all asynchronous on `st`)
+int launch_resolve_obs(const tb2_layout* l, const float* base, const float* pred, float* out,
+                       cudaStream_t st);
+int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hidden,
+                        const float* obs1, const float* obs2, int skip_masked, Workspace* ws,
+                        cudaStream_t st);
+int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float* pooled_out,
+                    cudaStream_t st);
+int launch_gates(const tb2_lstm* m, const tb2_layout* l, int phase, const float* obs1,
+                 const float* obs2, const float* pooled, const float* h_in, const float* c_in,
+                 float* h_out, float* c_out, float* normal_out, float* pos_out, cudaStream_t st);
+int launch_repack(tb2_lstm* m, const tb2_lstm_weights* w, cudaStream_t st);
+int launch_grid_indices_copy(const tb2_layout* l, const Workspace* ws, int32_t* cell_out,
+                             uint8_t* flag_out, cudaStream_t st);
+
+}  // namespace tb2

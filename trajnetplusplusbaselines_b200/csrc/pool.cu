@@ -1,0 +1,575 @@
+// Grid pooling: neighbour binning, last-writer-wins scatter, sparse grid-embedding layer.
+//
+// Replaces GridBasedPooling.{occupancies,directional,social,occupancy} and the first Linear of
+// the grid embedding (reference: trajnetbaselines/lstm/gridbased_pooling.py:112-170,227-305,
+// 308-335).  The reference materialises a dense [B*N, C, n, n] grid (84 MB per step for
+// Social-LSTM at B=256) of which <= N-1 cells per pedestrian are non-constant; here the grid
+// never exists: pool_prepare_kernel resolves the scatter-overwrite into a per-pedestrian list
+// of winning (cell, neighbour) pairs, and sparse_layer1_kernel applies the first Linear as
+//     out[i, :] = base + sum_{winning (cell, j) of i} (val(i, j) - constant) . W1[:, cell-slab]
+// streaming the cell-major weight slabs once per scene group.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace tb2 {
+
+// ------------------------------------------------------------------------------------------
+// resolve_obs: decoder input rule (lstm.py:240-250) -- rows of the scene primaries come from
+// the previous predictions, everything else from the teacher-forcing / observed frame.
+// ------------------------------------------------------------------------------------------
+__global__ void resolve_obs_kernel(const float2* __restrict__ base, const float2* __restrict__ pred,
+                                   const int* __restrict__ row_scene,
+                                   const int* __restrict__ scene_off, float2* __restrict__ out, int M) {
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    bool primary = (scene_off[row_scene[m]] == m);
+    out[m] = primary ? pred[m] : base[m];
+}
+
+int launch_resolve_obs(const tb2_layout* l, const float* base, const float* pred, float* out,
+                       cudaStream_t st) {
+    int threads = 256, blocks = (l->M + threads - 1) / threads;
+    resolve_obs_kernel<<<blocks, threads, 0, st>>>((const float2*)base, (const float2*)pred,
+                                                   l->row_scene, l->scene_off, (float2*)out, l->M);
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// pool_prepare: one CTA per scene.
+//   * positions: NaN -> -500 (gridbased_pooling.py:248-249)
+//   * social: lat[j] = W_enc . nan_to_num(h_j) + b_enc (:160-167; computed once per j, the
+//     reference recomputes it for each of the N-1 observers)
+//   * every ordered pair (i, jj): cell index with fp32 true division (:276), range test
+//     (:278-279), out-of-range -> cell 0 (:281)
+//   * scatter-overwrite in ascending j (:293) resolved to "is this pair the last writer of its
+//     cell"; padded slots (scene smaller than the batch maximum) are trailing out-of-range
+//     writers of cell 0 exactly like the reference's NaN padding (lstm.py:31-40).
+// ------------------------------------------------------------------------------------------
+constexpr int kPrepThreads = 128;
+constexpr int kPrepWarps = kPrepThreads / 32;
+constexpr int kMaxSceneForPrep = 256;   // per-warp cell row buffer
+
+struct PrepParams {
+    const float2* obs1;
+    const float2* obs2;
+    const float* hidden;      // [M, H] or null
+    const int* scene_off;
+    const float* WencT;       // [H, C]
+    const float* benc;
+    float* lat;               // [M, C]
+    int* win_count;
+    uint32_t* win_ent;
+    float* win_val;
+    int* pair_cell;
+    uint8_t* pair_flag;
+    int n_max, H, C, n, pool_type, front, skip_masked;
+    float side, width;
+};
+
+__device__ __forceinline__ float nan_to_num_f(float x) {
+    if (isnan(x)) return 0.f;
+    if (isinf(x)) return x > 0 ? 3.402823466e+38f : -3.402823466e+38f;
+    return x;
+}
+
+__global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p) {
+    extern __shared__ float smem_prep[];
+    const int scene = blockIdx.x;
+    const int row0 = p.scene_off[scene];
+    const int n_s = p.scene_off[scene + 1] - row0;
+    const int nm1 = p.n_max - 1;
+    float2* pos = reinterpret_cast<float2*>(smem_prep);                 // [n_s] obs2 with -500
+    float2* vel = pos + n_s;                                            // [n_s] obs2 - obs1 (may be NaN)
+    int* cellrow = reinterpret_cast<int*>(vel + n_s);                   // [kPrepWarps][nm1]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int j = tid; j < n_s; j += kPrepThreads) {
+        float2 a = p.obs1[row0 + j], b = p.obs2[row0 + j];
+        vel[j] = make_float2(b.x - a.x, b.y - a.y);
+        if (isnan(b.x) || isnan(b.y)) b = make_float2(-500.f, -500.f);
+        pos[j] = b;
+    }
+    if (p.pool_type == TB2_POOL_SOCIAL) {
+        // lat[j][c] = sum_k nan_to_num(h[j][k]) * WencT[k][c] + benc[c]
+        const int total = n_s * p.C;
+        for (int idx = tid; idx < total; idx += kPrepThreads) {
+            int j = idx / p.C, c = idx - j * p.C;
+            const float* hrow = p.hidden + (size_t)(row0 + j) * p.H;
+            float acc = 0.f;
+            for (int k = 0; k < p.H; ++k) acc = fmaf(nan_to_num_f(hrow[k]), p.WencT[k * p.C + c], acc);
+            p.lat[(size_t)(row0 + j) * p.C + c] = acc + p.benc[c];
+        }
+    }
+    __syncthreads();
+    if (nm1 <= 0) {   // single-pedestrian batch: constant grid (gridbased_pooling.py:252-253)
+        for (int i = tid; i < n_s; i += kPrepThreads) p.win_count[row0 + i] = 0;
+        return;
+    }
+
+    const float offx = p.width * 0.5f;
+    const float offy = p.front ? 0.f : p.width * 0.5f;
+    int* myrow = cellrow + warp * nm1;
+    const bool has_pad = n_s < p.n_max;
+
+    for (int i = warp; i < n_s; i += kPrepWarps) {
+        const size_t gi = (size_t)(row0 + i) * nm1;
+        const float2 pi = pos[i];
+        const float2 vi = vel[i];
+        // pass 1: cell index of every neighbour slot (padded slots are out of range)
+        for (int jj = lane; jj < nm1; jj += 32) {
+            int j = jj + (jj >= i);
+            int cell = 0, inr = 0;
+            if (j < n_s) {
+                float rx = pos[j].x - pi.x, ry = pos[j].y - pi.y;
+                float ox = __fadd_rn(__fdiv_rn(rx, p.side), offx);      // fp32 true division, :276
+                float oy = __fadd_rn(__fdiv_rn(ry, p.side), offy);
+                bool viol = (ox < 0.f) || (ox >= p.width) || (oy < 0.f) || (oy >= p.width);
+                if (!viol) {
+                    inr = 1;
+                    cell = (int)ox * p.n + (int)oy;                     // :284-287
+                }
+            }
+            myrow[jj] = inr ? cell : -1;
+            p.pair_cell[gi + jj] = cell;
+            p.pair_flag[gi + jj] = (uint8_t)inr;
+        }
+        __syncwarp();
+        // pass 2: winners, compacted in ascending jj
+        const float2 oi1 = p.obs1[row0 + i], oi2 = p.obs2[row0 + i];
+        const bool masked = isnan(oi1.x) || isnan(oi2.x);
+        int count = 0;
+        if (!(p.skip_masked && masked)) {
+            for (int base = 0; base < nm1; base += 32) {
+                int jj = base + lane;
+                bool win = false;
+                int cell = 0;
+                if (jj < nm1) {
+                    cell = myrow[jj];
+                    win = cell >= 0;
+                    if (win) {
+                        // a later in-range writer of the same cell, or (for cell 0) any later
+                        // out-of-range writer incl. padding, overrides this pair
+                        if (cell == 0 && has_pad) win = false;
+                        for (int k = jj + 1; win && k < nm1; ++k) {
+                            int ck = myrow[k];
+                            if (ck == cell || (cell == 0 && ck < 0)) win = false;
+                        }
+                    }
+                }
+                unsigned ball = __ballot_sync(0xffffffffu, win);
+                if (win) {
+                    int slot = count + __popc(ball & ((1u << lane) - 1u));
+                    int j = jj + (jj >= i);
+                    p.win_ent[gi + slot] = ((uint32_t)cell << 16) | (uint32_t)j;
+                    if (p.pool_type == TB2_POOL_DIRECTIONAL) {
+                        p.win_val[(gi + slot) * 2 + 0] = nan_to_num_f(vel[j].x - vi.x);   // :131-140
+                        p.win_val[(gi + slot) * 2 + 1] = nan_to_num_f(vel[j].y - vi.y);
+                    } else if (p.pool_type == TB2_POOL_OCCUPANCY) {
+                        p.win_val[(gi + slot) * 2 + 0] = 1.f;                             // :266-267
+                    }
+                }
+                count += __popc(ball);
+            }
+        }
+        if (lane == 0) p.win_count[row0 + i] = count;
+        __syncwarp();
+    }
+}
+
+int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hidden,
+                        const float* obs1, const float* obs2, int skip_masked, Workspace* ws,
+                        cudaStream_t st) {
+    TB2_REQUIRE(l->n_max <= kMaxSceneForPrep, "scene larger than 256 pedestrians");
+    PrepParams p;
+    p.obs1 = (const float2*)obs1;
+    p.obs2 = (const float2*)obs2;
+    p.hidden = hidden;
+    p.scene_off = l->scene_off;
+    p.WencT = m->WencT;
+    p.benc = m->benc;
+    p.lat = ws->lat;
+    p.win_count = ws->win_count;
+    p.win_ent = ws->win_ent;
+    p.win_val = ws->win_val;
+    p.pair_cell = ws->pair_cell;
+    p.pair_flag = ws->pair_flag;
+    p.n_max = l->n_max;
+    p.H = m->H;
+    p.C = m->C;
+    p.n = m->cfg.n;
+    p.pool_type = m->cfg.pool_type;
+    p.front = m->cfg.front;
+    p.skip_masked = skip_masked;
+    p.side = m->cfg.cell_side;        // pool_size == 1
+    p.width = (float)m->cfg.n;
+    int nm1 = l->n_max > 1 ? l->n_max - 1 : 1;
+    size_t smem = (size_t)l->n_max * 2 * sizeof(float2) + (size_t)kPrepWarps * nm1 * sizeof(int);
+    pool_prepare_kernel<<<l->B, kPrepThreads, smem, st>>>(p);
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
+}
+
+// Debug export (tb2_grid_indices): copy of the pair tables.
+__global__ void copy_pairs_kernel(const int* __restrict__ cell, const uint8_t* __restrict__ flag,
+                                  int32_t* __restrict__ cell_out, uint8_t* __restrict__ flag_out,
+                                  size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) {
+        cell_out[i] = cell[i];
+        flag_out[i] = flag[i];
+    }
+}
+
+int launch_grid_indices_copy(const tb2_layout* l, const Workspace* ws, int32_t* cell_out,
+                             uint8_t* flag_out, cudaStream_t st) {
+    size_t total = (size_t)l->M * (size_t)(l->n_max - 1);
+    if (total == 0) return TB2_OK;
+    int threads = 256;
+    unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    copy_pairs_kernel<<<blocks, threads, 0, st>>>(ws->pair_cell, ws->pair_flag, cell_out, flag_out, total);
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// dense grid writer (embedding_arch == 'None'): [M, C*cells], channel-major like
+// gridbased_pooling.py:294-295,107.  One CTA per pedestrian.
+// ------------------------------------------------------------------------------------------
+__global__ void dense_grid_kernel(const int* __restrict__ win_count, const uint32_t* __restrict__ win_ent,
+                                  const float* __restrict__ win_val, const float* __restrict__ lat,
+                                  const int* __restrict__ row_scene, const int* __restrict__ scene_off,
+                                  float* __restrict__ out, int C, int cells, int nm1, float constant,
+                                  int pool_type) {
+    const int m = blockIdx.x;
+    float* row = out + (size_t)m * C * cells;
+    for (int k = threadIdx.x; k < C * cells; k += blockDim.x) row[k] = constant;
+    __syncthreads();
+    const int cnt = win_count[m];
+    const int row0 = scene_off[row_scene[m]];
+    for (int idx = threadIdx.x; idx < cnt * C; idx += blockDim.x) {
+        int e = idx / C, c = idx - e * C;
+        uint32_t ent = win_ent[(size_t)m * nm1 + e];
+        int cell = ent >> 16, j = ent & 0xffff;
+        float v = (pool_type == TB2_POOL_SOCIAL) ? lat[(size_t)(row0 + j) * C + c]
+                                                 : win_val[((size_t)m * nm1 + e) * 2 + c];
+        row[c * cells + cell] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// sparse_layer1: first Linear of the grid embedding on the winner lists.
+//   grid  = (scene groups, OUT / 256 column chunks), 512 threads: thread = (half, column)
+//   smem  = acc[P][256] | lat[P][C] (social) | bucket tables | entries sorted by cell
+//   The CTA walks the cells in ascending order; the C x 256 weight slab of the next cell is
+//   prefetched into registers while the pairs binned in the current cell are applied.  Each
+//   (pedestrian, cell) has at most one winner, so the two halves never touch the same
+//   accumulator row and the result is deterministic.
+// ------------------------------------------------------------------------------------------
+constexpr int kL1Cols = 256;
+constexpr int kL1Threads = 512;
+
+struct L1Params {
+    const int* group_off;     // [G+1] scene indices
+    const int* scene_off;
+    const int* win_count;
+    const uint32_t* win_ent;
+    const float* win_val;
+    const float* lat;
+    const float* Wt;          // [cells, C, OUT]
+    const float* base;        // [OUT]
+    float* out;               // [M, OUT]
+    int OUT, cells, nm1, cap, relu;
+    float constant;
+};
+
+template <int C, bool SOCIAL>
+__global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_kernel(L1Params p) {
+    extern __shared__ __align__(16) unsigned char smem_l1[];
+    const int tid = threadIdx.x;
+    const int colc = tid & (kL1Cols - 1);
+    const int half = tid >> 8;
+    const int col = blockIdx.y * kL1Cols + colc;
+    const bool col_ok = col < p.OUT;
+    const int s0 = p.group_off[blockIdx.x], s1 = p.group_off[blockIdx.x + 1];
+    const int row0 = p.scene_off[s0];
+    const int P = p.scene_off[s1] - row0;
+
+    float* acc = reinterpret_cast<float*>(smem_l1);                       // [cap][256]
+    float* latS = acc + (size_t)p.cap * kL1Cols;                          // [cap][C] (social)
+    int* start = reinterpret_cast<int*>(latS + (SOCIAL ? (size_t)p.cap * C : 0));   // [cells+1]
+    int* cursor = start + p.cells + 1;                                    // [cells]
+    uint16_t* entP = reinterpret_cast<uint16_t*>(cursor + p.cells);       // [cap*nm1]
+    uint16_t* entS = entP + (size_t)p.cap * p.nm1;                        // [cap*nm1] (social)
+    float* entV = reinterpret_cast<float*>(                               // [cap*nm1][C] (non-social)
+        reinterpret_cast<unsigned char*>(entP) +
+        (((size_t)p.cap * p.nm1 * 2 * sizeof(uint16_t) + 15) & ~(size_t)15));
+
+    for (int c = tid; c < p.cells; c += kL1Threads) cursor[c] = 0;
+    if (SOCIAL) {
+        for (int idx = tid; idx < P * C; idx += kL1Threads) latS[idx] = p.lat[(size_t)row0 * C + idx] - p.constant;
+    }
+    const float b = col_ok ? p.base[col] : 0.f;
+    for (int r = half; r < P; r += 2) acc[r * kL1Cols + colc] = b;
+    __syncthreads();
+    // histogram of winners per cell
+    const int total = P * p.nm1;
+    for (int idx = tid; idx < total; idx += kL1Threads) {
+        int r = idx / p.nm1, k = idx - r * p.nm1;
+        if (k < p.win_count[row0 + r]) atomicAdd(&cursor[p.win_ent[(size_t)(row0 + r) * p.nm1 + k] >> 16], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {   // exclusive scan of the histogram by one warp
+        int per = (p.cells + 31) / 32;
+        int lo = tid * per, hi = min(lo + per, p.cells);
+        int sum = 0;
+        for (int c = lo; c < hi; ++c) sum += cursor[c];
+        int incl = sum;
+        for (int d = 1; d < 32; d <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (tid >= d) incl += v;
+        }
+        int run = incl - sum;
+        for (int c = lo; c < hi; ++c) {
+            int cnt = cursor[c];
+            start[c] = run;
+            cursor[c] = run;
+            run += cnt;
+        }
+        if (tid == 31) start[p.cells] = incl;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < total; idx += kL1Threads) {
+        int r = idx / p.nm1, k = idx - r * p.nm1;
+        if (k < p.win_count[row0 + r]) {
+            size_t g = (size_t)(row0 + r) * p.nm1 + k;
+            uint32_t ent = p.win_ent[g];
+            int pos = atomicAdd(&cursor[ent >> 16], 1);
+            entP[pos] = (uint16_t)r;
+            if (SOCIAL) {
+                // scene-local j -> group-local row
+                int m = row0 + r;
+                // find the scene start of row r inside the group (scenes are few per group)
+                int sb = s0;
+                while (p.scene_off[sb + 1] <= m) ++sb;
+                entS[pos] = (uint16_t)(p.scene_off[sb] - row0 + (int)(ent & 0xffff));
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; ++c) entV[(size_t)pos * C + c] = p.win_val[g * 2 + c] - p.constant;
+            }
+        }
+    }
+    __syncthreads();
+
+    float w[C], wn[C];
+    const float* wcol = p.Wt + col;
+#pragma unroll
+    for (int c = 0; c < C; ++c) w[c] = col_ok ? wcol[(size_t)c * p.OUT] : 0.f;
+    for (int cell = 0; cell < p.cells; ++cell) {
+        if (cell + 1 < p.cells) {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                wn[c] = col_ok ? wcol[((size_t)(cell + 1) * C + c) * p.OUT] : 0.f;
+        }
+        const int e0 = start[cell], e1 = start[cell + 1];
+        for (int e = e0 + half; e < e1; e += 2) {
+            const int r = entP[e];
+            float a = acc[r * kL1Cols + colc];
+            if (SOCIAL) {
+                const float4* lv = reinterpret_cast<const float4*>(latS + (size_t)entS[e] * C);
+#pragma unroll
+                for (int c4 = 0; c4 < C / 4; ++c4) {
+                    float4 v = lv[c4];
+                    a = fmaf(v.x, w[c4 * 4 + 0], a);
+                    a = fmaf(v.y, w[c4 * 4 + 1], a);
+                    a = fmaf(v.z, w[c4 * 4 + 2], a);
+                    a = fmaf(v.w, w[c4 * 4 + 3], a);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; ++c) a = fmaf(entV[(size_t)e * C + c], w[c], a);
+            }
+            acc[r * kL1Cols + colc] = a;
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) w[c] = wn[c];
+    }
+    __syncthreads();
+    if (col_ok) {
+        for (int r = half; r < P; r += 2) {
+            float v = acc[r * kL1Cols + colc];
+            if (p.relu) v = fmaxf(v, 0.f);
+            p.out[(size_t)(row0 + r) * p.OUT + col] = v;
+        }
+    }
+}
+
+static size_t l1_smem_bytes(int cap, int C, bool social, int cells, int nm1) {
+    size_t b = (size_t)cap * kL1Cols * sizeof(float);
+    if (social) b += (size_t)cap * C * sizeof(float);
+    b += (size_t)(2 * cells + 1) * sizeof(int);
+    size_t ents = ((size_t)cap * nm1 * 2 * sizeof(uint16_t) + 15) & ~(size_t)15;
+    b += ents;
+    if (!social) b += (size_t)cap * nm1 * C * sizeof(float);
+    return b + 16;
+}
+
+// ------------------------------------------------------------------------------------------
+// dense_layer: Y = act(X . W^T + b), X [M, K], WT [K, N] (transposed at repack).  fp32 FFMA,
+// 64 x 64 x 16 tiles, 4 x 4 micro-tiles.  (Layers >= 2 of the grid embedding.)
+// ------------------------------------------------------------------------------------------
+constexpr int kDT = 64, kDK = 16;
+
+__global__ void __launch_bounds__(256) dense_layer_kernel(const float* __restrict__ X,
+                                                          const float* __restrict__ WT,
+                                                          const float* __restrict__ bias,
+                                                          float* __restrict__ Y, int M, int K, int N,
+                                                          int relu) {
+    __shared__ float As[kDK][kDT + 4];
+    __shared__ float Bs[kDK][kDT];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * kDT, n0 = blockIdx.x * kDT;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += kDK) {
+        // A tile: 64 rows x 16 k  (thread loads 4 consecutive k of one row)
+        {
+            int r = tid >> 2, kq = (tid & 3) * 4;
+            int m = m0 + r;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int k = k0 + kq + q;
+                As[kq + q][r] = (m < M && k < K) ? X[(size_t)m * K + k] : 0.f;
+            }
+        }
+        // B tile: 16 k x 64 cols
+        {
+            int kk = tid >> 4, cq = (tid & 15) * 4;
+            int k = k0 + kk;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                int n = n0 + cq + q;
+                Bs[kk][cq + q] = (k < K && n < N) ? WT[(size_t)k * N + n] : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < kDK; ++kk) {
+            float a[4], bb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bb[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + tx * 4 + j;
+            if (n >= N) continue;
+            float v = acc[i][j] + bias[n];
+            if (relu) v = fmaxf(v, 0.f);
+            Y[(size_t)m * N + n] = v;
+        }
+    }
+}
+
+static int launch_dense(const float* X, const float* WT, const float* b, float* Y, int M, int K, int N,
+                        int relu, cudaStream_t st) {
+    dim3 grid((N + kDT - 1) / kDT, (M + kDT - 1) / kDT);
+    dense_layer_kernel<<<grid, 256, 0, st>>>(X, WT, b, Y, M, K, N, relu);
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
+}
+
+template <int C, bool SOCIAL>
+static int launch_l1_t(const L1Params& p, int groups, size_t smem, cudaStream_t st) {
+    static size_t configured = 0;
+    if (smem > configured) {
+        TB2_CHECK_CUDA(cudaFuncSetAttribute(sparse_layer1_kernel<C, SOCIAL>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid(groups, (p.OUT + kL1Cols - 1) / kL1Cols);
+    sparse_layer1_kernel<C, SOCIAL><<<grid, kL1Threads, smem, st>>>(p);
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
+}
+
+// Grid -> pooled vector (GridBasedPooling.forward after the grid is known, :106-110).
+int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float* pooled_out,
+                    cudaStream_t st) {
+    const int nm1 = l->n_max > 1 ? l->n_max - 1 : 1;
+    if (m->n_mlp == 0) {
+        dense_grid_kernel<<<l->M, 128, 0, st>>>(ws->win_count, ws->win_ent, ws->win_val, ws->lat,
+                                                l->row_scene, l->scene_off, pooled_out, m->C, m->cells,
+                                                nm1, m->cfg.constant, m->cfg.pool_type);
+        TB2_LAUNCH_CHECK();
+        return TB2_OK;
+    }
+    const int d1 = m->mlp_dims[1];
+    const bool social = m->cfg.pool_type == TB2_POOL_SOCIAL;
+    // few column chunks -> small scene groups so the grid still covers the SMs
+    const int chunks = (d1 + kL1Cols - 1) / kL1Cols;
+    int gsel = chunks >= 4 ? 0 : 1;
+    size_t smem = l1_smem_bytes(l->group_cap[gsel], m->C, social, m->cells, nm1);
+    if (smem > 227 * 1024 && gsel == 0) {
+        gsel = 1;
+        smem = l1_smem_bytes(l->group_cap[gsel], m->C, social, m->cells, nm1);
+    }
+    TB2_REQUIRE(smem <= 227 * 1024, "scene group does not fit in shared memory (scene too large)");
+    L1Params p;
+    p.group_off = l->group_off[gsel];
+    p.scene_off = l->scene_off;
+    p.win_count = ws->win_count;
+    p.win_ent = ws->win_ent;
+    p.win_val = ws->win_val;
+    p.lat = ws->lat;
+    p.Wt = m->Wt1;
+    p.base = m->base1;
+    p.OUT = d1;
+    p.cells = m->cells;
+    p.nm1 = nm1;
+    p.cap = l->group_cap[gsel];
+    p.relu = 1;
+    p.constant = m->cfg.constant;
+    float* l1_out = (m->n_mlp == 1) ? pooled_out : ws->act[0];
+    p.out = l1_out;
+    int rc;
+    switch (m->cfg.pool_type) {
+        case TB2_POOL_OCCUPANCY: rc = launch_l1_t<1, false>(p, l->num_groups[gsel], smem, st); break;
+        case TB2_POOL_DIRECTIONAL: rc = launch_l1_t<2, false>(p, l->num_groups[gsel], smem, st); break;
+        case TB2_POOL_SOCIAL:
+            if (m->C == 16) rc = launch_l1_t<16, true>(p, l->num_groups[gsel], smem, st);
+            else if (m->C == 8) rc = launch_l1_t<8, true>(p, l->num_groups[gsel], smem, st);
+            else if (m->C == 4) rc = launch_l1_t<4, true>(p, l->num_groups[gsel], smem, st);
+            else if (m->C == 32) rc = launch_l1_t<32, true>(p, l->num_groups[gsel], smem, st);
+            else { set_error("social latent_dim must be 4, 8, 16 or 32"); return TB2_ERR_UNSUPPORTED; }
+            break;
+        default: set_error("bad pool type"); return TB2_ERR_INVALID;
+    }
+    if (rc != TB2_OK) return rc;
+    const float* x = l1_out;
+    for (int layer = 1; layer < m->n_mlp; ++layer) {
+        float* y = (layer == m->n_mlp - 1) ? pooled_out : ws->act[layer & 1];
+        rc = launch_dense(x, m->WT[layer], m->bl[layer], y, l->M, m->mlp_dims[layer], m->mlp_dims[layer + 1], 1, st);
+        if (rc != TB2_OK) return rc;
+        x = y;
+    }
+    return TB2_OK;
+}
+
+}  // namespace tb2

@@ -1,0 +1,153 @@
+"""Thin host-side owner of the C-ABI handles (model weights, scene layout, scratch).
+
+PyTorch is plumbing here: it owns device memory and streams; every computation on the hot
+path happens inside libtrajnet_b200.so.
+"""
+import ctypes
+import weakref
+from collections import OrderedDict
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class SceneLayout:
+    """tb2_layout wrapper: the `batch_split` partition of tracks into scenes."""
+
+    def __init__(self, batch_split):
+        lib = _lib.load()
+        offs = [int(v) for v in batch_split]
+        self.offsets = offs
+        arr = (ctypes.c_int64 * len(offs))(*offs)
+        handle = ctypes.c_void_p()
+        _lib.check(lib.tb2_layout_create(arr, len(offs) - 1, ctypes.byref(handle)))
+        self.handle = handle
+        self.num_scenes = len(offs) - 1
+        self.num_tracks = offs[-1]
+        self.max_scene = int(lib.tb2_layout_max_scene(handle))
+        self._finalizer = weakref.finalize(self, lib.tb2_layout_destroy, handle)
+
+
+class LayoutCache:
+    def __init__(self, capacity=8):
+        self.capacity = capacity
+        self._items = OrderedDict()
+
+    def get(self, batch_split):
+        key = tuple(int(v) for v in batch_split)
+        item = self._items.get(key)
+        if item is None:
+            item = SceneLayout(key)
+            self._items[key] = item
+            if len(self._items) > self.capacity:
+                self._items.popitem(last=False)
+        else:
+            self._items.move_to_end(key)
+        return item
+
+
+class ModelHandle:
+    """tb2_lstm wrapper: configuration + repacked weights on one device."""
+
+    def __init__(self, config, device):
+        _lib.require_cuda()
+        lib = _lib.load()
+        self.device = torch.device(device)
+        self.config = config
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.tb2_lstm_create(ctypes.byref(config), ctypes.byref(handle)))
+        self.handle = handle
+        self._finalizer = weakref.finalize(self, lib.tb2_lstm_destroy, handle)
+        self._weights_key = None
+        self._workspace = None
+
+    def set_weights(self, named, key=None):
+        """named: dict field name -> CUDA fp32 contiguous tensor (or list of 3 for the MLP)."""
+        if key is not None and key == self._weights_key:
+            return
+        lib = _lib.load()
+        w = _lib.LstmWeights()
+        keep = []
+        for field, value in named.items():
+            if isinstance(value, (list, tuple)):
+                arr = getattr(w, field)
+                for i, t in enumerate(value):
+                    if t is not None:
+                        t = self._prep(t)
+                        keep.append(t)
+                        arr[i] = t.data_ptr()
+            elif value is not None:
+                t = self._prep(value)
+                keep.append(t)
+                setattr(w, field, t.data_ptr())
+        with torch.cuda.device(self.device):
+            _lib.check(lib.tb2_lstm_set_weights(self.handle, ctypes.byref(w), _stream(self.device)))
+        # the repack kernels read `keep` asynchronously on the current stream; record usage
+        for t in keep:
+            t.record_stream(torch.cuda.current_stream(self.device))
+        self._weights_key = key
+
+    def _prep(self, t):
+        t = t.detach()
+        if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+            t = t.to(device=self.device, dtype=torch.float32).contiguous()
+        return t
+
+    def workspace(self, layout):
+        lib = _lib.load()
+        need = int(lib.tb2_lstm_workspace_bytes(self.handle, layout.handle))
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._workspace, need
+
+    # -- compute entry points ---------------------------------------------------------------
+    def grid_indices(self, layout, obs):
+        lib = _lib.load()
+        nm1 = max(layout.max_scene - 1, 0)
+        cells = torch.empty((layout.num_tracks, nm1), dtype=torch.int32, device=self.device)
+        flags = torch.empty((layout.num_tracks, nm1), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.tb2_grid_indices(self.handle, layout.handle, _ptr(obs), _ptr(cells),
+                                            _ptr(flags), _stream(self.device)))
+        return cells, flags
+
+    def pool_forward(self, layout, hidden, obs1, obs2, out_dim):
+        lib = _lib.load()
+        ws, need = self.workspace(layout)
+        out = torch.empty((layout.num_tracks, out_dim), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.tb2_pool_forward(self.handle, layout.handle, _ptr(hidden), _ptr(obs1),
+                                            _ptr(obs2), _ptr(out), _ptr(ws), need, _stream(self.device)))
+        return out
+
+    def step_forward(self, layout, phase, obs1, obs2, h, c):
+        """One step; h, c updated in place.  Returns (normal [M,5], pos [M,2])."""
+        lib = _lib.load()
+        ws, need = self.workspace(layout)
+        M = layout.num_tracks
+        normal = torch.empty((M, 5), dtype=torch.float32, device=self.device)
+        pos = torch.empty((M, 2), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.tb2_lstm_step_forward(self.handle, layout.handle, phase, _ptr(obs1), _ptr(obs2),
+                                                 _ptr(h), _ptr(c), _ptr(h), _ptr(c), _ptr(normal),
+                                                 _ptr(pos), _ptr(ws), need, _stream(self.device)))
+        return normal, pos
+
+    def forward_sequence(self, layout, observed, truth, n_decode, normals, positions, h, c, states=None):
+        lib = _lib.load()
+        ws, need = self.workspace(layout)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.tb2_lstm_forward_sequence(
+                self.handle, layout.handle, _ptr(observed), int(observed.shape[0]), _ptr(truth),
+                int(n_decode), _ptr(normals), _ptr(positions), _ptr(h), _ptr(c), _ptr(states),
+                _ptr(ws), need, _stream(self.device)))

@@ -1,0 +1,4 @@
+"""Drop-in surface of trajnetbaselines.lstm (reference: trajnetbaselines/lstm/__init__.py)."""
+from .loss import PredictionLoss, L2Loss
+from .lstm import LSTM, LSTMPredictor, drop_distant
+from .gridbased_pooling import GridBasedPooling

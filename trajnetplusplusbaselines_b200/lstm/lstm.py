@@ -1,0 +1,277 @@
+"""LSTM forecaster + predictor with the reference's API, backed by libtrajnet_b200.
+
+Mirrors trajnetbaselines/lstm/lstm.py: drop_distant :16-22, LSTM :45-264, LSTMPredictor
+:266-313.  Same constructor arguments, same state_dict keys, same
+forward signature and return shapes; the time loop, the per-step mask / embed / pool /
+LSTMCell / Gaussian head and the decoder feedback rule all run on the GPU through
+tb2_lstm_forward_sequence (csrc/capi.cu).  There is no torch or CPU implementation of the
+step in this package: without the CUDA library the calls raise.
+"""
+import numpy as np
+import torch
+
+from .. import _lib
+from ..data import paths_to_xy
+from ..engine import LayoutCache, ModelHandle
+from .modules import Hidden2Normal, InputEmbedding
+
+NAN = float('nan')
+
+
+def drop_distant(xy, r=6.0):
+    """Drops pedestrians more than r meters away from the primary ped (lstm.py:16-22)."""
+    distance_2 = np.sum(np.square(xy - xy[:, 0:1]), axis=2)
+    mask = np.nanmin(distance_2, axis=0) < r**2
+    return xy[:, mask], mask
+
+
+def theta_rotation(xy, theta):
+    ct, st = np.cos(theta), np.sin(theta)
+    r = np.array([[ct, st], [-st, ct]])
+    return np.einsum('ptc,ci->pti', xy, r)
+
+
+def center_scene(xy, obs_length=9, ped_id=0, goals=None):
+    """Host-side scene normalisation (reference lstm/utils.py:32-51)."""
+    if goals is not None:
+        goals = goals[np.newaxis, :, :]
+    center = xy[obs_length - 1, ped_id]
+    xy = xy - center[np.newaxis, np.newaxis, :]
+    if goals is not None:
+        goals = goals - center[np.newaxis, np.newaxis, :]
+    last_obs = xy[obs_length - 1, ped_id]
+    second_last_obs = xy[obs_length - 2, ped_id]
+    diff = np.array([last_obs[0] - second_last_obs[0], last_obs[1] - second_last_obs[1]])
+    thet = np.arctan2(diff[1], diff[0])
+    rotation = -thet + np.pi / 2
+    xy = theta_rotation(xy, rotation)
+    if goals is not None:
+        goals = theta_rotation(goals, rotation)
+        return xy, rotation, center, goals[0]
+    return xy, rotation, center
+
+
+def inverse_scene(xy, rotation, center):
+    """Reference augmentation.py:65-68."""
+    xy = theta_rotation(xy, -rotation)
+    return xy + center[np.newaxis, np.newaxis, :]
+
+
+class LSTM(torch.nn.Module):
+    def __init__(self, embedding_dim=64, hidden_dim=128, pool=None, pool_to_input=True, goal_dim=None, goal_flag=False):
+        """Same arguments as the reference (lstm.py:46-60)."""
+        super().__init__()
+        self.hidden_dim = hidden_dim
+        self.embedding_dim = embedding_dim
+        self.pool = pool
+        self.pool_to_input = pool_to_input
+
+        scale = 4.0
+        self.input_embedding = InputEmbedding(2, self.embedding_dim, scale)
+
+        self.goal_flag = goal_flag
+        self.goal_dim = goal_dim or embedding_dim
+        self.goal_embedding = InputEmbedding(2, self.goal_dim, scale)   # kept for state_dict parity
+        goal_rep_dim = self.goal_dim if self.goal_flag else 0
+
+        pooling_dim = 0
+        if pool is not None and self.pool_to_input:
+            pooling_dim = self.pool.out_dim
+
+        self.encoder = torch.nn.LSTMCell(self.embedding_dim + goal_rep_dim + pooling_dim, self.hidden_dim)
+        self.decoder = torch.nn.LSTMCell(self.embedding_dim + goal_rep_dim + pooling_dim, self.hidden_dim)
+        self.hidden2normal = Hidden2Normal(self.hidden_dim)
+
+        self._handle = None
+        self._layouts = LayoutCache()
+        self._pinned = {}
+
+    # -- engine plumbing ---------------------------------------------------------------------
+    def _device(self):
+        return self.hidden2normal.linear.weight.device
+
+    def _engine(self):
+        if self.goal_flag:
+            raise NotImplementedError("goal_flag=True is not built (off in every BASELINE config)")
+        device = self._device()
+        if device.type != 'cuda':
+            _lib.require_cuda()
+            raise RuntimeError("LSTM parameters are on %s: move the model to a CUDA device (model.to('cuda')); "
+                               "there is no CPU path" % device)
+        if self._handle is None or self._handle.device != device:
+            cfg = _lib.LstmConfig()
+            cfg.hidden_dim = int(self.hidden_dim)
+            cfg.embedding_dim = int(self.embedding_dim)
+            cfg.pool_to_input = int(bool(self.pool_to_input))
+            cfg.pool_type = _lib.POOL_NONE
+            cfg.pool_size = cfg.blur_size = 1
+            if self.pool is not None:
+                if not hasattr(self.pool, 'fill_config'):
+                    raise NotImplementedError("only GridBasedPooling interaction modules are built")
+                self.pool.fill_config(cfg)
+            self._handle = ModelHandle(cfg, device)
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if key != self._handle._weights_key:
+            lin = self.input_embedding.input_embeddings[0]
+            fields = dict(
+                input_embedding_weight=lin.weight, input_embedding_bias=lin.bias,
+                encoder_weight_ih=self.encoder.weight_ih, encoder_weight_hh=self.encoder.weight_hh,
+                encoder_bias_ih=self.encoder.bias_ih, encoder_bias_hh=self.encoder.bias_hh,
+                decoder_weight_ih=self.decoder.weight_ih, decoder_weight_hh=self.decoder.weight_hh,
+                decoder_bias_ih=self.decoder.bias_ih, decoder_bias_hh=self.decoder.bias_hh,
+                hidden2normal_weight=self.hidden2normal.linear.weight,
+                hidden2normal_bias=self.hidden2normal.linear.bias)
+            if self.pool is not None:
+                fields.update(self.pool.weight_fields())
+            self._handle.set_weights(fields, key=key)
+        return self._handle
+
+    def _to_device(self, t, device):
+        """Host tensors go through pinned staging (H2D inside the caller's timed region)."""
+        if t is None:
+            return None
+        t = t.detach()
+        if t.device.type == 'cuda':
+            return t.to(device=device, dtype=torch.float32).contiguous()
+        t = t.to(dtype=torch.float32).contiguous()
+        key = (tuple(t.shape), 'in')
+        buf = self._pinned.get(key)
+        if buf is None:
+            buf = torch.empty(t.shape, dtype=torch.float32, pin_memory=True)
+            self._pinned[key] = buf
+        buf.copy_(t)
+        return buf.to(device, non_blocking=True)
+
+    # -- reference API -----------------------------------------------------------------------
+    def step(self, lstm, hidden_cell_state, obs1, obs2, goals, batch_split):
+        """One step (lstm.py:91-168).  hidden_cell_state = (h [M, H], c [M, H]) flat CUDA tensors
+        (the reference's per-track Python lists are also accepted and converted)."""
+        handle = self._engine()
+        device = handle.device
+        phase = _lib.PHASE_ENCODER if lstm is self.encoder else _lib.PHASE_DECODER
+        h, c = hidden_cell_state
+        was_list = isinstance(h, (list, tuple))
+        if was_list:
+            h, c = torch.stack(list(h)), torch.stack(list(c))
+        h = h.detach().to(device=device, dtype=torch.float32).contiguous().clone()
+        c = c.detach().to(device=device, dtype=torch.float32).contiguous().clone()
+        layout = self._layouts.get(batch_split.tolist() if torch.is_tensor(batch_split) else batch_split)
+        o1 = self._to_device(obs1, device)
+        o2 = self._to_device(obs2, device)
+        normal, _ = handle.step_forward(layout, phase, o1, o2, h, c)
+        if was_list:
+            return (list(h), list(c)), normal
+        return (h, c), normal
+
+    def forward(self, observed, goals, batch_split, prediction_truth=None, n_predict=None):
+        """Forecast the entire sequence (lstm.py:170-264).
+
+        observed [obs_length, M, 2]; batch_split [B + 1]; prediction_truth [pred_length - 1, M, 2]
+        (teacher forcing) xor n_predict.  Returns rel_pred_scene [S, M, 5], pred_scene [S, M, 2]
+        on the device `observed` came from.
+        """
+        assert ((prediction_truth is None) + (n_predict is None)) == 1
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .training import sequence_with_grad
+            return sequence_with_grad(self, observed, batch_split, prediction_truth, n_predict)
+        return self._forward_nograd(observed, batch_split, prediction_truth, n_predict)
+
+    def _forward_nograd(self, observed, batch_split, prediction_truth, n_predict, want_states=False):
+        handle = self._engine()
+        device = handle.device
+        out_device = observed.device
+        layout = self._layouts.get(batch_split.tolist() if torch.is_tensor(batch_split) else batch_split)
+        M = layout.num_tracks
+        if observed.shape[1] != M:
+            raise ValueError("batch_split[-1] != number of tracks")
+        obs = self._to_device(observed, device)
+        obs_length = int(obs.shape[0])
+        if prediction_truth is not None:
+            if isinstance(prediction_truth, (list, tuple)):
+                prediction_truth = torch.stack(list(prediction_truth))
+            truth = self._to_device(prediction_truth, device)
+            n_decode = int(truth.shape[0])
+            if n_decode == 0:
+                truth = None
+        else:
+            truth = None
+            n_decode = int(n_predict) - 1
+        S = obs_length - 1 + n_decode
+        f32 = dict(dtype=torch.float32, device=device)
+        normals = torch.empty((S, M, 5), **f32)
+        positions = torch.empty((S, M, 2), **f32)
+        h = torch.empty((M, self.hidden_dim), **f32)
+        c = torch.empty((M, self.hidden_dim), **f32)
+        states = torch.empty((S, 2, M, self.hidden_dim), **f32) if want_states else None
+        handle.forward_sequence(layout, obs, truth, n_decode, normals, positions, h, c, states)
+        if obs_length == 2:                      # lstm.py:222-223: positions seeded with observed[-1]
+            positions = torch.cat([obs[-1:].clone(), positions], dim=0)
+        if want_states:
+            return normals, positions, states, (obs, truth, layout)
+        if out_device != device:
+            normals, positions = self._to_host(normals, positions)
+        return normals, positions
+
+    def _to_host(self, *tensors):
+        outs = []
+        for i, t in enumerate(tensors):
+            key = (tuple(t.shape), 'out', i)
+            buf = self._pinned.get(key)
+            if buf is None:
+                buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                self._pinned[key] = buf
+            buf.copy_(t, non_blocking=True)
+            outs.append(buf)
+        torch.cuda.current_stream(tensors[0].device).synchronize()
+        return [b.clone() for b in outs]
+
+    def __getstate__(self):
+        # handles / pinned staging are per-process; never pickled (LSTMPredictor.save pickles the model)
+        state = self.__dict__.copy()
+        state['_handle'] = None
+        state['_layouts'] = LayoutCache()
+        state['_pinned'] = {}
+        return state
+
+
+class LSTMPredictor(object):
+    """Reference lstm.py:266-313."""
+
+    def __init__(self, model):
+        self.model = model
+
+    def save(self, state, filename):
+        with open(filename, 'wb') as f:
+            torch.save(self, f)
+        with open(filename + '.state', 'wb') as f:
+            torch.save(state, f)
+
+    @staticmethod
+    def load(filename):
+        with open(filename, 'rb') as f:
+            return torch.load(f, weights_only=False)   # torch >= 2.6 default would reject the pickle
+
+    def __call__(self, paths, scene_goal, n_predict=12, modes=1, predict_all=True, obs_length=9, start_length=0, args=None):
+        self.model.eval()
+        with torch.no_grad():
+            xy = paths_to_xy(paths)
+            batch_split = [0, xy.shape[1]]
+
+            normalize = bool(getattr(args, 'normalize_scene', False))
+            if normalize:
+                xy, rotation, center, scene_goal = center_scene(xy, obs_length, goals=np.asarray(scene_goal))
+
+            xy = torch.Tensor(xy)
+            scene_goal = torch.Tensor(np.asarray(scene_goal))
+            batch_split = torch.Tensor(batch_split).long()
+
+            multimodal_outputs = {}
+            for num_p in range(modes):
+                _, output_scenes = self.model(xy[start_length:obs_length], scene_goal, batch_split, n_predict=n_predict)
+                output_scenes = output_scenes.cpu().numpy()
+                if normalize:
+                    output_scenes = inverse_scene(output_scenes, rotation, center)
+                output_primary = output_scenes[-n_predict:, 0]
+                output_neighs = output_scenes[-n_predict:, 1:]
+                multimodal_outputs[num_p] = [output_primary, output_neighs]
+        return multimodal_outputs
