@@ -44,6 +44,12 @@ int tb2_version(void);
 /* Number of library kernel launches issued by this process so far (bench "gpu_launches"). */
 uint64_t tb2_launch_count(void);
 
+/* Per-kernel timing for bench.py's roofline: between begin and end every library kernel is
+ * bracketed by CUDA events on its launching stream.  tb2_profile_end synchronises the device and
+ * writes {"kernel": {"launches": n, "total_ms": t}, ...} into json_out. */
+int tb2_profile_begin(void);
+int tb2_profile_end(char* json_out, size_t capacity);
+
 /* ---------------------------------------------------------------------------------------
  * Model configuration = constructor arguments of LSTM (lstm/lstm.py:46) and
  * GridBasedPooling (lstm/gridbased_pooling.py:16-19).

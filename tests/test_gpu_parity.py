@@ -1,0 +1,301 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the committed reference
+fixtures.  Run on the B200 box: `pytest -m gpu`.
+
+Bars (BASELINE.json north_star): grid cell indices bit-exact; predicted positions within 1e-4 m
+(ADE/FDE vs the reference), tolerance written at each assert.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lstm_oracle as O
+from oracle.make_golden import CASES
+
+pytestmark = pytest.mark.gpu
+
+TOL_POS = 1e-4      # metres, north_star: "within 1e-4 m on ADE/FDE"
+TOL_STEP = 2e-5     # single teacher-forced step / short chains (fp32, different summation order)
+
+
+def build_model(kind, W, device="cuda"):
+    from trajnetplusplusbaselines_b200.lstm import LSTM, GridBasedPooling
+    spec = O.MODEL_SPECS[kind]
+    pool = GridBasedPooling(**spec) if spec is not None else None
+    model = LSTM(pool=pool)
+    model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in W.items()}, strict=True)
+    return model.to(device).eval()
+
+
+def maxdiff(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else a
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert (np.isnan(a) == np.isnan(b)).all(), "NaN pattern differs"
+    return float(np.nanmax(np.abs(a - b))) if a.size else 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# grid cell indices: bit-exact
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["social", "directional", "occupancy_front"])
+def test_grid_indices_match_reference_fixture(golden, kind):
+    from trajnetplusplusbaselines_b200.engine import SceneLayout
+    obs = golden["cells_%s/obs" % kind]                      # [B, N, 2]
+    B, N, _ = obs.shape
+    model = build_model(kind, O.random_weights(kind, seed=0))
+    handle = model._engine()
+    layout = SceneLayout(range(0, B * N + 1, N))
+    cells, flags = handle.grid_indices(layout, torch.from_numpy(obs.reshape(B * N, 2)).cuda())
+    assert np.array_equal(flags.cpu().numpy().astype(bool).reshape(B, N, N - 1), golden["cells_%s/in_range" % kind])
+    assert np.array_equal(cells.cpu().numpy().reshape(B, N, N - 1), golden["cells_%s/cells" % kind])
+
+
+@pytest.mark.parametrize("kind,seed", [("social", 0), ("directional", 1), ("occupancy_front", 2)])
+def test_grid_indices_boundary_sweep_bit_exact(kind, seed):
+    """20k pairs snapped onto / one ulp around cell edges, ragged scenes: int equality vs oracle."""
+    from trajnetplusplusbaselines_b200.engine import SceneLayout
+    cfg = O.pool_config(kind)
+    rng = np.random.RandomState(seed)
+    B, N = 64, 18
+    sizes = rng.randint(2, N + 1, size=B)
+    sizes[0] = N
+    obs = np.full((B, N, 2), np.nan, dtype=np.float32)
+    side = np.float32(cfg.cell_side)
+    for b in range(B):
+        pts = (rng.randn(sizes[b], 2) * 2.0).astype(np.float32)
+        for j in range(1, sizes[b]):
+            r = rng.rand()
+            if r < 0.6:       # on a cell edge relative to ped 0, +- one ulp
+                k = rng.randint(-cfg.n // 2 - 1, cfg.n // 2 + 2, size=2).astype(np.float32)
+                edge = pts[0] + k * side
+                pts[j] = np.nextafter(edge, edge + rng.choice([-1.0, 0.0, 1.0], size=2).astype(np.float32))
+            if r > 0.95:
+                pts[j] = np.nan
+        obs[b, :sizes[b]] = pts
+    cells_o, inr_o = O.grid_cells(obs, cfg)                 # padded [B, N, N-1]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    flat = np.concatenate([obs[b, :sizes[b]] for b in range(B)]).astype(np.float32)
+    model = build_model(kind, O.random_weights(kind, seed=0))
+    layout = SceneLayout(offs.tolist())
+    cells, flags = model._engine().grid_indices(layout, torch.from_numpy(flat).cuda())
+    cells = cells.cpu().numpy()
+    flags = flags.cpu().numpy().astype(bool)
+    for b in range(B):
+        s, e = offs[b], offs[b + 1]
+        assert np.array_equal(flags[s:e], inr_o[b, :sizes[b]]), b
+        assert np.array_equal(cells[s:e], cells_o[b, :sizes[b]].astype(np.int32)), b
+
+
+# ---------------------------------------------------------------------------------------------
+# pool plug
+# ---------------------------------------------------------------------------------------------
+def test_pool_plug_reference_golden_vectors(golden):
+    """GridBasedPooling(embedding_arch='None') raw grids: adapted reference tests
+    at pool_size = blur_size = 1 (the only values the reference CLI can produce)."""
+    from trajnetplusplusbaselines_b200.lstm import GridBasedPooling
+    nan = float("nan")
+    pool = GridBasedPooling(n=2, cell_side=2.0, embedding_arch='None').cuda()
+    o = torch.tensor([[[0., 0.], [-1., -1.]]])
+    g = pool(torch.zeros(1, 2, 128), o, o)
+    assert np.array_equal(g.cpu().numpy(), golden["sec4/simple_grid_ps1"])
+    assert np.array_equal(g.cpu().numpy(), np.array([[1, 0, 0, 0], [0, 0, 0, 1]], dtype=np.float32))
+    o = torch.tensor([[[0., 0.], [nan, nan]]])
+    g = pool(torch.zeros(1, 2, 128), o, o)
+    assert np.array_equal(g.cpu().numpy(), golden["sec4/nan"])
+    pool = GridBasedPooling(n=2, cell_side=2.0, embedding_arch='None', type_='directional').cuda()
+    o1 = torch.tensor([[[0., 0.], [-1., -1.]]])
+    o2 = torch.tensor([[[0.1, 0.1], [-1.1, -1.1]]])
+    g = pool(torch.zeros(1, 2, 128), o1, o2)
+    assert np.allclose(g.cpu().numpy(), golden["sec4/directional_ps1"], atol=1e-7)
+    assert g.shape == (2, 8)
+
+
+@pytest.mark.parametrize("kind", ["occupancy", "directional", "social", "social_small",
+                                  "directional_const", "occupancy_front"])
+def test_pool_forward_matches_oracle(kind):
+    from trajnetplusplusbaselines_b200.lstm import GridBasedPooling
+    cfg = O.pool_config(kind)
+    W = O.random_weights(kind, seed=21)
+    rng = np.random.RandomState(5)
+    B, N = 9, 11
+    obs2 = (rng.randn(B, N, 2) * 2.0).astype(np.float32)
+    obs1 = obs2 - (rng.randn(B, N, 2) * 0.3).astype(np.float32)
+    hid = (rng.randn(B, N, 128) * 0.5).astype(np.float32)
+    obs2[1, 4:] = np.nan          # padded scene
+    obs1[1, 4:] = np.nan
+    hid[1, 4:] = np.nan
+    obs1[2, 3] = np.nan           # present now, absent before (velocity NaN -> 0 payload)
+    obs2[3, 5] = np.nan           # absent now
+    ref = O.pool_forward(cfg, W, hid, obs1, obs2)
+    pool = GridBasedPooling(**O.MODEL_SPECS[kind])
+    sd = {k[len("pool."):]: torch.from_numpy(v.copy()) for k, v in W.items() if k.startswith("pool.")}
+    pool.load_state_dict(sd, strict=True)
+    pool = pool.cuda()
+    out = pool(torch.from_numpy(hid).cuda(), torch.from_numpy(obs1).cuda(), torch.from_numpy(obs2).cuda())
+    assert out.shape == ref.shape
+    assert maxdiff(out, ref) < TOL_STEP
+
+
+# ---------------------------------------------------------------------------------------------
+# step and sequence
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["vanilla", "directional", "social_small", "social"])
+def test_single_step_matches_oracle(kind):
+    W = O.random_weights(kind, seed=31)
+    cfg = O.pool_config(kind)
+    xy, bs = O.synthetic_scenes(12, 10, seed=3, ragged=True, nan_tracks=True)
+    M = xy.shape[1]
+    rng = np.random.RandomState(0)
+    h = (rng.randn(M, 128) * 0.3).astype(np.float32)
+    c = (rng.randn(M, 128) * 0.3).astype(np.float32)
+    model = build_model(kind, W)
+    for phase, lstm in (("encoder", model.encoder), ("decoder", model.decoder)):
+        h_o, c_o, n_o = O.step(W, cfg, phase, h, c, xy[2], xy[3], bs)
+        (h_g, c_g), n_g = model.step(lstm, (torch.from_numpy(h).cuda(), torch.from_numpy(c).cuda()),
+                                     torch.from_numpy(xy[2]), torch.from_numpy(xy[3]), None, torch.from_numpy(bs))
+        assert maxdiff(n_g, n_o) < TOL_STEP
+        assert maxdiff(h_g, h_o) < TOL_STEP
+        assert maxdiff(c_g, c_o) < TOL_STEP
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_forward_matches_reference_fixture(golden, case):
+    name, kind, B, N, ragged, nan_tracks, dseed, wseed, wscale = case
+    xy, bs = O.synthetic_scenes(B, N, seed=dseed, ragged=ragged, nan_tracks=nan_tracks)
+    W = O.random_weights(kind, seed=wseed, scale=wscale)
+    model = build_model(kind, W)
+    M = xy.shape[1]
+    with torch.no_grad():
+        rel_f, pred_f = model(torch.from_numpy(xy[:9]), torch.zeros(M, 2), torch.from_numpy(bs), n_predict=12)
+        rel_t, pred_t = model(torch.from_numpy(xy[:9]), torch.zeros(M, 2), torch.from_numpy(bs),
+                              prediction_truth=torch.from_numpy(xy[9:20]).clone())
+    assert rel_f.device.type == "cpu"          # outputs follow the input device (predictor calls .numpy())
+    assert maxdiff(pred_t, golden[name + "/pred_teacher"]) < TOL_POS
+    assert maxdiff(rel_t, golden[name + "/rel_teacher"]) < TOL_POS
+    assert maxdiff(pred_f, golden[name + "/pred_free"]) < TOL_POS
+    assert maxdiff(rel_f, golden[name + "/rel_free"]) < TOL_POS
+
+
+@pytest.mark.parametrize("kind", ["vanilla", "occupancy", "directional", "social"])
+def test_baseline_config_ade_fde_vs_oracle(kind):
+    """BASELINE configs (N = 20, T = 9 + 12) at a batch the oracle finishes in seconds.  Gate on
+    ADE / FDE of the primaries vs the oracle, mean over scenes <= 1e-4 m; cell flips (chaotic
+    bin changes in a free-running rollout) are reported, not hidden."""
+    B, N = 48, 20
+    xy, bs = O.synthetic_scenes(B, N, seed=100 + len(kind))
+    W = O.random_weights(kind, seed=41)
+    model = build_model(kind, W)
+    M = xy.shape[1]
+    with torch.no_grad():
+        _, pred = model(torch.from_numpy(xy[:9]).cuda(), torch.zeros(M, 2), torch.from_numpy(bs), n_predict=12)
+        _, pred_tf = model(torch.from_numpy(xy[:9]).cuda(), torch.zeros(M, 2), torch.from_numpy(bs),
+                           prediction_truth=torch.from_numpy(xy[9:20]).cuda())
+    assert pred.device.type == "cuda"
+    _, pred_o = O.forward(W, O.pool_config(kind), xy[:9], bs, n_predict=12)
+    _, pred_tf_o = O.forward(W, O.pool_config(kind), xy[:9], bs, prediction_truth=xy[9:20])
+    pred = pred.cpu().numpy()
+    prim = bs[:-1]
+    ades, fdes = [], []
+    for p in prim:
+        a, f = O.ade_fde(pred[-12:, p], pred_o[-12:, p])
+        ades.append(a)
+        fdes.append(f)
+    flips = int((np.array(fdes) > 1e-3).sum())
+    print("%s: ADE mean %.3e max %.3e  FDE mean %.3e max %.3e  scenes with FDE>1e-3: %d/%d" %
+          (kind, np.mean(ades), np.max(ades), np.mean(fdes), np.max(fdes), flips, B))
+    assert maxdiff(pred_tf, pred_tf_o) < TOL_POS       # teacher-forced: every track, every step
+    assert np.median(ades) < TOL_POS and np.median(fdes) < TOL_POS
+    assert np.mean(ades) < TOL_POS and np.mean(fdes) < TOL_POS
+
+
+def test_obs_length_two_and_short_horizon():
+    """len(observed) == 2 seeds `positions` with observed[-1] (lstm.py:222-223)."""
+    kind = "directional"
+    xy, bs = O.synthetic_scenes(5, 6, seed=9)
+    W = O.random_weights(kind, seed=2)
+    model = build_model(kind, W)
+    M = xy.shape[1]
+    with torch.no_grad():
+        rel, pred = model(torch.from_numpy(xy[7:9]), torch.zeros(M, 2), torch.from_numpy(bs), n_predict=4)
+    rel_o, pred_o = O.forward(W, O.pool_config(kind), xy[7:9], bs, n_predict=4)
+    assert maxdiff(rel, rel_o) < TOL_STEP * 5
+    assert maxdiff(pred, pred_o) < TOL_STEP * 5
+    assert pred.shape[0] == rel.shape[0] + 1
+
+
+def test_single_pedestrian_scenes():
+    """Nmax == 1: constant grid (gridbased_pooling.py:252-253)."""
+    kind = "social_small"
+    xy, bs = O.synthetic_scenes(1, 1, seed=4)
+    W = O.random_weights(kind, seed=2)
+    model = build_model(kind, W)
+    with torch.no_grad():
+        rel, pred = model(torch.from_numpy(xy[:9]), torch.zeros(1, 2), torch.from_numpy(bs), n_predict=12)
+    rel_o, pred_o = O.forward(W, O.pool_config(kind), xy[:9], bs, n_predict=12)
+    assert maxdiff(pred, pred_o) < TOL_POS
+
+
+def test_full_size_properties_social():
+    """BASELINE full size (B = 256, N = 20): size-independent properties instead of the oracle.
+    (1) scenes are independent: the batched result equals per-shard results bit-for-bit
+        (this is also what the multi-GPU sharding relies on);
+    (2) determinism across repeated runs (the scatter is last-writer-wins, never atomic-add);
+    (3) tracks absent at the last observed frame stay NaN for the whole free-running rollout
+        (lstm.py:158)."""
+    kind = "social"
+    B, N = 256, 20
+    xy, bs = O.synthetic_scenes(B, N, seed=77, nan_tracks=True)
+    W = O.random_weights(kind, seed=8)
+    model = build_model(kind, W)
+    M = xy.shape[1]
+    obs = torch.from_numpy(xy[:9]).cuda()
+    with torch.no_grad():
+        rel, pred = model(obs, torch.zeros(M, 2), torch.from_numpy(bs), n_predict=12)
+        rel2, pred2 = model(obs, torch.zeros(M, 2), torch.from_numpy(bs), n_predict=12)
+        half = B // 2
+        cut = int(bs[half])
+        rel_a, pred_a = model(obs[:, :cut].contiguous(), torch.zeros(cut, 2), torch.from_numpy(bs[:half + 1]), n_predict=12)
+        rel_b, pred_b = model(obs[:, cut:].contiguous(), torch.zeros(M - cut, 2),
+                              torch.from_numpy(bs[half:] - cut), n_predict=12)
+    assert torch.equal(torch.nan_to_num(pred, nan=-1.0), torch.nan_to_num(pred2, nan=-1.0))
+    both = torch.cat([pred_a, pred_b], dim=1)
+    assert torch.equal(torch.nan_to_num(pred, nan=-1.0), torch.nan_to_num(both, nan=-1.0))
+    gone = np.isnan(xy[8, :, 0])
+    assert torch.isnan(pred[:, torch.from_numpy(gone).cuda()]).all()
+    always = ~np.isnan(xy[:9, :, 0]).any(axis=0)
+    assert not torch.isnan(pred[:, torch.from_numpy(always).cuda()]).any()
+    # sanity vs the oracle on a 16-scene slice of the same batch (scene independence makes this valid)
+    k = 16
+    cutk = int(bs[k])
+    _, pred_o = O.forward(W, O.pool_config(kind), xy[:9, :cutk], bs[:k + 1], n_predict=12)
+    d = np.abs(pred[:, :cutk].cpu().numpy() - pred_o)
+    assert (np.isnan(d) == np.isnan(pred_o)).all()
+    assert np.nanmedian(d) < TOL_POS
+
+
+def test_predictor_boundary_roundtrip(tmp_path):
+    """LSTMPredictor.__call__ / save / load (lstm.py:266-313) on the collision-test style scene."""
+    from types import SimpleNamespace
+    from trajnetplusplusbaselines_b200.data import TrackRow
+    from trajnetplusplusbaselines_b200.lstm import LSTMPredictor
+    kind = "directional"
+    W = O.random_weights(kind, seed=12)
+    model = build_model(kind, W)
+    paths = [[TrackRow(f, 1, 0.1, 6.2 - 0.4 * (f - 1)) for f in range(1, 10)],
+             [TrackRow(f, 2, 0.0, -6.2 + 0.4 * (f - 1)) for f in range(1, 10)],
+             [TrackRow(f, 3, 1.0 + 0.1 * f, 2.0) for f in range(4, 10)]]
+    predictor = LSTMPredictor(model)
+    args = SimpleNamespace(normalize_scene=False)
+    out = predictor(paths, np.zeros((3, 2)), n_predict=12, obs_length=9, modes=1, args=args)
+    prim, neigh = out[0]
+    assert prim.shape == (12, 2) and neigh.shape == (12, 2, 2)
+    xy = np.full((9, 3, 2), np.nan, dtype=np.float32)
+    for p, path in enumerate(paths):
+        for r in path:
+            xy[r.frame - 1, p] = (r.x, r.y)
+    _, pred_o = O.forward(W, O.pool_config(kind), xy, [0, 3], n_predict=12)
+    assert np.nanmax(np.abs(prim - pred_o[-12:, 0])) < TOL_POS
+    fn = str(tmp_path / "model.pkl")
+    predictor.save({"epoch": 1, "state_dict": model.state_dict()}, fn)
+    again = LSTMPredictor.load(fn)
+    out2 = again(paths, np.zeros((3, 2)), n_predict=12, obs_length=9, modes=1, args=args)
+    assert np.array_equal(out2[0][0], prim)

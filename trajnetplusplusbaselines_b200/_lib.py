@@ -89,6 +89,8 @@ PROTOTYPES = {
     "tb2_last_error": (ctypes.c_char_p, []),
     "tb2_version": (ctypes.c_int, []),
     "tb2_launch_count": (ctypes.c_uint64, []),
+    "tb2_profile_begin": (ctypes.c_int, []),
+    "tb2_profile_end": (ctypes.c_int, [ctypes.c_char_p, _sz]),
     "tb2_lstm_create": (ctypes.c_int, [ctypes.POINTER(LstmConfig), ctypes.POINTER(_vp)]),
     "tb2_lstm_destroy": (ctypes.c_int, [_vp]),
     "tb2_lstm_set_weights": (ctypes.c_int, [_vp, ctypes.POINTER(LstmWeights), _vp]),

@@ -1,5 +1,6 @@
 // extern "C" boundary of libtrajnet_b200 (see include/trajnet_b200.h).
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <new>
 
@@ -11,6 +12,24 @@ static thread_local std::string g_error;
 std::atomic<uint64_t> g_launch_count{0};
 
 void set_error(const std::string& msg) { g_error = msg; }
+
+// ---- optional per-kernel CUDA-event timing ---------------------------------------------------
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+static bool g_profiling = false;
+static std::vector<ProfRec> g_prof;
+
+KernelTimer::KernelTimer(const char* name, cudaStream_t s) : slot(-1), st(s) {
+    if (!g_profiling) return;
+    ProfRec r;
+    r.name = name;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    g_prof.push_back(r);
+    slot = (int)g_prof.size() - 1;
+}
+KernelTimer::~KernelTimer() {
+    if (slot >= 0) cudaEventRecord(g_prof[slot].b, st);
+}
 
 static int dev_alloc(std::vector<void*>& owned, void** out, size_t bytes) {
     *out = nullptr;
@@ -59,6 +78,41 @@ extern "C" {
 const char* tb2_last_error(void) { return g_error.c_str(); }
 int tb2_version(void) { return 100; }
 uint64_t tb2_launch_count(void) { return g_launch_count.load(); }
+
+int tb2_profile_begin(void) {
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_profiling = true;
+    return TB2_OK;
+}
+
+int tb2_profile_end(char* json_out, size_t capacity) {
+    g_profiling = false;
+    TB2_CHECK_CUDA(cudaDeviceSynchronize());
+    struct Agg { const char* name; double ms; long n; };
+    std::vector<Agg> agg;
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        bool found = false;
+        for (auto& a : agg) if (std::strcmp(a.name, r.name) == 0) { a.ms += ms; a.n++; found = true; break; }
+        if (!found) agg.push_back({r.name, (double)ms, 1});
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    std::string s = "{";
+    for (size_t i = 0; i < agg.size(); ++i) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "%s\"%s\": {\"launches\": %ld, \"total_ms\": %.6f}", i ? ", " : "",
+                 agg[i].name, agg[i].n, agg[i].ms);
+        s += buf;
+    }
+    s += "}";
+    TB2_REQUIRE(json_out && capacity > s.size(), "profile buffer too small");
+    std::memcpy(json_out, s.c_str(), s.size() + 1);
+    return TB2_OK;
+}
 
 int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
     TB2_REQUIRE(cfg && out, "null argument");

@@ -37,6 +37,15 @@ extern std::atomic<uint64_t> g_launch_count;
         TB2_CHECK_CUDA(cudaGetLastError());                                               \
     } while (0)
 
+// Optional per-kernel timing (tb2_profile_begin / tb2_profile_end): CUDA events recorded on the
+// launching stream around every kernel of the library.  Off by default (zero overhead).
+struct KernelTimer {
+    KernelTimer(const char* name, cudaStream_t st);
+    ~KernelTimer();
+    int slot;
+    cudaStream_t st;
+};
+
 constexpr int kMaxMlpLayers = 3;
 constexpr int kGateBK = 16;        // K-chunk of the gate GEMM; weight rows are padded to it
 

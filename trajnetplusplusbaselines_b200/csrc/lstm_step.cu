@@ -256,7 +256,10 @@ int launch_gates(const tb2_lstm* m, const tb2_layout* l, int phase, const float*
         configured = true;
     }
     int blocks = (l->M + kGM - 1) / kGM;
-    lstm_gates_kernel<<<blocks, kGThreads, smem, st>>>(p);
+    {
+        KernelTimer kt("lstm_gates", st);
+        lstm_gates_kernel<<<blocks, kGThreads, smem, st>>>(p);
+    }
     TB2_LAUNCH_CHECK();
     return TB2_OK;
 }

@@ -30,8 +30,11 @@ __global__ void resolve_obs_kernel(const float2* __restrict__ base, const float2
 int launch_resolve_obs(const tb2_layout* l, const float* base, const float* pred, float* out,
                        cudaStream_t st) {
     int threads = 256, blocks = (l->M + threads - 1) / threads;
-    resolve_obs_kernel<<<blocks, threads, 0, st>>>((const float2*)base, (const float2*)pred,
-                                                   l->row_scene, l->scene_off, (float2*)out, l->M);
+    {
+        KernelTimer kt("resolve_obs", st);
+        resolve_obs_kernel<<<blocks, threads, 0, st>>>((const float2*)base, (const float2*)pred,
+                                                       l->row_scene, l->scene_off, (float2*)out, l->M);
+    }
     TB2_LAUNCH_CHECK();
     return TB2_OK;
 }
@@ -206,7 +209,10 @@ int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hid
     p.width = (float)m->cfg.n;
     int nm1 = l->n_max > 1 ? l->n_max - 1 : 1;
     size_t smem = (size_t)l->n_max * 2 * sizeof(float2) + (size_t)kPrepWarps * nm1 * sizeof(int);
-    pool_prepare_kernel<<<l->B, kPrepThreads, smem, st>>>(p);
+    {
+        KernelTimer kt("pool_prepare", st);
+        pool_prepare_kernel<<<l->B, kPrepThreads, smem, st>>>(p);
+    }
     TB2_LAUNCH_CHECK();
     return TB2_OK;
 }
@@ -490,7 +496,10 @@ __global__ void __launch_bounds__(256) dense_layer_kernel(const float* __restric
 static int launch_dense(const float* X, const float* WT, const float* b, float* Y, int M, int K, int N,
                         int relu, cudaStream_t st) {
     dim3 grid((N + kDT - 1) / kDT, (M + kDT - 1) / kDT);
-    dense_layer_kernel<<<grid, 256, 0, st>>>(X, WT, b, Y, M, K, N, relu);
+    {
+        KernelTimer kt("dense_layer", st);
+        dense_layer_kernel<<<grid, 256, 0, st>>>(X, WT, b, Y, M, K, N, relu);
+    }
     TB2_LAUNCH_CHECK();
     return TB2_OK;
 }
@@ -504,7 +513,10 @@ static int launch_l1_t(const L1Params& p, int groups, size_t smem, cudaStream_t 
         configured = smem;
     }
     dim3 grid(groups, (p.OUT + kL1Cols - 1) / kL1Cols);
-    sparse_layer1_kernel<C, SOCIAL><<<grid, kL1Threads, smem, st>>>(p);
+    {
+        KernelTimer kt("sparse_layer1", st);
+        sparse_layer1_kernel<C, SOCIAL><<<grid, kL1Threads, smem, st>>>(p);
+    }
     TB2_LAUNCH_CHECK();
     return TB2_OK;
 }

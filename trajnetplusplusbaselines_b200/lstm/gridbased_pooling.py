@@ -122,6 +122,8 @@ class GridBasedPooling(torch.nn.Module):
         if device.type != 'cuda':
             if obs1.device.type == 'cuda':
                 device = obs1.device
+            elif not params:      # nothing to .cuda(): parameter-free grid on host inputs
+                device = torch.device('cuda', torch.cuda.current_device())
             else:
                 raise RuntimeError("GridBasedPooling runs on CUDA only: move the module (or inputs) to a B200")
         if self._handle is None or self._handle.device != device:
