@@ -167,19 +167,20 @@ int tb2_lstm_forward_sequence(const tb2_lstm* model, const tb2_layout* layout,
  * State is SoA-free AoS fp32: scenes are contiguous ranges of agents (layout handle).
  * ------------------------------------------------------------------------------------- */
 typedef struct tb2_sf_params {
-    float delta_t;      /* 1/fps = 0.05            socialforce.py:80,91 */
-    float tau;          /* sf_params[0] = 0.5      socialforce.py:92    */
-    float v0;           /* sf_params[1] = 2.1      socialforce.py:89    */
-    float sigma;        /* sf_params[2] = 0.3      socialforce.py:89    */
+    double delta_t;     /* 1/fps = 0.05            socialforce.py:80,91 (float64 like upstream) */
+    double tau;         /* sf_params[0] = 0.5      socialforce.py:92    */
+    double v0;          /* sf_params[1] = 2.1      socialforce.py:89    */
+    double sigma;       /* sf_params[2] = 0.3      socialforce.py:89    */
     int32_t n_steps;    /* pred_length * sampling_rate = 96   socialforce.py:93 */
     int32_t sample_every; /* sampling_rate = 8; sample kept when step_index % 8 == 0 (:95) */
 } tb2_sf_params;
 
-/* Replaces socialforce.Simulator(...).step() x n_steps (socialforce.py:91-95).
- *   state_dev  [A, 6] (x, y, vx, vy, dx, dy) initial state, socialforce.py:15-55
- *   out_dev    [n_samples, A, 2] sampled positions, n_samples = ceil(n_steps / sample_every) */
-int tb2_sf_simulate(const tb2_layout* layout, const tb2_sf_params* p, const float* state_dev,
-                    float* out_dev, void* stream);
+/* Replaces socialforce.Simulator(...).step() x n_steps (socialforce.py:91-95).  float64 like
+ * the upstream numpy package.
+ *   state_dev  [A, 6] double (x, y, vx, vy, dx, dy) initial state, socialforce.py:15-55
+ *   out_dev    [n_samples, A, 2] double sampled positions, n_samples = ceil(n_steps / sample_every) */
+int tb2_sf_simulate(const tb2_layout* layout, const tb2_sf_params* p, const double* state_dev,
+                    double* out_dev, void* stream);
 
 typedef struct tb2_orca_params {
     float time_step;       /* 1/fps                         orca.py:90 */
@@ -187,17 +188,30 @@ typedef struct tb2_orca_params {
     int32_t max_neighbors; /* 10                                       */
     float time_horizon;    /* orca_params[1] = 1.5                     */
     float radius;          /* orca_params[2] = 0.4                     */
-    float end_range;       /* 0.05 (orca.py:97)                        */
+    double end_range;      /* 0.05 (orca.py:97), compared in double like the reference */
     int32_t n_steps;       /* sampling_rate * pred_length + 1 = 97 (orca.py:99) */
     int32_t sample_every;  /* 8: sample when step_count % 8 == 0 (orca.py:107) */
 } tb2_orca_params;
 
 /* Replaces rvo2.PyRVOSimulator + the doStep/setAgentPrefVelocity loop (orca.py:90-119).
- *   pos_dev [A,2], vel_dev [A,2], goal_dev [A,2], speed_dev [A] (initial speed; maxSpeed = 1.3x)
- *   out_dev [n_samples, A, 2], n_samples = n_steps / sample_every */
+ *   pos_dev [A,2] float, vel_dev [A,2] float (RVO2 is float), goal_dev [A,2] double,
+ *   speed_dev [A] double (initial speed; maxSpeed = 1.3 x, pref-velocity clip; orca.py:36,116)
+ *   out_dev [n_samples, A, 2] float, n_samples = n_steps / sample_every */
 int tb2_orca_simulate(const tb2_layout* layout, const tb2_orca_params* p, const float* pos_dev,
-                      const float* vel_dev, const float* goal_dev, const float* speed_dev,
+                      const float* vel_dev, const double* goal_dev, const double* speed_dev,
                       float* out_dev, void* stream);
+
+/* Kalman predictor, HOST code (BASELINE configs[0] is CPU-only), float64.  Replaces
+ * pykalman.KalmanFilter(...).em / .smooth / expected .sample rollout (classical/kalman.py:40-60).
+ *   obs_host            [total_obs, 2] observed positions of all tracks, concatenated
+ *   track_offsets_host  [n_tracks + 1]
+ *   pred_out_host       [n_tracks, n_predict, 2] expectation C A^k x_last, k = 1..n_predict
+ *   q_out_host [n_tracks,4,4], r_out_host [n_tracks,2,2], last_state_out_host [n_tracks,4]:
+ *   fitted noise covariances / last smoothed state (optional, NULL to skip) so the caller can
+ *   add the reference's mean-of-5 sampled noise (kalman.py:53-60). */
+int tb2_kalman_predict(const double* obs_host, const int64_t* track_offsets_host, int32_t n_tracks,
+                       int32_t n_predict, int32_t em_iterations, double* pred_out_host,
+                       double* q_out_host, double* r_out_host, double* last_state_out_host);
 
 #ifdef __cplusplus
 }

@@ -58,10 +58,10 @@ class LstmWeights(ctypes.Structure):
 
 class SfParams(ctypes.Structure):
     _fields_ = [
-        ("delta_t", ctypes.c_float),
-        ("tau", ctypes.c_float),
-        ("v0", ctypes.c_float),
-        ("sigma", ctypes.c_float),
+        ("delta_t", ctypes.c_double),
+        ("tau", ctypes.c_double),
+        ("v0", ctypes.c_double),
+        ("sigma", ctypes.c_double),
         ("n_steps", ctypes.c_int32),
         ("sample_every", ctypes.c_int32),
     ]
@@ -74,7 +74,7 @@ class OrcaParams(ctypes.Structure):
         ("max_neighbors", ctypes.c_int32),
         ("time_horizon", ctypes.c_float),
         ("radius", ctypes.c_float),
-        ("end_range", ctypes.c_float),
+        ("end_range", ctypes.c_double),
         ("n_steps", ctypes.c_int32),
         ("sample_every", ctypes.c_int32),
     ]
@@ -104,6 +104,7 @@ PROTOTYPES = {
     "tb2_lstm_step_forward": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "tb2_lstm_forward_sequence": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "tb2_sf_simulate": (ctypes.c_int, [_vp, ctypes.POINTER(SfParams), _vp, _vp, _vp]),
+    "tb2_kalman_predict": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "tb2_orca_simulate": (ctypes.c_int, [_vp, ctypes.POINTER(OrcaParams), _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -23,6 +23,10 @@ NVCC_FLAGS = [
 ]
 
 
+# classical.cu is compared operation-by-operation with the CPU restatement (oracle/): no FMA contraction
+PER_FILE_FLAGS = {"classical.cu": ["-fmad=false"]}
+
+
 def _nvcc():
     exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(exe):
@@ -53,7 +57,8 @@ def build(force=False, verbose=False):
     procs = []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        extra = PER_FILE_FLAGS.get(os.path.basename(src), [])
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:

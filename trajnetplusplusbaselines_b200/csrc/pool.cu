@@ -114,7 +114,6 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
     const float offx = p.width * 0.5f;
     const float offy = p.front ? 0.f : p.width * 0.5f;
     int* myrow = cellrow + warp * nm1;
-    const bool has_pad = n_s < p.n_max;
 
     for (int i = warp; i < n_s; i += kPrepWarps) {
         const size_t gi = (size_t)(row0 + i) * nm1;
@@ -124,8 +123,10 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
         for (int jj = lane; jj < nm1; jj += 32) {
             int j = jj + (jj >= i);
             int cell = 0, inr = 0;
-            if (j < n_s) {
-                float rx = pos[j].x - pi.x, ry = pos[j].y - pi.y;
+            {
+                // padded slots (j >= n_s) are NaN rows in the reference's padded batch -> -500
+                const float2 pj = (j < n_s) ? pos[j] : make_float2(-500.f, -500.f);
+                float rx = pj.x - pi.x, ry = pj.y - pi.y;
                 float ox = __fadd_rn(__fdiv_rn(rx, p.side), offx);      // fp32 true division, :276
                 float oy = __fadd_rn(__fdiv_rn(ry, p.side), offy);
                 bool viol = (ox < 0.f) || (ox >= p.width) || (oy < 0.f) || (oy >= p.width);
@@ -154,7 +155,6 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
                     if (win) {
                         // a later in-range writer of the same cell, or (for cell 0) any later
                         // out-of-range writer incl. padding, overrides this pair
-                        if (cell == 0 && has_pad) win = false;
                         for (int k = jj + 1; win && k < nm1; ++k) {
                             int ck = myrow[k];
                             if (ck == cell || (cell == 0 && ck < 0)) win = false;
@@ -165,10 +165,12 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
                 if (win) {
                     int slot = count + __popc(ball & ((1u << lane) - 1u));
                     int j = jj + (jj >= i);
-                    p.win_ent[gi + slot] = ((uint32_t)cell << 16) | (uint32_t)j;
+                    // a padded slot can only win in the (discarded) row of an absent pedestrian
+                    p.win_ent[gi + slot] = ((uint32_t)cell << 16) | (uint32_t)(j < n_s ? j : 0xffff);
                     if (p.pool_type == TB2_POOL_DIRECTIONAL) {
-                        p.win_val[(gi + slot) * 2 + 0] = nan_to_num_f(vel[j].x - vi.x);   // :131-140
-                        p.win_val[(gi + slot) * 2 + 1] = nan_to_num_f(vel[j].y - vi.y);
+                        const float2 vj = (j < n_s) ? vel[j] : make_float2(CUDART_NAN_F, CUDART_NAN_F);
+                        p.win_val[(gi + slot) * 2 + 0] = nan_to_num_f(vj.x - vi.x);      // :131-140
+                        p.win_val[(gi + slot) * 2 + 1] = nan_to_num_f(vj.y - vi.y);
                     } else if (p.pool_type == TB2_POOL_OCCUPANCY) {
                         p.win_val[(gi + slot) * 2 + 0] = 1.f;                             // :266-267
                     }
@@ -246,8 +248,8 @@ int launch_grid_indices_copy(const tb2_layout* l, const Workspace* ws, int32_t* 
 __global__ void dense_grid_kernel(const int* __restrict__ win_count, const uint32_t* __restrict__ win_ent,
                                   const float* __restrict__ win_val, const float* __restrict__ lat,
                                   const int* __restrict__ row_scene, const int* __restrict__ scene_off,
-                                  float* __restrict__ out, int C, int cells, int nm1, float constant,
-                                  int pool_type) {
+                                  const float* __restrict__ benc, float* __restrict__ out, int C,
+                                  int cells, int nm1, float constant, int pool_type) {
     const int m = blockIdx.x;
     float* row = out + (size_t)m * C * cells;
     for (int k = threadIdx.x; k < C * cells; k += blockDim.x) row[k] = constant;
@@ -258,8 +260,9 @@ __global__ void dense_grid_kernel(const int* __restrict__ win_count, const uint3
         int e = idx / C, c = idx - e * C;
         uint32_t ent = win_ent[(size_t)m * nm1 + e];
         int cell = ent >> 16, j = ent & 0xffff;
-        float v = (pool_type == TB2_POOL_SOCIAL) ? lat[(size_t)(row0 + j) * C + c]
-                                                 : win_val[((size_t)m * nm1 + e) * 2 + c];
+        float v;
+        if (pool_type == TB2_POOL_SOCIAL) v = (j == 0xffff) ? benc[c] : lat[(size_t)(row0 + j) * C + c];
+        else v = win_val[((size_t)m * nm1 + e) * 2 + c];
         row[c * cells + cell] = v;
     }
 }
@@ -283,6 +286,7 @@ struct L1Params {
     const uint32_t* win_ent;
     const float* win_val;
     const float* lat;
+    const float* benc;        // [C] (social): lat of a NaN-padded slot
     const float* Wt;          // [cells, C, OUT]
     const float* base;        // [OUT]
     float* out;               // [M, OUT]
@@ -303,8 +307,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_kernel(L1Params p
     const int P = p.scene_off[s1] - row0;
 
     float* acc = reinterpret_cast<float*>(smem_l1);                       // [cap][256]
-    float* latS = acc + (size_t)p.cap * kL1Cols;                          // [cap][C] (social)
-    int* start = reinterpret_cast<int*>(latS + (SOCIAL ? (size_t)p.cap * C : 0));   // [cells+1]
+    float* latS = acc + (size_t)p.cap * kL1Cols;                          // [cap + 1][C] (social)
+    int* start = reinterpret_cast<int*>(latS + (SOCIAL ? (size_t)(p.cap + 1) * C : 0));   // [cells+1]
     int* cursor = start + p.cells + 1;                                    // [cells]
     uint16_t* entP = reinterpret_cast<uint16_t*>(cursor + p.cells);       // [cap*nm1]
     uint16_t* entS = entP + (size_t)p.cap * p.nm1;                        // [cap*nm1] (social)
@@ -315,6 +319,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_kernel(L1Params p
     for (int c = tid; c < p.cells; c += kL1Threads) cursor[c] = 0;
     if (SOCIAL) {
         for (int idx = tid; idx < P * C; idx += kL1Threads) latS[idx] = p.lat[(size_t)row0 * C + idx] - p.constant;
+        if (tid < C) latS[(size_t)p.cap * C + tid] = p.benc[tid] - p.constant;   // row `cap`: padded slot
     }
     const float b = col_ok ? p.base[col] : 0.f;
     for (int r = half; r < P; r += 2) acc[r * kL1Cols + colc] = b;
@@ -359,7 +364,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_kernel(L1Params p
                 // find the scene start of row r inside the group (scenes are few per group)
                 int sb = s0;
                 while (p.scene_off[sb + 1] <= m) ++sb;
-                entS[pos] = (uint16_t)(p.scene_off[sb] - row0 + (int)(ent & 0xffff));
+                const int j = (int)(ent & 0xffff);
+                entS[pos] = (uint16_t)(j == 0xffff ? p.cap : p.scene_off[sb] - row0 + j);
             } else {
 #pragma unroll
                 for (int c = 0; c < C; ++c) entV[(size_t)pos * C + c] = p.win_val[g * 2 + c] - p.constant;
@@ -413,7 +419,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_kernel(L1Params p
 
 static size_t l1_smem_bytes(int cap, int C, bool social, int cells, int nm1) {
     size_t b = (size_t)cap * kL1Cols * sizeof(float);
-    if (social) b += (size_t)cap * C * sizeof(float);
+    if (social) b += (size_t)(cap + 1) * C * sizeof(float);
     b += (size_t)(2 * cells + 1) * sizeof(int);
     size_t ents = ((size_t)cap * nm1 * 2 * sizeof(uint16_t) + 15) & ~(size_t)15;
     b += ents;
@@ -527,8 +533,8 @@ int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float
     const int nm1 = l->n_max > 1 ? l->n_max - 1 : 1;
     if (m->n_mlp == 0) {
         dense_grid_kernel<<<l->M, 128, 0, st>>>(ws->win_count, ws->win_ent, ws->win_val, ws->lat,
-                                                l->row_scene, l->scene_off, pooled_out, m->C, m->cells,
-                                                nm1, m->cfg.constant, m->cfg.pool_type);
+                                                l->row_scene, l->scene_off, m->benc, pooled_out, m->C,
+                                                m->cells, nm1, m->cfg.constant, m->cfg.pool_type);
         TB2_LAUNCH_CHECK();
         return TB2_OK;
     }
@@ -550,6 +556,7 @@ int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float
     p.win_ent = ws->win_ent;
     p.win_val = ws->win_val;
     p.lat = ws->lat;
+    p.benc = m->benc;
     p.Wt = m->Wt1;
     p.base = m->base1;
     p.OUT = d1;
