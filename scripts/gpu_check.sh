@@ -1,0 +1,28 @@
+#!/bin/bash
+# One GPU-box session: tcgen05 canary first (short timeout), then the full GPU suite, then bench.
+# Usage (under gpurun): bash scripts/gpu_check.sh <tag>
+tag=${1:-rX}
+out=gpurun_out
+mkdir -p $out
+echo "== canary: tcgen05 dense layer ==" > $out/${tag}_canary.log
+timeout 180 python -m pytest tests/test_gpu_parity.py -q -x --timeout 120 \
+    -k "pool_forward_matches_oracle and social" >> $out/${tag}_canary.log 2>&1
+rc=$?
+echo "canary rc=$rc" >> $out/${tag}_canary.log
+if [ $rc -ne 0 ]; then
+    echo "tcgen05 canary failed -> rest of the session runs with TB2_DISABLE_TC=1" >> $out/${tag}_canary.log
+    export TB2_DISABLE_TC=1
+fi
+timeout 900 python -m pytest tests -q -m gpu --timeout 300 > $out/${tag}_pytest.log 2>&1
+echo "pytest rc=$?" >> $out/${tag}_pytest.log
+if [ -z "$TB2_DISABLE_TC" ]; then
+    TB2_DISABLE_TC=1 timeout 600 python -m pytest tests/test_gpu_parity.py -q --timeout 300 -k "social" \
+        > $out/${tag}_pytest_notc.log 2>&1
+    echo "pytest(no tc) rc=$?" >> $out/${tag}_pytest_notc.log
+fi
+timeout 300 python bench.py --steps 10 --warmup 3 > $out/${tag}_bench.log 2>&1
+echo "bench rc=$?" >> $out/${tag}_bench.log
+tail -4 $out/${tag}_canary.log
+grep -E "passed|failed|FAILED|ADE mean|teacher-forced" $out/${tag}_pytest.log | tail -30
+[ -f $out/${tag}_pytest_notc.log ] && tail -3 $out/${tag}_pytest_notc.log
+tail -2 $out/${tag}_bench.log

@@ -22,7 +22,7 @@ def simulate_batch(pos, vel, goals, speeds, batch_split, orca_params=(1.5, 1.5, 
     """pos, vel [A, 2]; goals [A, 2]; speeds [A]; -> [n_steps // sample_every, A, 2] float32."""
     _lib.require_cuda()
     lib = _lib.load()
-    device = torch.device(device if device is not None else ('cuda', torch.cuda.current_device()))
+    device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
     pos_t = torch.as_tensor(np.asarray(pos), dtype=torch.float32).to(device).contiguous()
     vel_t = torch.as_tensor(np.asarray(vel), dtype=torch.float32).to(device).contiguous()
     goal_t = torch.as_tensor(np.asarray(goals), dtype=torch.float64).to(device).contiguous()

@@ -21,7 +21,7 @@ def simulate_batch(states, batch_split, sf_params=(0.5, 2.1, 0.3), n_steps=96, s
     sampled positions [ceil(n_steps / sample_every), A, 2] float64 (CUDA tensor)."""
     _lib.require_cuda()
     lib = _lib.load()
-    device = torch.device(device if device is not None else ('cuda', torch.cuda.current_device()))
+    device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
     st = torch.as_tensor(states, dtype=torch.float64).to(device).contiguous()
     layout = SceneLayout(batch_split)
     if layout.num_tracks != st.shape[0]:

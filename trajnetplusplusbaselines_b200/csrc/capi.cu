@@ -1,6 +1,7 @@
 // extern "C" boundary of libtrajnet_b200 (see include/trajnet_b200.h).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -63,6 +64,7 @@ size_t carve_workspace(const tb2_lstm* m, const tb2_layout* l, void* base, Works
     for (int i = 1; i <= m->n_mlp; ++i) wmax = std::max(wmax, (size_t)m->mlp_dims[i]);
     w.act[0] = (float*)take(M * wmax * sizeof(float));
     w.act[1] = (float*)take(M * wmax * sizeof(float));
+    w.act2 = (float*)take(m->n_mlp > 2 ? M * wmax * sizeof(float) : 16);
     w.pooled = (float*)take(M * (size_t)std::max(m->pool_out, 1) * sizeof(float));
     w.bytes = off;
     if (ws) *ws = w;
@@ -129,7 +131,7 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
     m->C = 0; m->cells = 0; m->n_mlp = 0; m->P = 0; m->pool_out = 0;
     m->We = m->be = m->Wn = m->bn = m->WencT = m->benc = m->Wt1 = m->base1 = nullptr;
     for (int i = 0; i < 2; ++i) m->WgT[i] = m->bg[i] = nullptr;
-    for (int i = 0; i < kMaxMlpLayers; ++i) m->WT[i] = m->bl[i] = nullptr;
+    for (int i = 0; i < kMaxMlpLayers; ++i) { m->WT[i] = m->bl[i] = nullptr; m->W_hi[i] = m->W_lo[i] = nullptr; }
     auto fail = [&](int rc) { tb2_lstm_destroy(m); return rc; };
     if (cfg->pool_type != TB2_POOL_NONE) {
         if (cfg->pool_size != 1 || cfg->blur_size != 1) {
@@ -176,6 +178,16 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
         for (int layer = 1; layer < m->n_mlp; ++layer) {
             ALLOC(m->WT[layer], (size_t)m->mlp_dims[layer] * m->mlp_dims[layer + 1]);
             ALLOC(m->bl[layer], m->mlp_dims[layer + 1]);
+            // TB2_DISABLE_TC=1: debug knob for A/B parity runs (fp32 FFMA layer instead of tcgen05)
+            const char* no_tc = getenv("TB2_DISABLE_TC");
+            if (layer == 1 && !(no_tc && no_tc[0] == '1') && dense_tc_supported(m->mlp_dims[1], m->mlp_dims[2])) {
+                const size_t half = ((size_t)m->mlp_dims[1] * m->mlp_dims[2] + 1) / 2;   // bf16 pairs in float units
+                float *hi, *lo;
+                ALLOC(hi, half);
+                ALLOC(lo, half);
+                m->W_hi[1] = hi;
+                m->W_lo[1] = lo;
+            }
         }
     }
 #undef ALLOC

@@ -73,6 +73,8 @@ struct tb2_lstm {
     float* base1;          // [d1] = b1 + constant * rowsum(W1)
     float* WT[tb2::kMaxMlpLayers];   // layers >= 2: [K, N] transposed
     float* bl[tb2::kMaxMlpLayers];   // biases of layers >= 2
+    void* W_hi[tb2::kMaxMlpLayers];  // bf16 [N, K] (hi, lo) split for the tcgen05 path (null: FFMA path)
+    void* W_lo[tb2::kMaxMlpLayers];
     std::vector<void*> owned;
 };
 
@@ -100,6 +102,7 @@ struct Workspace {
     int* pair_cell;        // [M, nm1]
     uint8_t* pair_flag;    // [M, nm1]
     float* act[2];         // ping-pong MLP activations [M, max width]
+    float* act2;           // third scratch (three_layer with a tensor-core second layer)
     float* pooled;         // [M, pool_out]
     size_t bytes;
 };
@@ -117,6 +120,10 @@ int launch_gates(const tb2_lstm* m, const tb2_layout* l, int phase, const float*
                  const float* obs2, const float* pooled, const float* h_in, const float* c_in,
                  float* h_out, float* c_out, float* normal_out, float* pos_out, cudaStream_t st);
 int launch_repack(tb2_lstm* m, const tb2_lstm_weights* w, cudaStream_t st);
+bool dense_tc_supported(int K, int N);
+int launch_dense_tc(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                    float* Y, int M, int K, int N, int relu, cudaStream_t st);
+int launch_split_bf16(const float* src, void* hi, void* lo, size_t n, cudaStream_t st);
 int launch_grid_indices_copy(const tb2_layout* l, const Workspace* ws, int32_t* cell_out,
                              uint8_t* flag_out, cudaStream_t st);
 

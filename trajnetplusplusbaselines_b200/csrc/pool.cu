@@ -8,6 +8,7 @@
 // of winning (cell, neighbour) pairs, and sparse_layer1_kernel applies the first Linear as
 //     out[i, :] = base + sum_{winning (cell, j) of i} (val(i, j) - constant) . W1[:, cell-slab]
 // streaming the cell-major weight slabs once per scene group.
+#include <cuda_bf16.h>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -272,9 +273,11 @@ __global__ void dense_grid_kernel(const int* __restrict__ win_count, const uint3
 //   grid  = (scene groups, OUT / 256 column chunks), 512 threads: thread = (half, column)
 //   smem  = acc[P][256] | lat[P][C] (social) | bucket tables | entries sorted by cell
 //   The CTA walks the cells in ascending order; the C x 256 weight slab of the next cell is
-//   prefetched into registers while the pairs binned in the current cell are applied.  Each
-//   (pedestrian, cell) has at most one winner, so the two halves never touch the same
-//   accumulator row and the result is deterministic.
+//   prefetched into registers while the pairs binned in the current cell are applied.  Pairs are
+//   binned by (cell, parity of the pedestrian row): half h of the CTA only ever updates
+//   accumulator rows of parity h, so the two halves need no synchronisation while they drift
+//   apart across cells, every row is accumulated in ascending cell order by one thread per
+//   column, and the result is deterministic.
 // ------------------------------------------------------------------------------------------
 constexpr int kL1Cols = 256;
 constexpr int kL1Threads = 512;
@@ -289,7 +292,9 @@ struct L1Params {
     const float* benc;        // [C] (social): lat of a NaN-padded slot
     const float* Wt;          // [cells, C, OUT]
     const float* base;        // [OUT]
-    float* out;               // [M, OUT]
+    float* out;               // [M, OUT] fp32, or null when the split outputs below are used
+    __nv_bfloat16* out_hi;    // [M, OUT] bf16 (hi, lo) split for the tensor-core layer that follows
+    __nv_bfloat16* out_lo;
     int OUT, cells, nm1, cap, relu;
     float constant;
 };
@@ -308,15 +313,16 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_kernel(L1Params p
 
     float* acc = reinterpret_cast<float*>(smem_l1);                       // [cap][256]
     float* latS = acc + (size_t)p.cap * kL1Cols;                          // [cap + 1][C] (social)
-    int* start = reinterpret_cast<int*>(latS + (SOCIAL ? (size_t)(p.cap + 1) * C : 0));   // [cells+1]
-    int* cursor = start + p.cells + 1;                                    // [cells]
-    uint16_t* entP = reinterpret_cast<uint16_t*>(cursor + p.cells);       // [cap*nm1]
+    const int bins = 2 * p.cells;                                         // bin = cell * 2 + (row & 1)
+    int* start = reinterpret_cast<int*>(latS + (SOCIAL ? (size_t)(p.cap + 1) * C : 0));   // [bins+1]
+    int* cursor = start + bins + 1;                                       // [bins]
+    uint16_t* entP = reinterpret_cast<uint16_t*>(cursor + bins);          // [cap*nm1]
     uint16_t* entS = entP + (size_t)p.cap * p.nm1;                        // [cap*nm1] (social)
     float* entV = reinterpret_cast<float*>(                               // [cap*nm1][C] (non-social)
         reinterpret_cast<unsigned char*>(entP) +
         (((size_t)p.cap * p.nm1 * 2 * sizeof(uint16_t) + 15) & ~(size_t)15));
 
-    for (int c = tid; c < p.cells; c += kL1Threads) cursor[c] = 0;
+    for (int c = tid; c < bins; c += kL1Threads) cursor[c] = 0;
     if (SOCIAL) {
         for (int idx = tid; idx < P * C; idx += kL1Threads) latS[idx] = p.lat[(size_t)row0 * C + idx] - p.constant;
         if (tid < C) latS[(size_t)p.cap * C + tid] = p.benc[tid] - p.constant;   // row `cap`: padded slot
@@ -328,12 +334,13 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_kernel(L1Params p
     const int total = P * p.nm1;
     for (int idx = tid; idx < total; idx += kL1Threads) {
         int r = idx / p.nm1, k = idx - r * p.nm1;
-        if (k < p.win_count[row0 + r]) atomicAdd(&cursor[p.win_ent[(size_t)(row0 + r) * p.nm1 + k] >> 16], 1);
+        if (k < p.win_count[row0 + r])
+            atomicAdd(&cursor[(p.win_ent[(size_t)(row0 + r) * p.nm1 + k] >> 16) * 2 + (r & 1)], 1);
     }
     __syncthreads();
     if (tid < 32) {   // exclusive scan of the histogram by one warp
-        int per = (p.cells + 31) / 32;
-        int lo = tid * per, hi = min(lo + per, p.cells);
+        int per = (bins + 31) / 32;
+        int lo = tid * per, hi = min(lo + per, bins);
         int sum = 0;
         for (int c = lo; c < hi; ++c) sum += cursor[c];
         int incl = sum;
@@ -348,7 +355,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_kernel(L1Params p
             cursor[c] = run;
             run += cnt;
         }
-        if (tid == 31) start[p.cells] = incl;
+        if (tid == 31) start[bins] = incl;
     }
     __syncthreads();
     for (int idx = tid; idx < total; idx += kL1Threads) {
@@ -356,7 +363,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_kernel(L1Params p
         if (k < p.win_count[row0 + r]) {
             size_t g = (size_t)(row0 + r) * p.nm1 + k;
             uint32_t ent = p.win_ent[g];
-            int pos = atomicAdd(&cursor[ent >> 16], 1);
+            int pos = atomicAdd(&cursor[(ent >> 16) * 2 + (r & 1)], 1);
             entP[pos] = (uint16_t)r;
             if (SOCIAL) {
                 // scene-local j -> group-local row
@@ -384,8 +391,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_kernel(L1Params p
             for (int c = 0; c < C; ++c)
                 wn[c] = col_ok ? wcol[((size_t)(cell + 1) * C + c) * p.OUT] : 0.f;
         }
-        const int e0 = start[cell], e1 = start[cell + 1];
-        for (int e = e0 + half; e < e1; e += 2) {
+        const int e0 = start[cell * 2 + half], e1 = start[cell * 2 + half + 1];
+        for (int e = e0; e < e1; ++e) {
             const int r = entP[e];
             float a = acc[r * kL1Cols + colc];
             if (SOCIAL) {
@@ -412,7 +419,14 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_kernel(L1Params p
         for (int r = half; r < P; r += 2) {
             float v = acc[r * kL1Cols + colc];
             if (p.relu) v = fmaxf(v, 0.f);
-            p.out[(size_t)(row0 + r) * p.OUT + col] = v;
+            const size_t o = (size_t)(row0 + r) * p.OUT + col;
+            if (p.out_hi) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                p.out_hi[o] = h;
+                p.out_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+            } else {
+                p.out[o] = v;
+            }
         }
     }
 }
@@ -420,7 +434,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_kernel(L1Params p
 static size_t l1_smem_bytes(int cap, int C, bool social, int cells, int nm1) {
     size_t b = (size_t)cap * kL1Cols * sizeof(float);
     if (social) b += (size_t)(cap + 1) * C * sizeof(float);
-    b += (size_t)(2 * cells + 1) * sizeof(int);
+    b += (size_t)(4 * cells + 1) * sizeof(int);
     size_t ents = ((size_t)cap * nm1 * 2 * sizeof(uint16_t) + 15) & ~(size_t)15;
     b += ents;
     if (!social) b += (size_t)cap * nm1 * C * sizeof(float);
@@ -566,7 +580,11 @@ int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float
     p.relu = 1;
     p.constant = m->cfg.constant;
     float* l1_out = (m->n_mlp == 1) ? pooled_out : ws->act[0];
-    p.out = l1_out;
+    // second Linear on the tensor cores: layer 1 hands its activations over as bf16 (hi, lo)
+    const bool tc2 = m->n_mlp >= 2 && m->W_hi[1] != nullptr;
+    p.out = tc2 ? nullptr : l1_out;
+    p.out_hi = tc2 ? reinterpret_cast<__nv_bfloat16*>(ws->act[0]) : nullptr;
+    p.out_lo = tc2 ? reinterpret_cast<__nv_bfloat16*>(ws->act[1]) : nullptr;
     int rc;
     switch (m->cfg.pool_type) {
         case TB2_POOL_OCCUPANCY: rc = launch_l1_t<1, false>(p, l->num_groups[gsel], smem, st); break;
@@ -584,6 +602,12 @@ int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float
     const float* x = l1_out;
     for (int layer = 1; layer < m->n_mlp; ++layer) {
         float* y = (layer == m->n_mlp - 1) ? pooled_out : ws->act[layer & 1];
+        if (layer == 1 && tc2) {
+            // act[0] / act[1] hold the split input; a third layer (if any) reads fp32 from ws->pooled-sized scratch
+            if (m->n_mlp > 2) y = ws->act2;
+            rc = launch_dense_tc(ws->act[0], ws->act[1], m->W_hi[1], m->W_lo[1], m->bl[1], y, l->M,
+                                 m->mlp_dims[1], m->mlp_dims[2], 1, st);
+        } else
         rc = launch_dense(x, m->WT[layer], m->bl[layer], y, l->M, m->mlp_dims[layer], m->mlp_dims[layer + 1], 1, st);
         if (rc != TB2_OK) return rc;
         x = y;
