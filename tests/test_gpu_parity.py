@@ -26,6 +26,17 @@ def build_model(kind, W, device="cuda"):
     return model.to(device).eval()
 
 
+def report(line):
+    """Parity numbers of passing tests are kept (gpurun_out/parity_report.txt) for profiles/."""
+    import os
+    print(line)
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    tag = "[no-tc] " if os.environ.get("TB2_DISABLE_TC") == "1" else ""
+    with open(os.path.join(d, "parity_report.txt"), "a") as f:
+        f.write(tag + line + "\n")
+
+
 def maxdiff(a, b):
     a = a.detach().cpu().numpy() if torch.is_tensor(a) else a
     assert a.shape == b.shape, (a.shape, b.shape)
@@ -200,15 +211,16 @@ def test_baseline_config_ade_fde_vs_oracle(kind):
         ades.append(a)
         fdes.append(f)
     flips = int((np.array(fdes) > 1e-3).sum())
-    print("%s: ADE mean %.3e max %.3e  FDE mean %.3e max %.3e  scenes with FDE>1e-3: %d/%d" %
-          (kind, np.mean(ades), np.max(ades), np.mean(fdes), np.max(fdes), flips, B))
+    report("%s: ADE mean %.3e max %.3e  FDE mean %.3e max %.3e  scenes with FDE>1e-3: %d/%d" %
+           (kind, np.mean(ades), np.max(ades), np.mean(fdes), np.max(fdes), flips, B))
     # teacher-forced: neighbours follow the truth, only the primaries feed predictions back.  A
     # primary whose fed-back position sits within float rounding of a cell edge can land in the
     # other cell (SURVEY.md section 7 "chaotic sensitivity"); such scenes are counted, not hidden.
     d_tf = np.abs(pred_tf.cpu().numpy() - pred_tf_o)
     assert (np.isnan(d_tf) == np.isnan(pred_tf_o)).all()
     bad_tf = int((np.nanmax(d_tf, axis=(0, 2)) > TOL_POS).sum())
-    print("%s: teacher-forced tracks off by > 1e-4 m: %d/%d, median %.2e" % (kind, bad_tf, M, np.nanmedian(d_tf)))
+    report("%s: teacher-forced tracks off by > 1e-4 m: %d/%d, median %.2e, max %.2e" %
+           (kind, bad_tf, M, np.nanmedian(d_tf), np.nanmax(d_tf)))
     assert bad_tf <= max(1, M // 100)
     assert np.nanmedian(d_tf) < 1e-6
     assert np.median(ades) < TOL_POS and np.median(fdes) < TOL_POS
@@ -267,8 +279,9 @@ def test_full_size_properties_social():
     assert torch.equal(torch.nan_to_num(pred, nan=-1.0), torch.nan_to_num(pred2, nan=-1.0))
     both = torch.cat([pred_a, pred_b], dim=1)
     assert torch.equal(torch.nan_to_num(pred, nan=-1.0), torch.nan_to_num(both, nan=-1.0))
-    gone = np.isnan(xy[8, :, 0])
-    assert torch.isnan(pred[:, torch.from_numpy(gone).cuda()]).all()
+    gone = np.isnan(xy[8, :, 0])                 # absent at the last observed frame
+    assert gone.any()
+    assert torch.isnan(pred[7:, torch.from_numpy(gone).cuda()]).all()    # from encoder step (7, 8) onwards
     always = ~np.isnan(xy[:9, :, 0]).any(axis=0)
     assert not torch.isnan(pred[:, torch.from_numpy(always).cuda()]).any()
     # sanity vs the oracle on a 16-scene slice of the same batch (scene independence makes this valid)

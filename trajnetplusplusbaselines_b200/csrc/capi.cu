@@ -130,6 +130,7 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
     m->weights_set = false;
     m->C = 0; m->cells = 0; m->n_mlp = 0; m->P = 0; m->pool_out = 0;
     m->We = m->be = m->Wn = m->bn = m->WencT = m->benc = m->Wt1 = m->base1 = nullptr;
+    m->Wt1_hi = m->Wt1_lo = nullptr;
     for (int i = 0; i < 2; ++i) m->WgT[i] = m->bg[i] = nullptr;
     for (int i = 0; i < kMaxMlpLayers; ++i) { m->WT[i] = m->bl[i] = nullptr; m->W_hi[i] = m->W_lo[i] = nullptr; }
     auto fail = [&](int rc) { tb2_lstm_destroy(m); return rc; };
@@ -175,6 +176,17 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
     if (m->n_mlp >= 1) {
         ALLOC(m->Wt1, (size_t)m->cells * m->C * m->mlp_dims[1]);
         ALLOC(m->base1, m->mlp_dims[1]);
+        {
+            const char* no_tc = getenv("TB2_DISABLE_TC");
+            if (cfg->pool_type == TB2_POOL_SOCIAL && m->C == 16 && !(no_tc && no_tc[0] == '1')) {
+                const size_t half = ((size_t)m->cells * 16 * m->mlp_dims[1] + 1) / 2;
+                float *hi, *lo;
+                ALLOC(hi, half);
+                ALLOC(lo, half);
+                m->Wt1_hi = hi;
+                m->Wt1_lo = lo;
+            }
+        }
         for (int layer = 1; layer < m->n_mlp; ++layer) {
             ALLOC(m->WT[layer], (size_t)m->mlp_dims[layer] * m->mlp_dims[layer + 1]);
             ALLOC(m->bl[layer], m->mlp_dims[layer + 1]);
@@ -303,7 +315,7 @@ int tb2_grid_indices(const tb2_lstm* m, const tb2_layout* l, const float* obs, i
     tb2_lstm tmp_model = *m;
     tmp_model.owned.clear();
     tmp_model.cfg.pool_type = TB2_POOL_OCCUPANCY;   // indices do not depend on the payload
-    int rc = launch_pool_prepare(&tmp_model, l, nullptr, obs, obs, 0, &ws, st);
+    int rc = launch_pool_prepare(&tmp_model, l, nullptr, obs, obs, 0, 1, &ws, st);
     if (rc == TB2_OK) rc = launch_grid_indices_copy(l, &ws, cell_out, in_range_out, st);
     cudaError_t e = cudaStreamSynchronize(st);       // debug export: synchronous so tmp can be freed
     cudaFree(tmp);
@@ -323,7 +335,7 @@ int tb2_pool_forward(const tb2_lstm* m, const tb2_layout* l, const float* hidden
     Workspace ws;
     carve_workspace(m, l, workspace, &ws);
     cudaStream_t st = (cudaStream_t)stream;
-    if ((rc = launch_pool_prepare(m, l, hidden, obs1, obs2, 0, &ws, st))) return rc;
+    if ((rc = launch_pool_prepare(m, l, hidden, obs1, obs2, 0, 0, &ws, st))) return rc;
     return launch_pool_mlp(m, l, &ws, pooled_out, st);
 }
 
@@ -333,7 +345,7 @@ static int step_impl(const tb2_lstm* m, const tb2_layout* l, int phase, const fl
     int rc;
     const float* pooled = nullptr;
     if (m->cfg.pool_type != TB2_POOL_NONE) {
-        if ((rc = launch_pool_prepare(m, l, h_in, obs1, obs2, 1, ws, st))) return rc;
+        if ((rc = launch_pool_prepare(m, l, h_in, obs1, obs2, 1, 0, ws, st))) return rc;
         if ((rc = launch_pool_mlp(m, l, ws, ws->pooled, st))) return rc;
         pooled = ws->pooled;
     }

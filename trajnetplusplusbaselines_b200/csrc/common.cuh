@@ -71,6 +71,8 @@ struct tb2_lstm {
     float* benc;           // [C]
     float* Wt1;            // [cells, C, d1]  cell-major slabs of pool.embedding.0.weight
     float* base1;          // [d1] = b1 + constant * rowsum(W1)
+    void* Wt1_hi;          // social, C == 16: bf16 [cells, d1, 16] (hi, lo) slabs for sparse_layer1_mma
+    void* Wt1_lo;
     float* WT[tb2::kMaxMlpLayers];   // layers >= 2: [K, N] transposed
     float* bl[tb2::kMaxMlpLayers];   // biases of layers >= 2
     void* W_hi[tb2::kMaxMlpLayers];  // bf16 [N, K] (hi, lo) split for the tcgen05 path (null: FFMA path)
@@ -112,14 +114,15 @@ size_t carve_workspace(const tb2_lstm* m, const tb2_layout* l, void* base, Works
 int launch_resolve_obs(const tb2_layout* l, const float* base, const float* pred, float* out,
                        cudaStream_t st);
 int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hidden,
-                        const float* obs1, const float* obs2, int skip_masked, Workspace* ws,
-                        cudaStream_t st);
+                        const float* obs1, const float* obs2, int skip_masked, int write_pairs,
+                        Workspace* ws, cudaStream_t st);
 int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float* pooled_out,
                     cudaStream_t st);
 int launch_gates(const tb2_lstm* m, const tb2_layout* l, int phase, const float* obs1,
                  const float* obs2, const float* pooled, const float* h_in, const float* c_in,
                  float* h_out, float* c_out, float* normal_out, float* pos_out, cudaStream_t st);
 int launch_repack(tb2_lstm* m, const tb2_lstm_weights* w, cudaStream_t st);
+int launch_repack_layer1_mma(const float* W1, void* hi, void* lo, int OUT, int cells, cudaStream_t st);
 bool dense_tc_supported(int K, int N);
 int launch_dense_tc(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                     float* Y, int M, int K, int N, int relu, cudaStream_t st);

@@ -51,7 +51,7 @@ int launch_resolve_obs(const tb2_layout* l, const float* base, const float* pred
 //     cell"; padded slots (scene smaller than the batch maximum) are trailing out-of-range
 //     writers of cell 0 exactly like the reference's NaN padding (lstm.py:31-40).
 // ------------------------------------------------------------------------------------------
-constexpr int kPrepThreads = 128;
+constexpr int kPrepThreads = 256;
 constexpr int kPrepWarps = kPrepThreads / 32;
 constexpr int kMaxSceneForPrep = 256;   // per-warp cell row buffer
 
@@ -68,7 +68,7 @@ struct PrepParams {
     float* win_val;
     int* pair_cell;
     uint8_t* pair_flag;
-    int n_max, H, C, n, pool_type, front, skip_masked;
+    int n_max, H, C, n, pool_type, front, skip_masked, write_pairs;
     float side, width;
 };
 
@@ -79,7 +79,7 @@ __device__ __forceinline__ float nan_to_num_f(float x) {
 }
 
 __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p) {
-    extern __shared__ float smem_prep[];
+    extern __shared__ __align__(16) float smem_prep[];
     const int scene = blockIdx.x;
     const int row0 = p.scene_off[scene];
     const int n_s = p.scene_off[scene + 1] - row0;
@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
     float2* pos = reinterpret_cast<float2*>(smem_prep);                 // [n_s] obs2 with -500
     float2* vel = pos + n_s;                                            // [n_s] obs2 - obs1 (may be NaN)
     int* cellrow = reinterpret_cast<int*>(vel + n_s);                   // [kPrepWarps][nm1]
+    float* Ws = reinterpret_cast<float*>(cellrow + kPrepWarps * (nm1 > 0 ? nm1 : 1));   // [H][C]   (social)
+    float* hs = Ws + p.H * p.C;                                         // [n_s][H] (social)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     for (int j = tid; j < n_s; j += kPrepThreads) {
@@ -96,17 +98,31 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
         pos[j] = b;
     }
     if (p.pool_type == TB2_POOL_SOCIAL) {
+        // stage nan_to_num(h) of the scene and W_enc^T in shared memory (coalesced float4 loads)
+        const float4* hsrc = reinterpret_cast<const float4*>(p.hidden + (size_t)row0 * p.H);
+        float4* hdst = reinterpret_cast<float4*>(hs);
+        for (int idx = tid; idx < n_s * p.H / 4; idx += kPrepThreads) {
+            float4 v = hsrc[idx];
+            v.x = nan_to_num_f(v.x); v.y = nan_to_num_f(v.y); v.z = nan_to_num_f(v.z); v.w = nan_to_num_f(v.w);
+            hdst[idx] = v;
+        }
+        const float4* wsrc = reinterpret_cast<const float4*>(p.WencT);
+        float4* wdst = reinterpret_cast<float4*>(Ws);
+        for (int idx = tid; idx < p.H * p.C / 4; idx += kPrepThreads) wdst[idx] = wsrc[idx];
+    }
+    __syncthreads();
+    if (p.pool_type == TB2_POOL_SOCIAL) {
         // lat[j][c] = sum_k nan_to_num(h[j][k]) * WencT[k][c] + benc[c]
         const int total = n_s * p.C;
         for (int idx = tid; idx < total; idx += kPrepThreads) {
             int j = idx / p.C, c = idx - j * p.C;
-            const float* hrow = p.hidden + (size_t)(row0 + j) * p.H;
+            const float* hrow = hs + j * p.H;
             float acc = 0.f;
-            for (int k = 0; k < p.H; ++k) acc = fmaf(nan_to_num_f(hrow[k]), p.WencT[k * p.C + c], acc);
+#pragma unroll 8
+            for (int k = 0; k < p.H; ++k) acc = fmaf(hrow[k], Ws[k * p.C + c], acc);
             p.lat[(size_t)(row0 + j) * p.C + c] = acc + p.benc[c];
         }
     }
-    __syncthreads();
     if (nm1 <= 0) {   // single-pedestrian batch: constant grid (gridbased_pooling.py:252-253)
         for (int i = tid; i < n_s; i += kPrepThreads) p.win_count[row0 + i] = 0;
         return;
@@ -137,8 +153,10 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
                 }
             }
             myrow[jj] = inr ? cell : -1;
-            p.pair_cell[gi + jj] = cell;
-            p.pair_flag[gi + jj] = (uint8_t)inr;
+            if (p.write_pairs) {      // debug export (tb2_grid_indices) only
+                p.pair_cell[gi + jj] = cell;
+                p.pair_flag[gi + jj] = (uint8_t)inr;
+            }
         }
         __syncwarp();
         // pass 2: winners, compacted in ascending jj
@@ -185,8 +203,8 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
 }
 
 int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hidden,
-                        const float* obs1, const float* obs2, int skip_masked, Workspace* ws,
-                        cudaStream_t st) {
+                        const float* obs1, const float* obs2, int skip_masked, int write_pairs,
+                        Workspace* ws, cudaStream_t st) {
     TB2_REQUIRE(l->n_max <= kMaxSceneForPrep, "scene larger than 256 pedestrians");
     PrepParams p;
     p.obs1 = (const float2*)obs1;
@@ -208,10 +226,19 @@ int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hid
     p.pool_type = m->cfg.pool_type;
     p.front = m->cfg.front;
     p.skip_masked = skip_masked;
+    p.write_pairs = write_pairs;
     p.side = m->cfg.cell_side;        // pool_size == 1
     p.width = (float)m->cfg.n;
     int nm1 = l->n_max > 1 ? l->n_max - 1 : 1;
     size_t smem = (size_t)l->n_max * 2 * sizeof(float2) + (size_t)kPrepWarps * nm1 * sizeof(int);
+    if (m->cfg.pool_type == TB2_POOL_SOCIAL) smem += ((size_t)m->H * m->C + (size_t)l->n_max * m->H) * sizeof(float);
+    smem = (smem + 15) & ~(size_t)15;
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        TB2_REQUIRE(smem <= 227 * 1024, "scene too large for pool_prepare shared memory");
+        TB2_CHECK_CUDA(cudaFuncSetAttribute(pool_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
     {
         KernelTimer kt("pool_prepare", st);
         pool_prepare_kernel<<<l->B, kPrepThreads, smem, st>>>(p);
@@ -431,6 +458,233 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_kernel(L1Params p
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// sparse_layer1_mma: the social grid (C = 16 latent channels) on the tensor cores.
+//   For one cell the pairs binned there form A [pairs x 16] (latent vectors of the winning
+//   neighbours) and the cell's weight slab is B [16 x 256]; pairs-per-cell is ~10, far below the
+//   64/128-row minimum of tcgen05.mma, so this irregular piece uses warp-level
+//   mma.sync.m16n8k16 (bf16 inputs, fp32 accumulate) with the same 3-pass (hi, lo) split as the
+//   dense layers.  Warp w owns output columns [16w, 16w+16) of the chunk for ALL pedestrians of
+//   the scene group, so accumulator rows are never shared between warps: no atomics, no
+//   barriers inside the cell loop, deterministic ascending-cell summation.
+//   smem: acc[P][264] fp32 | lat_hi, lat_lo [P+1][16] bf16 (k-permuted) | buckets | entries
+//   Weights: Wt_hi / Wt_lo [cell][OUT][16] bf16, k permuted so a lane's B fragment is one 8-byte
+//   load (position 4t..4t+3 = k {2t, 2t+1, 2t+8, 2t+9}); next cell's fragments are prefetched.
+// ------------------------------------------------------------------------------------------
+constexpr int kMmaAccStride = kL1Cols + 8;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+        "{%0, %1, %2, %3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ int kperm16(int k) { return 4 * ((k & 7) >> 1) + 2 * (k >> 3) + (k & 1); }
+
+struct L1MmaParams {
+    const int* group_off;
+    const int* scene_off;
+    const int* win_count;
+    const uint32_t* win_ent;
+    const float* lat;
+    const float* benc;
+    const __nv_bfloat16* Wt_hi;   // [cells, OUT, 16]
+    const __nv_bfloat16* Wt_lo;
+    const float* base;
+    float* out;
+    __nv_bfloat16* out_hi;
+    __nv_bfloat16* out_lo;
+    int OUT, cells, nm1, cap, relu;
+    float constant;
+};
+
+__global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_mma_kernel(L1MmaParams p) {
+    extern __shared__ __align__(16) unsigned char smem_l1m[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int s0 = p.group_off[blockIdx.x], s1 = p.group_off[blockIdx.x + 1];
+    const int row0 = p.scene_off[s0];
+    const int P = p.scene_off[s1] - row0;
+    const int chunk0 = blockIdx.y * kL1Cols;
+
+    float* acc = reinterpret_cast<float*>(smem_l1m);                                       // [cap][264]
+    __nv_bfloat16* latH = reinterpret_cast<__nv_bfloat16*>(acc + (size_t)p.cap * kMmaAccStride);   // [cap+1][16]
+    __nv_bfloat16* latL = latH + (size_t)(p.cap + 1) * 16;
+    int* start = reinterpret_cast<int*>(latL + (size_t)(p.cap + 1) * 16);                  // [cells+1]
+    int* cursor = start + p.cells + 1;                                                     // [cells]
+    uint16_t* entP = reinterpret_cast<uint16_t*>(cursor + p.cells);                        // [cap*nm1]
+    uint16_t* entS = entP + (size_t)p.cap * p.nm1;
+
+    for (int c = tid; c < p.cells; c += kL1Threads) cursor[c] = 0;
+    for (int idx = tid; idx < (P + 1) * 16; idx += kL1Threads) {
+        const int r = idx >> 4, k = idx & 15;
+        const float v = (r < P ? p.lat[(size_t)(row0 + r) * 16 + k] : p.benc[k]) - p.constant;
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const int dst = (r < P ? r : p.cap) * 16 + kperm16(k);
+        latH[dst] = h;
+        latL[dst] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+    {
+        const int colc = tid & (kL1Cols - 1);
+        const int col = chunk0 + colc;
+        const float b = col < p.OUT ? p.base[col] : 0.f;
+        for (int r = tid >> 8; r < P; r += 2) acc[r * kMmaAccStride + colc] = b;
+    }
+    __syncthreads();
+    const int total = P * p.nm1;
+    for (int idx = tid; idx < total; idx += kL1Threads) {
+        int r = idx / p.nm1, k = idx - r * p.nm1;
+        if (k < p.win_count[row0 + r]) atomicAdd(&cursor[p.win_ent[(size_t)(row0 + r) * p.nm1 + k] >> 16], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {
+        int per = (p.cells + 31) / 32;
+        int lo = tid * per, hi = min(lo + per, p.cells);
+        int sum = 0;
+        for (int c = lo; c < hi; ++c) sum += cursor[c];
+        int incl = sum;
+        for (int d = 1; d < 32; d <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (tid >= d) incl += v;
+        }
+        int run = incl - sum;
+        for (int c = lo; c < hi; ++c) {
+            int cnt = cursor[c];
+            start[c] = run;
+            cursor[c] = run;
+            run += cnt;
+        }
+        if (tid == 31) start[p.cells] = incl;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < total; idx += kL1Threads) {
+        int r = idx / p.nm1, k = idx - r * p.nm1;
+        if (k < p.win_count[row0 + r]) {
+            const uint32_t ent = p.win_ent[(size_t)(row0 + r) * p.nm1 + k];
+            const int pos = atomicAdd(&cursor[ent >> 16], 1);
+            entP[pos] = (uint16_t)r;
+            int sb = s0;
+            while (p.scene_off[sb + 1] <= row0 + r) ++sb;
+            const int j = (int)(ent & 0xffff);
+            entS[pos] = (uint16_t)(j == 0xffff ? p.cap : p.scene_off[sb] - row0 + j);
+        }
+    }
+    __syncthreads();
+
+    // B fragments of this warp's two n-tiles: one 8-byte load per (tile, part)
+    const int ncol0 = chunk0 + warp * 16 + g;            // column of n-tile 0 this lane loads; tile 1: + 8
+    const bool ok0 = ncol0 < p.OUT, ok1 = ncol0 + 8 < p.OUT;
+    const size_t cell_stride = (size_t)p.OUT * 16;       // bf16 elements per cell
+    const __nv_bfloat16* wh = p.Wt_hi + (size_t)ncol0 * 16 + 4 * t;
+    const __nv_bfloat16* wl = p.Wt_lo + (size_t)ncol0 * 16 + 4 * t;
+    auto ldb = [&](const __nv_bfloat16* base, bool ok) -> uint2 {
+        return ok ? *reinterpret_cast<const uint2*>(base) : make_uint2(0u, 0u);
+    };
+    uint2 bh0 = ldb(wh, ok0), bh1 = ldb(wh + 8 * 16, ok1), bl0 = ldb(wl, ok0), bl1 = ldb(wl + 8 * 16, ok1);
+    float* accw = acc + warp * 16 + 2 * t;
+    for (int cell = 0; cell < p.cells; ++cell) {
+        uint2 nh0 = bh0, nh1 = bh1, nl0 = bl0, nl1 = bl1;
+        if (cell + 1 < p.cells) {
+            const size_t o = (size_t)(cell + 1) * cell_stride;
+            nh0 = ldb(wh + o, ok0); nh1 = ldb(wh + o + 8 * 16, ok1);
+            nl0 = ldb(wl + o, ok0); nl1 = ldb(wl + o + 8 * 16, ok1);
+        }
+        const int e0 = start[cell], e1 = start[cell + 1];
+        for (int eb = e0; eb < e1; eb += 16) {
+            const int i0 = eb + g, i1 = eb + g + 8;
+            const bool v0 = i0 < e1, v1 = i1 < e1;
+            int pr0 = 0, pr1 = 0;
+            uint32_t ah[4] = {0u, 0u, 0u, 0u}, al[4] = {0u, 0u, 0u, 0u};
+            if (v0) {
+                pr0 = entP[i0];
+                const int ls = entS[i0];
+                const uint2 x = *reinterpret_cast<const uint2*>(latH + ls * 16 + 4 * t);
+                const uint2 y = *reinterpret_cast<const uint2*>(latL + ls * 16 + 4 * t);
+                ah[0] = x.x; ah[2] = x.y; al[0] = y.x; al[2] = y.y;
+            }
+            if (v1) {
+                pr1 = entP[i1];
+                const int ls = entS[i1];
+                const uint2 x = *reinterpret_cast<const uint2*>(latH + ls * 16 + 4 * t);
+                const uint2 y = *reinterpret_cast<const uint2*>(latL + ls * 16 + 4 * t);
+                ah[1] = x.x; ah[3] = x.y; al[1] = y.x; al[3] = y.y;
+            }
+            float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_bf16_16816(d0, ah, bh0.x, bh0.y);
+            mma_bf16_16816(d1, ah, bh1.x, bh1.y);
+            mma_bf16_16816(d0, ah, bl0.x, bl0.y);
+            mma_bf16_16816(d1, ah, bl1.x, bl1.y);
+            mma_bf16_16816(d0, al, bh0.x, bh0.y);
+            mma_bf16_16816(d1, al, bh1.x, bh1.y);
+            if (v0) {
+                float2* a0 = reinterpret_cast<float2*>(accw + pr0 * kMmaAccStride);
+                float2 u = a0[0], w = a0[4];
+                u.x += d0[0]; u.y += d0[1]; w.x += d1[0]; w.y += d1[1];
+                a0[0] = u; a0[4] = w;
+            }
+            if (v1) {
+                float2* a1 = reinterpret_cast<float2*>(accw + pr1 * kMmaAccStride);
+                float2 u = a1[0], w = a1[4];
+                u.x += d0[2]; u.y += d0[3]; w.x += d1[2]; w.y += d1[3];
+                a1[0] = u; a1[4] = w;
+            }
+        }
+        bh0 = nh0; bh1 = nh1; bl0 = nl0; bl1 = nl1;
+    }
+    __syncthreads();
+    {
+        const int colc = tid & (kL1Cols - 1);
+        const int col = chunk0 + colc;
+        if (col < p.OUT) {
+            for (int r = tid >> 8; r < P; r += 2) {
+                float v = acc[r * kMmaAccStride + colc];
+                if (p.relu) v = fmaxf(v, 0.f);
+                const size_t o = (size_t)(row0 + r) * p.OUT + col;
+                if (p.out_hi) {
+                    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                    p.out_hi[o] = h;
+                    p.out_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+                } else {
+                    p.out[o] = v;
+                }
+            }
+        }
+    }
+}
+
+static size_t l1_mma_smem_bytes(int cap, int cells, int nm1) {
+    size_t b = (size_t)cap * kMmaAccStride * sizeof(float);
+    b += (size_t)(cap + 1) * 16 * 2 * sizeof(__nv_bfloat16);
+    b += (size_t)(2 * cells + 1) * sizeof(int);
+    b += (size_t)cap * nm1 * 2 * sizeof(uint16_t);
+    return b + 16;
+}
+
+// weight repack for the mma path: W1[o][c * cells + cell] -> (hi, lo)[cell][o][kperm(c)]
+__global__ void repack_layer1_mma_kernel(const float* __restrict__ W1, __nv_bfloat16* __restrict__ hi,
+                                         __nv_bfloat16* __restrict__ lo, int OUT, int cells) {
+    size_t total = (size_t)cells * OUT * 16;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx & 15);
+        const size_t co = idx >> 4;
+        const int o = (int)(co % OUT), cell = (int)(co / OUT);
+        const float v = W1[(size_t)o * 16 * cells + (size_t)c * cells + cell];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const size_t dst = (co << 4) + kperm16(c);
+        hi[dst] = h;
+        lo[dst] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+int launch_repack_layer1_mma(const float* W1, void* hi, void* lo, int OUT, int cells, cudaStream_t st) {
+    repack_layer1_mma_kernel<<<1024, 256, 0, st>>>(W1, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, OUT, cells);
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
+}
+
 static size_t l1_smem_bytes(int cap, int C, bool social, int cells, int nm1) {
     size_t b = (size_t)cap * kL1Cols * sizeof(float);
     if (social) b += (size_t)(cap + 1) * C * sizeof(float);
@@ -586,6 +840,31 @@ int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float
     p.out_hi = tc2 ? reinterpret_cast<__nv_bfloat16*>(ws->act[0]) : nullptr;
     p.out_lo = tc2 ? reinterpret_cast<__nv_bfloat16*>(ws->act[1]) : nullptr;
     int rc;
+    if (m->Wt1_hi != nullptr) {      // social, 16 latent channels: tensor-core path
+        int gm = 0;
+        size_t sm = l1_mma_smem_bytes(l->group_cap[gm], m->cells, nm1);
+        if (sm > 227 * 1024) { gm = 1; sm = l1_mma_smem_bytes(l->group_cap[gm], m->cells, nm1); }
+        TB2_REQUIRE(sm <= 227 * 1024, "scene group does not fit in shared memory (scene too large)");
+        L1MmaParams q;
+        q.group_off = l->group_off[gm]; q.scene_off = l->scene_off; q.win_count = ws->win_count;
+        q.win_ent = ws->win_ent; q.lat = ws->lat; q.benc = m->benc;
+        q.Wt_hi = (const __nv_bfloat16*)m->Wt1_hi; q.Wt_lo = (const __nv_bfloat16*)m->Wt1_lo;
+        q.base = m->base1; q.out = p.out; q.out_hi = p.out_hi; q.out_lo = p.out_lo;
+        q.OUT = d1; q.cells = m->cells; q.nm1 = nm1; q.cap = l->group_cap[gm]; q.relu = 1;
+        q.constant = m->cfg.constant;
+        static size_t configured = 0;
+        if (sm > configured) {
+            TB2_CHECK_CUDA(cudaFuncSetAttribute(sparse_layer1_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            configured = sm;
+        }
+        dim3 grid(l->num_groups[gm], (d1 + kL1Cols - 1) / kL1Cols);
+        {
+            KernelTimer kt("sparse_layer1_mma", st);
+            sparse_layer1_mma_kernel<<<grid, kL1Threads, sm, st>>>(q);
+        }
+        TB2_LAUNCH_CHECK();
+        rc = TB2_OK;
+    } else
     switch (m->cfg.pool_type) {
         case TB2_POOL_OCCUPANCY: rc = launch_l1_t<1, false>(p, l->num_groups[gsel], smem, st); break;
         case TB2_POOL_DIRECTIONAL: rc = launch_l1_t<2, false>(p, l->num_groups[gsel], smem, st); break;
