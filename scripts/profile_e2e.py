@@ -38,3 +38,36 @@ with torch.no_grad():
         model(obs_host, goals, bs_t, n_predict=12)
     pr.disable()
     pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+
+# ---- bench-like loops: what does the L2 flush / the sync before each step cost? -------------
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+
+def timed(label, obs, do_flush, sync_before, n=10):
+    with torch.no_grad():
+        for _ in range(2):
+            model(obs, goals, bs_t, n_predict=12)
+        torch.cuda.synchronize()
+        tot = 0.0
+        ev = []
+        for _ in range(n):
+            if do_flush:
+                flush.zero_()
+            if sync_before:
+                torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            a.record()
+            model(obs, goals, bs_t, n_predict=12)
+            b.record()
+            torch.cuda.synchronize()
+            tot += time.perf_counter() - t0
+            ev.append(a.elapsed_time(b))
+        print("%-34s wall %.3f ms  gpu(events) %.3f ms" % (label, 1e3 * tot / n, sum(ev) / n))
+
+
+timed("resident  noflush nosync", obs_dev, False, False)
+timed("resident  flush   nosync", obs_dev, True, False)
+timed("resident  flush   sync", obs_dev, True, True)
+timed("host      noflush sync", obs_host, False, True)
+timed("host      flush   sync", obs_host, True, True)

@@ -66,6 +66,14 @@ size_t carve_workspace(const tb2_lstm* m, const tb2_layout* l, void* base, Works
     w.act[1] = (float*)take(M * wmax * sizeof(float));
     w.act2 = (float*)take(m->n_mlp > 2 ? M * wmax * sizeof(float) : 16);
     w.pooled = (float*)take(M * (size_t)std::max(m->pool_out, 1) * sizeof(float));
+    w.emb_hi = take(M * 64 * 2);
+    w.emb_lo = take(M * 64 * 2);
+    w.pool_hi = take(M * (size_t)std::max(m->P, 1) * 2);
+    w.pool_lo = take(M * (size_t)std::max(m->P, 1) * 2);
+    for (int i = 0; i < 2; ++i) {
+        w.hs_hi[i] = take(M * 128 * 2);
+        w.hs_lo[i] = take(M * 128 * 2);
+    }
     w.bytes = off;
     if (ws) *ws = w;
     return off;
@@ -131,7 +139,7 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
     m->C = 0; m->cells = 0; m->n_mlp = 0; m->P = 0; m->pool_out = 0;
     m->We = m->be = m->Wn = m->bn = m->WencT = m->benc = m->Wt1 = m->base1 = nullptr;
     m->Wt1_hi = m->Wt1_lo = nullptr;
-    for (int i = 0; i < 2; ++i) m->WgT[i] = m->bg[i] = nullptr;
+    for (int i = 0; i < 2; ++i) { m->WgT[i] = m->bg[i] = nullptr; m->Wg_hi[i] = m->Wg_lo[i] = nullptr; }
     for (int i = 0; i < kMaxMlpLayers; ++i) { m->WT[i] = m->bl[i] = nullptr; m->W_hi[i] = m->W_lo[i] = nullptr; }
     auto fail = [&](int rc) { tb2_lstm_destroy(m); return rc; };
     if (cfg->pool_type != TB2_POOL_NONE) {
@@ -168,6 +176,19 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
     for (int ph = 0; ph < 2; ++ph) {
         ALLOC(m->WgT[ph], (size_t)m->K_gate_pad * 4 * m->H);
         ALLOC(m->bg[ph], 4 * m->H);
+    }
+    {
+        const char* no_tc = getenv("TB2_DISABLE_TC");
+        if (!(no_tc && no_tc[0] == '1') && gates_tc_supported(m)) {
+            const size_t half = ((size_t)4 * m->H * m->K_gate + 1) / 2;
+            for (int ph = 0; ph < 2; ++ph) {
+                float *hi, *lo;
+                ALLOC(hi, half);
+                ALLOC(lo, half);
+                m->Wg_hi[ph] = hi;
+                m->Wg_lo[ph] = lo;
+            }
+        }
     }
     if (cfg->pool_type == TB2_POOL_SOCIAL) {
         ALLOC(m->WencT, m->H * m->C);
@@ -336,18 +357,29 @@ int tb2_pool_forward(const tb2_lstm* m, const tb2_layout* l, const float* hidden
     carve_workspace(m, l, workspace, &ws);
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = launch_pool_prepare(m, l, hidden, obs1, obs2, 0, 0, &ws, st))) return rc;
-    return launch_pool_mlp(m, l, &ws, pooled_out, st);
+    return launch_pool_mlp(m, l, &ws, pooled_out, nullptr, nullptr, st);
 }
 
+// hs_cur: index (0/1) of the ping-pong buffer holding the bf16 split of h_in (tensor-core gates)
 static int step_impl(const tb2_lstm* m, const tb2_layout* l, int phase, const float* obs1,
                      const float* obs2, const float* h_in, const float* c_in, float* h_out,
-                     float* c_out, float* normal_out, float* pos_out, Workspace* ws, cudaStream_t st) {
+                     float* c_out, float* normal_out, float* pos_out, Workspace* ws, int hs_cur,
+                     cudaStream_t st) {
     int rc;
+    const bool tc = m->Wg_hi[0] != nullptr;
     const float* pooled = nullptr;
     if (m->cfg.pool_type != TB2_POOL_NONE) {
         if ((rc = launch_pool_prepare(m, l, h_in, obs1, obs2, 1, 0, ws, st))) return rc;
-        if ((rc = launch_pool_mlp(m, l, ws, ws->pooled, st))) return rc;
+        if (tc) rc = launch_pool_mlp(m, l, ws, nullptr, ws->pool_hi, ws->pool_lo, st);
+        else rc = launch_pool_mlp(m, l, ws, ws->pooled, nullptr, nullptr, st);
+        if (rc) return rc;
         pooled = ws->pooled;
+    }
+    if (tc) {
+        if ((rc = launch_embed_split(m, l->M, obs1, obs2, ws->emb_hi, ws->emb_lo, st))) return rc;
+        return launch_gates_tc(m, l, phase, obs1, obs2, ws->emb_hi, ws->emb_lo, ws->pool_hi, ws->pool_lo,
+                               ws->hs_hi[hs_cur], ws->hs_lo[hs_cur], ws->hs_hi[hs_cur ^ 1], ws->hs_lo[hs_cur ^ 1],
+                               h_in, c_in, h_out, c_out, normal_out, pos_out, st);
     }
     return launch_gates(m, l, phase, obs1, obs2, pooled, h_in, c_in, h_out, c_out, normal_out, pos_out, st);
 }
@@ -362,8 +394,11 @@ int tb2_lstm_step_forward(const tb2_lstm* m, const tb2_layout* l, int32_t phase,
     TB2_REQUIRE(obs1 && obs2 && h_in && c_in && h_out && c_out && normal_out, "null argument");
     Workspace ws;
     carve_workspace(m, l, workspace, &ws);
-    return step_impl(m, l, phase, obs1, obs2, h_in, c_in, h_out, c_out, normal_out, pos_out, &ws,
-                     (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m->Wg_hi[0] &&
+        (rc = launch_split_rows(h_in, ws.hs_hi[0], ws.hs_lo[0], (size_t)l->M * m->H, st)))
+        return rc;
+    return step_impl(m, l, phase, obs1, obs2, h_in, c_in, h_out, c_out, normal_out, pos_out, &ws, 0, st);
 }
 
 int tb2_lstm_forward_sequence(const tb2_lstm* m, const tb2_layout* l, const float* observed,
@@ -381,6 +416,10 @@ int tb2_lstm_forward_sequence(const tb2_lstm* m, const tb2_layout* l, const floa
     const size_t frame = M * 2;
     TB2_CHECK_CUDA(cudaMemsetAsync(h, 0, M * H * sizeof(float), st));     // lstm.py:207-210
     TB2_CHECK_CUDA(cudaMemsetAsync(c, 0, M * H * sizeof(float), st));
+    if (m->Wg_hi[0]) {
+        TB2_CHECK_CUDA(cudaMemsetAsync(ws.hs_hi[0], 0, M * H * 2, st));
+        TB2_CHECK_CUDA(cudaMemsetAsync(ws.hs_lo[0], 0, M * H * 2, st));
+    }
     const int S = obs_length - 1 + n_decode;
     const float* h_prev = h;
     const float* c_prev = c;
@@ -420,7 +459,7 @@ int tb2_lstm_forward_sequence(const tb2_lstm* m, const tb2_layout* l, const floa
         float* h_next = states_out ? states_out + ((size_t)s * 2 + 0) * M * H : h;
         float* c_next = states_out ? states_out + ((size_t)s * 2 + 1) * M * H : c;
         if ((rc = step_impl(m, l, phase, o1, o2, h_prev, c_prev, h_next, c_next,
-                            normals_out + (size_t)s * M * 5, positions_out + (size_t)s * frame, &ws, st)))
+                            normals_out + (size_t)s * M * 5, positions_out + (size_t)s * frame, &ws, s & 1, st)))
             return rc;
         h_prev = h_next;
         c_prev = c_next;

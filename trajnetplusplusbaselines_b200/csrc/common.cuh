@@ -77,6 +77,8 @@ struct tb2_lstm {
     float* bl[tb2::kMaxMlpLayers];   // biases of layers >= 2
     void* W_hi[tb2::kMaxMlpLayers];  // bf16 [N, K] (hi, lo) split for the tcgen05 path (null: FFMA path)
     void* W_lo[tb2::kMaxMlpLayers];
+    void* Wg_hi[2];        // gate weights [4H (rank, gate, unit), K_gate] bf16 split (null: FFMA gates)
+    void* Wg_lo[2];
     std::vector<void*> owned;
 };
 
@@ -106,6 +108,12 @@ struct Workspace {
     float* act[2];         // ping-pong MLP activations [M, max width]
     float* act2;           // third scratch (three_layer with a tensor-core second layer)
     float* pooled;         // [M, pool_out]
+    void* emb_hi;          // [M, 64] bf16 split operands of the tensor-core gate kernel
+    void* emb_lo;
+    void* pool_hi;         // [M, P]
+    void* pool_lo;
+    void* hs_hi[2];        // [M, 128] ping-pong split of the hidden state
+    void* hs_lo[2];
     size_t bytes;
 };
 size_t carve_workspace(const tb2_lstm* m, const tb2_layout* l, void* base, Workspace* ws);
@@ -116,8 +124,9 @@ int launch_resolve_obs(const tb2_layout* l, const float* base, const float* pred
 int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hidden,
                         const float* obs1, const float* obs2, int skip_masked, int write_pairs,
                         Workspace* ws, cudaStream_t st);
+// pooled_out fp32 and/or (pool_hi, pool_lo) bf16 split (either may be null, not both)
 int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float* pooled_out,
-                    cudaStream_t st);
+                    void* pool_hi, void* pool_lo, cudaStream_t st);
 int launch_gates(const tb2_lstm* m, const tb2_layout* l, int phase, const float* obs1,
                  const float* obs2, const float* pooled, const float* h_in, const float* c_in,
                  float* h_out, float* c_out, float* normal_out, float* pos_out, cudaStream_t st);
@@ -125,7 +134,16 @@ int launch_repack(tb2_lstm* m, const tb2_lstm_weights* w, cudaStream_t st);
 int launch_repack_layer1_mma(const float* W1, void* hi, void* lo, int OUT, int cells, cudaStream_t st);
 bool dense_tc_supported(int K, int N);
 int launch_dense_tc(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
-                    float* Y, int M, int K, int N, int relu, cudaStream_t st);
+                    float* Y, void* Y_hi, void* Y_lo, int M, int K, int N, int relu, cudaStream_t st);
+bool gates_tc_supported(const tb2_lstm* m);
+int launch_repack_gates_tc(const float* w_ih, const float* w_hh, void* hi, void* lo, int in_dim, int H, cudaStream_t st);
+int launch_embed_split(const tb2_lstm* m, int M, const float* obs1, const float* obs2, void* hi, void* lo, cudaStream_t st);
+int launch_split_rows(const float* src, void* hi, void* lo, size_t n, cudaStream_t st);
+int launch_gates_tc(const tb2_lstm* m, const tb2_layout* l, int phase, const float* obs1, const float* obs2,
+                    const void* emb_hi, const void* emb_lo, const void* pool_hi, const void* pool_lo,
+                    const void* hs_in_hi, const void* hs_in_lo, void* hs_out_hi, void* hs_out_lo,
+                    const float* h_in, const float* c_in, float* h_out, float* c_out, float* normal_out,
+                    float* pos_out, cudaStream_t st);
 int launch_split_bf16(const float* src, void* hi, void* lo, size_t n, cudaStream_t st);
 int launch_grid_indices_copy(const tb2_layout* l, const Workspace* ws, int32_t* cell_out,
                              uint8_t* flag_out, cudaStream_t st);

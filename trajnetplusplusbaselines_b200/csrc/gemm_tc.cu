@@ -81,7 +81,9 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 
 struct TcParams {
     const float* bias;
-    float* Y;
+    float* Y;                  // fp32 output, or null
+    __nv_bfloat16* Y_hi;       // bf16 (hi, lo) split output for a tensor-core consumer, or null
+    __nv_bfloat16* Y_lo;
     int M, N, K, relu;
 };
 
@@ -185,7 +187,7 @@ dense_layer_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (row < p.M) {
-                float* yrow = p.Y + (size_t)row * p.N + n0 + half * 32;
+                const size_t yoff = (size_t)row * p.N + n0 + half * 32;
                 const float* brow = p.bias + n0 + half * 32;
 #pragma unroll
                 for (int c = 0; c < 32; c += 4) {
@@ -197,7 +199,21 @@ dense_layer_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                     if (p.relu) {
                         v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
                     }
-                    *reinterpret_cast<float4*>(yrow + c) = v;
+                    if (p.Y) *reinterpret_cast<float4*>(p.Y + yoff + c) = v;
+                    if (p.Y_hi) {
+                        const float f[4] = {v.x, v.y, v.z, v.w};
+                        unsigned short hh[4], hl[4];
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            const __nv_bfloat16 h = __float2bfloat16_rn(f[w]);
+                            hh[w] = __bfloat16_as_ushort(h);
+                            hl[w] = __bfloat16_as_ushort(__float2bfloat16_rn(f[w] - __bfloat162float(h)));
+                        }
+                        *reinterpret_cast<uint2*>(p.Y_hi + yoff + c) =
+                            make_uint2((uint32_t)hh[0] | ((uint32_t)hh[1] << 16), (uint32_t)hh[2] | ((uint32_t)hh[3] << 16));
+                        *reinterpret_cast<uint2*>(p.Y_lo + yoff + c) =
+                            make_uint2((uint32_t)hl[0] | ((uint32_t)hl[1] << 16), (uint32_t)hl[2] | ((uint32_t)hl[3] << 16));
+                    }
                 }
             }
         }
@@ -247,7 +263,7 @@ int make_bf16_tile_map(CUtensorMap* map, const void* base, int rows, int cols, i
 bool dense_tc_supported(int K, int N) { return K >= kTcBK && K % kTcBK == 0 && N % kTcBN == 0; }
 
 int launch_dense_tc(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
-                    float* Y, int M, int K, int N, int relu, cudaStream_t st) {
+                    float* Y, void* Y_hi, void* Y_lo, int M, int K, int N, int relu, cudaStream_t st) {
     TB2_REQUIRE(dense_tc_supported(K, N), "tensor-core dense layer needs K % 64 == 0 and N % 64 == 0");
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
@@ -264,6 +280,8 @@ int launch_dense_tc(const void* a_hi, const void* a_lo, const void* w_hi, const 
     TcParams p;
     p.bias = bias;
     p.Y = Y;
+    p.Y_hi = (__nv_bfloat16*)Y_hi;
+    p.Y_lo = (__nv_bfloat16*)Y_lo;
     p.M = M;
     p.N = N;
     p.K = K;

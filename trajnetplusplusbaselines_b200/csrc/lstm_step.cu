@@ -350,6 +350,9 @@ int launch_repack(tb2_lstm* m, const tb2_lstm_weights* w, cudaStream_t st) {
         repack_gates_kernel<<<512, 256, 0, st>>>(wih[ph], whh[ph], bih[ph], bhh[ph], m->WgT[ph], m->bg[ph],
                                                  m->E + m->P, m->H, m->K_gate_pad);
         TB2_LAUNCH_CHECK();
+        if (m->Wg_hi[ph] &&
+            (rc = launch_repack_gates_tc(wih[ph], whh[ph], m->Wg_hi[ph], m->Wg_lo[ph], m->E + m->P, m->H, st)))
+            return rc;
     }
     if (m->cfg.pool_type == TB2_POOL_SOCIAL) {
         TB2_REQUIRE(w->pool_encoding_weight && w->pool_encoding_bias, "pool.hidden_dim_encoding missing");

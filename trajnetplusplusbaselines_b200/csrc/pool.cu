@@ -797,14 +797,22 @@ static int launch_l1_t(const L1Params& p, int groups, size_t smem, cudaStream_t 
 
 // Grid -> pooled vector (GridBasedPooling.forward after the grid is known, :106-110).
 int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float* pooled_out,
-                    cudaStream_t st) {
+                    void* pool_hi, void* pool_lo, cudaStream_t st) {
     const int nm1 = l->n_max > 1 ? l->n_max - 1 : 1;
+    // producers that cannot write the bf16 split themselves go through fp32 scratch + split_rows
+    const bool want_split = pool_hi != nullptr;
+    const bool last_is_l1 = m->n_mlp == 1;
+    const bool last_is_tc = m->n_mlp == 2 && m->W_hi[1] != nullptr;
+    const bool direct_split = want_split && (last_is_l1 || last_is_tc);
+    if (want_split && !direct_split && pooled_out == nullptr) pooled_out = ws->pooled;
+    int rc_all = TB2_OK;
     if (m->n_mlp == 0) {
         dense_grid_kernel<<<l->M, 128, 0, st>>>(ws->win_count, ws->win_ent, ws->win_val, ws->lat,
                                                 l->row_scene, l->scene_off, m->benc, pooled_out, m->C,
                                                 m->cells, nm1, m->cfg.constant, m->cfg.pool_type);
         TB2_LAUNCH_CHECK();
-        return TB2_OK;
+        if (want_split) rc_all = launch_split_rows(pooled_out, pool_hi, pool_lo, (size_t)l->M * m->pool_out, st);
+        return rc_all;
     }
     const int d1 = m->mlp_dims[1];
     const bool social = m->cfg.pool_type == TB2_POOL_SOCIAL;
@@ -839,6 +847,11 @@ int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float
     p.out = tc2 ? nullptr : l1_out;
     p.out_hi = tc2 ? reinterpret_cast<__nv_bfloat16*>(ws->act[0]) : nullptr;
     p.out_lo = tc2 ? reinterpret_cast<__nv_bfloat16*>(ws->act[1]) : nullptr;
+    if (last_is_l1 && direct_split) {      // one_layer embedding feeding the tensor-core gates
+        p.out = pooled_out;                // may be null
+        p.out_hi = reinterpret_cast<__nv_bfloat16*>(pool_hi);
+        p.out_lo = reinterpret_cast<__nv_bfloat16*>(pool_lo);
+    }
     int rc;
     if (m->Wt1_hi != nullptr) {      // social, 16 latent channels: tensor-core path
         int gm = 0;
@@ -884,13 +897,17 @@ int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float
         if (layer == 1 && tc2) {
             // act[0] / act[1] hold the split input; a third layer (if any) reads fp32 from ws->pooled-sized scratch
             if (m->n_mlp > 2) y = ws->act2;
-            rc = launch_dense_tc(ws->act[0], ws->act[1], m->W_hi[1], m->W_lo[1], m->bl[1], y, l->M,
-                                 m->mlp_dims[1], m->mlp_dims[2], 1, st);
+            const bool last = (m->n_mlp == 2);
+            rc = launch_dense_tc(ws->act[0], ws->act[1], m->W_hi[1], m->W_lo[1], m->bl[1],
+                                 (last && direct_split) ? pooled_out : y,
+                                 (last && direct_split) ? pool_hi : nullptr, (last && direct_split) ? pool_lo : nullptr,
+                                 l->M, m->mlp_dims[1], m->mlp_dims[2], 1, st);
         } else
         rc = launch_dense(x, m->WT[layer], m->bl[layer], y, l->M, m->mlp_dims[layer], m->mlp_dims[layer + 1], 1, st);
         if (rc != TB2_OK) return rc;
         x = y;
     }
+    if (want_split && !direct_split) return launch_split_rows(pooled_out, pool_hi, pool_lo, (size_t)l->M * m->pool_out, st);
     return TB2_OK;
 }
 
