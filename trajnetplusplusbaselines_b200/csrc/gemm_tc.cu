@@ -23,14 +23,17 @@
 namespace tb2 {
 
 constexpr int kTcBM = 128;
-constexpr int kTcBN = 64;
 constexpr int kTcBK = 64;          // 64 bf16 = 128 bytes = one swizzle atom
-constexpr int kTcStages = 4;
 constexpr int kTcThreads = 192;
 constexpr uint32_t kTcABytes = kTcBM * kTcBK * 2;     // 16 KB
-constexpr uint32_t kTcBBytes = kTcBN * kTcBK * 2;     // 8 KB
-constexpr uint32_t kTcStageBytes = 2 * kTcABytes + 2 * kTcBBytes;   // 48 KB
-constexpr uint32_t kTcTmemCols = 64;
+// BN = 128: 64 KB / stage, 3 stages (M = 5120, N = 256 -> 80 CTAs, one wave on 148 SMs)
+// BN =  64: 48 KB / stage, 4 stages (narrow layers)
+template <int BN> struct TcCfg {
+    static constexpr uint32_t kBBytes = BN * kTcBK * 2;
+    static constexpr uint32_t kStageBytes = 2 * kTcABytes + 2 * kBBytes;
+    static constexpr int kStages = BN == 128 ? 3 : 4;
+    static constexpr uint32_t kTmemCols = BN;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -87,10 +90,15 @@ struct TcParams {
     int M, N, K, relu;
 };
 
+template <int kTcBN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 dense_layer_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                       const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                       TcParams p) {
+    constexpr int kTcStages = TcCfg<kTcBN>::kStages;
+    constexpr uint32_t kTcBBytes = TcCfg<kTcBN>::kBBytes;
+    constexpr uint32_t kTcStageBytes = TcCfg<kTcBN>::kStageBytes;
+    constexpr uint32_t kTcTmemCols = TcCfg<kTcBN>::kTmemCols;
     extern __shared__ __align__(1024) unsigned char smem_tc[];
     __shared__ __align__(8) uint64_t full_bar[kTcStages];
     __shared__ __align__(8) uint64_t empty_bar[kTcStages];
@@ -172,8 +180,8 @@ dense_layer_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
         mbar_wait(smem_u32(&tmem_full_bar), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = m0 + q * 32 + lane;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+#pragma unroll 1
+        for (int half = 0; half < kTcBN / 32; ++half) {
             uint32_t r[32];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32);
             asm volatile(
@@ -260,7 +268,25 @@ int make_bf16_tile_map(CUtensorMap* map, const void* base, int rows, int cols, i
     return TB2_OK;
 }
 
-bool dense_tc_supported(int K, int N) { return K >= kTcBK && K % kTcBK == 0 && N % kTcBN == 0; }
+bool dense_tc_supported(int K, int N) { return K >= kTcBK && K % kTcBK == 0 && N % 64 == 0; }
+
+template <int BN>
+static int launch_dense_tc_t(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
+                             const CUtensorMap& mb_lo, const TcParams& p, cudaStream_t st) {
+    const size_t smem = (size_t)TcCfg<BN>::kStages * TcCfg<BN>::kStageBytes + 1024;
+    static bool configured = false;
+    if (!configured) {
+        TB2_CHECK_CUDA(cudaFuncSetAttribute(dense_layer_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(p.N / BN, (p.M + kTcBM - 1) / kTcBM);
+    {
+        KernelTimer kt("dense_layer_tc", st);
+        dense_layer_tc_kernel<BN><<<grid, kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+    }
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
+}
 
 int launch_dense_tc(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                     float* Y, void* Y_hi, void* Y_lo, int M, int K, int N, int relu, cudaStream_t st) {
@@ -269,14 +295,9 @@ int launch_dense_tc(const void* a_hi, const void* a_lo, const void* w_hi, const 
     int rc;
     if ((rc = make_bf16_tile_map(&ma_hi, a_hi, M, K, kTcBM))) return rc;
     if ((rc = make_bf16_tile_map(&ma_lo, a_lo, M, K, kTcBM))) return rc;
-    if ((rc = make_bf16_tile_map(&mb_hi, w_hi, N, K, kTcBN))) return rc;
-    if ((rc = make_bf16_tile_map(&mb_lo, w_lo, N, K, kTcBN))) return rc;
-    const size_t smem = (size_t)kTcStages * kTcStageBytes + 1024;
-    static bool configured = false;
-    if (!configured) {
-        TB2_CHECK_CUDA(cudaFuncSetAttribute(dense_layer_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    const int bn = (N % 128 == 0) ? 128 : 64;
+    if ((rc = make_bf16_tile_map(&mb_hi, w_hi, N, K, bn))) return rc;
+    if ((rc = make_bf16_tile_map(&mb_lo, w_lo, N, K, bn))) return rc;
     TcParams p;
     p.bias = bias;
     p.Y = Y;
@@ -286,13 +307,8 @@ int launch_dense_tc(const void* a_hi, const void* a_lo, const void* w_hi, const 
     p.N = N;
     p.K = K;
     p.relu = relu;
-    dim3 grid(N / kTcBN, (M + kTcBM - 1) / kTcBM);
-    {
-        KernelTimer kt("dense_layer_tc", st);
-        dense_layer_tc_kernel<<<grid, kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
-    }
-    TB2_LAUNCH_CHECK();
-    return TB2_OK;
+    return bn == 128 ? launch_dense_tc_t<128>(ma_hi, ma_lo, mb_hi, mb_lo, p, st)
+                     : launch_dense_tc_t<64>(ma_hi, ma_lo, mb_hi, mb_lo, p, st);
 }
 
 // fp32 -> (hi, lo) bf16 split of a weight matrix (repack time)

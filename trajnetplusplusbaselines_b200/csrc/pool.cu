@@ -509,20 +509,23 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_mma_kernel(L1MmaP
     const int P = p.scene_off[s1] - row0;
     const int chunk0 = blockIdx.y * kL1Cols;
 
-    float* acc = reinterpret_cast<float*>(smem_l1m);                                       // [cap][264]
-    __nv_bfloat16* latH = reinterpret_cast<__nv_bfloat16*>(acc + (size_t)p.cap * kMmaAccStride);   // [cap+1][16]
-    __nv_bfloat16* latL = latH + (size_t)(p.cap + 1) * 16;
-    int* start = reinterpret_cast<int*>(latL + (size_t)(p.cap + 1) * 16);                  // [cells+1]
+    // acc rows [0, cap) real, [cap, cap + 16) dummies absorbing the padding rows of an MMA tile;
+    // lat rows [0, cap) real, cap = NaN-padded slot (b_enc), cap + 1 = zeros (padding rows)
+    float* acc = reinterpret_cast<float*>(smem_l1m);                                       // [cap+16][264]
+    __nv_bfloat16* latH = reinterpret_cast<__nv_bfloat16*>(acc + (size_t)(p.cap + 16) * kMmaAccStride);   // [cap+2][16]
+    __nv_bfloat16* latL = latH + (size_t)(p.cap + 2) * 16;
+    int* start = reinterpret_cast<int*>(latL + (size_t)(p.cap + 2) * 16);                  // [cells+1]
     int* cursor = start + p.cells + 1;                                                     // [cells]
-    uint16_t* entP = reinterpret_cast<uint16_t*>(cursor + p.cells);                        // [cap*nm1]
-    uint16_t* entS = entP + (size_t)p.cap * p.nm1;
+    uint32_t* ent = reinterpret_cast<uint32_t*>(cursor + p.cells);                         // [cap*nm1 + 16]: lat row << 16 | acc row
 
     for (int c = tid; c < p.cells; c += kL1Threads) cursor[c] = 0;
-    for (int idx = tid; idx < (P + 1) * 16; idx += kL1Threads) {
+    for (int idx = tid; idx < (P + 2) * 16; idx += kL1Threads) {
         const int r = idx >> 4, k = idx & 15;
-        const float v = (r < P ? p.lat[(size_t)(row0 + r) * 16 + k] : p.benc[k]) - p.constant;
+        float v = 0.f;
+        if (r < P) v = p.lat[(size_t)(row0 + r) * 16 + k] - p.constant;
+        else if (r == P) v = p.benc[k] - p.constant;
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        const int dst = (r < P ? r : p.cap) * 16 + kperm16(k);
+        const int dst = (r < P ? r : p.cap + (r - P)) * 16 + kperm16(k);
         latH[dst] = h;
         latL[dst] = __float2bfloat16_rn(v - __bfloat162float(h));
     }
@@ -562,76 +565,78 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_mma_kernel(L1MmaP
     for (int idx = tid; idx < total; idx += kL1Threads) {
         int r = idx / p.nm1, k = idx - r * p.nm1;
         if (k < p.win_count[row0 + r]) {
-            const uint32_t ent = p.win_ent[(size_t)(row0 + r) * p.nm1 + k];
-            const int pos = atomicAdd(&cursor[ent >> 16], 1);
-            entP[pos] = (uint16_t)r;
+            const uint32_t e = p.win_ent[(size_t)(row0 + r) * p.nm1 + k];
+            const int pos = atomicAdd(&cursor[e >> 16], 1);
             int sb = s0;
             while (p.scene_off[sb + 1] <= row0 + r) ++sb;
-            const int j = (int)(ent & 0xffff);
-            entS[pos] = (uint16_t)(j == 0xffff ? p.cap : p.scene_off[sb] - row0 + j);
+            const int j = (int)(e & 0xffff);
+            const uint32_t lrow = (uint32_t)(j == 0xffff ? p.cap : p.scene_off[sb] - row0 + j);
+            ent[pos] = (lrow << 16) | (uint32_t)r;
         }
     }
     __syncthreads();
 
-    // B fragments of this warp's two n-tiles: one 8-byte load per (tile, part)
+    // padding rows of a tile: zero latent row, per-lane dummy accumulator rows
+    const uint32_t dummy0 = ((uint32_t)(p.cap + 1) << 16) | (uint32_t)(p.cap + g);
+    const uint32_t dummy1 = ((uint32_t)(p.cap + 1) << 16) | (uint32_t)(p.cap + 8 + g);
     const int ncol0 = chunk0 + warp * 16 + g;            // column of n-tile 0 this lane loads; tile 1: + 8
     const bool ok0 = ncol0 < p.OUT, ok1 = ncol0 + 8 < p.OUT;
     const size_t cell_stride = (size_t)p.OUT * 16;       // bf16 elements per cell
     const __nv_bfloat16* wh = p.Wt_hi + (size_t)ncol0 * 16 + 4 * t;
     const __nv_bfloat16* wl = p.Wt_lo + (size_t)ncol0 * 16 + 4 * t;
-    auto ldb = [&](const __nv_bfloat16* base, bool ok) -> uint2 {
-        return ok ? *reinterpret_cast<const uint2*>(base) : make_uint2(0u, 0u);
+    struct BFrag { uint2 h0, h1, l0, l1; };
+    auto load_b = [&](int cell) -> BFrag {
+        BFrag f;
+        const size_t o = (size_t)cell * cell_stride;
+        f.h0 = ok0 ? *reinterpret_cast<const uint2*>(wh + o) : make_uint2(0u, 0u);
+        f.h1 = ok1 ? *reinterpret_cast<const uint2*>(wh + o + 8 * 16) : make_uint2(0u, 0u);
+        f.l0 = ok0 ? *reinterpret_cast<const uint2*>(wl + o) : make_uint2(0u, 0u);
+        f.l1 = ok1 ? *reinterpret_cast<const uint2*>(wl + o + 8 * 16) : make_uint2(0u, 0u);
+        return f;
     };
-    uint2 bh0 = ldb(wh, ok0), bh1 = ldb(wh + 8 * 16, ok1), bl0 = ldb(wl, ok0), bl1 = ldb(wl + 8 * 16, ok1);
     float* accw = acc + warp * 16 + 2 * t;
-    for (int cell = 0; cell < p.cells; ++cell) {
-        uint2 nh0 = bh0, nh1 = bh1, nl0 = bl0, nl1 = bl1;
-        if (cell + 1 < p.cells) {
-            const size_t o = (size_t)(cell + 1) * cell_stride;
-            nh0 = ldb(wh + o, ok0); nh1 = ldb(wh + o + 8 * 16, ok1);
-            nl0 = ldb(wl + o, ok0); nl1 = ldb(wl + o + 8 * 16, ok1);
-        }
-        const int e0 = start[cell], e1 = start[cell + 1];
+    const __nv_bfloat16* latHt = latH + 4 * t;
+    const __nv_bfloat16* latLt = latL + 4 * t;
+    auto process = [&](int e0, int e1, const BFrag& b) {
         for (int eb = e0; eb < e1; eb += 16) {
-            const int i0 = eb + g, i1 = eb + g + 8;
-            const bool v0 = i0 < e1, v1 = i1 < e1;
-            int pr0 = 0, pr1 = 0;
-            uint32_t ah[4] = {0u, 0u, 0u, 0u}, al[4] = {0u, 0u, 0u, 0u};
-            if (v0) {
-                pr0 = entP[i0];
-                const int ls = entS[i0];
-                const uint2 x = *reinterpret_cast<const uint2*>(latH + ls * 16 + 4 * t);
-                const uint2 y = *reinterpret_cast<const uint2*>(latL + ls * 16 + 4 * t);
-                ah[0] = x.x; ah[2] = x.y; al[0] = y.x; al[2] = y.y;
-            }
-            if (v1) {
-                pr1 = entP[i1];
-                const int ls = entS[i1];
-                const uint2 x = *reinterpret_cast<const uint2*>(latH + ls * 16 + 4 * t);
-                const uint2 y = *reinterpret_cast<const uint2*>(latL + ls * 16 + 4 * t);
-                ah[1] = x.x; ah[3] = x.y; al[1] = y.x; al[3] = y.y;
-            }
+            const int i0 = eb + g, i1 = i0 + 8;
+            const uint32_t en0 = i0 < e1 ? ent[i0] : dummy0;
+            const uint32_t en1 = i1 < e1 ? ent[i1] : dummy1;
+            const uint2 x0 = *reinterpret_cast<const uint2*>(latHt + (en0 >> 16) * 16);
+            const uint2 y0 = *reinterpret_cast<const uint2*>(latLt + (en0 >> 16) * 16);
+            const uint2 x1 = *reinterpret_cast<const uint2*>(latHt + (en1 >> 16) * 16);
+            const uint2 y1 = *reinterpret_cast<const uint2*>(latLt + (en1 >> 16) * 16);
+            const uint32_t ah[4] = {x0.x, x1.x, x0.y, x1.y};
+            const uint32_t al[4] = {y0.x, y1.x, y0.y, y1.y};
             float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
-            mma_bf16_16816(d0, ah, bh0.x, bh0.y);
-            mma_bf16_16816(d1, ah, bh1.x, bh1.y);
-            mma_bf16_16816(d0, ah, bl0.x, bl0.y);
-            mma_bf16_16816(d1, ah, bl1.x, bl1.y);
-            mma_bf16_16816(d0, al, bh0.x, bh0.y);
-            mma_bf16_16816(d1, al, bh1.x, bh1.y);
-            if (v0) {
-                float2* a0 = reinterpret_cast<float2*>(accw + pr0 * kMmaAccStride);
-                float2 u = a0[0], w = a0[4];
-                u.x += d0[0]; u.y += d0[1]; w.x += d1[0]; w.y += d1[1];
-                a0[0] = u; a0[4] = w;
-            }
-            if (v1) {
-                float2* a1 = reinterpret_cast<float2*>(accw + pr1 * kMmaAccStride);
-                float2 u = a1[0], w = a1[4];
-                u.x += d0[2]; u.y += d0[3]; w.x += d1[2]; w.y += d1[3];
-                a1[0] = u; a1[4] = w;
-            }
+            mma_bf16_16816(d0, ah, b.h0.x, b.h0.y);
+            mma_bf16_16816(d1, ah, b.h1.x, b.h1.y);
+            mma_bf16_16816(d0, ah, b.l0.x, b.l0.y);
+            mma_bf16_16816(d1, ah, b.l1.x, b.l1.y);
+            mma_bf16_16816(d0, al, b.h0.x, b.h0.y);
+            mma_bf16_16816(d1, al, b.h1.x, b.h1.y);
+            float2* a0 = reinterpret_cast<float2*>(accw + (en0 & 0xffffu) * kMmaAccStride);
+            float2* a1 = reinterpret_cast<float2*>(accw + (en1 & 0xffffu) * kMmaAccStride);
+            float2 u0 = a0[0], w0 = a0[4], u1 = a1[0], w1 = a1[4];
+            u0.x += d0[0]; u0.y += d0[1]; w0.x += d1[0]; w0.y += d1[1];
+            u1.x += d0[2]; u1.y += d0[3]; w1.x += d1[2]; w1.y += d1[3];
+            a0[0] = u0; a0[4] = w0; a1[0] = u1; a1[4] = w1;
         }
-        bh0 = nh0; bh1 = nh1; bl0 = nl0; bl1 = nl1;
+    };
+    // two fragment sets in flight: cell c is consumed while cells c+1 (loaded) and c+2 (issued) follow
+    BFrag b0 = load_b(0);
+    BFrag b1 = p.cells > 1 ? load_b(1) : b0;
+    int e_lo = start[0];
+    for (int cell = 0; cell < p.cells; cell += 2) {
+        const int e_mid = start[cell + 1];
+        process(e_lo, e_mid, b0);
+        if (cell + 2 < p.cells) b0 = load_b(cell + 2);
+        if (cell + 1 < p.cells) {
+            const int e_hi = start[cell + 2];
+            process(e_mid, e_hi, b1);
+            if (cell + 3 < p.cells) b1 = load_b(cell + 3);
+            e_lo = e_hi;
+        }
     }
     __syncthreads();
     {
@@ -655,10 +660,10 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_mma_kernel(L1MmaP
 }
 
 static size_t l1_mma_smem_bytes(int cap, int cells, int nm1) {
-    size_t b = (size_t)cap * kMmaAccStride * sizeof(float);
-    b += (size_t)(cap + 1) * 16 * 2 * sizeof(__nv_bfloat16);
+    size_t b = (size_t)(cap + 16) * kMmaAccStride * sizeof(float);
+    b += (size_t)(cap + 2) * 16 * 2 * sizeof(__nv_bfloat16);
     b += (size_t)(2 * cells + 1) * sizeof(int);
-    b += (size_t)cap * nm1 * 2 * sizeof(uint16_t);
+    b += ((size_t)cap * nm1 + 16) * sizeof(uint32_t);
     return b + 16;
 }
 
