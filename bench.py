@@ -34,8 +34,11 @@ STEPS_PER_FORWARD = (OBS - 1) + (PRED - 1)       # 19
 STATE_BYTES_PER_PED_STEP = 2092                   # xy 16 + h,c in 1024 + h,c out 1024 + normal 20 + pos 8
 DENSE_FLOP_PER_PED_STEP = {                       # SURVEY.md 8d, dense-equivalent forward FLOPs
     "sparse_layer1": 2 * 4096 * 1024,             # first Linear of the grid embedding (4096 -> 1024)
+    "sparse_layer1_mma": 2 * 4096 * 1024,
     "dense_layer": 2 * 1024 * 256,
+    "dense_layer_tc": 2 * 1024 * 256,
     "lstm_gates": 2 * (64 + 256 + 128) * 512 + 2 * 128 * 5,
+    "lstm_gates_tc": 2 * (64 + 256 + 128) * 512 + 2 * 128 * 5,
 }
 
 
@@ -273,7 +276,7 @@ def main():
                         "unit": "TFLOP/s", "frac": achieved / tf_sust, "traffic": None,
                         "peak_source": how + " bf16 sustained (kernel timed inside a long step)",
                         "note": "achieved = dense-equivalent algorithmic FLOPs (SURVEY 8d) / CUDA-event time; "
-                                "the kernel runs fp32 FFMA on the <=19 occupied cells only"}
+                                "the grid layer only touches the <=19 occupied cells per pedestrian"}
         else:
             bytes_ = STATE_BYTES_PER_PED_STEP * M
             achieved = bytes_ / (dom_avg_ms * 1e-3) / 1e9

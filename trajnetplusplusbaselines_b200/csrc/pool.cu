@@ -623,18 +623,36 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_mma_kernel(L1MmaP
             a0[0] = u0; a0[4] = w0; a1[0] = u1; a1[4] = w1;
         }
     };
-    // two fragment sets in flight: cell c is consumed while cells c+1 (loaded) and c+2 (issued) follow
+    // register ring of 4 fragment sets: the slab of cell c+4 is requested right after cell c is
+    // consumed, i.e. three cell-times ahead of its use (L2 latency under this all-CTA streaming
+    // load measured ~1000 cycles, one cell is ~300-400)
+    const int nc = p.cells;
     BFrag b0 = load_b(0);
-    BFrag b1 = p.cells > 1 ? load_b(1) : b0;
+    BFrag b1 = load_b(min(1, nc - 1));
+    BFrag b2 = load_b(min(2, nc - 1));
+    BFrag b3 = load_b(min(3, nc - 1));
     int e_lo = start[0];
-    for (int cell = 0; cell < p.cells; cell += 2) {
-        const int e_mid = start[cell + 1];
-        process(e_lo, e_mid, b0);
-        if (cell + 2 < p.cells) b0 = load_b(cell + 2);
-        if (cell + 1 < p.cells) {
-            const int e_hi = start[cell + 2];
-            process(e_mid, e_hi, b1);
-            if (cell + 3 < p.cells) b1 = load_b(cell + 3);
+    for (int cell = 0; cell < nc; cell += 4) {
+        int e_hi = start[cell + 1];
+        process(e_lo, e_hi, b0);
+        if (cell + 4 < nc) b0 = load_b(cell + 4);
+        e_lo = e_hi;
+        if (cell + 1 < nc) {
+            e_hi = start[cell + 2];
+            process(e_lo, e_hi, b1);
+            if (cell + 5 < nc) b1 = load_b(cell + 5);
+            e_lo = e_hi;
+        }
+        if (cell + 2 < nc) {
+            e_hi = start[cell + 3];
+            process(e_lo, e_hi, b2);
+            if (cell + 6 < nc) b2 = load_b(cell + 6);
+            e_lo = e_hi;
+        }
+        if (cell + 3 < nc) {
+            e_hi = start[cell + 4];
+            process(e_lo, e_hi, b3);
+            if (cell + 7 < nc) b3 = load_b(cell + 7);
             e_lo = e_hi;
         }
     }

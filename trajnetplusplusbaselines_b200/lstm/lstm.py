@@ -134,6 +134,8 @@ class LSTM(torch.nn.Module):
         if t.device.type == 'cuda':
             return t.to(device=device, dtype=torch.float32).contiguous()
         t = t.to(dtype=torch.float32).contiguous()
+        if t.is_pinned():
+            return t.to(device, non_blocking=True)
         key = (tuple(t.shape), 'in')
         buf = self._pinned.get(key)
         if buf is None:
@@ -213,17 +215,26 @@ class LSTM(torch.nn.Module):
         return normals, positions
 
     def _to_host(self, *tensors):
+        """D2H into a pool of pinned buffers and hand out VIEWS of them (no per-call allocation:
+        fresh host pages cost ~2 ms per result under the box's virtualisation).  A buffer is
+        reused only once nothing derived from an earlier result (views, .numpy() arrays) is
+        alive any more, which the storage use-count tells."""
         outs = []
         for i, t in enumerate(tensors):
             key = (tuple(t.shape), 'out', i)
-            buf = self._pinned.get(key)
+            pool = self._pinned.setdefault(key, [])
+            buf = None
+            for cand in pool:
+                if torch._C._storage_Use_Count(cand.untyped_storage()._cdata) <= 2:
+                    buf = cand
+                    break
             if buf is None:
                 buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                self._pinned[key] = buf
+                pool.append(buf)
             buf.copy_(t, non_blocking=True)
-            outs.append(buf)
+            outs.append(buf.view(buf.shape))
         torch.cuda.current_stream(tensors[0].device).synchronize()
-        return [b.clone() for b in outs]
+        return outs
 
     def __getstate__(self):
         # handles / pinned staging are per-process; never pickled (LSTMPredictor.save pickles the model)
