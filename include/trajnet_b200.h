@@ -162,6 +162,48 @@ int tb2_lstm_forward_sequence(const tb2_lstm* model, const tb2_layout* layout,
                               void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Training: backward of the whole time loop (what autograd does for Trainer.train_batch,
+ * lstm/trainer.py:229-269, through LSTM.forward).  Gradient accumulators are fp32 device
+ * buffers in the reference's parameter layout (+=, caller zeroes them).
+ * ------------------------------------------------------------------------------------- */
+typedef struct tb2_lstm_grads {
+    float* input_embedding_weight;   /* [E-2, 2] */
+    float* input_embedding_bias;     /* [E-2]    */
+    float* encoder_weight_ih;        /* [4H, E (+out_dim)] */
+    float* encoder_weight_hh;        /* [4H, H] */
+    float* encoder_bias_ih;          /* [4H] */
+    float* encoder_bias_hh;          /* [4H] */
+    float* decoder_weight_ih;
+    float* decoder_weight_hh;
+    float* decoder_bias_ih;
+    float* decoder_bias_hh;
+    float* hidden2normal_weight;     /* [5, H] */
+    float* hidden2normal_bias;       /* [5] */
+    float* pool_embedding_weight0;   /* pool.embedding.0.weight grad [out_dim, C*n*n] (one_layer) or NULL */
+    float* pool_embedding_bias0;     /* [out_dim] or NULL */
+} tb2_lstm_grads;
+
+size_t tb2_lstm_backward_workspace_bytes(const tb2_lstm* model, int32_t num_active);
+
+/* BPTT over the rows that receive gradient.
+ *   weights          the same fp32 parameter pointers given to tb2_lstm_set_weights
+ *   observed/truth   inputs of the forward call (truth: teacher forcing or NULL)
+ *   positions_dev    [S, M, 2] and states_dev [S, 2, M, H]: outputs of tb2_lstm_forward_sequence
+ *   d_normals_dev    [S, M, 5] upstream gradient wrt rel_pred_scene (d pred_scene already added to
+ *                    its first two columns by the caller: pred = obs2 + mu, lstm.py:232,255)
+ *   active_rows_dev  int32 [num_active]: tracks with a non-zero upstream gradient (PredictionLoss
+ *                    touches the scene primaries only, lstm/loss.py:57,67)
+ * Supported: vanilla and occupancy / directional pooling with a one_layer embedding (the D-LSTM
+ * training config); social pooling couples tracks through the hidden-state scatter and returns
+ * TB2_ERR_UNSUPPORTED. */
+int tb2_lstm_sequence_backward(const tb2_lstm* model, const tb2_layout* layout, const tb2_lstm_weights* weights,
+                               const float* observed_dev, int32_t obs_length, const float* truth_dev,
+                               int32_t n_decode, const float* positions_dev, const float* states_dev,
+                               const float* d_normals_dev, const int32_t* active_rows_dev, int32_t num_active,
+                               const tb2_lstm_grads* grads, void* workspace_dev, size_t workspace_bytes,
+                               void* bwd_workspace_dev, size_t bwd_workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Classical crowd simulators (classical/socialforce.py, classical/orca.py).  One simulator
  * per scene, all scenes stepped in lockstep by one persistent kernel; no collective.
  * State is SoA-free AoS fp32: scenes are contiguous ranges of agents (layout handle).

@@ -1,0 +1,73 @@
+"""Host logic of the multi-GPU path on CPU: scene sharding and the flat-bucket gradient
+all-reduce with world_size = 2 over gloo."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from trajnetplusplusbaselines_b200.parallel import allreduce_gradients, shard_scenes
+
+
+def test_shard_scenes_partitions_every_scene_once():
+    rng = np.random.RandomState(0)
+    sizes = rng.randint(1, 40, size=57)
+    bs = np.concatenate([[0], np.cumsum(sizes)])
+    for world in (1, 2, 3, 8):
+        seen = []
+        costs = []
+        for rank in range(world):
+            lo, hi, t_lo, t_hi, local = shard_scenes(bs, world, rank)
+            seen += list(range(lo, hi))
+            assert t_lo == bs[lo] and t_hi == bs[hi]
+            assert local[0] == 0 and local[-1] == t_hi - t_lo and len(local) == hi - lo + 1
+            costs.append(float((sizes[lo:hi].astype(float) ** 2).sum()))
+        assert seen == list(range(len(sizes)))
+        if world > 1:
+            assert max(costs) <= 2.0 * (sum(costs) / world) + sizes.max() ** 2
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+    frozen = torch.nn.Linear(2, 2)            # never used -> grad None, must be skipped on all ranks
+    x = torch.arange(24, dtype=torch.float32).reshape(4, 6) * (rank + 1)
+    model(x).sum().backward()
+    n = allreduce_gradients(list(model.parameters()) + list(frozen.parameters()))
+    out[rank] = (n, [p.grad.clone() for p in model.parameters()])
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2_gloo():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+    expect = None
+    for rank in range(world):
+        model.zero_grad()
+        x = torch.arange(24, dtype=torch.float32).reshape(4, 6) * (rank + 1)
+        model(x).sum().backward()
+        g = [p.grad.clone() for p in model.parameters()]
+        expect = g if expect is None else [a + b for a, b in zip(expect, g)]
+    for rank in range(world):
+        n, grads = out[rank]
+        assert n == sum(p.numel() for p in model.parameters())
+        for a, b in zip(grads, expect):
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)

@@ -56,6 +56,15 @@ class LstmWeights(ctypes.Structure):
     ]
 
 
+class LstmGrads(ctypes.Structure):
+    _fields_ = [(name, ctypes.c_void_p) for name in (
+        "input_embedding_weight", "input_embedding_bias",
+        "encoder_weight_ih", "encoder_weight_hh", "encoder_bias_ih", "encoder_bias_hh",
+        "decoder_weight_ih", "decoder_weight_hh", "decoder_bias_ih", "decoder_bias_hh",
+        "hidden2normal_weight", "hidden2normal_bias",
+        "pool_embedding_weight0", "pool_embedding_bias0")]
+
+
 class SfParams(ctypes.Structure):
     _fields_ = [
         ("delta_t", ctypes.c_double),
@@ -103,6 +112,10 @@ PROTOTYPES = {
     "tb2_pool_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "tb2_lstm_step_forward": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "tb2_lstm_forward_sequence": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "tb2_lstm_backward_workspace_bytes": (_sz, [_vp, _i32]),
+    "tb2_lstm_sequence_backward": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(LstmWeights), _vp, _i32, _vp, _i32,
+                                                  _vp, _vp, _vp, _vp, _i32, ctypes.POINTER(LstmGrads),
+                                                  _vp, _sz, _vp, _sz, _vp]),
     "tb2_sf_simulate": (ctypes.c_int, [_vp, ctypes.POINTER(SfParams), _vp, _vp, _vp]),
     "tb2_kalman_predict": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "tb2_orca_simulate": (ctypes.c_int, [_vp, ctypes.POINTER(OrcaParams), _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -79,6 +79,45 @@ size_t carve_workspace(const tb2_lstm* m, const tb2_layout* l, void* base, Works
     return off;
 }
 
+// Inputs of recurrence step s (encoder: lstm.py:226-232; decoder feedback rule: lstm.py:240-250).
+// positions[s'] is the output of step s' (obs2 + mu).  May launch resolve_obs into ws->obs1/obs2.
+int resolve_step_inputs(const tb2_layout* l, const float* observed, int obs_length, const float* truth,
+                        const float* positions, int s, Workspace* ws, const float** o1, const float** o2,
+                        int* phase, cudaStream_t st) {
+    const size_t frame = (size_t)l->M * 2;
+    int rc;
+    if (s < obs_length - 1) {
+        *phase = TB2_PHASE_ENCODER;
+        *o1 = observed + (size_t)s * frame;
+        *o2 = observed + (size_t)(s + 1) * frame;
+        return TB2_OK;
+    }
+    *phase = TB2_PHASE_DECODER;
+    const int k = s - (obs_length - 1);
+    // positions[-1] = output of step s-1, positions[-2] = output of step s-2
+    // (or observed[-1] when obs_length == 2, lstm.py:222-223)
+    const float* pos_m1 = positions + (size_t)(s - 1) * frame;
+    const float* pos_m2 = (s >= 2) ? positions + (size_t)(s - 2) * frame
+                                   : observed + (size_t)(obs_length - 1) * frame;
+    // obs1 = seq[k]: seq[0] = observed[-1] (always a tensor -> primary rows only)
+    if (k == 0) {
+        if ((rc = launch_resolve_obs(l, observed + (size_t)(obs_length - 1) * frame, pos_m2, ws->obs1, st))) return rc;
+        *o1 = ws->obs1;
+    } else if (truth) {
+        if ((rc = launch_resolve_obs(l, truth + (size_t)(k - 1) * frame, pos_m2, ws->obs1, st))) return rc;
+        *o1 = ws->obs1;
+    } else {
+        *o1 = pos_m2;                                                      // :242 all rows predicted
+    }
+    if (truth) {
+        if ((rc = launch_resolve_obs(l, truth + (size_t)k * frame, pos_m1, ws->obs2, st))) return rc;
+        *o2 = ws->obs2;
+    } else {
+        *o2 = pos_m1;                                                      // :247
+    }
+    return TB2_OK;
+}
+
 }  // namespace tb2
 
 using namespace tb2;
@@ -427,35 +466,8 @@ int tb2_lstm_forward_sequence(const tb2_lstm* m, const tb2_layout* l, const floa
         const float* o1;
         const float* o2;
         int phase;
-        if (s < obs_length - 1) {                                          // encoder, lstm.py:226-232
-            phase = TB2_PHASE_ENCODER;
-            o1 = observed + (size_t)s * frame;
-            o2 = observed + (size_t)(s + 1) * frame;
-        } else {                                                           // decoder, lstm.py:240-255
-            phase = TB2_PHASE_DECODER;
-            const int k = s - (obs_length - 1);
-            // positions[-1] = output of step s-1, positions[-2] = output of step s-2
-            // (or observed[-1] when obs_length == 2, lstm.py:222-223)
-            const float* pos_m1 = positions_out + (size_t)(s - 1) * frame;
-            const float* pos_m2 = (s >= 2) ? positions_out + (size_t)(s - 2) * frame
-                                           : observed + (size_t)(obs_length - 1) * frame;
-            // obs1 = seq[k]: seq[0] = observed[-1] (always a tensor -> primary rows only)
-            if (k == 0) {
-                if ((rc = launch_resolve_obs(l, observed + (size_t)(obs_length - 1) * frame, pos_m2, ws.obs1, st))) return rc;
-                o1 = ws.obs1;
-            } else if (truth) {
-                if ((rc = launch_resolve_obs(l, truth + (size_t)(k - 1) * frame, pos_m2, ws.obs1, st))) return rc;
-                o1 = ws.obs1;
-            } else {
-                o1 = pos_m2;                                               // :242 all rows predicted
-            }
-            if (truth) {
-                if ((rc = launch_resolve_obs(l, truth + (size_t)k * frame, pos_m1, ws.obs2, st))) return rc;
-                o2 = ws.obs2;
-            } else {
-                o2 = pos_m1;                                               // :247
-            }
-        }
+        if ((rc = resolve_step_inputs(l, observed, obs_length, truth, positions_out, s, &ws, &o1, &o2, &phase, st)))
+            return rc;
         float* h_next = states_out ? states_out + ((size_t)s * 2 + 0) * M * H : h;
         float* c_next = states_out ? states_out + ((size_t)s * 2 + 1) * M * H : c;
         if ((rc = step_impl(m, l, phase, o1, o2, h_prev, c_prev, h_next, c_next,

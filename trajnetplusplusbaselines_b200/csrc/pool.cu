@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_kernel(L1Params p
 //   neighbours) and the cell's weight slab is B [16 x 256]; pairs-per-cell is ~10, far below the
 //   64/128-row minimum of tcgen05.mma, so this irregular piece uses warp-level
 //   mma.sync.m16n8k16 (bf16 inputs, fp32 accumulate) with the same 3-pass (hi, lo) split as the
-//   dense layers.  Warp w owns output columns [16w, 16w+16) of the chunk for ALL pedestrians of
+//   dense layers.  Warp w owns output columns [32w, 32w+32) of the chunk for ALL pedestrians of
 //   the scene group, so accumulator rows are never shared between warps: no atomics, no
 //   barriers inside the cell loop, deterministic ascending-cell summation.
 //   smem: acc[P][264] fp32 | lat_hi, lat_lo [P+1][16] bf16 (k-permuted) | buckets | entries
@@ -500,7 +500,9 @@ struct L1MmaParams {
     float constant;
 };
 
-__global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_mma_kernel(L1MmaParams p) {
+constexpr int kMmaThreads = 256;          // 8 warps x 32 output columns
+
+__global__ void __launch_bounds__(kMmaThreads, 1) sparse_layer1_mma_kernel(L1MmaParams p) {
     extern __shared__ __align__(16) unsigned char smem_l1m[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -518,8 +520,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_mma_kernel(L1MmaP
     int* cursor = start + p.cells + 1;                                                     // [cells]
     uint32_t* ent = reinterpret_cast<uint32_t*>(cursor + p.cells);                         // [cap*nm1 + 16]: lat row << 16 | acc row
 
-    for (int c = tid; c < p.cells; c += kL1Threads) cursor[c] = 0;
-    for (int idx = tid; idx < (P + 2) * 16; idx += kL1Threads) {
+    for (int c = tid; c < p.cells; c += kMmaThreads) cursor[c] = 0;
+    for (int idx = tid; idx < (P + 2) * 16; idx += kMmaThreads) {
         const int r = idx >> 4, k = idx & 15;
         float v = 0.f;
         if (r < P) v = p.lat[(size_t)(row0 + r) * 16 + k] - p.constant;
@@ -530,14 +532,13 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_mma_kernel(L1MmaP
         latL[dst] = __float2bfloat16_rn(v - __bfloat162float(h));
     }
     {
-        const int colc = tid & (kL1Cols - 1);
-        const int col = chunk0 + colc;
+        const int col = chunk0 + tid;                     // 256 threads = 256 columns of the chunk
         const float b = col < p.OUT ? p.base[col] : 0.f;
-        for (int r = tid >> 8; r < P; r += 2) acc[r * kMmaAccStride + colc] = b;
+        for (int r = 0; r < P; ++r) acc[r * kMmaAccStride + tid] = b;
     }
     __syncthreads();
     const int total = P * p.nm1;
-    for (int idx = tid; idx < total; idx += kL1Threads) {
+    for (int idx = tid; idx < total; idx += kMmaThreads) {
         int r = idx / p.nm1, k = idx - r * p.nm1;
         if (k < p.win_count[row0 + r]) atomicAdd(&cursor[p.win_ent[(size_t)(row0 + r) * p.nm1 + k] >> 16], 1);
     }
@@ -562,7 +563,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_mma_kernel(L1MmaP
         if (tid == 31) start[p.cells] = incl;
     }
     __syncthreads();
-    for (int idx = tid; idx < total; idx += kL1Threads) {
+    for (int idx = tid; idx < total; idx += kMmaThreads) {
         int r = idx / p.nm1, k = idx - r * p.nm1;
         if (k < p.win_count[row0 + r]) {
             const uint32_t e = p.win_ent[(size_t)(row0 + r) * p.nm1 + k];
@@ -579,53 +580,55 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_mma_kernel(L1MmaP
     // padding rows of a tile: zero latent row, per-lane dummy accumulator rows
     const uint32_t dummy0 = ((uint32_t)(p.cap + 1) << 16) | (uint32_t)(p.cap + g);
     const uint32_t dummy1 = ((uint32_t)(p.cap + 1) << 16) | (uint32_t)(p.cap + 8 + g);
-    const int ncol0 = chunk0 + warp * 16 + g;            // column of n-tile 0 this lane loads; tile 1: + 8
-    const bool ok0 = ncol0 < p.OUT, ok1 = ncol0 + 8 < p.OUT;
+    // this lane loads, for n-tile j (j = 0..3), column chunk0 + 32 warp + 8 j + g
+    const int ncol0 = chunk0 + warp * 32 + g;
     const size_t cell_stride = (size_t)p.OUT * 16;       // bf16 elements per cell
     const __nv_bfloat16* wh = p.Wt_hi + (size_t)ncol0 * 16 + 4 * t;
     const __nv_bfloat16* wl = p.Wt_lo + (size_t)ncol0 * 16 + 4 * t;
-    struct BFrag { uint2 h0, h1, l0, l1; };
+    bool okc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) okc[j] = ncol0 + 8 * j < p.OUT;
+    struct BFrag { uint2 h[4], l[4]; };
     auto load_b = [&](int cell) -> BFrag {
         BFrag f;
         const size_t o = (size_t)cell * cell_stride;
-        f.h0 = ok0 ? *reinterpret_cast<const uint2*>(wh + o) : make_uint2(0u, 0u);
-        f.h1 = ok1 ? *reinterpret_cast<const uint2*>(wh + o + 8 * 16) : make_uint2(0u, 0u);
-        f.l0 = ok0 ? *reinterpret_cast<const uint2*>(wl + o) : make_uint2(0u, 0u);
-        f.l1 = ok1 ? *reinterpret_cast<const uint2*>(wl + o + 8 * 16) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            f.h[j] = okc[j] ? *reinterpret_cast<const uint2*>(wh + o + (size_t)j * 8 * 16) : make_uint2(0u, 0u);
+            f.l[j] = okc[j] ? *reinterpret_cast<const uint2*>(wl + o + (size_t)j * 8 * 16) : make_uint2(0u, 0u);
+        }
         return f;
     };
-    float* accw = acc + warp * 16 + 2 * t;
-    const __nv_bfloat16* latHt = latH + 4 * t;
-    const __nv_bfloat16* latLt = latL + 4 * t;
+    float* accw = acc + warp * 32 + 2 * t;
+    const uint32_t* latHw = reinterpret_cast<const uint32_t*>(latH) + 2 * t;   // 32-bit words: row stride 8
+    const uint32_t* latLw = reinterpret_cast<const uint32_t*>(latL) + 2 * t;
     auto process = [&](int e0, int e1, const BFrag& b) {
         for (int eb = e0; eb < e1; eb += 16) {
             const int i0 = eb + g, i1 = i0 + 8;
             const uint32_t en0 = i0 < e1 ? ent[i0] : dummy0;
             const uint32_t en1 = i1 < e1 ? ent[i1] : dummy1;
-            const uint2 x0 = *reinterpret_cast<const uint2*>(latHt + (en0 >> 16) * 16);
-            const uint2 y0 = *reinterpret_cast<const uint2*>(latLt + (en0 >> 16) * 16);
-            const uint2 x1 = *reinterpret_cast<const uint2*>(latHt + (en1 >> 16) * 16);
-            const uint2 y1 = *reinterpret_cast<const uint2*>(latLt + (en1 >> 16) * 16);
-            const uint32_t ah[4] = {x0.x, x1.x, x0.y, x1.y};
-            const uint32_t al[4] = {y0.x, y1.x, y0.y, y1.y};
-            float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
-            mma_bf16_16816(d0, ah, b.h0.x, b.h0.y);
-            mma_bf16_16816(d1, ah, b.h1.x, b.h1.y);
-            mma_bf16_16816(d0, ah, b.l0.x, b.l0.y);
-            mma_bf16_16816(d1, ah, b.l1.x, b.l1.y);
-            mma_bf16_16816(d0, al, b.h0.x, b.h0.y);
-            mma_bf16_16816(d1, al, b.h1.x, b.h1.y);
-            float2* a0 = reinterpret_cast<float2*>(accw + (en0 & 0xffffu) * kMmaAccStride);
-            float2* a1 = reinterpret_cast<float2*>(accw + (en1 & 0xffffu) * kMmaAccStride);
-            float2 u0 = a0[0], w0 = a0[4], u1 = a1[0], w1 = a1[4];
-            u0.x += d0[0]; u0.y += d0[1]; w0.x += d1[0]; w0.y += d1[1];
-            u1.x += d0[2]; u1.y += d0[3]; w1.x += d1[2]; w1.y += d1[3];
-            a0[0] = u0; a0[4] = w0; a1[0] = u1; a1[4] = w1;
+            const uint32_t l0 = (en0 >> 16) * 8, l1 = (en1 >> 16) * 8;
+            uint32_t ah[4], al[4];
+            ah[0] = latHw[l0]; ah[1] = latHw[l1]; ah[2] = latHw[l0 + 1]; ah[3] = latHw[l1 + 1];
+            al[0] = latLw[l0]; al[1] = latLw[l1]; al[2] = latLw[l0 + 1]; al[3] = latLw[l1 + 1];
+            float* a0 = accw + (en0 & 0xffffu) * kMmaAccStride;
+            float* a1 = accw + (en1 & 0xffffu) * kMmaAccStride;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float d[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_bf16_16816(d, ah, b.h[j].x, b.h[j].y);
+                mma_bf16_16816(d, ah, b.l[j].x, b.l[j].y);
+                mma_bf16_16816(d, al, b.h[j].x, b.h[j].y);
+                float2* q0 = reinterpret_cast<float2*>(a0 + 8 * j);
+                float2* q1 = reinterpret_cast<float2*>(a1 + 8 * j);
+                float2 u0 = *q0, u1 = *q1;
+                u0.x += d[0]; u0.y += d[1]; u1.x += d[2]; u1.y += d[3];
+                *q0 = u0; *q1 = u1;
+            }
         }
     };
     // register ring of 4 fragment sets: the slab of cell c+4 is requested right after cell c is
-    // consumed, i.e. three cell-times ahead of its use (L2 latency under this all-CTA streaming
-    // load measured ~1000 cycles, one cell is ~300-400)
+    // consumed, i.e. three cell-times ahead of its use
     const int nc = p.cells;
     BFrag b0 = load_b(0);
     BFrag b1 = load_b(min(1, nc - 1));
@@ -658,11 +661,10 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_mma_kernel(L1MmaP
     }
     __syncthreads();
     {
-        const int colc = tid & (kL1Cols - 1);
-        const int col = chunk0 + colc;
+        const int col = chunk0 + tid;
         if (col < p.OUT) {
-            for (int r = tid >> 8; r < P; r += 2) {
-                float v = acc[r * kMmaAccStride + colc];
+            for (int r = 0; r < P; ++r) {
+                float v = acc[r * kMmaAccStride + tid];
                 if (p.relu) v = fmaxf(v, 0.f);
                 const size_t o = (size_t)(row0 + r) * p.OUT + col;
                 if (p.out_hi) {
@@ -801,6 +803,11 @@ static int launch_dense(const float* X, const float* WT, const float* b, float* 
     return TB2_OK;
 }
 
+int launch_dense_plain(const float* X, const float* WT, const float* b, float* Y, int M, int K, int N, int relu,
+                       cudaStream_t st) {
+    return launch_dense(X, WT, b, Y, M, K, N, relu, st);
+}
+
 template <int C, bool SOCIAL>
 static int launch_l1_t(const L1Params& p, int groups, size_t smem, cudaStream_t st) {
     static size_t configured = 0;
@@ -896,7 +903,7 @@ int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float
         dim3 grid(l->num_groups[gm], (d1 + kL1Cols - 1) / kL1Cols);
         {
             KernelTimer kt("sparse_layer1_mma", st);
-            sparse_layer1_mma_kernel<<<grid, kL1Threads, sm, st>>>(q);
+            sparse_layer1_mma_kernel<<<grid, kMmaThreads, sm, st>>>(q);
         }
         TB2_LAUNCH_CHECK();
         rc = TB2_OK;

@@ -71,6 +71,24 @@ class ModelHandle:
         self._weights_key = None
         self._workspace = None
 
+    def weights_struct(self, named):
+        """tb2_lstm_weights from a dict field name -> tensor (or list of 3 for the MLP)."""
+        w = _lib.LstmWeights()
+        keep = []
+        for field, value in named.items():
+            if isinstance(value, (list, tuple)):
+                arr = getattr(w, field)
+                for i, t in enumerate(value):
+                    if t is not None:
+                        t = self._prep(t)
+                        keep.append(t)
+                        arr[i] = t.data_ptr()
+            elif value is not None:
+                t = self._prep(value)
+                keep.append(t)
+                setattr(w, field, t.data_ptr())
+        return w, keep
+
     def set_weights(self, named, key=None):
         """named: dict field name -> CUDA fp32 contiguous tensor (or list of 3 for the MLP)."""
         if key is not None and key == self._weights_key:

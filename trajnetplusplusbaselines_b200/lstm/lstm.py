@@ -112,19 +112,22 @@ class LSTM(torch.nn.Module):
             self._handle = ModelHandle(cfg, device)
         key = tuple((p.data_ptr(), p._version) for p in self.parameters())
         if key != self._handle._weights_key:
-            lin = self.input_embedding.input_embeddings[0]
-            fields = dict(
-                input_embedding_weight=lin.weight, input_embedding_bias=lin.bias,
-                encoder_weight_ih=self.encoder.weight_ih, encoder_weight_hh=self.encoder.weight_hh,
-                encoder_bias_ih=self.encoder.bias_ih, encoder_bias_hh=self.encoder.bias_hh,
-                decoder_weight_ih=self.decoder.weight_ih, decoder_weight_hh=self.decoder.weight_hh,
-                decoder_bias_ih=self.decoder.bias_ih, decoder_bias_hh=self.decoder.bias_hh,
-                hidden2normal_weight=self.hidden2normal.linear.weight,
-                hidden2normal_bias=self.hidden2normal.linear.bias)
-            if self.pool is not None:
-                fields.update(self.pool.weight_fields())
-            self._handle.set_weights(fields, key=key)
+            self._handle.set_weights(self._weight_fields(), key=key)
         return self._handle
+
+    def _weight_fields(self):
+        lin = self.input_embedding.input_embeddings[0]
+        fields = dict(
+            input_embedding_weight=lin.weight, input_embedding_bias=lin.bias,
+            encoder_weight_ih=self.encoder.weight_ih, encoder_weight_hh=self.encoder.weight_hh,
+            encoder_bias_ih=self.encoder.bias_ih, encoder_bias_hh=self.encoder.bias_hh,
+            decoder_weight_ih=self.decoder.weight_ih, decoder_weight_hh=self.decoder.weight_hh,
+            decoder_bias_ih=self.decoder.bias_ih, decoder_bias_hh=self.decoder.bias_hh,
+            hidden2normal_weight=self.hidden2normal.linear.weight,
+            hidden2normal_bias=self.hidden2normal.linear.bias)
+        if self.pool is not None:
+            fields.update(self.pool.weight_fields())
+        return fields
 
     def _to_device(self, t, device):
         """Host tensors go through pinned staging (H2D inside the caller's timed region)."""
