@@ -24,7 +24,7 @@ timeout 300 python bench.py --steps 10 --warmup 3 > $out/${tag}_bench.log 2>&1
 timeout 200 python scripts/train_bench.py > $out/${tag}_train_bench.log 2>&1
 echo "bench rc=$?" >> $out/${tag}_bench.log
 timeout 120 python scripts/profile_e2e.py > $out/${tag}_e2e_profile.log 2>&1
-timeout 200 python scripts/train_bench.py > $out/${tag}_train_bench.log 2>&1
+timeout 600 python scripts/classical_bench.py > $out/${tag}_classical_bench.log 2>&1
 tail -4 $out/${tag}_canary.log
 grep -E "passed|failed|FAILED|ADE mean|teacher-forced" $out/${tag}_pytest.log | tail -30
 [ -f $out/${tag}_pytest_notc.log ] && tail -3 $out/${tag}_pytest_notc.log
@@ -32,3 +32,4 @@ tail -2 $out/${tag}_bench.log
 cat $out/parity_report.txt 2>/dev/null | tail -20; head -3 $out/${tag}_e2e_profile.log; tail -6 $out/${tag}_e2e_profile.log
 
 tail -2 $out/${tag}_train_bench.log
+cat $out/${tag}_classical_bench.log

@@ -375,7 +375,7 @@ int tb2_grid_indices(const tb2_lstm* m, const tb2_layout* l, const float* obs, i
     tb2_lstm tmp_model = *m;
     tmp_model.owned.clear();
     tmp_model.cfg.pool_type = TB2_POOL_OCCUPANCY;   // indices do not depend on the payload
-    int rc = launch_pool_prepare(&tmp_model, l, nullptr, obs, obs, 0, 1, &ws, st);
+    int rc = launch_pool_prepare(&tmp_model, l, nullptr, obs, obs, 0, 1, 0, &ws, st);
     if (rc == TB2_OK) rc = launch_grid_indices_copy(l, &ws, cell_out, in_range_out, st);
     cudaError_t e = cudaStreamSynchronize(st);       // debug export: synchronous so tmp can be freed
     cudaFree(tmp);
@@ -395,7 +395,7 @@ int tb2_pool_forward(const tb2_lstm* m, const tb2_layout* l, const float* hidden
     Workspace ws;
     carve_workspace(m, l, workspace, &ws);
     cudaStream_t st = (cudaStream_t)stream;
-    if ((rc = launch_pool_prepare(m, l, hidden, obs1, obs2, 0, 0, &ws, st))) return rc;
+    if ((rc = launch_pool_prepare(m, l, hidden, obs1, obs2, 0, 0, 0, &ws, st))) return rc;
     return launch_pool_mlp(m, l, &ws, pooled_out, nullptr, nullptr, st);
 }
 
@@ -408,14 +408,16 @@ static int step_impl(const tb2_lstm* m, const tb2_layout* l, int phase, const fl
     const bool tc = m->Wg_hi[0] != nullptr;
     const float* pooled = nullptr;
     if (m->cfg.pool_type != TB2_POOL_NONE) {
-        if ((rc = launch_pool_prepare(m, l, h_in, obs1, obs2, 1, 0, ws, st))) return rc;
+        if ((rc = launch_pool_prepare(m, l, h_in, obs1, obs2, 1, 0, tc ? 1 : 0, ws, st))) return rc;
         if (tc) rc = launch_pool_mlp(m, l, ws, nullptr, ws->pool_hi, ws->pool_lo, st);
         else rc = launch_pool_mlp(m, l, ws, ws->pooled, nullptr, nullptr, st);
         if (rc) return rc;
         pooled = ws->pooled;
     }
     if (tc) {
-        if ((rc = launch_embed_split(m, l->M, obs1, obs2, ws->emb_hi, ws->emb_lo, st))) return rc;
+        if (m->cfg.pool_type == TB2_POOL_NONE &&     // pooled models: pool_prepare already wrote emb
+            (rc = launch_embed_split(m, l->M, obs1, obs2, ws->emb_hi, ws->emb_lo, st)))
+            return rc;
         return launch_gates_tc(m, l, phase, obs1, obs2, ws->emb_hi, ws->emb_lo, ws->pool_hi, ws->pool_lo,
                                ws->hs_hi[hs_cur], ws->hs_lo[hs_cur], ws->hs_hi[hs_cur ^ 1], ws->hs_lo[hs_cur ^ 1],
                                h_in, c_in, h_out, c_out, normal_out, pos_out, st);

@@ -123,7 +123,7 @@ int launch_resolve_obs(const tb2_layout* l, const float* base, const float* pred
                        cudaStream_t st);
 int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hidden,
                         const float* obs1, const float* obs2, int skip_masked, int write_pairs,
-                        Workspace* ws, cudaStream_t st);
+                        int write_emb, Workspace* ws, cudaStream_t st);
 // pooled_out fp32 and/or (pool_hi, pool_lo) bf16 split (either may be null, not both)
 int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float* pooled_out,
                     void* pool_hi, void* pool_lo, cudaStream_t st);

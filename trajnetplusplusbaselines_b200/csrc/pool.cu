@@ -68,6 +68,11 @@ struct PrepParams {
     float* win_val;
     int* pair_cell;
     uint8_t* pair_flag;
+    const float* We;          // input embedding (fused producer of the gate kernel's emb operand)
+    const float* be;
+    __nv_bfloat16* emb_hi;    // [M, E] bf16 split or null
+    __nv_bfloat16* emb_lo;
+    int E;
     int n_max, H, C, n, pool_type, front, skip_masked, write_pairs;
     float side, width;
 };
@@ -111,6 +116,19 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
         for (int idx = tid; idx < p.H * p.C / 4; idx += kPrepThreads) wdst[idx] = wsrc[idx];
     }
     __syncthreads();
+    if (p.emb_hi != nullptr) {
+        // emb = cat(relu(W_e . (4 v) + b_e), 0, 0) (modules.py:24-30) as bf16 (hi, lo) for the gate GEMM
+        for (int idx = tid; idx < n_s * p.E; idx += kPrepThreads) {
+            const int j = idx / p.E, k = idx - j * p.E;
+            const float2 v = vel[j];
+            float e = 0.f;
+            if (k < p.E - 2 && !isnan(v.x))
+                e = fmaxf(fmaf(p.We[2 * k + 1], v.y * 4.0f, fmaf(p.We[2 * k], v.x * 4.0f, p.be[k])), 0.f);
+            const __nv_bfloat16 h = __float2bfloat16_rn(e);
+            p.emb_hi[(size_t)(row0 + j) * p.E + k] = h;
+            p.emb_lo[(size_t)(row0 + j) * p.E + k] = __float2bfloat16_rn(e - __bfloat162float(h));
+        }
+    }
     if (p.pool_type == TB2_POOL_SOCIAL) {
         // lat[j][c] = sum_k nan_to_num(h[j][k]) * WencT[k][c] + benc[c]
         const int total = n_s * p.C;
@@ -204,7 +222,7 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
 
 int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hidden,
                         const float* obs1, const float* obs2, int skip_masked, int write_pairs,
-                        Workspace* ws, cudaStream_t st) {
+                        int write_emb, Workspace* ws, cudaStream_t st) {
     TB2_REQUIRE(l->n_max <= kMaxSceneForPrep, "scene larger than 256 pedestrians");
     PrepParams p;
     p.obs1 = (const float2*)obs1;
@@ -227,6 +245,11 @@ int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hid
     p.front = m->cfg.front;
     p.skip_masked = skip_masked;
     p.write_pairs = write_pairs;
+    p.We = m->We;
+    p.be = m->be;
+    p.E = m->E;
+    p.emb_hi = write_emb ? (__nv_bfloat16*)ws->emb_hi : nullptr;
+    p.emb_lo = write_emb ? (__nv_bfloat16*)ws->emb_lo : nullptr;
     p.side = m->cfg.cell_side;        // pool_size == 1
     p.width = (float)m->cfg.n;
     int nm1 = l->n_max > 1 ? l->n_max - 1 : 1;
@@ -519,8 +542,21 @@ __global__ void __launch_bounds__(kMmaThreads, 1) sparse_layer1_mma_kernel(L1Mma
     int* start = reinterpret_cast<int*>(latL + (size_t)(p.cap + 2) * 16);                  // [cells+1]
     int* cursor = start + p.cells + 1;                                                     // [cells]
     uint32_t* ent = reinterpret_cast<uint32_t*>(cursor + p.cells);                         // [cap*nm1 + 16]: lat row << 16 | acc row
+    uint32_t* raw = ent + (size_t)p.cap * p.nm1 + 16;                                      // [cap*nm1] winner lists as written by pool_prepare
+    int* cnt_s = reinterpret_cast<int*>(raw + (size_t)p.cap * p.nm1);                      // [cap] winners per row
+    int* sbase = cnt_s + p.cap;                                                            // [cap] first group-local row of the row's scene
 
     for (int c = tid; c < p.cells; c += kMmaThreads) cursor[c] = 0;
+    // one coalesced pass over the group's winner lists (rows of a group are contiguous in memory)
+    for (int r = tid; r < P; r += kMmaThreads) cnt_s[r] = p.win_count[row0 + r];
+    {
+        const uint32_t* src = p.win_ent + (size_t)row0 * p.nm1;
+        for (int idx = tid; idx < P * p.nm1; idx += kMmaThreads) raw[idx] = src[idx];
+    }
+    for (int sb = s0 + warp; sb < s1; sb += kMmaThreads / 32) {
+        const int a = p.scene_off[sb] - row0, b = p.scene_off[sb + 1] - row0;
+        for (int r = a + lane; r < b; r += 32) sbase[r] = a;
+    }
     for (int idx = tid; idx < (P + 2) * 16; idx += kMmaThreads) {
         const int r = idx >> 4, k = idx & 15;
         float v = 0.f;
@@ -540,7 +576,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) sparse_layer1_mma_kernel(L1Mma
     const int total = P * p.nm1;
     for (int idx = tid; idx < total; idx += kMmaThreads) {
         int r = idx / p.nm1, k = idx - r * p.nm1;
-        if (k < p.win_count[row0 + r]) atomicAdd(&cursor[p.win_ent[(size_t)(row0 + r) * p.nm1 + k] >> 16], 1);
+        if (k < cnt_s[r]) atomicAdd(&cursor[raw[idx] >> 16], 1);
     }
     __syncthreads();
     if (tid < 32) {
@@ -565,13 +601,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) sparse_layer1_mma_kernel(L1Mma
     __syncthreads();
     for (int idx = tid; idx < total; idx += kMmaThreads) {
         int r = idx / p.nm1, k = idx - r * p.nm1;
-        if (k < p.win_count[row0 + r]) {
-            const uint32_t e = p.win_ent[(size_t)(row0 + r) * p.nm1 + k];
+        if (k < cnt_s[r]) {
+            const uint32_t e = raw[idx];
             const int pos = atomicAdd(&cursor[e >> 16], 1);
-            int sb = s0;
-            while (p.scene_off[sb + 1] <= row0 + r) ++sb;
             const int j = (int)(e & 0xffff);
-            const uint32_t lrow = (uint32_t)(j == 0xffff ? p.cap : p.scene_off[sb] - row0 + j);
+            const uint32_t lrow = (uint32_t)(j == 0xffff ? p.cap : sbase[r] + j);
             ent[pos] = (lrow << 16) | (uint32_t)r;
         }
     }
@@ -683,7 +717,9 @@ static size_t l1_mma_smem_bytes(int cap, int cells, int nm1) {
     size_t b = (size_t)(cap + 16) * kMmaAccStride * sizeof(float);
     b += (size_t)(cap + 2) * 16 * 2 * sizeof(__nv_bfloat16);
     b += (size_t)(2 * cells + 1) * sizeof(int);
-    b += ((size_t)cap * nm1 + 16) * sizeof(uint32_t);
+    b += ((size_t)cap * nm1 + 16) * sizeof(uint32_t);     // sorted entries
+    b += (size_t)cap * nm1 * sizeof(uint32_t);            // raw winner lists
+    b += (size_t)cap * 2 * sizeof(int);                   // winners per row, scene base per row
     return b + 16;
 }
 

@@ -326,7 +326,7 @@ int tb2_lstm_sequence_backward(const tb2_lstm* m, const tb2_layout* l, const tb2
         const float* h_prev = s > 0 ? states + ((size_t)(s - 1) * 2 + 0) * M * kBH : nullptr;
         const float* c_prev = s > 0 ? states + ((size_t)(s - 1) * 2 + 1) * M * kBH : nullptr;
         if (m->cfg.pool_type != TB2_POOL_NONE) {
-            if ((rc = launch_pool_prepare(m, l, h_prev, o1, o2, 1, 0, &ws, st))) return rc;
+            if ((rc = launch_pool_prepare(m, l, h_prev, o1, o2, 1, 0, 0, &ws, st))) return rc;
             if ((rc = launch_pool_mlp(m, l, &ws, ws.pooled, nullptr, nullptr, st))) return rc;
         }
         bwd_gather_kernel<<<R, 128, 0, st>>>(active_rows, R, (const float2*)o1, (const float2*)o2, m->We, m->be,
