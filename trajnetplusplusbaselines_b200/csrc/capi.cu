@@ -241,8 +241,8 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
             if (cfg->pool_type == TB2_POOL_SOCIAL && m->C == 16 && !(no_tc && no_tc[0] == '1')) {
                 const size_t half = ((size_t)m->cells * 16 * m->mlp_dims[1] + 1) / 2;
                 float *hi, *lo;
-                ALLOC(hi, half);
-                ALLOC(lo, half);
+                ALLOC(hi, 2 * half);      // interleaved (hi | lo) slabs
+                ALLOC(lo, 4);
                 m->Wt1_hi = hi;
                 m->Wt1_lo = lo;
             }

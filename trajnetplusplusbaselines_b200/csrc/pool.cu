@@ -10,6 +10,10 @@
 // streaming the cell-major weight slabs once per scene group.
 #include <cuda_bf16.h>
 #include <math_constants.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 
@@ -371,8 +375,21 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_kernel(L1Params p
     float* entV = reinterpret_cast<float*>(                               // [cap*nm1][C] (non-social)
         reinterpret_cast<unsigned char*>(entP) +
         (((size_t)p.cap * p.nm1 * 2 * sizeof(uint16_t) + 15) & ~(size_t)15));
+    uint32_t* raw = reinterpret_cast<uint32_t*>(entV + (SOCIAL ? 0 : (size_t)p.cap * p.nm1 * C));   // [cap*nm1]
+    int* cnt_s = reinterpret_cast<int*>(raw + (size_t)p.cap * p.nm1);    // [cap]
+    int* sbase = cnt_s + p.cap;                                           // [cap]
 
     for (int c = tid; c < bins; c += kL1Threads) cursor[c] = 0;
+    // one coalesced pass over the group's winner lists (rows of a group are contiguous in memory)
+    for (int r = tid; r < P; r += kL1Threads) cnt_s[r] = p.win_count[row0 + r];
+    {
+        const uint32_t* src = p.win_ent + (size_t)row0 * p.nm1;
+        for (int idx = tid; idx < P * p.nm1; idx += kL1Threads) raw[idx] = src[idx];
+    }
+    for (int sb = s0 + (tid >> 5); sb < s1; sb += kL1Threads / 32) {
+        const int a = p.scene_off[sb] - row0, b2 = p.scene_off[sb + 1] - row0;
+        for (int r = a + (tid & 31); r < b2; r += 32) sbase[r] = a;
+    }
     if (SOCIAL) {
         for (int idx = tid; idx < P * C; idx += kL1Threads) latS[idx] = p.lat[(size_t)row0 * C + idx] - p.constant;
         if (tid < C) latS[(size_t)p.cap * C + tid] = p.benc[tid] - p.constant;   // row `cap`: padded slot
@@ -384,8 +401,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_kernel(L1Params p
     const int total = P * p.nm1;
     for (int idx = tid; idx < total; idx += kL1Threads) {
         int r = idx / p.nm1, k = idx - r * p.nm1;
-        if (k < p.win_count[row0 + r])
-            atomicAdd(&cursor[(p.win_ent[(size_t)(row0 + r) * p.nm1 + k] >> 16) * 2 + (r & 1)], 1);
+        if (k < cnt_s[r]) atomicAdd(&cursor[(raw[idx] >> 16) * 2 + (r & 1)], 1);
     }
     __syncthreads();
     if (tid < 32) {   // exclusive scan of the histogram by one warp
@@ -410,19 +426,14 @@ __global__ void __launch_bounds__(kL1Threads, 1) sparse_layer1_kernel(L1Params p
     __syncthreads();
     for (int idx = tid; idx < total; idx += kL1Threads) {
         int r = idx / p.nm1, k = idx - r * p.nm1;
-        if (k < p.win_count[row0 + r]) {
+        if (k < cnt_s[r]) {
             size_t g = (size_t)(row0 + r) * p.nm1 + k;
-            uint32_t ent = p.win_ent[g];
+            uint32_t ent = raw[idx];
             int pos = atomicAdd(&cursor[(ent >> 16) * 2 + (r & 1)], 1);
             entP[pos] = (uint16_t)r;
             if (SOCIAL) {
-                // scene-local j -> group-local row
-                int m = row0 + r;
-                // find the scene start of row r inside the group (scenes are few per group)
-                int sb = s0;
-                while (p.scene_off[sb + 1] <= m) ++sb;
-                const int j = (int)(ent & 0xffff);
-                entS[pos] = (uint16_t)(j == 0xffff ? p.cap : p.scene_off[sb] - row0 + j);
+                const int j = (int)(ent & 0xffff);      // scene-local j -> group-local row
+                entS[pos] = (uint16_t)(j == 0xffff ? p.cap : sbase[r] + j);
             } else {
 #pragma unroll
                 for (int c = 0; c < C; ++c) entV[(size_t)pos * C + c] = p.win_val[g * 2 + c] - p.constant;
@@ -513,14 +524,16 @@ struct L1MmaParams {
     const uint32_t* win_ent;
     const float* lat;
     const float* benc;
-    const __nv_bfloat16* Wt_hi;   // [cells, OUT, 16]
-    const __nv_bfloat16* Wt_lo;
+    const __nv_bfloat16* Wt_hi;   // [cells, OUT, 4 (t), 8]: per (column, t) the 4 hi then the 4 lo values
+    const __nv_bfloat16* Wt_lo;   //   of k = {2t, 2t+1, 2t+8, 2t+9} -> one 16-byte load per lane and n-tile (Wt_lo unused)
     const float* base;
     float* out;
     __nv_bfloat16* out_hi;
     __nv_bfloat16* out_lo;
     int OUT, cells, nm1, cap, relu;
     float constant;
+    int stagger;                  // experiment: per-group rotation of the cell order
+    long long* dbg;               // optional [grid, 8] clock64 phase stamps (TB2_L1_DEBUG=1)
 };
 
 constexpr int kMmaThreads = 256;          // 8 warps x 32 output columns
@@ -533,6 +546,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) sparse_layer1_mma_kernel(L1Mma
     const int row0 = p.scene_off[s0];
     const int P = p.scene_off[s1] - row0;
     const int chunk0 = blockIdx.y * kL1Cols;
+    long long* dbg = p.dbg ? p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+    if (dbg && tid == 0) dbg[0] = clock64();
 
     // acc rows [0, cap) real, [cap, cap + 16) dummies absorbing the padding rows of an MMA tile;
     // lat rows [0, cap) real, cap = NaN-padded slot (b_enc), cap + 1 = zeros (padding rows)
@@ -610,15 +625,15 @@ __global__ void __launch_bounds__(kMmaThreads, 1) sparse_layer1_mma_kernel(L1Mma
         }
     }
     __syncthreads();
+    if (dbg && tid == 0) dbg[1] = clock64();
 
     // padding rows of a tile: zero latent row, per-lane dummy accumulator rows
     const uint32_t dummy0 = ((uint32_t)(p.cap + 1) << 16) | (uint32_t)(p.cap + g);
     const uint32_t dummy1 = ((uint32_t)(p.cap + 1) << 16) | (uint32_t)(p.cap + 8 + g);
     // this lane loads, for n-tile j (j = 0..3), column chunk0 + 32 warp + 8 j + g
     const int ncol0 = chunk0 + warp * 32 + g;
-    const size_t cell_stride = (size_t)p.OUT * 16;       // bf16 elements per cell
-    const __nv_bfloat16* wh = p.Wt_hi + (size_t)ncol0 * 16 + 4 * t;
-    const __nv_bfloat16* wl = p.Wt_lo + (size_t)ncol0 * 16 + 4 * t;
+    const size_t cell_stride = (size_t)p.OUT * 32;       // bf16 elements per cell (hi + lo interleaved)
+    const __nv_bfloat16* wh = p.Wt_hi + (size_t)ncol0 * 32 + 8 * t;
     bool okc[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) okc[j] = ncol0 + 8 * j < p.OUT;
@@ -628,8 +643,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) sparse_layer1_mma_kernel(L1Mma
         const size_t o = (size_t)cell * cell_stride;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            f.h[j] = okc[j] ? *reinterpret_cast<const uint2*>(wh + o + (size_t)j * 8 * 16) : make_uint2(0u, 0u);
-            f.l[j] = okc[j] ? *reinterpret_cast<const uint2*>(wl + o + (size_t)j * 8 * 16) : make_uint2(0u, 0u);
+            // one 16-byte L2 load per n-tile: (hi.x, hi.y, lo.x, lo.y) fragments of column ncol0 + 8 j
+            const uint4 v = okc[j] ? __ldcg(reinterpret_cast<const uint4*>(wh + o + (size_t)j * 8 * 32))
+                                   : make_uint4(0u, 0u, 0u, 0u);
+            f.h[j] = make_uint2(v.x, v.y);
+            f.l[j] = make_uint2(v.z, v.w);
         }
         return f;
     };
@@ -664,36 +682,35 @@ __global__ void __launch_bounds__(kMmaThreads, 1) sparse_layer1_mma_kernel(L1Mma
     // register ring of 4 fragment sets: the slab of cell c+4 is requested right after cell c is
     // consumed, i.e. three cell-times ahead of its use
     const int nc = p.cells;
-    BFrag b0 = load_b(0);
-    BFrag b1 = load_b(min(1, nc - 1));
-    BFrag b2 = load_b(min(2, nc - 1));
-    BFrag b3 = load_b(min(3, nc - 1));
-    int e_lo = start[0];
+    const int off = p.stagger ? (int)((blockIdx.x * 37u) % (unsigned)nc) : 0;
+    auto phys = [&](int i) { int c = i + off; return c >= nc ? c - nc : c; };
+    BFrag b0 = load_b(phys(0));
+    BFrag b1 = load_b(phys(min(1, nc - 1)));
+    BFrag b2 = load_b(phys(min(2, nc - 1)));
+    BFrag b3 = load_b(phys(min(3, nc - 1)));
     for (int cell = 0; cell < nc; cell += 4) {
-        int e_hi = start[cell + 1];
-        process(e_lo, e_hi, b0);
-        if (cell + 4 < nc) b0 = load_b(cell + 4);
-        e_lo = e_hi;
+        int c = phys(cell);
+        process(start[c], start[c + 1], b0);
+        if (cell + 4 < nc) b0 = load_b(phys(cell + 4));
         if (cell + 1 < nc) {
-            e_hi = start[cell + 2];
-            process(e_lo, e_hi, b1);
-            if (cell + 5 < nc) b1 = load_b(cell + 5);
-            e_lo = e_hi;
+            c = phys(cell + 1);
+            process(start[c], start[c + 1], b1);
+            if (cell + 5 < nc) b1 = load_b(phys(cell + 5));
         }
         if (cell + 2 < nc) {
-            e_hi = start[cell + 3];
-            process(e_lo, e_hi, b2);
-            if (cell + 6 < nc) b2 = load_b(cell + 6);
-            e_lo = e_hi;
+            c = phys(cell + 2);
+            process(start[c], start[c + 1], b2);
+            if (cell + 6 < nc) b2 = load_b(phys(cell + 6));
         }
         if (cell + 3 < nc) {
-            e_hi = start[cell + 4];
-            process(e_lo, e_hi, b3);
-            if (cell + 7 < nc) b3 = load_b(cell + 7);
-            e_lo = e_hi;
+            c = phys(cell + 3);
+            process(start[c], start[c + 1], b3);
+            if (cell + 7 < nc) b3 = load_b(phys(cell + 7));
         }
     }
+    if (dbg && lane == 0) dbg[2 + (warp & 3)] = clock64();      // main loop end of warps 0..3
     __syncthreads();
+    if (dbg && tid == 0) dbg[6] = clock64();
     {
         const int col = chunk0 + tid;
         if (col < p.OUT) {
@@ -711,6 +728,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) sparse_layer1_mma_kernel(L1Mma
             }
         }
     }
+    if (dbg && tid == 0) dbg[7] = clock64();
 }
 
 static size_t l1_mma_smem_bytes(int cap, int cells, int nm1) {
@@ -734,9 +752,11 @@ __global__ void repack_layer1_mma_kernel(const float* __restrict__ W1, __nv_bflo
         const int o = (int)(co % OUT), cell = (int)(co / OUT);
         const float v = W1[(size_t)o * 16 * cells + (size_t)c * cells + cell];
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        const size_t dst = (co << 4) + kperm16(c);
-        hi[dst] = h;
-        lo[dst] = __float2bfloat16_rn(v - __bfloat162float(h));
+        const int kp = kperm16(c);                      // = 4 t + i
+        const size_t dst = (co << 5) + (size_t)(kp >> 2) * 8 + (kp & 3);
+        hi[dst] = h;                                    // `hi` holds the interleaved (hi | lo) slabs
+        hi[dst + 4] = __float2bfloat16_rn(v - __bfloat162float(h));
+        (void)lo;
     }
 }
 
@@ -753,6 +773,7 @@ static size_t l1_smem_bytes(int cap, int C, bool social, int cells, int nm1) {
     size_t ents = ((size_t)cap * nm1 * 2 * sizeof(uint16_t) + 15) & ~(size_t)15;
     b += ents;
     if (!social) b += (size_t)cap * nm1 * C * sizeof(float);
+    b += (size_t)cap * nm1 * sizeof(uint32_t) + (size_t)cap * 2 * sizeof(int);    // raw winner lists, per-row tables
     return b + 16;
 }
 
@@ -931,6 +952,19 @@ int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float
         q.base = m->base1; q.out = p.out; q.out_hi = p.out_hi; q.out_lo = p.out_lo;
         q.OUT = d1; q.cells = m->cells; q.nm1 = nm1; q.cap = l->group_cap[gm]; q.relu = 1;
         q.constant = m->cfg.constant;
+        {
+            const char* sg = getenv("TB2_STAGGER");
+            q.stagger = (sg && sg[0] == '1') ? 1 : 0;
+        }
+        q.dbg = nullptr;
+        static long long* dbg_buf = nullptr;
+        static int dbg_calls = 0;
+        const char* dbgenv = getenv("TB2_L1_DEBUG");
+        const int n_cta = l->num_groups[gm] * ((d1 + kL1Cols - 1) / kL1Cols);
+        if (dbgenv && dbgenv[0] == '1') {
+            if (!dbg_buf) cudaMalloc(&dbg_buf, (size_t)n_cta * 8 * sizeof(long long));
+            q.dbg = dbg_buf;
+        }
         static size_t configured = 0;
         if (sm > configured) {
             TB2_CHECK_CUDA(cudaFuncSetAttribute(sparse_layer1_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -942,6 +976,20 @@ int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float
             sparse_layer1_mma_kernel<<<grid, kMmaThreads, sm, st>>>(q);
         }
         TB2_LAUNCH_CHECK();
+        if (q.dbg && ++dbg_calls == 60) {       // one warm launch, printed once
+            std::vector<long long> hbuf((size_t)n_cta * 8);
+            cudaStreamSynchronize(st);
+            cudaMemcpy(hbuf.data(), dbg_buf, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+            double setup = 0, loop = 0, tail = 0, epi = 0;
+            for (int c = 0; c < n_cta; ++c) {
+                const long long* d = &hbuf[(size_t)c * 8];
+                long long lmax = std::max(std::max(d[2], d[3]), std::max(d[4], d[5]));
+                long long lmin = std::min(std::min(d[2], d[3]), std::min(d[4], d[5]));
+                setup += d[1] - d[0]; loop += lmin - d[1]; tail += lmax - lmin; epi += d[7] - d[6];
+            }
+            fprintf(stderr, "[tb2 l1 debug] per-CTA cycles: setup %.0f  main loop (fastest of 4 warps) %.0f  "
+                            "spread %.0f  epilogue %.0f\n", setup / n_cta, loop / n_cta, tail / n_cta, epi / n_cta);
+        }
         rc = TB2_OK;
     } else
     switch (m->cfg.pool_type) {
