@@ -73,6 +73,8 @@ struct tb2_lstm {
     float* base1;          // [d1] = b1 + constant * rowsum(W1)
     void* Wt1_hi;          // social, C == 16: bf16 [cells, d1, 16] (hi, lo) slabs for sparse_layer1_mma
     void* Wt1_lo;
+    void* Wt1_nat_hi;      // social, C == 16: bf16 [cells, d1, 16] natural k order (TMA source of sparse_layer1_tc)
+    void* Wt1_nat_lo;
     float* WT[tb2::kMaxMlpLayers];   // layers >= 2: [K, N] transposed
     float* bl[tb2::kMaxMlpLayers];   // biases of layers >= 2
     void* W_hi[tb2::kMaxMlpLayers];  // bf16 [N, K] (hi, lo) split for the tcgen05 path (null: FFMA path)
@@ -132,6 +134,10 @@ int launch_gates(const tb2_lstm* m, const tb2_layout* l, int phase, const float*
                  float* h_out, float* c_out, float* normal_out, float* pos_out, cudaStream_t st);
 int launch_repack(tb2_lstm* m, const tb2_lstm_weights* w, cudaStream_t st);
 int launch_repack_layer1_mma(const float* W1, void* hi, void* lo, int OUT, int cells, cudaStream_t st);
+int launch_repack_layer1_nat(const float* W1, void* hi, void* lo, int OUT, int cells, cudaStream_t st);
+bool sparse_tc_supported(const tb2_lstm* m, const tb2_layout* l, int gsel);
+int launch_sparse_tc(const tb2_lstm* m, const tb2_layout* l, int gsel, Workspace* ws, float* out, void* out_hi,
+                     void* out_lo, cudaStream_t st);
 bool dense_tc_supported(int K, int N);
 int launch_dense_tc(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                     float* Y, void* Y_hi, void* Y_lo, int M, int K, int N, int relu, cudaStream_t st);

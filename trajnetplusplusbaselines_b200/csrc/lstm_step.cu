@@ -369,6 +369,9 @@ int launch_repack(tb2_lstm* m, const tb2_lstm_weights* w, cudaStream_t st) {
         if (m->Wt1_hi &&
             (rc = launch_repack_layer1_mma(w->pool_embedding_weight[0], m->Wt1_hi, m->Wt1_lo, m->mlp_dims[1], m->cells, st)))
             return rc;
+        if (m->Wt1_nat_hi &&
+            (rc = launch_repack_layer1_nat(w->pool_embedding_weight[0], m->Wt1_nat_hi, m->Wt1_nat_lo, m->mlp_dims[1], m->cells, st)))
+            return rc;
         for (int layer = 1; layer < m->n_mlp; ++layer) {
             TB2_REQUIRE(w->pool_embedding_weight[layer] && w->pool_embedding_bias[layer], "pool.embedding layer missing");
             transpose_kernel<<<512, 256, 0, st>>>(w->pool_embedding_weight[layer], m->WT[layer],

@@ -940,7 +940,12 @@ int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float
         p.out_lo = reinterpret_cast<__nv_bfloat16*>(pool_lo);
     }
     int rc;
-    if (m->Wt1_hi != nullptr) {      // social, 16 latent channels: tensor-core path
+    const char* sp_env = getenv("TB2_SPARSE");       // debug knob: "mma" forces the warp-level MMA kernel
+    const bool allow_tc = !(sp_env && sp_env[0] == 'm');
+    if (allow_tc && sparse_tc_supported(m, l, 0)) {  // social, 16 latent channels: tcgen05 path
+        rc = launch_sparse_tc(m, l, 0, ws, p.out, p.out_hi, p.out_lo, st);
+    } else
+    if (m->Wt1_hi != nullptr) {      // social, 16 latent channels: warp-level tensor-core path
         int gm = 0;
         size_t sm = l1_mma_smem_bytes(l->group_cap[gm], m->cells, nm1);
         if (sm > 227 * 1024) { gm = 1; sm = l1_mma_smem_bytes(l->group_cap[gm], m->cells, nm1); }
