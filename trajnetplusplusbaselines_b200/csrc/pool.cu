@@ -532,7 +532,6 @@ struct L1MmaParams {
     __nv_bfloat16* out_lo;
     int OUT, cells, nm1, cap, relu;
     float constant;
-    int stagger;                  // experiment: per-group rotation of the cell order
     long long* dbg;               // optional [grid, 8] clock64 phase stamps (TB2_L1_DEBUG=1)
 };
 
@@ -682,8 +681,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) sparse_layer1_mma_kernel(L1Mma
     // register ring of 4 fragment sets: the slab of cell c+4 is requested right after cell c is
     // consumed, i.e. three cell-times ahead of its use
     const int nc = p.cells;
-    const int off = p.stagger ? (int)((blockIdx.x * 37u) % (unsigned)nc) : 0;
-    auto phys = [&](int i) { int c = i + off; return c >= nc ? c - nc : c; };
+    auto phys = [&](int i) { return i; };
     BFrag b0 = load_b(phys(0));
     BFrag b1 = load_b(phys(min(1, nc - 1)));
     BFrag b2 = load_b(phys(min(2, nc - 1)));
@@ -957,10 +955,6 @@ int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float
         q.base = m->base1; q.out = p.out; q.out_hi = p.out_hi; q.out_lo = p.out_lo;
         q.OUT = d1; q.cells = m->cells; q.nm1 = nm1; q.cap = l->group_cap[gm]; q.relu = 1;
         q.constant = m->cfg.constant;
-        {
-            const char* sg = getenv("TB2_STAGGER");
-            q.stagger = (sg && sg[0] == '1') ? 1 : 0;
-        }
         q.dbg = nullptr;
         static long long* dbg_buf = nullptr;
         static int dbg_calls = 0;

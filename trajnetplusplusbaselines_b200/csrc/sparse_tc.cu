@@ -19,17 +19,21 @@
 // zero-padded product ~2x faster end to end even though it multiplies the zeros.
 //
 // Warp roles (384 threads): 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2 = L-tile builder,
-// 4..11 = epilogue (lane quarter = warp % 4, column block = (warp - 4) / 4).
+// 4..11 = epilogue (lane quarter = warp % 4, column block = (warp - 4) / 4), 3, 12, 13 = more builders.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 
 namespace tb2 {
 
-constexpr int kScThreads = 384;
+constexpr int kScThreads = 448;          // 14 warps: TMA, MMA, 4 builders (2, 3, 12, 13), 8 epilogue (4..11)
+constexpr int kScBuilders = 4;
 constexpr int kScCols = 256;            // output columns per CTA (2 blocks of M = 128)
-constexpr int kScStages = 8;
+constexpr int kScStages = 7;
 constexpr int kScMaxN = 160;            // pedestrians per group (MMA N, multiple of 16)
 constexpr uint32_t kScABytes = 128 * 32;                 // one (block, part) weight tile: 128 cols x 16 k bf16
 constexpr uint32_t kScBBytes = kScMaxN * 32;             // one part of L_c: N rows x 16 k bf16
@@ -103,6 +107,7 @@ struct ScParams {
     __nv_bfloat16* out_lo;
     int OUT, cells, nm1, cap;
     float constant;
+    long long* dbg;              // optional [grid, 8] cycle counters (TB2_L1_DEBUG=1)
 };
 
 // byte offset of (row r, 16-byte chunk c) inside a SWIZZLE_32B K-major tile
@@ -117,7 +122,6 @@ sparse_layer1_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __gr
     __shared__ __align__(8) uint64_t empty_bar[kScStages];
     __shared__ __align__(8) uint64_t acc_full_bar;
     __shared__ uint32_t tmem_base_slot;
-    __shared__ int n_items_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int s0 = p.group_off[blockIdx.x], s1 = p.group_off[blockIdx.x + 1];
@@ -125,6 +129,8 @@ sparse_layer1_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __gr
     const int P = p.scene_off[s1] - row0;
     const int Npad = (P + 15) & ~15;
     const int chunk0 = blockIdx.y * kScCols;
+    long long* dbg = p.dbg ? p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+    const long long t_begin = clock64();
 
     const uint32_t ring = (sc_smem_u32(smem_sc) + 1023u) & ~1023u;
     unsigned char* ring_ptr = smem_sc + (ring - sc_smem_u32(smem_sc));
@@ -135,8 +141,11 @@ sparse_layer1_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __gr
     int* cnt_s = reinterpret_cast<int*>(ent + (size_t)p.cap * p.nm1);     // [cap]
     int* sbase = cnt_s + p.cap;                                           // [cap]
     uint16_t* item_cell = reinterpret_cast<uint16_t*>(sbase + p.cap);     // [cells] non-empty cells, ascending
+    // latent vectors of the group, already split: [cap + 1][16] bf16 x 2 (row cap = NaN-padded slot, b_enc)
+    uint4* latH = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(item_cell + p.cells) + 15) & ~(uintptr_t)15);
+    uint4* latL = latH + (size_t)(p.cap + 1) * 2;
 
-    // ---- setup: barriers, TMEM, zeroed L tiles, buckets ------------------------------------------
+    // ---- phase 0 (all warps): barriers + TMEM, so the TMA producer can start streaming at once -----
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kScStages; ++s) {
             sc_mbar_init(sc_smem_u32(&full_a[s]), 1);
@@ -152,63 +161,82 @@ sparse_layer1_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __gr
                      ::"r"(sc_smem_u32(&tmem_base_slot)), "r"(ncols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int s = 0; s < kScStages; ++s) {        // L tiles start as all-zero
-        uint4* b = reinterpret_cast<uint4*>(ring_ptr + (size_t)s * kScStageBytes + 4 * kScABytes);
-        for (int i = tid; i < (int)(2 * kScBBytes / 16); i += kScThreads) b[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    for (int c = tid; c < p.cells; c += kScThreads) cursor[c] = 0;
-    for (int r = tid; r < P; r += kScThreads) cnt_s[r] = p.win_count[row0 + r];
-    for (int sb = s0 + warp; sb < s1; sb += kScThreads / 32) {
-        const int a = p.scene_off[sb] - row0, b2 = p.scene_off[sb + 1] - row0;
-        for (int r = a + lane; r < b2; r += 32) sbase[r] = a;
-    }
-    __syncthreads();
-    const int total = P * p.nm1;
-    const uint32_t* raw = p.win_ent + (size_t)row0 * p.nm1;    // rows of a group are contiguous
-    for (int idx = tid; idx < total; idx += kScThreads) {
-        int r = idx / p.nm1, k = idx - r * p.nm1;
-        if (k < cnt_s[r]) atomicAdd(&cursor[raw[idx] >> 16], 1);
-    }
-    __syncthreads();
-    if (tid < 32) {
-        int per = (p.cells + 31) / 32;
-        int lo = tid * per, hi = min(lo + per, p.cells);
-        int sum = 0, nz = 0;
-        for (int c = lo; c < hi; ++c) { sum += cursor[c]; nz += cursor[c] > 0; }
-        int incl = sum, incl_nz = nz;
-        for (int d = 1; d < 32; d <<= 1) {
-            int v = __shfl_up_sync(0xffffffffu, incl, d);
-            int w = __shfl_up_sync(0xffffffffu, incl_nz, d);
-            if (tid >= d) { incl += v; incl_nz += w; }
-        }
-        int run = incl - sum, it = incl_nz - nz;
-        for (int c = lo; c < hi; ++c) {
-            int cnt = cursor[c];
-            start[c] = run;
-            cursor[c] = run;
-            if (cnt > 0) item_cell[it++] = (uint16_t)c;
-            run += cnt;
-        }
-        if (tid == 31) { start[p.cells] = incl; n_items_s = incl_nz; }
-    }
-    __syncthreads();
-    for (int idx = tid; idx < total; idx += kScThreads) {
-        int r = idx / p.nm1, k = idx - r * p.nm1;
-        if (k < cnt_s[r]) {
-            const uint32_t e = raw[idx];
-            const int pos = atomicAdd(&cursor[e >> 16], 1);
-            const int j = (int)(e & 0xffff);
-            const uint32_t lrow = (uint32_t)(j == 0xffff ? 0xffffu : sbase[r] + j);
-            ent[pos] = (lrow << 16) | (uint32_t)r;
-        }
-    }
-    // generic-proxy writes (zeroed tiles) must be visible to the tensor core's async-proxy reads
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
-    const int n_items = n_items_s;
+    const int n_items = p.cells;          // every cell is one pipeline item (empty buckets multiply zeros)
+
+    // ---- phase 1 (warps 1..13, 416 threads): zeroed L tiles, split latent vectors, per-cell buckets,
+    //      while warp 0 already streams the first weight slabs -------------------------------------------
+    constexpr int kSetupThreads = kScThreads - 32;
+    auto setup_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kSetupThreads) : "memory"); };
+    if (warp != 0) {
+        const int t2 = tid - 32;
+        for (int s = 0; s < kScStages; ++s) {        // L tiles start as all-zero
+            uint4* b = reinterpret_cast<uint4*>(ring_ptr + (size_t)s * kScStageBytes + 4 * kScABytes);
+            for (int i = t2; i < (int)(2 * kScBBytes / 16); i += kSetupThreads) b[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        for (int c = t2; c < p.cells; c += kSetupThreads) cursor[c] = 0;
+        for (int idx = t2; idx < (P + 1) * 8; idx += kSetupThreads) {       // 2 values per thread
+            const int r = idx >> 3, k = (idx & 7) * 2;
+            const float* src = r < P ? p.lat + (size_t)(row0 + r) * 16 : p.benc;
+            const float v0 = src[k] - p.constant, v1 = src[k + 1] - p.constant;
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+            const int dst = (r < P ? r : p.cap) * 8 + (k >> 1);           // 32-bit words, 8 per row
+            reinterpret_cast<uint32_t*>(latH)[dst] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            reinterpret_cast<uint32_t*>(latL)[dst] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        for (int r = t2; r < P; r += kSetupThreads) cnt_s[r] = p.win_count[row0 + r];
+        for (int sb = s0 + (warp - 1); sb < s1; sb += kSetupThreads / 32) {
+            const int a = p.scene_off[sb] - row0, b2 = p.scene_off[sb + 1] - row0;
+            for (int r = a + lane; r < b2; r += 32) sbase[r] = a;
+        }
+        setup_sync();
+        const int total = P * p.nm1;
+        const uint32_t* raw = p.win_ent + (size_t)row0 * p.nm1;    // rows of a group are contiguous
+        for (int idx = t2; idx < total; idx += kSetupThreads) {
+            int r = idx / p.nm1, k = idx - r * p.nm1;
+            if (k < cnt_s[r]) atomicAdd(&cursor[raw[idx] >> 16], 1);
+        }
+        setup_sync();
+        if (t2 < 32) {
+            int per = (p.cells + 31) / 32;
+            int lo = t2 * per, hi = min(lo + per, p.cells);
+            int sum = 0;
+            for (int c = lo; c < hi; ++c) sum += cursor[c];
+            int incl = sum;
+            for (int d = 1; d < 32; d <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (t2 >= d) incl += v;
+            }
+            int run = incl - sum;
+            for (int c = lo; c < hi; ++c) {
+                int cnt = cursor[c];
+                start[c] = run;
+                cursor[c] = run;
+                run += cnt;
+            }
+            if (t2 == 31) start[p.cells] = incl;
+        }
+        setup_sync();
+        for (int idx = t2; idx < total; idx += kSetupThreads) {
+            int r = idx / p.nm1, k = idx - r * p.nm1;
+            if (k < cnt_s[r]) {
+                const uint32_t e = raw[idx];
+                const int pos = atomicAdd(&cursor[e >> 16], 1);
+                const int j = (int)(e & 0xffff);
+                const uint32_t lrow = (uint32_t)(j == 0xffff ? p.cap : sbase[r] + j);
+                ent[pos] = (lrow << 16) | (uint32_t)r;
+            }
+        }
+        // generic-proxy writes (zeroed tiles) must be visible to the tensor core's async-proxy reads
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        setup_sync();
+    }
+    const long long t_setup = clock64();
 
     if (warp == 0) {
         // ===== TMA producer: weight slabs of the non-empty cells =====
@@ -219,7 +247,7 @@ sparse_layer1_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __gr
                 sc_mbar_wait(sc_smem_u32(&empty_bar[s]), ph ^ 1);
                 const uint32_t bar = sc_smem_u32(&full_a[s]);
                 const uint32_t base = ring + s * kScStageBytes;
-                const int wrow = (int)item_cell[it] * p.OUT + chunk0;
+                const int wrow = it * p.OUT + chunk0;
                 sc_mbar_expect_tx(bar, 4 * kScABytes);
                 sc_tma_load_2d(base + 0 * kScABytes, &map_w_hi, bar, 0, wrow);
                 sc_tma_load_2d(base + 1 * kScABytes, &map_w_hi, bar, 0, wrow + 128);
@@ -232,11 +260,16 @@ sparse_layer1_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __gr
         // ===== MMA issuer =====
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Npad >> 3) << 17) | (8u << 24);
+            long long wait_a = 0, wait_b = 0;
             for (int it = 0; it < n_items; ++it) {
                 const int s = it % kScStages;
                 const uint32_t ph = (it / kScStages) & 1;
+                const long long t0 = clock64();
                 sc_mbar_wait(sc_smem_u32(&full_a[s]), ph);
+                const long long t1 = clock64();
                 sc_mbar_wait(sc_smem_u32(&full_b[s]), ph);
+                wait_a += t1 - t0;
+                wait_b += clock64() - t1;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t base = ring + s * kScStageBytes;
                 const uint64_t b_hi = sc_umma_desc(base + 4 * kScABytes);
@@ -253,63 +286,51 @@ sparse_layer1_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __gr
                 sc_umma_commit(sc_smem_u32(&empty_bar[s]));
             }
             sc_umma_commit(sc_smem_u32(&acc_full_bar));
+            if (dbg) { dbg[0] = t_setup - t_begin; dbg[1] = clock64() - t_setup; dbg[2] = wait_a; dbg[3] = wait_b; dbg[4] = n_items; }
         }
         __syncwarp();
-    } else if (warp == 2) {
-        // ===== L-tile builder: rows of the previous use are re-zeroed, rows of this cell written =====
-        int sp_e0[kScStages], sp_e1[kScStages];
-#pragma unroll
-        for (int s = 0; s < kScStages; ++s) { sp_e0[s] = 0; sp_e1[s] = 0; }
-        for (int it = 0; it < n_items; ++it) {
+    } else if (warp == 2 || warp == 3 || warp >= 12) {
+        // ===== L-tile builders (4 warps, items round-robin).  Stateless: the rows written by the
+        // previous user of a stage (item it - kScStages) are re-derived from its bucket and zeroed,
+        // then the rows of this item's bucket are written. =====
+        const int bidx = warp < 4 ? warp - 2 : warp - 10;          // 0..3
+        for (int it = bidx; it < n_items; it += kScBuilders) {
             const int s = it % kScStages;
             const uint32_t ph = (it / kScStages) & 1;
             sc_mbar_wait(sc_smem_u32(&empty_bar[s]), ph ^ 1);
             unsigned char* bh = ring_ptr + (size_t)s * kScStageBytes + 4 * kScABytes;
             unsigned char* bl = bh + kScBBytes;
-            int pe0 = 0, pe1 = 0;
-#pragma unroll
-            for (int q = 0; q < kScStages; ++q) if (q == s) { pe0 = sp_e0[q]; pe1 = sp_e1[q]; }
-            for (int e = pe0 + lane; e < pe1; e += 32) {
-                const uint32_t r = ent[e] & 0xffffu;
-                *reinterpret_cast<uint4*>(bh + sw32(r, 0)) = make_uint4(0u, 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(bh + sw32(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(bl + sw32(r, 0)) = make_uint4(0u, 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(bl + sw32(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
+            if (it >= kScStages) {
+                const int pc = it - kScStages;
+                for (int e = start[pc] + lane; e < start[pc + 1]; e += 32) {
+                    const uint32_t r = ent[e] & 0xffffu;
+                    *reinterpret_cast<uint4*>(bh + sw32(r, 0)) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(bh + sw32(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(bl + sw32(r, 0)) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(bl + sw32(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
+                }
+                __syncwarp();
             }
-            __syncwarp();
-            const int cell = item_cell[it];
-            const int e0 = start[cell], e1 = start[cell + 1];
-            for (int e = e0 + lane; e < e1; e += 32) {
+            const int cell = it;
+            for (int e = start[cell] + lane; e < start[cell + 1]; e += 32) {
                 const uint32_t en = ent[e];
                 const uint32_t r = en & 0xffffu, lr = en >> 16;
-                const float* src = (lr == 0xffffu) ? p.benc : p.lat + (size_t)(row0 + lr) * 16;
-                uint32_t hw[8], lw[8];
-#pragma unroll
-                for (int k = 0; k < 16; k += 2) {
-                    const float v0 = src[k] - p.constant, v1 = src[k + 1] - p.constant;
-                    const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-                    const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
-                    const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-                    hw[k >> 1] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                    lw[k >> 1] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                }
-                *reinterpret_cast<uint4*>(bh + sw32(r, 0)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                *reinterpret_cast<uint4*>(bh + sw32(r, 1)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-                *reinterpret_cast<uint4*>(bl + sw32(r, 0)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-                *reinterpret_cast<uint4*>(bl + sw32(r, 1)) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
+                *reinterpret_cast<uint4*>(bh + sw32(r, 0)) = latH[lr * 2];
+                *reinterpret_cast<uint4*>(bh + sw32(r, 1)) = latH[lr * 2 + 1];
+                *reinterpret_cast<uint4*>(bl + sw32(r, 0)) = latL[lr * 2];
+                *reinterpret_cast<uint4*>(bl + sw32(r, 1)) = latL[lr * 2 + 1];
             }
-#pragma unroll
-            for (int q = 0; q < kScStages; ++q) if (q == s) { sp_e0[q] = e0; sp_e1[q] = e1; }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) sc_mbar_arrive(sc_smem_u32(&full_b[s]));
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 12) {
         // ===== epilogue: TMEM lane = output column, TMEM column = pedestrian =====
         const int q = warp & 3, blk = (warp - 4) >> 2;
         const int col = chunk0 + blk * 128 + q * 32 + lane;
         sc_mbar_wait(sc_smem_u32(&acc_full_bar), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (dbg && warp == 4 && lane == 0) dbg[5] = clock64() - t_setup;
         const float b = col < p.OUT ? p.base[col] : 0.f;
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * 256);
         for (int p0 = 0; p0 < Npad; p0 += 16) {
@@ -342,6 +363,7 @@ sparse_layer1_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __gr
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (dbg && tid == 0) dbg[6] = clock64() - t_begin;
     if (warp == 1) {
         uint32_t ncols = 512;
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
@@ -382,6 +404,7 @@ size_t sparse_tc_smem_bytes(int cap, int cells, int nm1) {
     b += (size_t)cap * nm1 * sizeof(uint32_t);
     b += (size_t)cap * 2 * sizeof(int);
     b += (size_t)cells * sizeof(uint16_t);
+    b += (size_t)(cap + 1) * 64 + 16;                     // split latent vectors
     return b + 64;
 }
 
@@ -417,6 +440,17 @@ int launch_sparse_tc(const tb2_lstm* m, const tb2_layout* l, int gsel, Workspace
     p.nm1 = nm1;
     p.cap = l->group_cap[gsel];
     p.constant = m->cfg.constant;
+    p.dbg = nullptr;
+    static long long* dbg_buf = nullptr;
+    static int dbg_calls = 0;
+    const int n_cta = l->num_groups[gsel] * (d1 / kScCols);
+    {
+        const char* e = getenv("TB2_L1_DEBUG");
+        if (e && e[0] == '1') {
+            if (!dbg_buf) cudaMalloc(&dbg_buf, (size_t)n_cta * 8 * sizeof(long long));
+            p.dbg = dbg_buf;
+        }
+    }
     const size_t smem = sparse_tc_smem_bytes(p.cap, m->cells, nm1);
     static size_t configured = 0;
     if (smem > configured) {
@@ -429,6 +463,15 @@ int launch_sparse_tc(const tb2_lstm* m, const tb2_layout* l, int gsel, Workspace
         sparse_layer1_tc_kernel<<<grid, kScThreads, smem, st>>>(mh, ml, p);
     }
     TB2_LAUNCH_CHECK();
+    if (p.dbg && ++dbg_calls == 60) {
+        std::vector<long long> h((size_t)n_cta * 8);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        double a[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < n_cta; ++c) for (int k = 0; k < 7; ++k) a[k] += (double)h[(size_t)c * 8 + k] / n_cta;
+        fprintf(stderr, "[tb2 sparse_tc debug] per-CTA cycles: setup %.0f | mma loop %.0f (wait TMA %.0f, wait builder %.0f, "
+                        "items %.0f) | acc ready at %.0f | total %.0f\n", a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+    }
     return TB2_OK;
 }
 
