@@ -35,6 +35,7 @@ STATE_BYTES_PER_PED_STEP = 2092                   # xy 16 + h,c in
 DENSE_FLOP_PER_PED_STEP = {                       # SURVEY.md 8d, dense-equivalent forward FLOPs
     "sparse_layer1": 2 * 4096 * 1024,             # first Linear of the grid embedding (4096 -> 1024)
     "sparse_layer1_mma": 2 * 4096 * 1024,
+    "sparse_layer1_tc": 2 * 4096 * 1024,
     "dense_layer": 2 * 1024 * 256,
     "dense_layer_tc": 2 * 1024 * 256,
     "lstm_gates": 2 * (64 + 256 + 128) * 512 + 2 * 128 * 5,
@@ -269,19 +270,24 @@ def main():
             avg = v["total_ms"] / v["launches"]
             kern[name] = {"avg_us": 1e3 * avg, "launches_per_forward": v["launches"] / prof_iters,
                           "share": v["total_ms"] / total_ms}
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "round1_traffic.json")
+        if os.path.exists(tpath):      # dram bytes per launch from the committed ncu --set full capture
+            traffic = json.load(open(tpath))["bytes_per_launch"].get(dom)
         if dom in DENSE_FLOP_PER_PED_STEP:
             flops = DENSE_FLOP_PER_PED_STEP[dom] * M
             achieved = flops / (dom_avg_ms * 1e-3) / 1e12
             roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": tf_sust,
-                        "unit": "TFLOP/s", "frac": achieved / tf_sust, "traffic": None,
+                        "unit": "TFLOP/s", "frac": achieved / tf_sust, "traffic": traffic,
                         "peak_source": how + " bf16 sustained (kernel timed inside a long step)",
-                        "note": "achieved = dense-equivalent algorithmic FLOPs (SURVEY 8d) / CUDA-event time; "
-                                "the grid layer only touches the <=19 occupied cells per pedestrian"}
+                        "note": "achieved = dense algorithmic FLOPs of the 4096->1024 grid Linear (SURVEY 8d: "
+                                "2*4096*1024 per ped-step) / CUDA-event time; the kernel issues 3 bf16 passes "
+                                "(hi/lo split for the 1e-4 m gate), so 1/3 of peak is its ceiling"}
         else:
             bytes_ = STATE_BYTES_PER_PED_STEP * M
             achieved = bytes_ / (dom_avg_ms * 1e-3) / 1e9
             roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                        "frac": achieved / hbm, "traffic": None, "peak_source": how}
+                        "frac": achieved / hbm, "traffic": traffic, "peak_source": how}
         # state-streaming view of the whole step (all kernels of one recurrence step)
         step_ms = total_ms / prof_iters / STEPS_PER_FORWARD
         roofline["step_hbm"] = {"achieved": STATE_BYTES_PER_PED_STEP * M / (step_ms * 1e-3) / 1e9,

@@ -24,6 +24,10 @@ timeout 300 python bench.py --steps 10 --warmup 3 > $out/${tag}_bench.log 2>&1
 timeout 200 python scripts/train_bench.py > $out/${tag}_train_bench.log 2>&1
 echo "bench rc=$?" >> $out/${tag}_bench.log
 timeout 120 python scripts/profile_e2e.py > $out/${tag}_e2e_profile.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 200 --csv --log-file $out/${tag}_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/${tag}_ncu_bench.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"sparse_layer1_tc|lstm_gates_tc|dense_layer_tc|pool_prepare" \
+    -s 40 -c 8 -o $out/${tag}_prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/${tag}_ncu_full.log 2>&1
 timeout 600 python scripts/classical_bench.py > $out/${tag}_classical_bench.log 2>&1
 tail -4 $out/${tag}_canary.log
 grep -E "passed|failed|FAILED|ADE mean|teacher-forced" $out/${tag}_pytest.log | tail -30

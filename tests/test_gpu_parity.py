@@ -315,6 +315,13 @@ def test_predictor_boundary_roundtrip(tmp_path):
             xy[r.frame - 1, p] = (r.x, r.y)
     _, pred_o = O.forward(W, O.pool_config(kind), xy, [0, 3], n_predict=12)
     assert np.nanmax(np.abs(prim - pred_o[-12:, 0])) < TOL_POS
+    # batched evaluator path: three scenes in one forward, each bit-identical to its single call
+    paths_b = [[TrackRow(f, 7, 1.0 + 0.2 * f, -1.0) for f in range(1, 10)],
+               [TrackRow(f, 8, 1.5, -2.0 + 0.3 * f) for f in range(1, 10)]]
+    singles = [predictor(p, np.zeros((len(p), 2)), n_predict=12, obs_length=9, modes=1, args=args) for p in (paths, paths_b, paths)]
+    batched = predictor.predict_batch([paths, paths_b, paths], n_predict=12, obs_length=9, args=args)
+    for s_out, b_out in zip(singles, batched):
+        assert np.array_equal(s_out[0][0], b_out[0][0]) and np.array_equal(s_out[0][1], b_out[0][1])
     fn = str(tmp_path / "model.pkl")
     predictor.save({"epoch": 1, "state_dict": model.state_dict()}, fn)
     again = LSTMPredictor.load(fn)

@@ -289,3 +289,34 @@ class LSTMPredictor(object):
                 output_neighs = output_scenes[-n_predict:, 1:]
                 multimodal_outputs[num_p] = [output_primary, output_neighs]
         return multimodal_outputs
+
+    def predict_batch(self, scenes, scene_goals=None, n_predict=12, obs_length=9, start_length=0, args=None):
+        """Many scenes in ONE forward call (replaces the evaluator's
+        joblib.Parallel(n_jobs=12) over predict_scene, lstm/trajnet_evaluator.py:61).
+
+        scenes: list of `paths` (each as for __call__).  Returns a list of {0: [primary, neighbours]}
+        in the same order.  Scenes never interact; the only batch effect is the reference's own:
+        scenes are padded to the batch maximum and padded slots clobber grid cell 0
+        (gridbased_pooling.py:281-293), exactly as when the reference trainer batches scenes."""
+        self.model.eval()
+        normalize = bool(getattr(args, 'normalize_scene', False))
+        xys, frames, split = [], [], [0]
+        for i, paths in enumerate(scenes):
+            xy = paths_to_xy(paths)
+            if normalize:
+                xy, rotation, center = center_scene(xy, obs_length)
+                frames.append((rotation, center))
+            xys.append(xy[start_length:obs_length])
+            split.append(split[-1] + xy.shape[1])
+        with torch.no_grad():
+            observed = torch.Tensor(np.concatenate(xys, axis=1))
+            goals = torch.zeros(observed.shape[1], 2)
+            _, output_scenes = self.model(observed, goals, torch.tensor(split).long(), n_predict=n_predict)
+            output_scenes = output_scenes.cpu().numpy()
+        results = []
+        for i in range(len(scenes)):
+            out = output_scenes[:, split[i]:split[i + 1]]
+            if normalize:
+                out = inverse_scene(out, *frames[i])
+            results.append({0: [np.array(out[-n_predict:, 0]), np.array(out[-n_predict:, 1:])]})
+        return results
