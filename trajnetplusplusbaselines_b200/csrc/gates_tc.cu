@@ -19,6 +19,9 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math_constants.h>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 
@@ -28,7 +31,8 @@ constexpr int kGtBM = 128;
 constexpr int kGtBN = 256;          // 64 units x 4 gates
 constexpr int kGtBK = 64;
 constexpr int kGtStages = 2;
-constexpr int kGtThreads = 192;
+constexpr int kGtThreads = 576;        // TMA warp, MMA warp, 16 epilogue warps (4 per TMEM lane quarter)
+constexpr int kGtEpiThreads = 512;
 constexpr int kGtH = 128;
 constexpr uint32_t kGtABytes = kGtBM * kGtBK * 2;      // 16 KB
 constexpr uint32_t kGtBBytes = kGtBN * kGtBK * 2;      // 32 KB
@@ -85,7 +89,11 @@ __device__ __forceinline__ void g_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
-__device__ __forceinline__ float g_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+// Gate non-linearities on the SFU (ex2.approx, ~2 ulp) -- the epilogue was bound by the ~200
+// instructions per hidden unit of the libm-accurate expf / tanhf.  Absolute error ~1e-7 per
+// activation, the same order as fp32 summation-order noise; parity is re-measured in the tests.
+__device__ __forceinline__ float g_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float g_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 
 struct GateTcParams {
     const float2* obs1;
@@ -104,6 +112,7 @@ struct GateTcParams {
     const float* Wn;            // [5, 128]
     const float* bn;            // [5]
     int M, P;
+    long long* dbg;             // optional [grid, 8] cycle stamps (TB2_GATES_DEBUG=1)
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGtThreads, 1)
@@ -120,6 +129,7 @@ lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap map_emb_hi, const __gri
     __shared__ float wn_s[5][64];          // Hidden2Normal weights of this CTA's 64 units
     __shared__ float bg_s[4][64];          // fused gate bias of this CTA's units
     __shared__ float peer_part[kGtBM][5];  // rank 0: partial head sums received from rank 1
+    __shared__ float part_s[4][kGtBM][5];  // per unit-group partial head sums of this CTA
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = blockIdx.x;           // cluster rank == n-tile: units [64 rank, 64 rank + 64)
@@ -127,6 +137,8 @@ lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap map_emb_hi, const __gri
     const int kb_pool = p.P / kGtBK;       // k-blocks: [emb | pooled x kb_pool | h x 2]
     const int num_kb = 1 + kb_pool + 2;
     const uint32_t ring = (g_smem_u32(smem_gt) + 1023u) & ~1023u;
+    long long* dbg = p.dbg ? p.dbg + (size_t)(blockIdx.y * 2 + blockIdx.x) * 8 : nullptr;
+    const long long t_begin = clock64();
 
     for (int i = threadIdx.x; i < 5 * 64; i += kGtThreads) wn_s[i / 64][i % 64] = p.Wn[(i / 64) * kGtH + rank * 64 + (i % 64)];
     for (int i = threadIdx.x; i < 4 * 64; i += kGtThreads) bg_s[i / 64][i % 64] = p.bg[(i / 64) * kGtH + rank * 64 + (i % 64)];
@@ -148,6 +160,7 @@ lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap map_emb_hi, const __gri
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
+    if (dbg && threadIdx.x == 0) dbg[0] = clock64() - t_begin;
 
     float part[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     bool row_valid = false, row_masked = true;
@@ -178,10 +191,13 @@ lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap map_emb_hi, const __gri
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kGtBN >> 3) << 17) |
                                    ((uint32_t)(kGtBM >> 4) << 24);
+            long long wait_tma = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % kGtStages;
                 const uint32_t phase = (kb / kGtStages) & 1;
+                const long long tw = clock64();
                 g_mbar_wait(g_smem_u32(&full_bar[s]), phase);
+                wait_tma += clock64() - tw;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t base = ring + s * kGtStageBytes;
                 const uint64_t a_hi = g_umma_desc(base);
@@ -198,10 +214,12 @@ lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap map_emb_hi, const __gri
                 g_umma_commit(g_smem_u32(&empty_bar[s]));
             }
             g_umma_commit(g_smem_u32(&tmem_full_bar));
+            if (dbg) { dbg[1] = clock64() - t_begin; dbg[2] = wait_tma; }
         }
         __syncwarp();
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3;              // TMEM lane quarter this warp may read
+        const int ug = (warp - 2) >> 2;      // 16-unit slice of the CTA's 64 hidden units
         row = m0 + q * 32 + lane;
         row_valid = row < p.M;
         float2 o1 = make_float2(CUDART_NAN_F, CUDART_NAN_F), o2 = o1;
@@ -209,10 +227,11 @@ lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap map_emb_hi, const __gri
         row_masked = isnan(o1.x) || isnan(o2.x);                             // lstm.py:118
         g_mbar_wait(g_smem_u32(&tmem_full_bar), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (dbg && warp == 2 && lane == 0) dbg[3] = clock64() - t_begin;
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
         const size_t off = (size_t)row * kGtH + rank * 64;
-#pragma unroll 1
-        for (int u0 = 0; u0 < 64; u0 += 16) {
+        {
+            const int u0 = ug * 16;
             uint32_t gi[16], gf[16], gg[16], go[16];
             g_tmem_ld16(trow + 0 * 64 + u0, gi);
             g_tmem_ld16(trow + 1 * 64 + u0, gf);
@@ -230,10 +249,10 @@ lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap map_emb_hi, const __gri
                         const int u = u0 + v + w;
                         const float ig = g_sigmoid(__uint_as_float(gi[v + w]) + bg_s[0][u]);
                         const float fg = g_sigmoid(__uint_as_float(gf[v + w]) + bg_s[1][u]);
-                        const float gt = tanhf(__uint_as_float(gg[v + w]) + bg_s[2][u]);
+                        const float gt = g_tanh(__uint_as_float(gg[v + w]) + bg_s[2][u]);
                         const float og = g_sigmoid(__uint_as_float(go[v + w]) + bg_s[3][u]);
                         cn[w] = fg * cold[w] + ig * gt;
-                        hn[w] = og * tanhf(cn[w]);
+                        hn[w] = og * g_tanh(cn[w]);
 #pragma unroll
                         for (int o = 0; o < 5; ++o) part[o] = fmaf(hn[w], wn_s[o][u], part[o]);
                     }
@@ -265,7 +284,19 @@ lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap map_emb_hi, const __gri
                 }
             }
         }
-        if (rank == 1) {
+        // combine the four unit-groups of a row (fixed order: deterministic)
+        {
+            const int rl = q * 32 + lane;
+#pragma unroll
+            for (int o = 0; o < 5; ++o) part_s[ug][rl][o] = part[o];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kGtEpiThreads) : "memory");
+        if (ug == 0) {
+            const int rl = q * 32 + lane;
+#pragma unroll
+            for (int o = 0; o < 5; ++o) part[o] = ((part_s[0][rl][o] + part_s[1][rl][o]) + part_s[2][rl][o]) + part_s[3][rl][o];
+        }
+        if (rank == 1 && ug == 0) {
             // ship this half's head sums to rank 0 through distributed shared memory
             const int rl = q * 32 + lane;
             const uint32_t local = g_smem_u32(&peer_part[rl][0]);
@@ -276,10 +307,12 @@ lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap map_emb_hi, const __gri
                 asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote + 4 * o), "f"(part[o]) : "memory");
         }
     }
+    if (dbg && warp == 2 && lane == 0) dbg[4] = clock64() - t_begin;
     // cluster barrier: rank 1's partial sums are visible in rank 0's shared memory afterwards
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    if (warp >= 2 && rank == 0 && row_valid) {
+    if (dbg && warp == 2 && lane == 0) dbg[5] = clock64() - t_begin;
+    if (warp >= 2 && warp < 6 && rank == 0 && row_valid) {
         const int rl = (warp & 3) * 32 + lane;
         float* no = p.normal_out + (size_t)row * 5;
         if (row_masked) {
@@ -304,6 +337,7 @@ lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap map_emb_hi, const __gri
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (dbg && threadIdx.x == 0) dbg[6] = clock64() - t_begin;
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kGtTmemCols) : "memory");
     }
@@ -427,6 +461,17 @@ int launch_gates_tc(const tb2_lstm* m, const tb2_layout* l, int phase, const flo
     p.bn = m->bn;
     p.M = M;
     p.P = m->P;
+    p.dbg = nullptr;
+    static long long* dbg_buf = nullptr;
+    static int dbg_calls = 0;
+    const int n_cta = 2 * ((M + kGtBM - 1) / kGtBM);
+    {
+        const char* e = getenv("TB2_GATES_DEBUG");
+        if (e && e[0] == '1') {
+            if (!dbg_buf) cudaMalloc(&dbg_buf, (size_t)n_cta * 8 * sizeof(long long));
+            p.dbg = dbg_buf;
+        }
+    }
     const size_t smem = (size_t)kGtStages * kGtStageBytes + 1024;
     static bool configured = false;
     if (!configured) {
@@ -439,6 +484,16 @@ int launch_gates_tc(const tb2_lstm* m, const tb2_layout* l, int phase, const flo
         lstm_gates_tc_kernel<<<grid, kGtThreads, smem, st>>>(me_hi, me_lo, mp_hi, mp_lo, mh_hi, mh_lo, mw_hi, mw_lo, p);
     }
     TB2_LAUNCH_CHECK();
+    if (p.dbg && ++dbg_calls == 60) {
+        std::vector<long long> h((size_t)n_cta * 8);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        double a[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < n_cta; ++c) for (int k = 0; k < 7; ++k) a[k] += (double)h[(size_t)c * 8 + k] / n_cta;
+        fprintf(stderr, "[tb2 gates_tc debug] per-CTA cycles since start: setup %.0f | mma issued %.0f (waited on TMA %.0f) | "
+                        "acc ready %.0f | epilogue done %.0f | cluster barrier %.0f | end %.0f\n",
+                a[0], a[1], a[2], a[3], a[4], a[5], a[6]);
+    }
     return TB2_OK;
 }
 
