@@ -161,6 +161,10 @@ lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap map_emb_hi, const __gri
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
     if (dbg && threadIdx.x == 0) dbg[0] = clock64() - t_begin;
+    // cluster barrier phase 1 (arrive now, wait before the first DSMEM access): a CTA may only
+    // touch its peer's shared memory once the peer is known to be resident
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    bool waited_phase1 = false;
 
     float part[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     bool row_valid = false, row_masked = true;
@@ -229,7 +233,23 @@ lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap map_emb_hi, const __gri
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (dbg && warp == 2 && lane == 0) dbg[3] = clock64() - t_begin;
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        const size_t off = (size_t)row * kGtH + rank * 64;
+        // All MMAs have retired, so the operand ring is free: each epilogue warp stages its
+        // [32 rows x 16 units] tiles of c and h there, so that global loads / stores run with
+        // lanes along the unit dimension (8 rows x 64 B per instruction) instead of one row per lane.
+        float* tile_h = reinterpret_cast<float*>(smem_gt + (ring - g_smem_u32(smem_gt))) + (size_t)(warp - 2) * (2 * 32 * 17);
+        float* tile_c = tile_h + 32 * 17;
+        const int rsub = lane >> 2, c4 = (lane & 3) * 4;
+        const size_t col0 = (size_t)rank * 64 + ug * 16 + c4;
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+            const int rl = ps * 8 + rsub;
+            const int gr = m0 + q * 32 + rl;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gr < p.M) v = *reinterpret_cast<const float4*>(p.c_in + (size_t)gr * kGtH + col0);
+            float* t = tile_c + rl * 17 + c4;
+            t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+        }
+        __syncwarp();
         {
             const int u0 = ug * 16;
             uint32_t gi[16], gf[16], gg[16], go[16];
@@ -238,50 +258,53 @@ lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap map_emb_hi, const __gri
             g_tmem_ld16(trow + 2 * 64 + u0, gg);
             g_tmem_ld16(trow + 3 * 64 + u0, go);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float* th = tile_h + lane * 17;
+            float* tc = tile_c + lane * 17;
             if (row_valid && !row_masked) {
 #pragma unroll
-                for (int v = 0; v < 16; v += 4) {
-                    const float4 c4 = *reinterpret_cast<const float4*>(p.c_in + off + u0 + v);
-                    const float cold[4] = {c4.x, c4.y, c4.z, c4.w};
-                    float hn[4], cn[4];
+                for (int v = 0; v < 16; ++v) {
+                    const int u = u0 + v;
+                    const float ig = g_sigmoid(__uint_as_float(gi[v]) + bg_s[0][u]);
+                    const float fg = g_sigmoid(__uint_as_float(gf[v]) + bg_s[1][u]);
+                    const float gt = g_tanh(__uint_as_float(gg[v]) + bg_s[2][u]);
+                    const float og = g_sigmoid(__uint_as_float(go[v]) + bg_s[3][u]);
+                    const float cn = fg * tc[v] + ig * gt;
+                    const float hn = og * g_tanh(cn);
+                    tc[v] = cn;
+                    th[v] = hn;
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        const int u = u0 + v + w;
-                        const float ig = g_sigmoid(__uint_as_float(gi[v + w]) + bg_s[0][u]);
-                        const float fg = g_sigmoid(__uint_as_float(gf[v + w]) + bg_s[1][u]);
-                        const float gt = g_tanh(__uint_as_float(gg[v + w]) + bg_s[2][u]);
-                        const float og = g_sigmoid(__uint_as_float(go[v + w]) + bg_s[3][u]);
-                        cn[w] = fg * cold[w] + ig * gt;
-                        hn[w] = og * g_tanh(cn[w]);
-#pragma unroll
-                        for (int o = 0; o < 5; ++o) part[o] = fmaf(hn[w], wn_s[o][u], part[o]);
-                    }
-                    *reinterpret_cast<float4*>(p.h_out + off + u0 + v) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                    *reinterpret_cast<float4*>(p.c_out + off + u0 + v) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                    __nv_bfloat16 hh[4], hl[4];
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        hh[w] = __float2bfloat16_rn(hn[w]);
-                        hl[w] = __float2bfloat16_rn(hn[w] - __bfloat162float(hh[w]));
-                    }
-                    *reinterpret_cast<uint2*>(p.hs_out_hi + off + u0 + v) =
-                        make_uint2((uint32_t)__bfloat16_as_ushort(hh[0]) | ((uint32_t)__bfloat16_as_ushort(hh[1]) << 16),
-                                   (uint32_t)__bfloat16_as_ushort(hh[2]) | ((uint32_t)__bfloat16_as_ushort(hh[3]) << 16));
-                    *reinterpret_cast<uint2*>(p.hs_out_lo + off + u0 + v) =
-                        make_uint2((uint32_t)__bfloat16_as_ushort(hl[0]) | ((uint32_t)__bfloat16_as_ushort(hl[1]) << 16),
-                                   (uint32_t)__bfloat16_as_ushort(hl[2]) | ((uint32_t)__bfloat16_as_ushort(hl[3]) << 16));
+                    for (int o = 0; o < 5; ++o) part[o] = fmaf(hn, wn_s[o][u], part[o]);
                 }
             } else if (row_valid) {
-                // absent track: state copied through unchanged (lstm.py:158-166)
+                // absent track: state copied through unchanged (lstm.py:158-166); tile_c already holds c_in
+                const float* hin = p.h_in + (size_t)row * kGtH + rank * 64 + u0;
 #pragma unroll
-                for (int v = 0; v < 16; v += 4) {
-                    if (p.h_out != p.h_in)
-                        *reinterpret_cast<float4*>(p.h_out + off + u0 + v) = *reinterpret_cast<const float4*>(p.h_in + off + u0 + v);
-                    if (p.c_out != p.c_in)
-                        *reinterpret_cast<float4*>(p.c_out + off + u0 + v) = *reinterpret_cast<const float4*>(p.c_in + off + u0 + v);
-                    *reinterpret_cast<uint2*>(p.hs_out_hi + off + u0 + v) = *reinterpret_cast<const uint2*>(p.hs_in_hi + off + u0 + v);
-                    *reinterpret_cast<uint2*>(p.hs_out_lo + off + u0 + v) = *reinterpret_cast<const uint2*>(p.hs_in_lo + off + u0 + v);
+                for (int v = 0; v < 16; ++v) th[v] = hin[v];
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+            const int rl = ps * 8 + rsub;
+            const int gr = m0 + q * 32 + rl;
+            if (gr < p.M) {
+                const float* sh = tile_h + rl * 17 + c4;
+                const float* sc = tile_c + rl * 17 + c4;
+                const float hv[4] = {sh[0], sh[1], sh[2], sh[3]};
+                const size_t o = (size_t)gr * kGtH + col0;
+                *reinterpret_cast<float4*>(p.h_out + o) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                *reinterpret_cast<float4*>(p.c_out + o) = make_float4(sc[0], sc[1], sc[2], sc[3]);
+                unsigned short hh[4], hl[4];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const __nv_bfloat16 h = __float2bfloat16_rn(hv[w]);
+                    hh[w] = __bfloat16_as_ushort(h);
+                    hl[w] = __bfloat16_as_ushort(__float2bfloat16_rn(hv[w] - __bfloat162float(h)));
                 }
+                *reinterpret_cast<uint2*>(p.hs_out_hi + o) =
+                    make_uint2((uint32_t)hh[0] | ((uint32_t)hh[1] << 16), (uint32_t)hh[2] | ((uint32_t)hh[3] << 16));
+                *reinterpret_cast<uint2*>(p.hs_out_lo + o) =
+                    make_uint2((uint32_t)hl[0] | ((uint32_t)hl[1] << 16), (uint32_t)hl[2] | ((uint32_t)hl[3] << 16));
             }
         }
         // combine the four unit-groups of a row (fixed order: deterministic)
@@ -297,6 +320,8 @@ lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap map_emb_hi, const __gri
             for (int o = 0; o < 5; ++o) part[o] = ((part_s[0][rl][o] + part_s[1][rl][o]) + part_s[2][rl][o]) + part_s[3][rl][o];
         }
         if (rank == 1 && ug == 0) {
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");     // phase 1: peer is resident
+            waited_phase1 = true;
             // ship this half's head sums to rank 0 through distributed shared memory
             const int rl = q * 32 + lane;
             const uint32_t local = g_smem_u32(&peer_part[rl][0]);
@@ -308,7 +333,8 @@ lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap map_emb_hi, const __gri
         }
     }
     if (dbg && warp == 2 && lane == 0) dbg[4] = clock64() - t_begin;
-    // cluster barrier: rank 1's partial sums are visible in rank 0's shared memory afterwards
+    // cluster barrier phase 2: rank 1's partial sums are visible in rank 0's shared memory afterwards
+    if (!waited_phase1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     if (dbg && warp == 2 && lane == 0) dbg[5] = clock64() - t_begin;

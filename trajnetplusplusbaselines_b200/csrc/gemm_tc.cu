@@ -194,22 +194,32 @@ dense_layer_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < p.M) {
-                const size_t yoff = (size_t)row * p.N + n0 + half * 32;
+            // stage the warp's [32 rows x 32 cols] chunk (bias + ReLU applied) in the now-free operand
+            // ring and write it out with lanes along the columns: 4 rows x 128 B (fp32) / 64 B (bf16)
+            // per instruction instead of one row per lane
+            float* tile = reinterpret_cast<float*>(smem_tc + (ring - smem_u32(smem_tc))) + (size_t)(warp - 2) * (32 * 33);
+            {
                 const float* brow = p.bias + n0 + half * 32;
+                float* trow_s = tile + lane * 33;
 #pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                    float4 v;
-                    v.x = __uint_as_float(r[c + 0]) + brow[c + 0];
-                    v.y = __uint_as_float(r[c + 1]) + brow[c + 1];
-                    v.z = __uint_as_float(r[c + 2]) + brow[c + 2];
-                    v.w = __uint_as_float(r[c + 3]) + brow[c + 3];
-                    if (p.relu) {
-                        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                    }
-                    if (p.Y) *reinterpret_cast<float4*>(p.Y + yoff + c) = v;
+                for (int c = 0; c < 32; ++c) {
+                    float v = __uint_as_float(r[c]) + brow[c];
+                    if (p.relu) v = fmaxf(v, 0.f);
+                    trow_s[c] = v;
+                }
+            }
+            __syncwarp();
+            const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+            for (int ps = 0; ps < 8; ++ps) {
+                const int rl = ps * 4 + rsub;
+                const int gr = m0 + q * 32 + rl;
+                if (gr < p.M) {
+                    const float* s = tile + rl * 33 + c4;
+                    const float f[4] = {s[0], s[1], s[2], s[3]};
+                    const size_t yoff = (size_t)gr * p.N + n0 + half * 32 + c4;
+                    if (p.Y) *reinterpret_cast<float4*>(p.Y + yoff) = make_float4(f[0], f[1], f[2], f[3]);
                     if (p.Y_hi) {
-                        const float f[4] = {v.x, v.y, v.z, v.w};
                         unsigned short hh[4], hl[4];
 #pragma unroll
                         for (int w = 0; w < 4; ++w) {
@@ -217,13 +227,14 @@ dense_layer_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
                             hh[w] = __bfloat16_as_ushort(h);
                             hl[w] = __bfloat16_as_ushort(__float2bfloat16_rn(f[w] - __bfloat162float(h)));
                         }
-                        *reinterpret_cast<uint2*>(p.Y_hi + yoff + c) =
+                        *reinterpret_cast<uint2*>(p.Y_hi + yoff) =
                             make_uint2((uint32_t)hh[0] | ((uint32_t)hh[1] << 16), (uint32_t)hh[2] | ((uint32_t)hh[3] << 16));
-                        *reinterpret_cast<uint2*>(p.Y_lo + yoff + c) =
+                        *reinterpret_cast<uint2*>(p.Y_lo + yoff) =
                             make_uint2((uint32_t)hl[0] | ((uint32_t)hl[1] << 16), (uint32_t)hl[2] | ((uint32_t)hl[3] << 16));
                     }
                 }
             }
+            __syncwarp();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -79,6 +79,7 @@ struct PrepParams {
     int E;
     int n_max, H, C, n, pool_type, front, skip_masked, write_pairs;
     float side, width;
+    long long* dbg;           // optional [B, 8] clock64 stamps (TB2_PREP_DEBUG=1)
 };
 
 __device__ __forceinline__ float nan_to_num_f(float x) {
@@ -99,6 +100,8 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
     float* Ws = reinterpret_cast<float*>(cellrow + kPrepWarps * (nm1 > 0 ? nm1 : 1));   // [H][C]   (social)
     float* hs = Ws + p.H * p.C;                                         // [n_s][H] (social)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 8 : nullptr;
+    const long long t_begin = clock64();
 
     for (int j = tid; j < n_s; j += kPrepThreads) {
         float2 a = p.obs1[row0 + j], b = p.obs2[row0 + j];
@@ -115,11 +118,14 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
             v.x = nan_to_num_f(v.x); v.y = nan_to_num_f(v.y); v.z = nan_to_num_f(v.z); v.w = nan_to_num_f(v.w);
             hdst[idx] = v;
         }
-        const float4* wsrc = reinterpret_cast<const float4*>(p.WencT);
-        float4* wdst = reinterpret_cast<float4*>(Ws);
-        for (int idx = tid; idx < p.H * p.C / 4; idx += kPrepThreads) wdst[idx] = wsrc[idx];
+        // W_enc in [C][H] order (k contiguous) so the dot products below run on float4 pairs
+        for (int idx = tid; idx < p.H * p.C; idx += kPrepThreads) {
+            const int k = idx / p.C, c = idx - k * p.C;          // WencT is [H][C]: coalesced read
+            Ws[c * p.H + k] = p.WencT[idx];
+        }
     }
     __syncthreads();
+    if (dbg && tid == 0) dbg[0] = clock64() - t_begin;
     if (p.emb_hi != nullptr) {
         // emb = cat(relu(W_e . (4 v) + b_e), 0, 0) (modules.py:24-30) as bf16 (hi, lo) for the gate GEMM
         for (int idx = tid; idx < n_s * p.E; idx += kPrepThreads) {
@@ -133,16 +139,22 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
             p.emb_lo[(size_t)(row0 + j) * p.E + k] = __float2bfloat16_rn(e - __bfloat162float(h));
         }
     }
+    if (dbg && tid == 0) dbg[1] = clock64() - t_begin;
     if (p.pool_type == TB2_POOL_SOCIAL) {
         // lat[j][c] = sum_k nan_to_num(h[j][k]) * WencT[k][c] + benc[c]
         const int total = n_s * p.C;
         for (int idx = tid; idx < total; idx += kPrepThreads) {
             int j = idx / p.C, c = idx - j * p.C;
-            const float* hrow = hs + j * p.H;
-            float acc = 0.f;
-#pragma unroll 8
-            for (int k = 0; k < p.H; ++k) acc = fmaf(hrow[k], Ws[k * p.C + c], acc);
-            p.lat[(size_t)(row0 + j) * p.C + c] = acc + p.benc[c];
+            const float4* hrow = reinterpret_cast<const float4*>(hs + j * p.H);
+            const float4* wrow = reinterpret_cast<const float4*>(Ws + c * p.H);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // 4 independent chains (sum order fixed)
+#pragma unroll 4
+            for (int k4 = 0; k4 < p.H / 4; ++k4) {
+                const float4 hv = hrow[k4], wv = wrow[k4];
+                a0 = fmaf(hv.x, wv.x, a0); a1 = fmaf(hv.y, wv.y, a1);
+                a2 = fmaf(hv.z, wv.z, a2); a3 = fmaf(hv.w, wv.w, a3);
+            }
+            p.lat[(size_t)(row0 + j) * p.C + c] = ((a0 + a1) + (a2 + a3)) + p.benc[c];
         }
     }
     if (nm1 <= 0) {   // single-pedestrian batch: constant grid (gridbased_pooling.py:252-253)
@@ -150,6 +162,7 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
         return;
     }
 
+    if (dbg && tid == 0) dbg[2] = clock64() - t_begin;
     const float offx = p.width * 0.5f;
     const float offy = p.front ? 0.f : p.width * 0.5f;
     int* myrow = cellrow + warp * nm1;
@@ -182,8 +195,7 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
         }
         __syncwarp();
         // pass 2: winners, compacted in ascending jj
-        const float2 oi1 = p.obs1[row0 + i], oi2 = p.obs2[row0 + i];
-        const bool masked = isnan(oi1.x) || isnan(oi2.x);
+        const bool masked = isnan(vi.x);      // obs2 - obs1 is NaN iff the track is absent at either frame
         int count = 0;
         if (!(p.skip_masked && masked)) {
             for (int base = 0; base < nm1; base += 32) {
@@ -222,6 +234,7 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
         if (lane == 0) p.win_count[row0 + i] = count;
         __syncwarp();
     }
+    if (dbg && lane == 0 && warp == 0) dbg[3] = clock64() - t_begin;
 }
 
 int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hidden,
@@ -254,6 +267,16 @@ int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hid
     p.E = m->E;
     p.emb_hi = write_emb ? (__nv_bfloat16*)ws->emb_hi : nullptr;
     p.emb_lo = write_emb ? (__nv_bfloat16*)ws->emb_lo : nullptr;
+    p.dbg = nullptr;
+    static long long* dbg_buf = nullptr;
+    static int dbg_calls = 0;
+    {
+        const char* e = getenv("TB2_PREP_DEBUG");
+        if (e && e[0] == '1') {
+            if (!dbg_buf) cudaMalloc(&dbg_buf, (size_t)l->B * 8 * sizeof(long long));
+            p.dbg = dbg_buf;
+        }
+    }
     p.side = m->cfg.cell_side;        // pool_size == 1
     p.width = (float)m->cfg.n;
     int nm1 = l->n_max > 1 ? l->n_max - 1 : 1;
@@ -271,6 +294,15 @@ int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hid
         pool_prepare_kernel<<<l->B, kPrepThreads, smem, st>>>(p);
     }
     TB2_LAUNCH_CHECK();
+    if (p.dbg && ++dbg_calls == 60) {
+        std::vector<long long> h((size_t)l->B * 8);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        double a[4] = {0, 0, 0, 0};
+        for (int c = 0; c < l->B; ++c) for (int k = 0; k < 4; ++k) a[k] += (double)h[(size_t)c * 8 + k] / l->B;
+        fprintf(stderr, "[tb2 pool_prepare debug] per-CTA cycles since start: staged %.0f | emb %.0f | lat %.0f | "
+                        "winners (warp 0) %.0f\n", a[0], a[1], a[2], a[3]);
+    }
     return TB2_OK;
 }
 
