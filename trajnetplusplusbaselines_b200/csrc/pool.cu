@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
     float2* vel = pos + n_s;                                            // [n_s] obs2 - obs1 (may be NaN)
     int* cellrow = reinterpret_cast<int*>(vel + n_s);                   // [kPrepWarps][nm1]
     float* Ws = reinterpret_cast<float*>(cellrow + kPrepWarps * (nm1 > 0 ? nm1 : 1));   // [H][C]   (social)
-    float* hs = Ws + p.H * p.C;                                         // [n_s][H] (social)
+    float* hs = Ws + (p.H + 4) * p.C;                                   // [n_s][H] (social); Ws rows padded by 4
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 8 : nullptr;
     const long long t_begin = clock64();
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
         // W_enc in [C][H] order (k contiguous) so the dot products below run on float4 pairs
         for (int idx = tid; idx < p.H * p.C; idx += kPrepThreads) {
             const int k = idx / p.C, c = idx - k * p.C;          // WencT is [H][C]: coalesced read
-            Ws[c * p.H + k] = p.WencT[idx];
+            Ws[c * (p.H + 4) + k] = p.WencT[idx];                // row stride H + 4: 2-way instead of 16-way conflicts
         }
     }
     __syncthreads();
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
         for (int idx = tid; idx < total; idx += kPrepThreads) {
             int j = idx / p.C, c = idx - j * p.C;
             const float4* hrow = reinterpret_cast<const float4*>(hs + j * p.H);
-            const float4* wrow = reinterpret_cast<const float4*>(Ws + c * p.H);
+            const float4* wrow = reinterpret_cast<const float4*>(Ws + c * (p.H + 4));
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // 4 independent chains (sum order fixed)
 #pragma unroll 4
             for (int k4 = 0; k4 < p.H / 4; ++k4) {
@@ -202,17 +202,17 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
                 int jj = base + lane;
                 bool win = false;
                 int cell = 0;
-                if (jj < nm1) {
-                    cell = myrow[jj];
-                    win = cell >= 0;
-                    if (win) {
-                        // a later in-range writer of the same cell, or (for cell 0) any later
-                        // out-of-range writer incl. padding, overrides this pair
-                        for (int k = jj + 1; win && k < nm1; ++k) {
-                            int ck = myrow[k];
-                            if (ck == cell || (cell == 0 && ck < 0)) win = false;
-                        }
-                    }
+                // a later in-range writer of the same cell, or (for cell 0) any later out-of-range
+                // writer incl. padding, overrides this pair.  Within the 32-slot chunk this is one
+                // warp match; only scenes with more than 33 pedestrians need the loop over later chunks.
+                cell = (jj < nm1) ? myrow[jj] : -2 - lane;                 // inactive lanes: unique keys
+                const unsigned same = __match_any_sync(0xffffffffu, cell);
+                const unsigned oor = __ballot_sync(0xffffffffu, jj < nm1 && cell == -1);
+                const unsigned later = lane == 31 ? 0u : (0xffffffffu << (lane + 1));
+                win = jj < nm1 && cell >= 0 && (same & later) == 0u && !(cell == 0 && (oor & later) != 0u);
+                for (int k = base + 32; win && k < nm1; ++k) {
+                    int ck = myrow[k];
+                    if (ck == cell || (cell == 0 && ck < 0)) win = false;
                 }
                 unsigned ball = __ballot_sync(0xffffffffu, win);
                 if (win) {
@@ -281,7 +281,7 @@ int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hid
     p.width = (float)m->cfg.n;
     int nm1 = l->n_max > 1 ? l->n_max - 1 : 1;
     size_t smem = (size_t)l->n_max * 2 * sizeof(float2) + (size_t)kPrepWarps * nm1 * sizeof(int);
-    if (m->cfg.pool_type == TB2_POOL_SOCIAL) smem += ((size_t)m->H * m->C + (size_t)l->n_max * m->H) * sizeof(float);
+    if (m->cfg.pool_type == TB2_POOL_SOCIAL) smem += ((size_t)(m->H + 4) * m->C + (size_t)l->n_max * m->H) * sizeof(float);
     smem = (smem + 15) & ~(size_t)15;
     static size_t configured = 48 * 1024;
     if (smem > configured) {
