@@ -183,7 +183,8 @@ typedef struct tb2_lstm_grads {
     float* pool_embedding_bias0;     /* [out_dim] or NULL */
 } tb2_lstm_grads;
 
-size_t tb2_lstm_backward_workspace_bytes(const tb2_lstm* model, int32_t num_active);
+/* scratch for tb2_lstm_sequence_backward: per (step, active row) records + per-step buffers */
+size_t tb2_lstm_backward_workspace_bytes(const tb2_lstm* model, int32_t num_active, int32_t num_steps);
 
 /* BPTT over the rows that receive gradient.
  *   weights          the same fp32 parameter pointers given to tb2_lstm_set_weights
@@ -202,6 +203,22 @@ int tb2_lstm_sequence_backward(const tb2_lstm* model, const tb2_layout* layout, 
                                const float* d_normals_dev, const int32_t* active_rows_dev, int32_t num_active,
                                const tb2_lstm_grads* grads, void* workspace_dev, size_t workspace_bytes,
                                void* bwd_workspace_dev, size_t bwd_workspace_bytes, void* stream);
+
+/* PredictionLoss on the device (lstm/loss.py:52-91, gaussian_2d :24-50): per (frame, scene)
+ *   values_out  [T, B]    = -log(0.01 + bg N(x|mu,3,3,0) + (0.99-bg) N(x|mu,s1,s2,rho)) of the primary
+ *   dinputs_out [T, B, 5] = d value / d (mu1, mu2, s1, s2, rho) (optional, NULL to skip)
+ * inputs [T, M, 5], targets [T, M, 2] device fp32; primary_rows int32 [B] = batch_split[:-1].
+ * The mean / keep_batch_dim reductions of the reference stay with the caller. */
+int tb2_prediction_loss(const float* inputs_dev, const float* targets_dev, const int32_t* primary_rows_dev,
+                        int32_t T, int32_t M, int32_t B, float background_rate, float* values_out_dev,
+                        float* dinputs_out_dev, void* stream);
+
+/* CollisionLoss (lstm/loss.py:138-162): per (frame, scene) col_wt * sum over neighbours closer
+ * than col_distance to the primary of (1 - dist / col_distance); NaN coordinates read as -1000;
+ * neighbours are constants.  positions [T, M, 2]; loss_out [T, B]; dprimary_out [T, B, 2]
+ * (gradient wrt the primary's position, optional). */
+int tb2_collision_loss(const tb2_layout* layout, const float* positions_dev, int32_t T, float col_wt,
+                       float col_distance, float* loss_out_dev, float* dprimary_out_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Classical crowd simulators (classical/socialforce.py, classical/orca.py).  One simulator

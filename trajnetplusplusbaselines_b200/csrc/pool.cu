@@ -895,6 +895,132 @@ int launch_dense_plain(const float* X, const float* WT, const float* b, float* Y
     return launch_dense(X, WT, b, Y, M, K, N, relu, st);
 }
 
+// ------------------------------------------------------------------------------------------
+// First Linear for occupancy / directional grids (C <= 2 payload channels): the whole weight
+// chunk [cells * C][CH output columns] fits in shared memory, so a CTA loads it once and then
+// walks its rows; each row is base + sum over its <= N-1 winners of C weight rows (a few dozen
+// FMAs per output).  grid = (row groups, column chunks), sized to one wave of the SMs.
+// ------------------------------------------------------------------------------------------
+struct RowsParams {
+    const int* win_count;
+    const uint32_t* win_ent;
+    const float* win_val;
+    const float* Wt;          // [cells, C, OUT]
+    const float* base;        // [OUT]
+    float* out;               // [M, OUT] fp32 or null
+    __nv_bfloat16* out_hi;    // [M, OUT] bf16 (hi, lo) split or null
+    __nv_bfloat16* out_lo;
+    int M, OUT, cells, C, nm1, CH, rows_per_cta, relu;
+    float constant;
+};
+
+constexpr int kRowsThreads = 1024;
+
+__global__ void __launch_bounds__(kRowsThreads, 1) pool_rows_kernel(RowsParams p) {
+    extern __shared__ __align__(16) unsigned char smem_rows[];
+    float* Ws = reinterpret_cast<float*>(smem_rows);                            // [cells * C][CH]
+    const int KW = p.cells * p.C;
+    int* cnt_s = reinterpret_cast<int*>(Ws + (size_t)KW * p.CH);                // [rows_per_cta]
+    uint32_t* ent_s = reinterpret_cast<uint32_t*>(cnt_s + p.rows_per_cta);      // [rows_per_cta][nm1]
+    float* val_s = reinterpret_cast<float*>(ent_s + (size_t)p.rows_per_cta * p.nm1);   // [rows_per_cta][nm1][2]
+    const int tid = threadIdx.x;
+    const int col0 = blockIdx.y * p.CH;
+    const int r0 = blockIdx.x * p.rows_per_cta;
+    const int nrows = min(p.rows_per_cta, p.M - r0);
+    if (nrows <= 0) return;
+    // weight chunk: rows of CH floats at stride OUT (CH is a multiple of 4, OUT too when vectorised)
+    const int cw = min(p.CH, p.OUT - col0);
+    if ((p.OUT & 3) == 0 && (cw & 3) == 0) {
+        const int q = cw >> 2;
+        for (int idx = tid; idx < KW * q; idx += kRowsThreads) {
+            const int k = idx / q, c4 = idx - k * q;
+            *reinterpret_cast<float4*>(Ws + (size_t)k * p.CH + c4 * 4) =
+                *reinterpret_cast<const float4*>(p.Wt + (size_t)k * p.OUT + col0 + c4 * 4);
+        }
+    } else {
+        for (int idx = tid; idx < KW * cw; idx += kRowsThreads) {
+            const int k = idx / cw, c = idx - k * cw;
+            Ws[(size_t)k * p.CH + c] = p.Wt[(size_t)k * p.OUT + col0 + c];
+        }
+    }
+    for (int r = tid; r < nrows; r += kRowsThreads) cnt_s[r] = p.win_count[r0 + r];
+    {
+        const uint32_t* esrc = p.win_ent + (size_t)r0 * p.nm1;
+        for (int idx = tid; idx < nrows * p.nm1; idx += kRowsThreads) ent_s[idx] = esrc[idx];
+        const float* vsrc = p.win_val + (size_t)r0 * p.nm1 * 2;
+        for (int idx = tid; idx < nrows * p.nm1 * 2; idx += kRowsThreads) val_s[idx] = vsrc[idx] - p.constant;
+    }
+    __syncthreads();
+    const int lanes = kRowsThreads / p.CH;          // row lanes (CH = 256 -> 1, 128 -> 2, 64 -> 4, 32 -> 8)
+    const int colc = tid % p.CH, lane = tid / p.CH;
+    const int col = col0 + colc;
+    if (col >= p.OUT) return;
+    const float b = p.base[col];
+    for (int r = lane; r < nrows; r += lanes) {
+        float acc = b;
+        const int cnt = cnt_s[r];
+        const uint32_t* er = ent_s + (size_t)r * p.nm1;
+        const float* vr = val_s + (size_t)r * p.nm1 * 2;
+        for (int e = 0; e < cnt; ++e) {
+            const float* w = Ws + (size_t)(er[e] >> 16) * p.C * p.CH + colc;
+            acc = fmaf(w[0], vr[2 * e], acc);
+            if (p.C == 2) acc = fmaf(w[p.CH], vr[2 * e + 1], acc);
+        }
+        if (p.relu) acc = fmaxf(acc, 0.f);
+        const size_t o = (size_t)(r0 + r) * p.OUT + col;
+        if (p.out_hi) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(acc);
+            p.out_hi[o] = h;
+            p.out_lo[o] = __float2bfloat16_rn(acc - __bfloat162float(h));
+        }
+        if (p.out) p.out[o] = acc;
+    }
+}
+
+// returns the column chunk width the row kernel can use for this model (0 = does not fit)
+static int pool_rows_chunk(const tb2_lstm* m, int OUT) {
+    if (m->cfg.pool_type == TB2_POOL_SOCIAL || m->C > 2) return 0;
+    const size_t KW = (size_t)m->cells * m->C;
+    for (int ch = 256; ch >= 32; ch >>= 1) {
+        if (ch > 32 && ch / 2 >= OUT) continue;          // do not pad tiny layers
+        if (KW * ch * sizeof(float) <= 160 * 1024) return ch;
+    }
+    return 0;
+}
+
+static int launch_pool_rows(const tb2_lstm* m, const tb2_layout* l, const Workspace* ws, int OUT, int nm1,
+                            float* out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, cudaStream_t st) {
+    RowsParams p;
+    p.win_count = ws->win_count; p.win_ent = ws->win_ent; p.win_val = ws->win_val;
+    p.Wt = m->Wt1; p.base = m->base1; p.out = out; p.out_hi = out_hi; p.out_lo = out_lo;
+    p.M = l->M; p.OUT = OUT; p.cells = m->cells; p.C = m->C; p.nm1 = nm1; p.relu = 1;
+    p.constant = m->cfg.constant;
+    p.CH = pool_rows_chunk(m, OUT);
+    const int chunks = (OUT + p.CH - 1) / p.CH;
+    // one wave: ~148 CTAs in total, winner lists of a CTA's rows must fit next to the weights
+    int groups = (148 + chunks - 1) / chunks;
+    int rows = (l->M + groups - 1) / groups;
+    const size_t wbytes = (size_t)m->cells * m->C * p.CH * sizeof(float);
+    const size_t per_row = sizeof(int) + (size_t)nm1 * (sizeof(uint32_t) + 2 * sizeof(float));
+    const int max_rows = (int)((220 * 1024 - wbytes) / per_row);
+    if (rows > max_rows) rows = max_rows;
+    if (rows < 1) rows = 1;
+    groups = (l->M + rows - 1) / rows;
+    p.rows_per_cta = rows;
+    const size_t smem = wbytes + (size_t)rows * per_row;
+    static size_t configured = 0;
+    if (smem > configured) {
+        TB2_CHECK_CUDA(cudaFuncSetAttribute(pool_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    {
+        KernelTimer kt("pool_rows", st);
+        pool_rows_kernel<<<dim3(groups, chunks), kRowsThreads, smem, st>>>(p);
+    }
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
+}
+
 template <int C, bool SOCIAL>
 static int launch_l1_t(const L1Params& p, int groups, size_t smem, cudaStream_t st) {
     static size_t configured = 0;
@@ -970,8 +1096,12 @@ int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float
         p.out_lo = reinterpret_cast<__nv_bfloat16*>(pool_lo);
     }
     int rc;
-    const char* sp_env = getenv("TB2_SPARSE");       // debug knob: "mma" forces the warp-level MMA kernel
-    const bool allow_tc = !(sp_env && sp_env[0] == 'm');
+    const char* sp_env = getenv("TB2_SPARSE");       // debug knob: "mma" forces the warp-level MMA kernel,
+    const bool allow_tc = !(sp_env && sp_env[0] == 'm');     // "bucket" the per-cell bucket kernel
+    const bool allow_rows = !(sp_env && sp_env[0] == 'b');
+    if (allow_rows && pool_rows_chunk(m, d1) > 0) {   // occupancy / directional: weights resident in smem
+        rc = launch_pool_rows(m, l, ws, d1, nm1, p.out, p.out_hi, p.out_lo, st);
+    } else
     if (allow_tc && sparse_tc_supported(m, l, 0)) {  // social, 16 latent channels: tcgen05 path
         rc = launch_sparse_tc(m, l, 0, ws, p.out, p.out_hi, p.out_lo, st);
     } else

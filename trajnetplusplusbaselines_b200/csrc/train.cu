@@ -7,15 +7,15 @@
 // pooled vector does not depend on any hidden state, so a track's gradient never leaves its own
 // LSTM chain.  The caller passes the list of ACTIVE rows (tracks that receive a non-zero upstream
 // gradient: the scene primaries for PredictionLoss, loss.py:57,67) and the whole backward runs
-// on those R rows only: per step one recompute of the gate pre-activations (R x K x 512), the
-// pointwise cell / head backward, two input-gradient GEMMs and the weight-gradient
-// accumulations.  Social pooling couples the tracks of a scene through W_enc h_j and is not
-// built yet (fails loudly).
-//
-// All accumulations into parameter gradients are deterministic (one thread owns one output
-// element, steps are processed sequentially) except the sparse scatter into the first
-// grid-embedding layer's weight gradient, which uses fp32 atomics like PyTorch's own index_put /
-// embedding backward.
+// on those R rows only.  Per step (reverse time): winners of the step (pool_prepare), gather of
+// X = [emb | pooled | h_prev] with the pooled rows recomputed from the winner list, recompute of
+// the gate pre-activations (R x K x 512), pointwise cell / head backward, one input-gradient GEMM
+// dX = dgates . [W_ih | W_hh], sparse scatter into dW1.  X, dgates, h, d(normal), velocity and
+// dX_emb of every (step, row) are kept, so each dense parameter gradient is ONE reduction over all
+// S * R records after the loop (a tile of the output is owned by one CTA: deterministic).
+// Social pooling couples the tracks of a scene through W_enc h_j and is not built yet (fails
+// loudly).  No floating-point atomics anywhere: the first grid-embedding layer's weight gradient is
+// dz^T . grid with the (R-row) grid of each step written out densely by the gather kernel.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -26,56 +26,126 @@ constexpr int kBH = 128;
 
 __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
 
-// X_act[r] = [emb(vel) | pooled | h_prev]  (row gather), K = E + P + H
-__global__ void bwd_gather_kernel(const int* __restrict__ rows, int R, const float2* __restrict__ obs1,
-                                  const float2* __restrict__ obs2, const float* __restrict__ We,
-                                  const float* __restrict__ be, const float* __restrict__ pooled,
-                                  const float* __restrict__ h_prev, float* __restrict__ X, int* __restrict__ masked,
-                                  int E, int P, int K) {
+// X[r] = [emb(vel) | pooled | h_prev] for the active rows (one CTA per row).  The pooled part is
+// recomputed from the step's winner list: pooled = relu(base + sum_winners Wt1[cell, c, :] * val)
+// (one_layer embedding, constant = 0) -- R rows instead of re-running the first Linear on all M.
+__global__ void __launch_bounds__(256) bwd_gather_kernel(
+    const int* __restrict__ rows, int R, const float2* __restrict__ obs1, const float2* __restrict__ obs2,
+    const float* __restrict__ We, const float* __restrict__ be, const float* __restrict__ h_prev,
+    const int* __restrict__ win_count, const uint32_t* __restrict__ win_ent, const float* __restrict__ win_val,
+    const float* __restrict__ Wt1, const float* __restrict__ base1, int nm1, int C, int cells,
+    float* __restrict__ X, float* __restrict__ G, float* __restrict__ vel, int* __restrict__ masked, int E, int P,
+    int K) {
+    __shared__ uint32_t ent_s[64];
+    __shared__ float val_s[64][2];
     const int r = blockIdx.x;
     if (r >= R) return;
     const int m = rows[r];
     const float2 a = obs1[m], b = obs2[m];
     const bool msk = isnan(a.x) || isnan(b.x);
-    if (threadIdx.x == 0) masked[r] = msk ? 1 : 0;
-    const float vx = (b.x - a.x) * 4.0f, vy = (b.y - a.y) * 4.0f;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        float v = 0.f;
-        if (!msk) {
-            if (k < E) {
-                if (k < E - 2) v = fmaxf(fmaf(We[2 * k + 1], vy, fmaf(We[2 * k], vx, be[k])), 0.f);
-            } else if (k < E + P) {
-                v = pooled[(size_t)m * P + (k - E)];
-            } else {
-                v = h_prev ? h_prev[(size_t)m * kBH + (k - E - P)] : 0.f;
+    const float vx = msk ? 0.f : (b.x - a.x) * 4.0f, vy = msk ? 0.f : (b.y - a.y) * 4.0f;
+    if (threadIdx.x == 0) {
+        masked[r] = msk ? 1 : 0;
+        vel[2 * r] = vx;
+        vel[2 * r + 1] = vy;
+    }
+    float* x = X + (size_t)r * K;
+    float* grow = G ? G + (size_t)r * C * cells : nullptr;     // the reference's grid row [C * n * n]
+    if (grow)
+        for (int k = threadIdx.x; k < C * cells; k += blockDim.x) grow[k] = 0.f;
+    if (msk) {
+        for (int k = threadIdx.x; k < K; k += blockDim.x) x[k] = 0.f;
+        return;
+    }
+    for (int k = threadIdx.x; k < E; k += blockDim.x)
+        x[k] = k < E - 2 ? fmaxf(fmaf(We[2 * k + 1], vy, fmaf(We[2 * k], vx, be[k])), 0.f) : 0.f;
+    for (int k = threadIdx.x; k < kBH; k += blockDim.x)
+        x[E + P + k] = h_prev ? h_prev[(size_t)m * kBH + k] : 0.f;
+    if (P > 0) {
+        const int cnt = win_count[m];
+        float acc[4];     // up to 4 output columns per thread (P <= 1024)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int o = threadIdx.x + q * blockDim.x;
+            acc[q] = o < P ? base1[o] : 0.f;
+        }
+        for (int e0 = 0; e0 < cnt; e0 += 64) {
+            const int n = min(64, cnt - e0);
+            __syncthreads();
+            if (threadIdx.x < n) {
+                const size_t g = (size_t)m * nm1 + e0 + threadIdx.x;
+                ent_s[threadIdx.x] = win_ent[g];
+                val_s[threadIdx.x][0] = win_val[g * 2];
+                val_s[threadIdx.x][1] = win_val[g * 2 + 1];
+            }
+            __syncthreads();
+            if (threadIdx.x < n)      // a cell has one winner per row: plain stores (after the zero fill above)
+                for (int c = 0; c < C; ++c)
+                    grow[c * cells + (ent_s[threadIdx.x] >> 16)] = val_s[threadIdx.x][c];
+            for (int e = 0; e < n; ++e) {
+                const int cell = ent_s[e] >> 16;
+                for (int c = 0; c < C; ++c) {
+                    const float v = val_s[e][c];
+                    const float* wrow = Wt1 + ((size_t)cell * C + c) * P;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int o = threadIdx.x + q * blockDim.x;
+                        if (o < P) acc[q] = fmaf(wrow[o], v, acc[q]);
+                    }
+                }
             }
         }
-        X[(size_t)r * K + k] = v;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int o = threadIdx.x + q * blockDim.x;
+            if (o < P) x[E + o] = fmaxf(acc[q], 0.f);
+        }
     }
 }
 
-// Pointwise backward of LSTMCell + Hidden2Normal for one active row per CTA (128 threads = units).
-//   in : gates_pre [R,512] (with bias), c_prev (state before the step, null = zeros), dh, dc [R,128]
-//        upstream dnormal [M,5] of this step (row-indexed by track), Wn, bn
-//   out: dgates [R,512], dc (in place: gradient wrt c_prev), hs [R,128] (h of this step),
-//        dn_raw [R,5]; dh is overwritten with the part that by-passes the cell for masked rows
+// Backward of LSTMCell + Hidden2Normal for one active row per CTA (128 threads = units): the only
+// kernel on the sequential chain of the BPTT.
+//   in : gates_pre [R,512] of this step (with bias), c_prev (state before the step, null = zeros),
+//        incoming dh = dg_next[r] . Whh_next (recurrent part of the LATER step's gate gradient,
+//        W_hh in torch layout [4H, H]) + pass_prev[r] (what by-passed the cell there); both null
+//        at the last step.  dc [R,128] in place; upstream dnormal [M,5] (row-indexed by track)
+//   out: dgates [R,512], dc (gradient wrt c_prev), hs [R,128] (h of this step), dn_raw [R,8],
+//        pass_cur [R,128] (masked rows: dh goes straight through, lstm.py:158-166)
 __global__ void __launch_bounds__(kBH) bwd_cell_head_kernel(
     const int* __restrict__ rows, const int* __restrict__ masked, const float* __restrict__ gates_pre,
-    const float* __restrict__ c_prev, float* __restrict__ dh, float* __restrict__ dc,
+    const float* __restrict__ c_prev, const float* __restrict__ dg_next, const float* __restrict__ Whh_next,
+    const float* __restrict__ pass_prev, float* __restrict__ pass_cur, float* __restrict__ dc,
     const float* __restrict__ dnormal, const float* __restrict__ Wn, const float* __restrict__ bn,
     float* __restrict__ dgates, float* __restrict__ hs, float* __restrict__ dn_raw, int R) {
     __shared__ float red[5][kBH];
     __shared__ float dn_s[5];
+    __shared__ __align__(16) float dgn_s[4 * kBH];
     const int r = blockIdx.x, u = threadIdx.x;
     const int m = rows[r];
     float* dg = dgates + (size_t)r * 4 * kBH;
-    if (masked[r]) {   // absent track: state passes through, no parameter gradient (lstm.py:158-166)
+    float dh_in = 0.f;
+    if (dg_next) {
+        reinterpret_cast<float4*>(dgn_s)[u] = reinterpret_cast<const float4*>(dg_next + (size_t)r * 4 * kBH)[u];
+        __syncthreads();
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+        for (int g = 0; g < 4 * kBH; g += 4) {
+            a0 = fmaf(dgn_s[g + 0], Whh_next[(size_t)(g + 0) * kBH + u], a0);
+            a1 = fmaf(dgn_s[g + 1], Whh_next[(size_t)(g + 1) * kBH + u], a1);
+            a2 = fmaf(dgn_s[g + 2], Whh_next[(size_t)(g + 2) * kBH + u], a2);
+            a3 = fmaf(dgn_s[g + 3], Whh_next[(size_t)(g + 3) * kBH + u], a3);
+        }
+        dh_in = (a0 + a1) + (a2 + a3) + pass_prev[(size_t)r * kBH + u];
+    }
+    if (masked[r]) {   // absent track: state passes through, no parameter gradient
 #pragma unroll
         for (int g = 0; g < 4; ++g) dg[g * kBH + u] = 0.f;
         hs[(size_t)r * kBH + u] = 0.f;
-        if (u < 5) dn_raw[r * 5 + u] = 0.f;
-        return;        // dh, dc stay as they are
+        if (u < 8) dn_raw[r * 8 + u] = 0.f;
+        pass_cur[(size_t)r * kBH + u] = dh_in;
+        return;        // dc stays as it is
     }
+    pass_cur[(size_t)r * kBH + u] = 0.f;
     const float* gp = gates_pre + (size_t)r * 4 * kBH;
     const float ig = sigm(gp[u]), fg = sigm(gp[kBH + u]), gg = tanhf(gp[2 * kBH + u]), og = sigm(gp[3 * kBH + u]);
     const float cp = c_prev ? c_prev[(size_t)m * kBH + u] : 0.f;
@@ -94,19 +164,22 @@ __global__ void __launch_bounds__(kBH) bwd_cell_head_kernel(
         }
         __syncthreads();
     }
-    if (u < 5) {
-        const float raw = red[u][0] + bn[u];
-        float d = dnormal[(size_t)m * 5 + u];
-        if (isnan(d)) d = 0.f;
-        if (u >= 2) {
-            const float sg = sigm(raw);
-            d *= (u == 4 ? 0.7f : 0.2f) * sg * (1.f - sg);     // modules.py:60-62
+    if (u < 8) {
+        float d = 0.f;
+        if (u < 5) {
+            const float raw = red[u][0] + bn[u];
+            d = dnormal[(size_t)m * 5 + u];
+            if (isnan(d)) d = 0.f;
+            if (u >= 2) {
+                const float sg = sigm(raw);
+                d *= (u == 4 ? 0.7f : 0.2f) * sg * (1.f - sg);     // modules.py:60-62
+            }
+            dn_s[u] = d;
         }
-        dn_s[u] = d;
-        dn_raw[r * 5 + u] = d;
+        dn_raw[r * 8 + u] = d;
     }
     __syncthreads();
-    float dht = dh[(size_t)r * kBH + u];
+    float dht = dh_in;
 #pragma unroll
     for (int o = 0; o < 5; ++o) dht = fmaf(Wn[o * kBH + u], dn_s[o], dht);
     float dct = dc[(size_t)r * kBH + u] + dht * og * (1.f - tc * tc);
@@ -117,43 +190,182 @@ __global__ void __launch_bounds__(kBH) bwd_cell_head_kernel(
     dg[2 * kBH + u] = dgg * (1.f - gg * gg);
     dg[3 * kBH + u] = dog * og * (1.f - og);
     dc[(size_t)r * kBH + u] = dct * fg;
-    dh[(size_t)r * kBH + u] = 0.f;        // the recurrent part arrives from dgates . W_hh
 }
 
-// C[n][k] += sum_r A[r][n] * B[r][k]     A [R, lda] (n < N), B [R, ldb] (k < Kc), C [N, ldc]
-__global__ void __launch_bounds__(256) gemm_tn_accum_kernel(const float* __restrict__ A, int lda,
-                                                            const float* __restrict__ B, int ldb,
-                                                            float* __restrict__ C, int ldc, int R, int N, int Kc) {
-    __shared__ float As[16][64 + 1];
-    __shared__ float Bs[16][64 + 1];
+// ------------------------------------------------------------------------------------------
+// Tiled fp32 GEMMs of the backward (64 x 64 tiles, 32-deep slices, register prefetch of the next
+// slice so one global-load latency is paid per slice instead of per 16 products).
+//   gemm_kernel<BT>:  C[M,N] = A[M,K] . op(B) (+ bias[n]);  op(B) = B[K,N] or (BT) B[N,K]^T
+//   gemm_tn_kernel :  C[n][k] (+)= sum_r A[r][n] * B[r][k]   (weight gradients; one CTA owns a
+//                     tile of C and walks all rows: deterministic)
+// ------------------------------------------------------------------------------------------
+constexpr int kGT = 64, kGK = 32;
+
+__device__ __forceinline__ float4 ld4(const float* base, size_t row, int ld, int col, int rows, int cols,
+                                      bool vec) {
+    // 4 consecutive elements of a row-major matrix, zero outside [rows, cols)
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((int)row >= rows) return v;
+    const float* p = base + row * (size_t)ld + col;
+    if (vec && col + 3 < cols) return *reinterpret_cast<const float4*>(p);
+    if (col < cols) v.x = p[0];
+    if (col + 1 < cols) v.y = p[1];
+    if (col + 2 < cols) v.z = p[2];
+    if (col + 3 < cols) v.w = p[3];
+    return v;
+}
+
+template <bool BT, int TM>
+__global__ void __launch_bounds__(TM * 4) gemm_kernel(const float* __restrict__ A, int lda,
+                                                      const float* __restrict__ B, int ldb,
+                                                      float* __restrict__ Cm, int ldc, int M, int N, int K,
+                                                      const float* __restrict__ bias, int vec) {
+    constexpr int NT = TM * 4;                 // threads; each owns a 4 x 4 micro-tile of TM x 64
+    constexpr int LA = TM * 8 / NT;            // float4 loads per thread for the A slice (TM x 32) = 2
+    constexpr int LB = 64 * 8 / NT;            // ... for the B slice (64 x 32): 2 (TM = 64) or 4 (TM = 32)
+    __shared__ __align__(16) float As[kGK][TM + 4];
+    __shared__ __align__(16) float Bs[kGK][kGT + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int n0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * kGT;
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int r0 = 0; r0 < R; r0 += 16) {
-        for (int idx = tid; idx < 16 * 64; idx += 256) {
-            const int rr = idx >> 6, cc = idx & 63;
-            const int r = r0 + rr;
-            As[rr][cc] = (r < R && n0 + cc < N) ? A[(size_t)r * lda + n0 + cc] : 0.f;
-            Bs[rr][cc] = (r < R && k0 + cc < Kc) ? B[(size_t)r * ldb + k0 + cc] : 0.f;
+    float4 ra[LA], rb[LB];
+    auto load = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < LA; ++i) {
+            const int f = tid + i * NT, row = f >> 3, kq = (f & 7) * 4;      // TM rows x 32 k
+            ra[i] = ld4(A, (size_t)(m0 + row), lda, k0 + kq, M, K, vec);
         }
-        __syncthreads();
 #pragma unroll
-        for (int rr = 0; rr < 16; ++rr) {
-            float a[4], b[4];
+        for (int i = 0; i < LB; ++i) {
+            const int f = tid + i * NT;
+            if (BT) {
+                const int row = f >> 3, kq = (f & 7) * 4;                    // 64 n x 32 k
+                rb[i] = ld4(B, (size_t)(n0 + row), ldb, k0 + kq, N, K, vec);
+            } else {
+                const int kk = f >> 4, nq = (f & 15) * 4;                    // 32 k x 64 n
+                rb[i] = ld4(B, (size_t)(k0 + kk), ldb, n0 + nq, K, N, vec);
+            }
+        }
+    };
+    auto store = [&]() {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[rr][ty * 4 + i];
+        for (int i = 0; i < LA; ++i) {
+            const int f = tid + i * NT, row = f >> 3, kq = (f & 7) * 4;
+            As[kq + 0][row] = ra[i].x; As[kq + 1][row] = ra[i].y; As[kq + 2][row] = ra[i].z; As[kq + 3][row] = ra[i].w;
+        }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[rr][tx * 4 + j];
+        for (int i = 0; i < LB; ++i) {
+            const int f = tid + i * NT;
+            if (BT) {
+                const int row = f >> 3, kq = (f & 7) * 4;
+                Bs[kq + 0][row] = rb[i].x; Bs[kq + 1][row] = rb[i].y; Bs[kq + 2][row] = rb[i].z; Bs[kq + 3][row] = rb[i].w;
+            } else {
+                const int kk = f >> 4, nq = (f & 15) * 4;
+                *reinterpret_cast<float4*>(&Bs[kk][nq]) = rb[i];
+            }
+        }
+    };
+    load(0);
+    store();
+    __syncthreads();
+    for (int k0 = 0; k0 < K; k0 += kGK) {
+        const bool more = k0 + kGK < K;
+        if (more) load(k0 + kGK);
+#pragma unroll
+        for (int kk = 0; kk < kGK; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
         __syncthreads();
+        if (more) {
+            store();
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n < N) Cm[(size_t)m * ldc + n] = acc[i][j] + (bias ? bias[n] : 0.f);
+        }
+    }
+}
+
+template <int TN>
+__global__ void __launch_bounds__(TN * 4) gemm_tn_kernel(const float* __restrict__ A, int lda,
+                                                         const float* __restrict__ B, int ldb,
+                                                         float* __restrict__ Cm, int ldc, int R, int N, int Kc,
+                                                         int vec) {
+    constexpr int NT = TN * 4;
+    constexpr int LA = TN * 8 / NT;            // A slice: 32 rows x TN cols
+    constexpr int LB = 64 * 8 / NT;            // B slice: 32 rows x 64 cols
+    __shared__ __align__(16) float As[kGK][TN + 4];
+    __shared__ __align__(16) float Bs[kGK][kGT + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int n0 = blockIdx.y * TN, k0c = blockIdx.x * kGT;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float4 ra[LA], rb[LB];
+    auto load = [&](int r0) {
+#pragma unroll
+        for (int i = 0; i < LA; ++i) {
+            const int f = tid + i * NT, rr = f / (TN / 4), cq = (f % (TN / 4)) * 4;
+            ra[i] = ld4(A, (size_t)(r0 + rr), lda, n0 + cq, R, N, vec);
+        }
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+            const int f = tid + i * NT, rr = f >> 4, cq = (f & 15) * 4;
+            rb[i] = ld4(B, (size_t)(r0 + rr), ldb, k0c + cq, R, Kc, vec);
+        }
+    };
+    auto store = [&]() {
+#pragma unroll
+        for (int i = 0; i < LA; ++i) {
+            const int f = tid + i * NT, rr = f / (TN / 4), cq = (f % (TN / 4)) * 4;
+            *reinterpret_cast<float4*>(&As[rr][cq]) = ra[i];
+        }
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+            const int f = tid + i * NT, rr = f >> 4, cq = (f & 15) * 4;
+            *reinterpret_cast<float4*>(&Bs[rr][cq]) = rb[i];
+        }
+    };
+    load(0);
+    store();
+    __syncthreads();
+    for (int r0 = 0; r0 < R; r0 += kGK) {
+        const bool more = r0 + kGK < R;
+        if (more) load(r0 + kGK);
+#pragma unroll
+        for (int rr = 0; rr < kGK; ++rr) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[rr][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[rr][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+        if (more) {
+            store();
+            __syncthreads();
+        }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -161,84 +373,166 @@ __global__ void __launch_bounds__(256) gemm_tn_accum_kernel(const float* __restr
         if (n >= N) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int k = k0 + tx * 4 + j;
-            if (k < Kc) C[(size_t)n * ldc + k] += acc[i][j];
+            const int k = k0c + tx * 4 + j;
+            if (k < Kc) Cm[(size_t)n * ldc + k] += acc[i][j];
         }
     }
 }
 
-// out[n] (+ out2[n]) += sum_r A[r][n]
-__global__ void colsum_accum_kernel(const float* __restrict__ A, int lda, int R, int N, float* __restrict__ out,
-                                    float* __restrict__ out2) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    float s = 0.f;
-    for (int r = 0; r < R; ++r) s += A[(size_t)r * lda + n];
-    out[n] += s;
-    if (out2) out2[n] += s;
+// same product, rows split over gridDim.z: slice z writes its partial tile sums to part[z][n][k]
+// (dense N x Kc); reduce_partials_kernel adds the slices in a fixed order.
+template <int TN>
+__global__ void __launch_bounds__(TN * 4) gemm_tn_split_kernel(const float* __restrict__ A, int lda,
+                                                               const float* __restrict__ B, int ldb,
+                                                               float* __restrict__ part, int R, int N, int Kc,
+                                                               int rows_per_slice, int vec) {
+    constexpr int NT = TN * 4;
+    constexpr int LA = TN * 8 / NT;
+    constexpr int LB = 64 * 8 / NT;
+    __shared__ __align__(16) float As[kGK][TN + 4];
+    __shared__ __align__(16) float Bs[kGK][kGT + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int n0 = blockIdx.y * TN, k0c = blockIdx.x * kGT;
+    const int rbeg = blockIdx.z * rows_per_slice, rend = min(R, rbeg + rows_per_slice);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float4 ra[LA], rb[LB];
+    auto load = [&](int r0) {
+#pragma unroll
+        for (int i = 0; i < LA; ++i) {
+            const int f = tid + i * NT, rr = f / (TN / 4), cq = (f % (TN / 4)) * 4;
+            ra[i] = ld4(A, (size_t)(r0 + rr), lda, n0 + cq, rend, N, vec);
+        }
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+            const int f = tid + i * NT, rr = f >> 4, cq = (f & 15) * 4;
+            rb[i] = ld4(B, (size_t)(r0 + rr), ldb, k0c + cq, rend, Kc, vec);
+        }
+    };
+    auto store = [&]() {
+#pragma unroll
+        for (int i = 0; i < LA; ++i) {
+            const int f = tid + i * NT, rr = f / (TN / 4), cq = (f % (TN / 4)) * 4;
+            *reinterpret_cast<float4*>(&As[rr][cq]) = ra[i];
+        }
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+            const int f = tid + i * NT, rr = f >> 4, cq = (f & 15) * 4;
+            *reinterpret_cast<float4*>(&Bs[rr][cq]) = rb[i];
+        }
+    };
+    if (rbeg < rend) {
+        load(rbeg);
+        store();
+    }
+    __syncthreads();
+    for (int r0 = rbeg; r0 < rend; r0 += kGK) {
+        const bool more = r0 + kGK < rend;
+        if (more) load(r0 + kGK);
+#pragma unroll
+        for (int rr = 0; rr < kGK; ++rr) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[rr][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[rr][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+        if (more) {
+            store();
+            __syncthreads();
+        }
+    }
+    float* out = part + (size_t)blockIdx.z * N * Kc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + ty * 4 + i;
+        if (n >= N) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0c + tx * 4 + j;
+            if (k < Kc) out[(size_t)n * Kc + k] = acc[i][j];
+        }
+    }
 }
 
-// InputEmbedding backward (modules.py:24-30): d pre[k] = dX[r][k] * (emb > 0); one thread per k
-__global__ void bwd_embed_kernel(const int* __restrict__ rows, const int* __restrict__ masked, int R,
-                                 const float2* __restrict__ obs1, const float2* __restrict__ obs2,
-                                 const float* __restrict__ X, int ldx, const float* __restrict__ dX, int lddx,
-                                 float* __restrict__ dWe, float* __restrict__ dbe, int E) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= E - 2) return;
+// C[n][k] (ldc) += sum_z part[z][n][k];  also used for column sums (N = 1)
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int Z, int N, int Kc, float* __restrict__ C,
+                                       int ldc, float* __restrict__ C2) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)N * Kc) return;
+    float s = 0.f;
+    for (int z = 0; z < Z; ++z) s += part[(size_t)z * N * Kc + idx];
+    const size_t n = idx / Kc, k = idx - n * Kc;
+    C[n * ldc + k] += s;
+    if (C2) C2[n * ldc + k] += s;
+}
+
+// part[z][n] = sum over the rows of slice z of A[r][n]
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ A, int lda, int R, int N,
+                                                             int rows_per_slice, float* __restrict__ part) {
+    __shared__ float sm[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + cx;
+    const int rbeg = blockIdx.y * rows_per_slice, rend = min(R, rbeg + rows_per_slice);
+    float s = 0.f;
+    if (n < N)
+        for (int r = rbeg + ry; r < rend; r += 8) s += A[(size_t)r * lda + n];
+    sm[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += sm[q][cx];
+        part[(size_t)blockIdx.y * N + n] = t;
+    }
+}
+
+// dz = dX_pooled * (pooled > 0) in place (one_layer: pooled = relu(W1 grid + b1))
+__global__ void relu_mask_kernel(const float* __restrict__ X, int ldx, float* __restrict__ dX, int ldd, int rows,
+                                 int E, int P) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)rows * P) return;
+    const size_t r = idx / P;
+    const int o = (int)(idx - r * P);
+    if (!(X[r * ldx + E + o] > 0.f)) dX[r * ldd + E + o] = 0.f;
+}
+
+// InputEmbedding backward (modules.py:24-30) over all saved (step, row) pairs: one CTA per
+// embedding unit k, d pre[k] = dX[k] * (emb[k] > 0), fixed-order tree reduction.
+__global__ void __launch_bounds__(256) bwd_embed_kernel(const float* __restrict__ X, int ldx,
+                                                        const float* __restrict__ dXe, int ldd,
+                                                        const float* __restrict__ vel, int rows_total,
+                                                        float* __restrict__ dWe, float* __restrict__ dbe) {
+    __shared__ float red[3][256];
+    const int k = blockIdx.x, t = threadIdx.x;
     float gx = 0.f, gy = 0.f, gb = 0.f;
-    for (int r = 0; r < R; ++r) {
-        if (masked[r]) continue;
+    for (int r = t; r < rows_total; r += 256) {
         if (X[(size_t)r * ldx + k] > 0.f) {
-            const int m = rows[r];
-            const float2 a = obs1[m], b = obs2[m];
-            const float d = dX[(size_t)r * lddx + k];
-            gx = fmaf(d, (b.x - a.x) * 4.0f, gx);
-            gy = fmaf(d, (b.y - a.y) * 4.0f, gy);
+            const float d = dXe[(size_t)r * ldd + k];
+            gx = fmaf(d, vel[2 * r], gx);
+            gy = fmaf(d, vel[2 * r + 1], gy);
             gb += d;
         }
     }
-    dWe[2 * k] += gx;
-    dWe[2 * k + 1] += gy;
-    dbe[k] += gb;
-}
-
-// First grid-embedding layer backward (one_layer: pooled = relu(W1 grid + b1)), sparse grid:
-//   dz[o] = dX[r][E + o] * (pooled > 0);  db1[o] += dz;  dW1[o][c * cells + cell] += dz[o] * val
-__global__ void bwd_pool1_kernel(const int* __restrict__ rows, const int* __restrict__ masked, int R,
-                                 const float* __restrict__ X, int ldx, const float* __restrict__ dX, int lddx,
-                                 const int* __restrict__ win_count, const uint32_t* __restrict__ win_ent,
-                                 const float* __restrict__ win_val, int nm1, int C, int cells, int E, int P,
-                                 float* __restrict__ dW1, float* __restrict__ dz_out) {
-    const int r = blockIdx.x;
-    const int m = rows[r];
-    const bool msk = masked[r] != 0;
-    const int cnt = msk ? 0 : win_count[m];
-    for (int o = threadIdx.x; o < P; o += blockDim.x) {
-        float dz = 0.f;
-        if (!msk && X[(size_t)r * ldx + E + o] > 0.f) dz = dX[(size_t)r * lddx + E + o];
-        dz_out[(size_t)r * P + o] = dz;
-        if (dz != 0.f) {
-            float* wrow = dW1 + (size_t)o * C * cells;
-            for (int e = 0; e < cnt; ++e) {
-                const uint32_t ent = win_ent[(size_t)m * nm1 + e];
-                const int cell = ent >> 16;
-                for (int c = 0; c < C; ++c)
-                    atomicAdd(&wrow[c * cells + cell], dz * win_val[((size_t)m * nm1 + e) * 2 + c]);
-            }
+    red[0][t] = gx; red[1][t] = gy; red[2][t] = gb;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (t < s) {
+            red[0][t] += red[0][t + s]; red[1][t] += red[1][t + s]; red[2][t] += red[2][t + s];
         }
+        __syncthreads();
     }
-}
-
-__global__ void add_masked_passthrough_kernel(const int* __restrict__ masked, const float* __restrict__ dh_keep,
-                                              float* __restrict__ dh_new, int R) {
-    // masked rows: dh passes through unchanged (their dgates are zero so dh_new is zero there)
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= R * kBH) return;
-    if (masked[idx / kBH]) dh_new[idx] = dh_keep[idx];
-}
-
-__global__ void fill_kernel(float* __restrict__ p, float v, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+    if (t == 0) {
+        dWe[2 * k] += red[0][0];
+        dWe[2 * k + 1] += red[1][0];
+        dbe[k] += red[2][0];
+    }
 }
 
 }  // namespace tb2
@@ -246,29 +540,137 @@ __global__ void fill_kernel(float* __restrict__ p, float v, size_t n) {
 using namespace tb2;
 
 namespace tb2 {
-int launch_dense_plain(const float* X, const float* WT, const float* b, float* Y, int M, int K, int N, int relu,
-                       cudaStream_t st);
 int resolve_step_inputs(const tb2_layout* l, const float* observed, int obs_length, const float* truth,
                         const float* positions, int s, Workspace* ws, const float** o1, const float** o2,
                         int* phase, cudaStream_t st);
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// C = A . B (+bias), B [K, N] row-major
+static int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
+                   const float* bias, cudaStream_t st) {
+    const int vec = (lda % 4 == 0 && ldb % 4 == 0 && aligned16(A) && aligned16(B)) ? 1 : 0;
+    const bool small = (size_t)((M + 63) / 64) * ((N + kGT - 1) / kGT) < 148;     // few tiles: halve them
+    {
+        KernelTimer kt("bwd_gemm", st);
+        if (small)
+            gemm_kernel<false, 32><<<dim3((N + kGT - 1) / kGT, (M + 31) / 32), 128, 0, st>>>(A, lda, B, ldb, C, ldc, M,
+                                                                                         N, K, bias, vec);
+        else
+            gemm_kernel<false, 64><<<dim3((N + kGT - 1) / kGT, (M + 63) / 64), 256, 0, st>>>(A, lda, B, ldb, C, ldc, M,
+                                                                                         N, K, bias, vec);
+    }
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
 }
+
+// C = A . B^T, B [N, K] row-major
+static int gemm_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
+                   cudaStream_t st) {
+    const int vec = (lda % 4 == 0 && ldb % 4 == 0 && aligned16(A) && aligned16(B)) ? 1 : 0;
+    const bool small = (size_t)((M + 63) / 64) * ((N + kGT - 1) / kGT) < 148;
+    {
+        KernelTimer kt("bwd_gemm", st);
+        if (small)
+            gemm_kernel<true, 32><<<dim3((N + kGT - 1) / kGT, (M + 31) / 32), 128, 0, st>>>(A, lda, B, ldb, C, ldc, M,
+                                                                                        N, K, nullptr, vec);
+        else
+            gemm_kernel<true, 64><<<dim3((N + kGT - 1) / kGT, (M + 63) / 64), 256, 0, st>>>(A, lda, B, ldb, C, ldc, M,
+                                                                                        N, K, nullptr, vec);
+    }
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
+}
+
+// C[n][k] += sum_r A[r][n] B[r][k]; rows are split over CTAs when the output has few tiles
+// (partials in `scratch`, summed in a fixed order: run-to-run deterministic)
+static int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int R, int N, int Kc,
+                   float* scratch, size_t scratch_floats, cudaStream_t st) {
+    if (R <= 0) return TB2_OK;
+    const int vec = (lda % 4 == 0 && ldb % 4 == 0 && aligned16(A) && aligned16(B)) ? 1 : 0;
+    const int tiles32 = ((N + 31) / 32) * ((Kc + kGT - 1) / kGT);
+    int Z = (2 * 148 + tiles32 - 1) / tiles32;
+    if (Z > (R + 127) / 128) Z = (R + 127) / 128;
+    while (Z > 1 && (size_t)Z * N * Kc > scratch_floats) --Z;
+    if (Z <= 1) {
+        KernelTimer kt("bwd_gemm_tn", st);
+        gemm_tn_kernel<32><<<dim3((Kc + kGT - 1) / kGT, (N + 31) / 32), 128, 0, st>>>(A, lda, B, ldb, C, ldc, R, N, Kc,
+                                                                                  vec);
+    } else {
+        int rps = (R + Z - 1) / Z;
+        rps = (rps + kGK - 1) / kGK * kGK;
+        Z = (R + rps - 1) / rps;
+        KernelTimer kt("bwd_gemm_tn", st);
+        gemm_tn_split_kernel<32><<<dim3((Kc + kGT - 1) / kGT, (N + 31) / 32, Z), 128, 0, st>>>(A, lda, B, ldb, scratch,
+                                                                                           R, N, Kc, rps, vec);
+        reduce_partials_kernel<<<(unsigned)(((size_t)N * Kc + 255) / 256), 256, 0, st>>>(scratch, Z, N, Kc, C, ldc,
+                                                                                      nullptr);
+    }
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
+}
+
+static int colsum(const float* A, int lda, int R, int N, float* out, float* out2, float* scratch,
+                  size_t scratch_floats, cudaStream_t st) {
+    if (R <= 0) return TB2_OK;
+    int Z = (R + 63) / 64;
+    if (Z > 64) Z = 64;
+    while (Z > 1 && (size_t)Z * N > scratch_floats) --Z;
+    const int rps = (R + Z - 1) / Z;
+    Z = (R + rps - 1) / rps;
+    colsum_partial_kernel<<<dim3((N + 31) / 32, Z), 256, 0, st>>>(A, lda, R, N, rps, scratch);
+    reduce_partials_kernel<<<(N + 255) / 256, 256, 0, st>>>(scratch, Z, 1, N, out, N, out2);
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
+}
+
+// Carving of the backward workspace (floats).  Per (step, row) records are kept so that every
+// weight gradient is one reduction over all S * R rows after the time loop.
+struct BwdBuffers {
+    float *X, *GP, *DG, *HS, *DN, *VEL, *DXIN, *G;     // [S][R][K | 512 | 512 | 128 | 8 | 2 | E+P | C n n]
+    float *pass[2], *dc;                               // [R][128] chain state
+    float* scratch;                                    // partial sums of the row-split reductions
+    size_t scratch_floats;
+    int* masked;                                       // [S][R]
+};
+
+static size_t carve_bwd(const tb2_lstm* m, size_t R, size_t S, void* base, BwdBuffers* b) {
+    const size_t K = (size_t)m->K_gate, E = (size_t)m->E, P = (size_t)(m->P > 0 ? m->P : 0);
+    size_t off = 0;
+    auto take = [&](size_t n) {
+        float* p = base ? reinterpret_cast<float*>(base) + off : nullptr;
+        off += (n + 3) & ~(size_t)3;       // keep every array 16-byte aligned
+        return p;
+    };
+    BwdBuffers tmp;
+    BwdBuffers* o = b ? b : &tmp;
+    const size_t CG = (size_t)m->C * (size_t)m->cells;
+    o->X = take(S * R * K);
+    o->GP = take(S * R * 512);
+    o->DG = take(S * R * 512);
+    o->HS = take(S * R * 128);
+    o->DN = take(S * R * 8);
+    o->VEL = take(S * R * 2);
+    o->DXIN = take(S * R * (E + P));
+    o->G = take(P ? S * R * CG : 4);
+    o->pass[0] = take(R * 128);
+    o->pass[1] = take(R * 128);
+    o->dc = take(R * 128);
+    size_t big = 512 * K;
+    if (P * CG > big) big = P * CG;
+    o->scratch_floats = 8 * big;
+    o->scratch = take(o->scratch_floats);
+    o->masked = reinterpret_cast<int*>(take(S * R));
+    return off * sizeof(float) + 256;
+}
+}  // namespace tb2
 
 extern "C" {
 
-size_t tb2_lstm_backward_workspace_bytes(const tb2_lstm* m, int32_t num_active) {
-    if (!m || num_active < 0) return 0;
-    const size_t R = (size_t)(num_active > 0 ? num_active : 1);
-    const size_t K = (size_t)m->K_gate;
-    size_t f = 0;
-    f += R * K;                 // X_act
-    f += R * 512 * 2;           // gates_pre, dgates
-    f += R * K;                 // dX (input part, width E + P; padded to K)
-    f += R * 128 * 4;           // dh, dh_new, dc, hs
-    f += R * 8;                 // dn_raw (5, padded)
-    f += R * (size_t)(m->P > 0 ? m->P : 1);   // dz
-    f += 1024;                  // zero bias
-    f += R;                     // masked flags (int)
-    return f * sizeof(float) + 4096;
+size_t tb2_lstm_backward_workspace_bytes(const tb2_lstm* m, int32_t num_active, int32_t num_steps) {
+    if (!m || num_active < 0 || num_steps < 0) return 0;
+    return carve_bwd(m, (size_t)(num_active > 0 ? num_active : 1), (size_t)(num_steps > 0 ? num_steps : 1),
+                     nullptr, nullptr);
 }
 
 int tb2_lstm_sequence_backward(const tb2_lstm* m, const tb2_layout* l, const tb2_lstm_weights* w,
@@ -287,12 +689,13 @@ int tb2_lstm_sequence_backward(const tb2_lstm* m, const tb2_layout* l, const tb2
         return TB2_ERR_UNSUPPORTED;
     }
     if (m->cfg.pool_type != TB2_POOL_NONE &&
-        (m->n_mlp != 1 || !m->cfg.pool_to_input || m->cfg.constant != 0.f)) {
+        (m->n_mlp != 1 || !m->cfg.pool_to_input || m->cfg.constant != 0.f || m->P > 1024 || m->C > 2)) {
         set_error("training backward supports one_layer grid embeddings with constant = 0 and pool_to_input");
         return TB2_ERR_UNSUPPORTED;
     }
+    const int S = obs_length - 1 + n_decode;
     TB2_REQUIRE(workspace && workspace_bytes >= carve_workspace(m, l, nullptr, nullptr), "workspace too small");
-    TB2_REQUIRE(bwd_workspace && bwd_workspace_bytes >= tb2_lstm_backward_workspace_bytes(m, num_active),
+    TB2_REQUIRE(bwd_workspace && bwd_workspace_bytes >= tb2_lstm_backward_workspace_bytes(m, num_active, S),
                 "backward workspace too small");
     if (num_active == 0) return TB2_OK;
     cudaStream_t st = (cudaStream_t)stream;
@@ -300,75 +703,90 @@ int tb2_lstm_sequence_backward(const tb2_lstm* m, const tb2_layout* l, const tb2
     carve_workspace(m, l, workspace, &ws);
     const int R = num_active, K = m->K_gate, E = m->E, P = m->P, EP = E + P;
     const size_t M = (size_t)l->M;
-    float* f = (float*)bwd_workspace;
-    float* X = f;              f += (size_t)R * K;
-    float* gates_pre = f;      f += (size_t)R * 512;
-    float* dgates = f;         f += (size_t)R * 512;
-    float* dX = f;             f += (size_t)R * K;
-    float* dh = f;             f += (size_t)R * 128;
-    float* dh_new = f;         f += (size_t)R * 128;
-    float* dc = f;             f += (size_t)R * 128;
-    float* hs = f;             f += (size_t)R * 128;
-    float* dn_raw = f;         f += (size_t)R * 8;
-    float* dz = f;             f += (size_t)R * (size_t)(P > 0 ? P : 1);
-    float* zero_bias = f;      f += 1024;
-    int* masked = (int*)f;
-    TB2_CHECK_CUDA(cudaMemsetAsync(dh, 0, (size_t)R * 128 * sizeof(float), st));
-    TB2_CHECK_CUDA(cudaMemsetAsync(dc, 0, (size_t)R * 128 * sizeof(float), st));
-    TB2_CHECK_CUDA(cudaMemsetAsync(zero_bias, 0, 1024 * sizeof(float), st));
-    const int S = obs_length - 1 + n_decode;
+    BwdBuffers b;
+    carve_bwd(m, (size_t)R, (size_t)S, bwd_workspace, &b);
+    TB2_CHECK_CUDA(cudaMemsetAsync(b.dc, 0, (size_t)R * 128 * sizeof(float), st));
     const int nm1 = l->n_max > 1 ? l->n_max - 1 : 1;
+    const bool pooled = m->cfg.pool_type != TB2_POOL_NONE;
+    const size_t CG = (size_t)m->C * (size_t)m->cells;
+    const int S_enc = obs_length - 1;
     int rc;
-    for (int s = S - 1; s >= 0; --s) {
+    // (A) inputs of every step for the active rows: winners -> X = [emb | pooled | h_prev], grid rows
+    for (int s = 0; s < S; ++s) {
         const float *o1, *o2;
         int phase;
         if ((rc = resolve_step_inputs(l, observed, obs_length, truth, positions, s, &ws, &o1, &o2, &phase, st))) return rc;
         const float* h_prev = s > 0 ? states + ((size_t)(s - 1) * 2 + 0) * M * kBH : nullptr;
-        const float* c_prev = s > 0 ? states + ((size_t)(s - 1) * 2 + 1) * M * kBH : nullptr;
-        if (m->cfg.pool_type != TB2_POOL_NONE) {
-            if ((rc = launch_pool_prepare(m, l, h_prev, o1, o2, 1, 0, 0, &ws, st))) return rc;
-            if ((rc = launch_pool_mlp(m, l, &ws, ws.pooled, nullptr, nullptr, st))) return rc;
+        if (pooled && (rc = launch_pool_prepare(m, l, h_prev, o1, o2, 1, 0, 0, &ws, st))) return rc;   // winners
+        {
+            KernelTimer kt("bwd_gather", st);
+            bwd_gather_kernel<<<R, 256, 0, st>>>(active_rows, R, (const float2*)o1, (const float2*)o2, m->We, m->be,
+                                                 h_prev, ws.win_count, ws.win_ent, ws.win_val, m->Wt1, m->base1,
+                                                 nm1, m->C, m->cells, b.X + (size_t)s * R * K,
+                                                 pooled ? b.G + (size_t)s * R * CG : nullptr,
+                                                 b.VEL + (size_t)s * R * 2, b.masked + (size_t)s * R, E, P, K);
         }
-        bwd_gather_kernel<<<R, 128, 0, st>>>(active_rows, R, (const float2*)o1, (const float2*)o2, m->We, m->be,
-                                             ws.pooled, h_prev, X, masked, E, P, K);
         TB2_LAUNCH_CHECK();
-        if ((rc = launch_dense_plain(X, m->WgT[phase], m->bg[phase], gates_pre, R, K, 512, 0, st))) return rc;
-        bwd_cell_head_kernel<<<R, kBH, 0, st>>>(active_rows, masked, gates_pre, c_prev, dh, dc,
-                                                d_normals + (size_t)s * M * 5, m->Wn, m->bn, dgates, hs, dn_raw, R);
+    }
+    // (B) gate pre-activations of all steps: one GEMM per cell (encoder / decoder weights)
+    for (int phase = 0; phase < 2; ++phase) {
+        const int s0 = phase == TB2_PHASE_ENCODER ? 0 : S_enc;
+        const int ns = phase == TB2_PHASE_ENCODER ? S_enc : S - S_enc;
+        if (ns <= 0) continue;
+        if ((rc = gemm_nn(b.X + (size_t)s0 * R * K, K, m->WgT[phase], 512, b.GP + (size_t)s0 * R * 512, 512, ns * R,
+                          512, K, m->bg[phase], st)))
+            return rc;
+    }
+    // (C) the sequential chain: one kernel per step
+    int cur = 0;
+    for (int s = S - 1; s >= 0; --s, cur ^= 1) {
+        const float* c_prev = s > 0 ? states + ((size_t)(s - 1) * 2 + 1) * M * kBH : nullptr;
+        const bool last = s == S - 1;
+        const int next_phase = (s + 1) < S_enc ? TB2_PHASE_ENCODER : TB2_PHASE_DECODER;
+        const float* Whh_next = next_phase == TB2_PHASE_ENCODER ? w->encoder_weight_hh : w->decoder_weight_hh;
+        {
+            KernelTimer kt("bwd_cell_head", st);
+            bwd_cell_head_kernel<<<R, kBH, 0, st>>>(
+                active_rows, b.masked + (size_t)s * R, b.GP + (size_t)s * R * 512, c_prev,
+                last ? nullptr : b.DG + (size_t)(s + 1) * R * 512, Whh_next, b.pass[cur ^ 1], b.pass[cur], b.dc,
+                d_normals + (size_t)s * M * 5, m->Wn, m->bn, b.DG + (size_t)s * R * 512,
+                b.HS + (size_t)s * R * 128, b.DN + (size_t)s * R * 8, R);
+        }
         TB2_LAUNCH_CHECK();
-        // weight gradients
+    }
+    // (D) + (E) input gradients of all steps and the parameter gradients: one reduction per tensor
+    for (int phase = 0; phase < 2; ++phase) {
+        const int s0 = phase == TB2_PHASE_ENCODER ? 0 : S_enc;
+        const int ns = phase == TB2_PHASE_ENCODER ? S_enc : S - S_enc;
+        if (ns <= 0) continue;
+        const float* DG = b.DG + (size_t)s0 * R * 512;
+        const float* X = b.X + (size_t)s0 * R * K;
+        const int rows = ns * R;
         float* gWih = phase == TB2_PHASE_ENCODER ? g->encoder_weight_ih : g->decoder_weight_ih;
         float* gWhh = phase == TB2_PHASE_ENCODER ? g->encoder_weight_hh : g->decoder_weight_hh;
         float* gbih = phase == TB2_PHASE_ENCODER ? g->encoder_bias_ih : g->decoder_bias_ih;
         float* gbhh = phase == TB2_PHASE_ENCODER ? g->encoder_bias_hh : g->decoder_bias_hh;
         const float* Wih = phase == TB2_PHASE_ENCODER ? w->encoder_weight_ih : w->decoder_weight_ih;
-        const float* Whh = phase == TB2_PHASE_ENCODER ? w->encoder_weight_hh : w->decoder_weight_hh;
-        gemm_tn_accum_kernel<<<dim3((EP + 63) / 64, 8), 256, 0, st>>>(dgates, 512, X, K, gWih, EP, R, 512, EP);
+        // dX_in = dgates . W_ih   (torch layout [4H, E+P] is the [K = 4H, N = E+P] operand as it stands)
+        if ((rc = gemm_nn(DG, 512, Wih, EP, b.DXIN + (size_t)s0 * R * EP, EP, rows, EP, 512, nullptr, st))) return rc;
+        if ((rc = gemm_tn(DG, 512, X, K, gWih, EP, rows, 512, EP, b.scratch, b.scratch_floats, st))) return rc;
+        if ((rc = gemm_tn(DG, 512, X + EP, K, gWhh, 128, rows, 512, 128, b.scratch, b.scratch_floats, st))) return rc;
+        if ((rc = colsum(DG, 512, rows, 512, gbih, gbhh, b.scratch, b.scratch_floats, st))) return rc;
+    }
+    if ((rc = gemm_tn(b.DN, 8, b.HS, 128, g->hidden2normal_weight, 128, S * R, 5, 128, b.scratch, b.scratch_floats, st)))
+        return rc;
+    if ((rc = colsum(b.DN, 8, S * R, 5, g->hidden2normal_bias, nullptr, b.scratch, b.scratch_floats, st))) return rc;
+    bwd_embed_kernel<<<E - 2, 256, 0, st>>>(b.X, K, b.DXIN, EP, b.VEL, S * R, g->input_embedding_weight,
+                                            g->input_embedding_bias);
+    TB2_LAUNCH_CHECK();
+    if (pooled) {
+        relu_mask_kernel<<<(unsigned)(((size_t)S * R * P + 255) / 256), 256, 0, st>>>(b.X, K, b.DXIN, EP, S * R, E, P);
         TB2_LAUNCH_CHECK();
-        gemm_tn_accum_kernel<<<dim3(2, 8), 256, 0, st>>>(dgates, 512, X + EP, K, gWhh, 128, R, 512, 128);
-        TB2_LAUNCH_CHECK();
-        colsum_accum_kernel<<<2, 256, 0, st>>>(dgates, 512, R, 512, gbih, gbhh);
-        TB2_LAUNCH_CHECK();
-        gemm_tn_accum_kernel<<<dim3(2, 1), 256, 0, st>>>(dn_raw, 5, hs, 128, g->hidden2normal_weight, 128, R, 5, 128);
-        TB2_LAUNCH_CHECK();
-        colsum_accum_kernel<<<1, 32, 0, st>>>(dn_raw, 5, R, 5, g->hidden2normal_bias, nullptr);
-        TB2_LAUNCH_CHECK();
-        // input gradients: dX = dgates . W_ih  (torch layout [512, E+P] read as WT[k = gate][n])
-        if ((rc = launch_dense_plain(dgates, Wih, zero_bias, dX, R, 512, EP, 0, st))) return rc;
-        if ((rc = launch_dense_plain(dgates, Whh, zero_bias, dh_new, R, 512, 128, 0, st))) return rc;
-        add_masked_passthrough_kernel<<<(R * kBH + 255) / 256, 256, 0, st>>>(masked, dh, dh_new, R);
-        TB2_LAUNCH_CHECK();
-        bwd_embed_kernel<<<1, 64, 0, st>>>(active_rows, masked, R, (const float2*)o1, (const float2*)o2, X, K, dX, EP,
-                                           g->input_embedding_weight, g->input_embedding_bias, E);
-        TB2_LAUNCH_CHECK();
-        if (m->cfg.pool_type != TB2_POOL_NONE) {
-            bwd_pool1_kernel<<<R, 256, 0, st>>>(active_rows, masked, R, X, K, dX, EP, ws.win_count, ws.win_ent,
-                                                ws.win_val, nm1, m->C, m->cells, E, P, g->pool_embedding_weight0, dz);
-            TB2_LAUNCH_CHECK();
-            colsum_accum_kernel<<<(P + 255) / 256, 256, 0, st>>>(dz, P, R, P, g->pool_embedding_bias0, nullptr);
-            TB2_LAUNCH_CHECK();
-        }
-        std::swap(dh, dh_new);
+        if ((rc = gemm_tn(b.DXIN + E, EP, b.G, (int)CG, g->pool_embedding_weight0, (int)CG, S * R, P, (int)CG,
+                          b.scratch, b.scratch_floats, st)))
+            return rc;
+        if ((rc = colsum(b.DXIN + E, EP, S * R, P, g->pool_embedding_bias0, nullptr, b.scratch, b.scratch_floats, st)))
+            return rc;
     }
     return TB2_OK;
 }

@@ -79,7 +79,7 @@ class _SequenceFn(torch.autograd.Function):
                 setattr(g, k, t.data_ptr())
             w, keep = handle.weights_struct(model._weight_fields())
             ws, need = handle.workspace(layout)
-            bneed = int(lib.tb2_lstm_backward_workspace_bytes(handle.handle, R))
+            bneed = int(lib.tb2_lstm_backward_workspace_bytes(handle.handle, R, S))
             bws = torch.empty(bneed, dtype=torch.uint8, device=device)
             pos_steps = positions[-S:].contiguous()
             n_decode = S - (int(ctx.obs.shape[0]) - 1)
