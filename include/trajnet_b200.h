@@ -179,12 +179,17 @@ typedef struct tb2_lstm_grads {
     float* decoder_bias_hh;
     float* hidden2normal_weight;     /* [5, H] */
     float* hidden2normal_bias;       /* [5] */
-    float* pool_embedding_weight0;   /* pool.embedding.0.weight grad [out_dim, C*n*n] (one_layer) or NULL */
-    float* pool_embedding_bias0;     /* [out_dim] or NULL */
+    float* pool_embedding_weight0;   /* pool.embedding.0.weight grad [d1, C*n*n] or NULL */
+    float* pool_embedding_bias0;     /* [d1] or NULL */
+    float* pool_embedding_weight1;   /* pool.embedding.2.weight grad [out_dim, d1] (two_layer, social) or NULL */
+    float* pool_embedding_bias1;     /* [out_dim] or NULL */
+    float* pool_encoding_weight;     /* pool.hidden_dim_encoding.weight grad [latent, H] (social) or NULL */
+    float* pool_encoding_bias;       /* [latent] or NULL */
 } tb2_lstm_grads;
 
 /* scratch for tb2_lstm_sequence_backward: per (step, active row) records + per-step buffers */
-size_t tb2_lstm_backward_workspace_bytes(const tb2_lstm* model, int32_t num_active, int32_t num_steps);
+size_t tb2_lstm_backward_workspace_bytes(const tb2_lstm* model, const tb2_layout* layout, int32_t num_active,
+                                         int32_t num_steps);
 
 /* BPTT over the rows that receive gradient.
  *   weights          the same fp32 parameter pointers given to tb2_lstm_set_weights
@@ -194,9 +199,11 @@ size_t tb2_lstm_backward_workspace_bytes(const tb2_lstm* model, int32_t num_acti
  *                    its first two columns by the caller: pred = obs2 + mu, lstm.py:232,255)
  *   active_rows_dev  int32 [num_active]: tracks with a non-zero upstream gradient (PredictionLoss
  *                    touches the scene primaries only, lstm/loss.py:57,67)
- * Supported: vanilla and occupancy / directional pooling with a one_layer embedding (the D-LSTM
- * training config); social pooling couples tracks through the hidden-state scatter and returns
- * TB2_ERR_UNSUPPORTED. */
+ * Supported: vanilla, occupancy / directional pooling with a one_layer embedding (the D-LSTM
+ * training config), and social pooling with a one_layer / two_layer embedding (constant = 0).
+ * Social pooling couples all tracks of a scene through the hidden-state scatter (the reference
+ * does not detach hidden_states_to_pool, lstm.py:26): the backward then runs on all M rows and
+ * active_rows is ignored. */
 int tb2_lstm_sequence_backward(const tb2_lstm* model, const tb2_layout* layout, const tb2_lstm_weights* weights,
                                const float* observed_dev, int32_t obs_length, const float* truth_dev,
                                int32_t n_decode, const float* positions_dev, const float* states_dev,

@@ -25,6 +25,9 @@ TRAIN_CASES = [
     ("train_vanilla", "vanilla", 5, 6, True, True, 31, 11),
     ("train_directional", "directional", 6, 8, True, True, 32, 12),
     ("train_occupancy", "occupancy", 4, 7, False, False, 33, 13),
+    # social pooling: the hidden-state scatter couples the tracks of a scene
+    ("train_social_small", "social_small", 5, 6, True, True, 34, 14),
+    ("train_social", "social", 4, 7, False, True, 35, 15),
 ]
 FULL_LIMIT = 20000
 N_SAMPLES = 2000

@@ -12,12 +12,12 @@ from trajnetplusplusbaselines_b200 import _lib
 from trajnetplusplusbaselines_b200.lstm import LSTM, GridBasedPooling, PredictionLoss
 
 kind = sys.argv[1] if len(sys.argv) > 1 else "directional"
-B, N = 256, 20
+B, N = int(os.environ.get("TB2_BENCH_SCENES", "256")), 20
 W = O.random_weights(kind, seed=1)
 model = LSTM(pool=GridBasedPooling(**O.MODEL_SPECS[kind]) if kind != "vanilla" else None)
 model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in W.items()})
 model = model.cuda().train()
-opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)
 crit = PredictionLoss()
 xy, bs = O.synthetic_scenes(B, N, seed=100)
 scene = torch.from_numpy(xy).cuda()

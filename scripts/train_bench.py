@@ -25,7 +25,7 @@ W = O.random_weights(kind, seed=1)
 model = LSTM(pool=GridBasedPooling(**O.MODEL_SPECS[kind]))
 model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in W.items()})
 model = model.cuda().train()
-opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=True)   # trainer.py:497 hyper-parameters
 crit = PredictionLoss()
 xy, bs = O.synthetic_scenes(B, N, seed=100 + rank)
 scene = torch.from_numpy(xy).cuda()

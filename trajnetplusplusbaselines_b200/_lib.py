@@ -62,7 +62,8 @@ class LstmGrads(ctypes.Structure):
         "encoder_weight_ih", "encoder_weight_hh", "encoder_bias_ih", "encoder_bias_hh",
         "decoder_weight_ih", "decoder_weight_hh", "decoder_bias_ih", "decoder_bias_hh",
         "hidden2normal_weight", "hidden2normal_bias",
-        "pool_embedding_weight0", "pool_embedding_bias0")]
+        "pool_embedding_weight0", "pool_embedding_bias0", "pool_embedding_weight1", "pool_embedding_bias1",
+        "pool_encoding_weight", "pool_encoding_bias")]
 
 
 class SfParams(ctypes.Structure):
@@ -112,7 +113,7 @@ PROTOTYPES = {
     "tb2_pool_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "tb2_lstm_step_forward": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "tb2_lstm_forward_sequence": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "tb2_lstm_backward_workspace_bytes": (_sz, [_vp, _i32, _i32]),
+    "tb2_lstm_backward_workspace_bytes": (_sz, [_vp, _vp, _i32, _i32]),
     "tb2_lstm_sequence_backward": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(LstmWeights), _vp, _i32, _vp, _i32,
                                                   _vp, _vp, _vp, _vp, _i32, ctypes.POINTER(LstmGrads),
                                                   _vp, _sz, _vp, _sz, _vp]),

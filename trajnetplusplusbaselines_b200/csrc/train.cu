@@ -16,6 +16,7 @@
 // Social pooling couples the tracks of a scene through W_enc h_j and is not built yet (fails
 // loudly).  No floating-point atomics anywhere: the first grid-embedding layer's weight gradient is
 // dz^T . grid with the (R-row) grid of each step written out densely by the gather kernel.
+#include <cuda_bf16.h>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -34,8 +35,8 @@ __global__ void __launch_bounds__(256) bwd_gather_kernel(
     const float* __restrict__ We, const float* __restrict__ be, const float* __restrict__ h_prev,
     const int* __restrict__ win_count, const uint32_t* __restrict__ win_ent, const float* __restrict__ win_val,
     const float* __restrict__ Wt1, const float* __restrict__ base1, int nm1, int C, int cells,
-    float* __restrict__ X, float* __restrict__ G, float* __restrict__ vel, int* __restrict__ masked, int E, int P,
-    int K) {
+    const float* __restrict__ pooled_src, float* __restrict__ X, float* __restrict__ G, float* __restrict__ vel,
+    int* __restrict__ masked, int E, int P, int K) {
     __shared__ uint32_t ent_s[64];
     __shared__ float val_s[64][2];
     const int r = blockIdx.x;
@@ -61,7 +62,9 @@ __global__ void __launch_bounds__(256) bwd_gather_kernel(
         x[k] = k < E - 2 ? fmaxf(fmaf(We[2 * k + 1], vy, fmaf(We[2 * k], vx, be[k])), 0.f) : 0.f;
     for (int k = threadIdx.x; k < kBH; k += blockDim.x)
         x[E + P + k] = h_prev ? h_prev[(size_t)m * kBH + k] : 0.f;
-    if (P > 0) {
+    if (pooled_src) {      // pooled vector of this row as the forward kernels produced it
+        for (int o = threadIdx.x; o < P; o += blockDim.x) x[E + o] = pooled_src[(size_t)m * P + o];
+    } else if (P > 0) {
         const int cnt = win_count[m];
         float acc[4];     // up to 4 output columns per thread (P <= 1024)
 #pragma unroll
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(256) bwd_gather_kernel(
 //        at the last step.  dc [R,128] in place; upstream dnormal [M,5] (row-indexed by track)
 //   out: dgates [R,512], dc (gradient wrt c_prev), hs [R,128] (h of this step), dn_raw [R,8],
 //        pass_cur [R,128] (masked rows: dh goes straight through, lstm.py:158-166)
-__global__ void __launch_bounds__(kBH) bwd_cell_head_kernel(
+__global__ void __launch_bounds__(4 * kBH) bwd_cell_head_kernel(
     const int* __restrict__ rows, const int* __restrict__ masked, const float* __restrict__ gates_pre,
     const float* __restrict__ c_prev, const float* __restrict__ dg_next, const float* __restrict__ Whh_next,
     const float* __restrict__ pass_prev, float* __restrict__ pass_cur, float* __restrict__ dc,
@@ -120,23 +123,29 @@ __global__ void __launch_bounds__(kBH) bwd_cell_head_kernel(
     __shared__ float red[5][kBH];
     __shared__ float dn_s[5];
     __shared__ __align__(16) float dgn_s[4 * kBH];
-    const int r = blockIdx.x, u = threadIdx.x;
+    __shared__ float part_s[4][kBH];
+    const int r = blockIdx.x, u = threadIdx.x & (kBH - 1), quarter = threadIdx.x >> 7;
     const int m = rows[r];
     float* dg = dgates + (size_t)r * 4 * kBH;
     float dh_in = 0.f;
-    if (dg_next) {
-        reinterpret_cast<float4*>(dgn_s)[u] = reinterpret_cast<const float4*>(dg_next + (size_t)r * 4 * kBH)[u];
+    if (dg_next) {      // 4 x 128 threads: each quarter of the CTA reduces one gate block of the mat-vec
+        dgn_s[threadIdx.x] = dg_next[(size_t)r * 4 * kBH + threadIdx.x];
         __syncthreads();
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float* wq = Whh_next + (size_t)quarter * kBH * kBH + u;
+        const float* dq = dgn_s + quarter * kBH;
 #pragma unroll 4
-        for (int g = 0; g < 4 * kBH; g += 4) {
-            a0 = fmaf(dgn_s[g + 0], Whh_next[(size_t)(g + 0) * kBH + u], a0);
-            a1 = fmaf(dgn_s[g + 1], Whh_next[(size_t)(g + 1) * kBH + u], a1);
-            a2 = fmaf(dgn_s[g + 2], Whh_next[(size_t)(g + 2) * kBH + u], a2);
-            a3 = fmaf(dgn_s[g + 3], Whh_next[(size_t)(g + 3) * kBH + u], a3);
+        for (int g = 0; g < kBH; g += 4) {
+            a0 = fmaf(dq[g + 0], wq[(size_t)(g + 0) * kBH], a0);
+            a1 = fmaf(dq[g + 1], wq[(size_t)(g + 1) * kBH], a1);
+            a2 = fmaf(dq[g + 2], wq[(size_t)(g + 2) * kBH], a2);
+            a3 = fmaf(dq[g + 3], wq[(size_t)(g + 3) * kBH], a3);
         }
-        dh_in = (a0 + a1) + (a2 + a3) + pass_prev[(size_t)r * kBH + u];
+        part_s[quarter][u] = (a0 + a1) + (a2 + a3);
+        __syncthreads();
+        dh_in = (part_s[0][u] + part_s[1][u]) + (part_s[2][u] + part_s[3][u]) + pass_prev[(size_t)r * kBH + u];
     }
+    if (quarter != 0) return;       // the cell / head math below is one thread per unit
     if (masked[r]) {   // absent track: state passes through, no parameter gradient
 #pragma unroll
         for (int g = 0; g < 4; ++g) dg[g * kBH + u] = 0.f;
@@ -156,13 +165,13 @@ __global__ void __launch_bounds__(kBH) bwd_cell_head_kernel(
     // head: n_raw = Wn h + bn (modules.py:57); recomputed for the sigmoid derivatives
 #pragma unroll
     for (int o = 0; o < 5; ++o) red[o][u] = Wn[o * kBH + u] * hn;
-    __syncthreads();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     for (int s = kBH / 2; s > 0; s >>= 1) {
         if (u < s) {
 #pragma unroll
             for (int o = 0; o < 5; ++o) red[o][u] += red[o][u + s];
         }
-        __syncthreads();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     if (u < 8) {
         float d = 0.f;
@@ -178,7 +187,7 @@ __global__ void __launch_bounds__(kBH) bwd_cell_head_kernel(
         }
         dn_raw[r * 8 + u] = d;
     }
-    __syncthreads();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     float dht = dh_in;
 #pragma unroll
     for (int o = 0; o < 5; ++o) dht = fmaf(Wn[o * kBH + u], dn_s[o], dht);
@@ -493,6 +502,16 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
     }
 }
 
+// dst[r][o] = ref[r][o] > 0 ? src[r][o] : 0   (row strides given; dst may alias src)
+__global__ void masked_copy_kernel(const float* __restrict__ ref, int ld_ref, const float* src, int ld_src,
+                                   float* dst, int ld_dst, int rows, int cols) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)rows * cols) return;
+    const size_t r = idx / cols;
+    const int o = (int)(idx - r * cols);
+    dst[r * ld_dst + o] = ref[r * ld_ref + o] > 0.f ? src[r * ld_src + o] : 0.f;
+}
+
 // dz = dX_pooled * (pooled > 0) in place (one_layer: pooled = relu(W1 grid + b1))
 __global__ void relu_mask_kernel(const float* __restrict__ X, int ldx, float* __restrict__ dX, int ldd, int rows,
                                  int E, int P) {
@@ -533,6 +552,263 @@ __global__ void __launch_bounds__(256) bwd_embed_kernel(const float* __restrict_
         dWe[2 * k + 1] += red[1][0];
         dbe[k] += red[2][0];
     }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Social pooling backward (gridbased_pooling.py:145-170 through autograd).  The grid of observer i
+// holds lat_j = W_enc h_j + b_enc of the winning neighbour of each occupied cell.
+//   * d W1 sees the grid as it was written: winners only.
+//   * d lat follows what autograd's index_put_ backward does for `occ[rows, oi] = other_values`
+//     (gridbased_pooling.py:290-293): grad_values = grad_occ[oi] for EVERY written pair, so each
+//     IN-RANGE pair (i, j) receives d grid_i[cell(i, j), :] = W1[:, cell-slab]^T dz1_i -- also the
+//     pairs a later writer of the same cell overwrote; out-of-range pairs were replaced by the
+//     constant before the write (:281-282) and receive nothing.
+// In-range pairs are bucketed by cell with a stable counting sort (scene by scene, slots
+// ascending), so every reduction below runs in a fixed order: results are run-to-run identical,
+// no float atomics.  A slot is row * nm1 + jj (neighbour slot jj <-> j = jj + (jj >= i)).
+// ------------------------------------------------------------------------------------------
+__global__ void pair_count_kernel(const int* __restrict__ scene_off, const int* __restrict__ masked,
+                                  const int* __restrict__ pair_cell, const uint8_t* __restrict__ pair_flag,
+                                  int nm1, int cells, int* __restrict__ counts) {
+    extern __shared__ int hist_s[];
+    const int b = blockIdx.x, row0 = scene_off[b], n_s = scene_off[b + 1] - row0;
+    for (int c = threadIdx.x; c < cells; c += blockDim.x) hist_s[c] = 0;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < n_s * nm1; idx += blockDim.x) {
+        const int r = idx / nm1;
+        const size_t slot = (size_t)row0 * nm1 + idx;
+        if (pair_flag[slot] && !masked[row0 + r]) atomicAdd(&hist_s[pair_cell[slot]], 1);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < cells; c += blockDim.x) counts[(size_t)b * cells + c] = hist_s[c];
+}
+
+// base[b][c] = pairs of cell c in scenes before b;  start[c] = pairs in cells before c
+__global__ void pair_offsets_kernel(const int* __restrict__ counts, int B, int cells, int* __restrict__ base,
+                                    int* __restrict__ start) {
+    extern __shared__ int total_s[];
+    for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+        int run = 0;
+        for (int b = 0; b < B; ++b) {
+            base[(size_t)b * cells + c] = run;
+            run += counts[(size_t)b * cells + c];
+        }
+        total_s[c] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int c = 0; c < cells; ++c) {
+            start[c] = run;
+            run += total_s[c];
+        }
+        start[cells] = run;
+    }
+}
+
+// sorted[start[c] + base[b][c] + rank] = slot id, bit 31 set when the pair is NOT the winner of its
+// cell (it then takes part in d lat but not in d W1); rank = earlier slots of the scene in cell c
+__global__ void pair_place_kernel(const int* __restrict__ scene_off, const int* __restrict__ masked,
+                                  const int* __restrict__ pair_cell, const uint8_t* __restrict__ pair_flag,
+                                  const int* __restrict__ win_count, const uint32_t* __restrict__ win_ent, int nm1,
+                                  int cells, const int* __restrict__ base, const int* __restrict__ start,
+                                  unsigned* __restrict__ sorted) {
+    extern __shared__ short cell_s[];         // [n_s * nm1] cell of the in-range pairs, -1 otherwise
+    const int b = blockIdx.x, row0 = scene_off[b], n_s = scene_off[b + 1] - row0;
+    for (int idx = threadIdx.x; idx < n_s * nm1; idx += blockDim.x) {
+        const size_t slot = (size_t)row0 * nm1 + idx;
+        cell_s[idx] = (short)((pair_flag[slot] && !masked[row0 + idx / nm1]) ? pair_cell[slot] : -1);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < n_s * nm1; idx += blockDim.x) {
+        const int cell = cell_s[idx];
+        if (cell < 0) continue;
+        int rank = 0;
+        for (int q = 0; q < idx; ++q) rank += cell_s[q] == cell;
+        const int r = idx / nm1, jj = idx - r * nm1, j = jj + (jj >= r);
+        const uint32_t want = ((uint32_t)cell << 16) | (uint32_t)j;
+        bool winner = false;
+        const int cnt = win_count[row0 + r];
+        for (int e = 0; e < cnt; ++e) winner |= win_ent[(size_t)(row0 + r) * nm1 + e] == want;
+        sorted[start[cell] + base[(size_t)b * cells + cell] + rank] =
+            (unsigned)((size_t)row0 * nm1 + idx) | (winner ? 0u : 0x80000000u);
+    }
+}
+
+// dgrid[slot][ch] = sum_o dz1[row(slot)][o] * Wt1[cell][ch][o]  for the pairs of one cell
+// (64 pairs x C channels per CTA, 64-deep slices of o through shared memory)
+constexpr int kDgPairs = 64, kDgK = 64;
+
+template <int C>
+__global__ void __launch_bounds__(256) social_dgrid_kernel(const unsigned* __restrict__ sorted,
+                                                           const int* __restrict__ start,
+                                                           const float* __restrict__ dz1, int d1,
+                                                           const float* __restrict__ Wt1, int nm1,
+                                                           float* __restrict__ dgrid) {
+    constexpr int CQ = C / 4;                       // channels per thread
+    __shared__ __align__(16) float As[kDgPairs][kDgK + 4];
+    __shared__ __align__(16) float Bs[C][kDgK + 4];
+    __shared__ int slot_s[kDgPairs];
+    const int cell = blockIdx.x;
+    const int p0 = start[cell] + blockIdx.y * kDgPairs, p1 = min(start[cell + 1], p0 + kDgPairs);
+    if (p0 >= p1) return;
+    const int np = p1 - p0, tid = threadIdx.x;
+    if (tid < kDgPairs) slot_s[tid] = tid < np ? (int)(sorted[p0 + tid] & 0x7fffffffu) : -1;
+    __syncthreads();
+    const int pr = tid >> 2, cq = tid & 3;
+    float acc[CQ];
+#pragma unroll
+    for (int q = 0; q < CQ; ++q) acc[q] = 0.f;
+    const float* Wc = Wt1 + (size_t)cell * C * d1;
+    for (int k0 = 0; k0 < d1; k0 += kDgK) {
+        for (int idx = tid; idx < kDgPairs * (kDgK / 4); idx += 256) {
+            const int r = idx / (kDgK / 4), c4 = (idx % (kDgK / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int slot = slot_s[r];
+            if (slot >= 0) {
+                const float* src = dz1 + (size_t)(slot / nm1) * d1 + k0 + c4;
+                if (k0 + c4 + 3 < d1) v = *reinterpret_cast<const float4*>(src);
+                else {
+                    if (k0 + c4 < d1) v.x = src[0];
+                    if (k0 + c4 + 1 < d1) v.y = src[1];
+                    if (k0 + c4 + 2 < d1) v.z = src[2];
+                }
+            }
+            *reinterpret_cast<float4*>(&As[r][c4]) = v;
+        }
+        for (int idx = tid; idx < C * (kDgK / 4); idx += 256) {
+            const int r = idx / (kDgK / 4), c4 = (idx % (kDgK / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* src = Wc + (size_t)r * d1 + k0 + c4;
+            if (k0 + c4 + 3 < d1) v = *reinterpret_cast<const float4*>(src);
+            else {
+                if (k0 + c4 < d1) v.x = src[0];
+                if (k0 + c4 + 1 < d1) v.y = src[1];
+                if (k0 + c4 + 2 < d1) v.z = src[2];
+            }
+            *reinterpret_cast<float4*>(&Bs[r][c4]) = v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int o = 0; o < kDgK; o += 4) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[pr][o]);
+#pragma unroll
+            for (int q = 0; q < CQ; ++q) {
+                const float4 w = *reinterpret_cast<const float4*>(&Bs[cq * CQ + q][o]);
+                acc[q] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, fmaf(a.w, w.w, acc[q]))));
+            }
+        }
+        __syncthreads();
+    }
+    if (pr < np) {
+        float* out = dgrid + (size_t)slot_s[pr] * C + cq * CQ;
+#pragma unroll
+        for (int q = 0; q < CQ; ++q) out[q] = acc[q];
+    }
+}
+
+// per scene: dlat[j] = sum over the observers i (rows ascending) whose pair (i, j) is in range of
+// that pair's dgrid slot; then the social part of d h_prev[j] = W_enc^T dlat[j] is added to the
+// by-pass buffer that the next (earlier) step's cell kernel reads.
+__global__ void __launch_bounds__(256) social_scene_reduce_kernel(
+    const int* __restrict__ scene_off, const int* __restrict__ masked, const uint8_t* __restrict__ pair_flag,
+    int nm1, int C, const float* __restrict__ dgrid, const float* __restrict__ Wenc, float* __restrict__ dlat,
+    float* __restrict__ dh_add) {
+    extern __shared__ float dl_s[];       // [n_s][C]
+    const int b = blockIdx.x, row0 = scene_off[b], n_s = scene_off[b + 1] - row0;
+    for (int idx = threadIdx.x; idx < n_s * C; idx += blockDim.x) {
+        const int j = idx / C, ch = idx - j * C;
+        float sum = 0.f;
+        for (int r = 0; r < n_s; ++r) {
+            if (r == j || masked[row0 + r]) continue;
+            const size_t slot = (size_t)(row0 + r) * nm1 + (j - (j > r));
+            if (pair_flag[slot]) sum += dgrid[slot * C + ch];
+        }
+        dl_s[idx] = sum;
+        dlat[(size_t)(row0 + j) * C + ch] = sum;
+    }
+    __syncthreads();
+    if (dh_add) {
+        for (int idx = threadIdx.x; idx < n_s * kBH; idx += blockDim.x) {
+            const int j = idx / kBH, u = idx - j * kBH;
+            float a = 0.f;
+            for (int ch = 0; ch < C; ++ch) a = fmaf(dl_s[j * C + ch], Wenc[ch * kBH + u], a);
+            dh_add[(size_t)(row0 + j) * kBH + u] += a;
+        }
+    }
+}
+
+// dWt1[cell][ch][o] += sum over the cell's pairs (sorted order) of dz1[i][o] * lat_j[ch]
+template <int C>
+__global__ void __launch_bounds__(256) social_dw1_kernel(const unsigned* __restrict__ sorted,
+                                                         const int* __restrict__ start, int nm1,
+                                                         const int* __restrict__ row_scene,
+                                                         const int* __restrict__ scene_off,
+                                                         const float* __restrict__ lat,
+                                                         const float* __restrict__ dz1, int d1,
+                                                         float* __restrict__ dWt1) {
+    __shared__ float lat_s[32][C];
+    __shared__ int row_s[32];
+    const int cell = blockIdx.x, o = blockIdx.y * 256 + threadIdx.x;
+    const int p0 = start[cell], p1 = start[cell + 1];
+    if (p0 >= p1) return;
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    for (int pb = p0; pb < p1; pb += 32) {
+        const int nb = min(32, p1 - pb);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < nb * C; idx += 256) {
+            const int t = idx / C, ch = idx - t * C;
+            const unsigned sv = sorted[pb + t];
+            const int slot = (int)(sv & 0x7fffffffu);
+            const int i = slot / nm1, jj = slot - i * nm1;
+            const int s0 = scene_off[row_scene[i]];
+            const int j = jj + (jj >= i - s0);
+            // overwritten pairs are not in the grid: they contribute to d lat only
+            lat_s[t][ch] = (sv & 0x80000000u) ? 0.f : lat[(size_t)(s0 + j) * C + ch];
+            if (ch == 0) row_s[t] = i;
+        }
+        __syncthreads();
+        if (o < d1) {
+#pragma unroll 4
+            for (int t = 0; t < nb; ++t) {
+                const float dz = dz1[(size_t)row_s[t] * d1 + o];
+#pragma unroll
+                for (int c = 0; c < C; ++c) acc[c] = fmaf(dz, lat_s[t][c], acc[c]);
+            }
+        }
+    }
+    if (o < d1) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) dWt1[((size_t)cell * C + c) * d1 + o] += acc[c];
+    }
+}
+
+// dW1[o][ch * cells + cell] += dWt1[cell][ch][o]   (back to the reference's parameter layout)
+__global__ void untranspose_add_kernel(const float* __restrict__ dWt1, float* __restrict__ dW1, int cells, int C,
+                                       int d1) {
+    const size_t total = (size_t)cells * C * d1;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int o = (int)(idx % d1);
+        const size_t cc = idx / d1;
+        const int ch = (int)(cc % C), cell = (int)(cc / C);
+        dW1[(size_t)o * C * cells + (size_t)ch * cells + cell] += dWt1[idx];
+    }
+}
+
+// hidden1 of a step as fp32: from the bf16 (hi, lo) pair the tensor-core layer consumed, or a copy
+__global__ void merge_split_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                                   const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = hi ? __bfloat162float(hi[i]) + __bfloat162float(lo[i]) : src[i];
+}
+
+__global__ void iota_kernel(int* __restrict__ p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
 }
 
 }  // namespace tb2
@@ -665,10 +941,269 @@ static size_t carve_bwd(const tb2_lstm* m, size_t R, size_t S, void* base, BwdBu
 }
 }  // namespace tb2
 
+namespace tb2 {
+
+struct SocBuffers {
+    float *X, *GP, *DG, *HS, *DN, *VEL, *DXIN, *H1, *DH1, *LAT, *DLAT, *DGRID, *dWt1;
+    float *pass[2], *dc, *zero_h, *scratch;
+    size_t scratch_floats;
+    int *masked, *rows, *winc, *counts, *base, *start, *pcell;
+    unsigned* sorted;
+    uint8_t* pflag;
+    uint32_t* wine;
+};
+
+static size_t carve_social(const tb2_lstm* m, const tb2_layout* l, size_t S, void* basep, SocBuffers* b) {
+    const size_t M = (size_t)l->M, K = (size_t)m->K_gate, E = (size_t)m->E, P = (size_t)m->P;
+    const size_t d1 = (size_t)m->mlp_dims[1], C = (size_t)m->C, cells = (size_t)m->cells;
+    const size_t nm1 = (size_t)(l->n_max > 1 ? l->n_max - 1 : 1);
+    size_t off = 0;
+    auto take = [&](size_t n) {
+        float* p = basep ? reinterpret_cast<float*>(basep) + off : nullptr;
+        off += (n + 3) & ~(size_t)3;
+        return p;
+    };
+    SocBuffers tmp;
+    SocBuffers* o = b ? b : &tmp;
+    o->X = take(S * M * K);
+    o->GP = take(S * M * 512);
+    o->DG = take(S * M * 512);
+    o->HS = take(S * M * 128);
+    o->DN = take(S * M * 8);
+    o->VEL = take(S * M * 2);
+    o->DXIN = take(S * M * (E + P));
+    o->H1 = take(m->n_mlp == 2 ? S * M * d1 : 4);
+    o->DH1 = take(M * d1);
+    o->LAT = take(S * M * C);
+    o->DLAT = take(S * M * C);
+    o->DGRID = take(M * nm1 * C);
+    o->dWt1 = take(cells * C * d1);
+    o->pass[0] = take(M * 128);
+    o->pass[1] = take(M * 128);
+    o->dc = take(M * 128);
+    o->zero_h = take(M * 128);
+    size_t big = 512 * K;
+    if (P * d1 > big) big = P * d1;
+    o->scratch_floats = 8 * big;
+    o->scratch = take(o->scratch_floats);
+    o->masked = reinterpret_cast<int*>(take(S * M));
+    o->rows = reinterpret_cast<int*>(take(M));
+    o->winc = reinterpret_cast<int*>(take(S * M));
+    o->wine = reinterpret_cast<uint32_t*>(take(S * M * nm1));
+    o->sorted = reinterpret_cast<unsigned*>(take(M * nm1));
+    o->pcell = reinterpret_cast<int*>(take(S * M * nm1));
+    o->pflag = reinterpret_cast<uint8_t*>(take((S * M * nm1 + 3) / 4));
+    o->counts = reinterpret_cast<int*>(take((size_t)l->B * cells));
+    o->base = reinterpret_cast<int*>(take((size_t)l->B * cells));
+    o->start = reinterpret_cast<int*>(take(cells + 1));
+    return off * sizeof(float) + 256;
+}
+
+template <int C>
+static int social_pair_kernels(const tb2_lstm* m, const tb2_layout* l, const SocBuffers& b, const float* lat,
+                               int nm1, int d1, cudaStream_t st) {
+    {
+        KernelTimer kt("social_dgrid", st);
+        social_dgrid_kernel<C><<<dim3(m->cells, (l->M + kDgPairs - 1) / kDgPairs), 256, 0, st>>>(
+            b.sorted, b.start, b.DH1, d1, m->Wt1, nm1, b.DGRID);
+    }
+    TB2_LAUNCH_CHECK();
+    {
+        KernelTimer kt("social_dw1", st);
+        social_dw1_kernel<C><<<dim3(m->cells, (d1 + 255) / 256), 256, 0, st>>>(
+            b.sorted, b.start, nm1, l->row_scene, l->scene_off, lat, b.DH1, d1, b.dWt1);
+    }
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
+}
+
+// BPTT through social pooling: every track of a scene receives gradient, so the backward runs on
+// all M rows (see the kernel comments above for the scatter part).
+static int social_backward(const tb2_lstm* m, const tb2_layout* l, const tb2_lstm_weights* w,
+                           const float* observed, int obs_length, const float* truth, int n_decode,
+                           const float* positions, const float* states, const float* d_normals,
+                           const tb2_lstm_grads* g, Workspace& ws, void* bwd_workspace, cudaStream_t st) {
+    const int S = obs_length - 1 + n_decode, S_enc = obs_length - 1;
+    const int Mi = l->M, K = m->K_gate, E = m->E, P = m->P, EP = E + P, C = m->C, cells = m->cells;
+    const int d1 = m->mlp_dims[1];
+    const bool two = m->n_mlp == 2;
+    const size_t M = (size_t)Mi;
+    const int nm1 = l->n_max > 1 ? l->n_max - 1 : 1;
+    TB2_REQUIRE(g->pool_embedding_weight0 && g->pool_embedding_bias0 && g->pool_encoding_weight &&
+                g->pool_encoding_bias && (!two || (g->pool_embedding_weight1 && g->pool_embedding_bias1)),
+                "social backward needs gradient buffers for pool.hidden_dim_encoding and pool.embedding");
+    SocBuffers b;
+    carve_social(m, l, (size_t)S, bwd_workspace, &b);
+    TB2_CHECK_CUDA(cudaMemsetAsync(b.dc, 0, M * 128 * sizeof(float), st));
+    TB2_CHECK_CUDA(cudaMemsetAsync(b.dWt1, 0, (size_t)cells * C * d1 * sizeof(float), st));
+    TB2_CHECK_CUDA(cudaMemsetAsync(b.zero_h, 0, M * 128 * sizeof(float), st));      // state before step 0
+    iota_kernel<<<(Mi + 255) / 256, 256, 0, st>>>(b.rows, Mi);
+    TB2_LAUNCH_CHECK();
+    int rc;
+    const bool tc2 = two && m->W_hi[1] != nullptr;
+    // (A) forward quantities of every step: winners + lat, hidden1, X = [emb | pooled | h_prev]
+    for (int s = 0; s < S; ++s) {
+        const float *o1, *o2;
+        int phase;
+        if ((rc = resolve_step_inputs(l, observed, obs_length, truth, positions, s, &ws, &o1, &o2, &phase, st))) return rc;
+        const float* h_prev = s > 0 ? states + ((size_t)(s - 1) * 2 + 0) * M * kBH : nullptr;
+        Workspace w2 = ws;
+        w2.lat = b.LAT + (size_t)s * M * C;
+        w2.win_count = b.winc + (size_t)s * M;
+        w2.win_ent = b.wine + (size_t)s * M * nm1;
+        w2.pair_cell = b.pcell + (size_t)s * M * nm1;
+        w2.pair_flag = b.pflag + (size_t)s * M * nm1;
+        if ((rc = launch_pool_prepare(m, l, h_prev ? h_prev : b.zero_h, o1, o2, 1, 1, 0, &w2, st))) return rc;
+        if ((rc = launch_pool_mlp(m, l, &w2, ws.pooled, nullptr, nullptr, st))) return rc;
+        if (two) {
+            merge_split_kernel<<<1024, 256, 0, st>>>(tc2 ? (const __nv_bfloat16*)ws.act[0] : nullptr,
+                                                     tc2 ? (const __nv_bfloat16*)ws.act[1] : nullptr, ws.act[0],
+                                                     b.H1 + (size_t)s * M * d1, M * d1);
+            TB2_LAUNCH_CHECK();
+        }
+        {
+            KernelTimer kt("bwd_gather", st);
+            bwd_gather_kernel<<<Mi, 256, 0, st>>>(b.rows, Mi, (const float2*)o1, (const float2*)o2, m->We, m->be,
+                                                  h_prev, nullptr, nullptr, nullptr, nullptr, nullptr, nm1, C, cells,
+                                                  ws.pooled, b.X + (size_t)s * M * K, nullptr,
+                                                  b.VEL + (size_t)s * M * 2, b.masked + (size_t)s * M, E, P, K);
+        }
+        TB2_LAUNCH_CHECK();
+    }
+    // (B) gate pre-activations of all steps
+    for (int phase = 0; phase < 2; ++phase) {
+        const int s0 = phase == TB2_PHASE_ENCODER ? 0 : S_enc;
+        const int ns = phase == TB2_PHASE_ENCODER ? S_enc : S - S_enc;
+        if (ns <= 0) continue;
+        if ((rc = gemm_nn(b.X + (size_t)s0 * M * K, K, m->WgT[phase], 512, b.GP + (size_t)s0 * M * 512, 512,
+                          ns * Mi, 512, K, m->bg[phase], st)))
+            return rc;
+    }
+    // (C) reverse time: cell -> input gradient -> grid MLP -> scatter to the neighbours' hidden states
+    const size_t place_smem = (size_t)l->n_max * nm1 * sizeof(short);
+    TB2_REQUIRE(place_smem <= 200 * 1024 && cells < 32768, "scene too large for the social backward");
+    {
+        static size_t configured = 48 * 1024;
+        if (place_smem > configured) {
+            TB2_CHECK_CUDA(cudaFuncSetAttribute(pair_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)place_smem));
+            configured = place_smem;
+        }
+    }
+    int cur = 0;
+    for (int s = S - 1; s >= 0; --s, cur ^= 1) {
+        const int phase = s < S_enc ? TB2_PHASE_ENCODER : TB2_PHASE_DECODER;
+        const float* c_prev = s > 0 ? states + ((size_t)(s - 1) * 2 + 1) * M * kBH : nullptr;
+        const bool last = s == S - 1;
+        const int next_phase = (s + 1) < S_enc ? TB2_PHASE_ENCODER : TB2_PHASE_DECODER;
+        const float* Whh_next = next_phase == TB2_PHASE_ENCODER ? w->encoder_weight_hh : w->decoder_weight_hh;
+        const float* Wih = phase == TB2_PHASE_ENCODER ? w->encoder_weight_ih : w->decoder_weight_ih;
+        float* DGs = b.DG + (size_t)s * M * 512;
+        float* DXs = b.DXIN + (size_t)s * M * EP;
+        const float* Xs = b.X + (size_t)s * M * K;
+        {
+            KernelTimer kt("bwd_cell_head", st);
+            bwd_cell_head_kernel<<<Mi, 4 * kBH, 0, st>>>(
+                b.rows, b.masked + (size_t)s * M, b.GP + (size_t)s * M * 512, c_prev,
+                last ? nullptr : b.DG + (size_t)(s + 1) * M * 512, Whh_next, b.pass[cur ^ 1], b.pass[cur], b.dc,
+                d_normals + (size_t)s * M * 5, m->Wn, m->bn, DGs, b.HS + (size_t)s * M * 128,
+                b.DN + (size_t)s * M * 8, Mi);
+        }
+        TB2_LAUNCH_CHECK();
+        if ((rc = gemm_nn(DGs, 512, Wih, EP, DXs, EP, Mi, EP, 512, nullptr, st))) return rc;
+        const unsigned eb = (unsigned)((M * d1 + 255) / 256);
+        if (two) {
+            const float* H1s = b.H1 + (size_t)s * M * d1;
+            relu_mask_kernel<<<(unsigned)((M * P + 255) / 256), 256, 0, st>>>(Xs, K, DXs, EP, Mi, E, P);   // dz2
+            TB2_LAUNCH_CHECK();
+            // d hidden1 = dz2 . W2 (torch layout [P, d1] is the [K = P, N = d1] operand), then the ReLU mask
+            if ((rc = gemm_nn(DXs + E, EP, w->pool_embedding_weight[1], d1, b.DH1, d1, Mi, d1, P, nullptr, st))) return rc;
+            masked_copy_kernel<<<eb, 256, 0, st>>>(H1s, d1, b.DH1, d1, b.DH1, d1, Mi, d1);
+            TB2_LAUNCH_CHECK();
+            if ((rc = gemm_tn(DXs + E, EP, H1s, d1, g->pool_embedding_weight1, d1, Mi, P, d1, b.scratch,
+                              b.scratch_floats, st)))
+                return rc;
+            if ((rc = colsum(DXs + E, EP, Mi, P, g->pool_embedding_bias1, nullptr, b.scratch, b.scratch_floats, st)))
+                return rc;
+        } else {
+            masked_copy_kernel<<<eb, 256, 0, st>>>(Xs + E, K, DXs + E, EP, b.DH1, d1, Mi, d1);
+            TB2_LAUNCH_CHECK();
+        }
+        if ((rc = colsum(b.DH1, d1, Mi, d1, g->pool_embedding_bias0, nullptr, b.scratch, b.scratch_floats, st))) return rc;
+        const int* winc = b.winc + (size_t)s * M;
+        const uint32_t* wine = b.wine + (size_t)s * M * nm1;
+        const int* pcell = b.pcell + (size_t)s * M * nm1;
+        const uint8_t* pflag = b.pflag + (size_t)s * M * nm1;
+        const int* msk = b.masked + (size_t)s * M;
+        const float* lat = b.LAT + (size_t)s * M * C;
+        {
+            KernelTimer kt("social_pair_sort", st);
+            pair_count_kernel<<<l->B, 256, cells * sizeof(int), st>>>(l->scene_off, msk, pcell, pflag, nm1, cells,
+                                                                       b.counts);
+            pair_offsets_kernel<<<1, 1024, cells * sizeof(int), st>>>(b.counts, l->B, cells, b.base, b.start);
+            pair_place_kernel<<<l->B, 256, place_smem, st>>>(
+                l->scene_off, msk, pcell, pflag, winc, wine, nm1, cells, b.base, b.start, b.sorted);
+        }
+        TB2_LAUNCH_CHECK();
+        switch (C) {
+            case 4: rc = social_pair_kernels<4>(m, l, b, lat, nm1, d1, st); break;
+            case 8: rc = social_pair_kernels<8>(m, l, b, lat, nm1, d1, st); break;
+            case 16: rc = social_pair_kernels<16>(m, l, b, lat, nm1, d1, st); break;
+            case 32: rc = social_pair_kernels<32>(m, l, b, lat, nm1, d1, st); break;
+            default: set_error("social latent_dim must be 4, 8, 16 or 32"); return TB2_ERR_UNSUPPORTED;
+        }
+        if (rc) return rc;
+        {
+            KernelTimer kt("social_scene_reduce", st);
+            social_scene_reduce_kernel<<<l->B, 256, (size_t)l->n_max * C * sizeof(float), st>>>(
+                l->scene_off, msk, pflag, nm1, C, b.DGRID, w->pool_encoding_weight, b.DLAT + (size_t)s * M * C,
+                s > 0 ? b.pass[cur] : nullptr);
+        }
+        TB2_LAUNCH_CHECK();
+    }
+    // (D) parameter gradients: one reduction over all (step, row) records per tensor
+    for (int phase = 0; phase < 2; ++phase) {
+        const int s0 = phase == TB2_PHASE_ENCODER ? 0 : S_enc;
+        const int ns = phase == TB2_PHASE_ENCODER ? S_enc : S - S_enc;
+        if (ns <= 0) continue;
+        const float* DG = b.DG + (size_t)s0 * M * 512;
+        const float* X = b.X + (size_t)s0 * M * K;
+        const int rows = ns * Mi;
+        float* gWih = phase == TB2_PHASE_ENCODER ? g->encoder_weight_ih : g->decoder_weight_ih;
+        float* gWhh = phase == TB2_PHASE_ENCODER ? g->encoder_weight_hh : g->decoder_weight_hh;
+        float* gbih = phase == TB2_PHASE_ENCODER ? g->encoder_bias_ih : g->decoder_bias_ih;
+        float* gbhh = phase == TB2_PHASE_ENCODER ? g->encoder_bias_hh : g->decoder_bias_hh;
+        if ((rc = gemm_tn(DG, 512, X, K, gWih, EP, rows, 512, EP, b.scratch, b.scratch_floats, st))) return rc;
+        if ((rc = gemm_tn(DG, 512, X + EP, K, gWhh, 128, rows, 512, 128, b.scratch, b.scratch_floats, st))) return rc;
+        if ((rc = colsum(DG, 512, rows, 512, gbih, gbhh, b.scratch, b.scratch_floats, st))) return rc;
+    }
+    if ((rc = gemm_tn(b.DN, 8, b.HS, 128, g->hidden2normal_weight, 128, S * Mi, 5, 128, b.scratch, b.scratch_floats, st)))
+        return rc;
+    if ((rc = colsum(b.DN, 8, S * Mi, 5, g->hidden2normal_bias, nullptr, b.scratch, b.scratch_floats, st))) return rc;
+    bwd_embed_kernel<<<E - 2, 256, 0, st>>>(b.X, K, b.DXIN, EP, b.VEL, S * Mi, g->input_embedding_weight,
+                                            g->input_embedding_bias);
+    TB2_LAUNCH_CHECK();
+    untranspose_add_kernel<<<2048, 256, 0, st>>>(b.dWt1, g->pool_embedding_weight0, cells, C, d1);
+    TB2_LAUNCH_CHECK();
+    // lat_j = W_enc h_j + b_enc (gridbased_pooling.py:160-167): h of step s-1 is states[s-1]
+    for (int s = 1; s < S; ++s) {
+        const float* h_prev = states + ((size_t)(s - 1) * 2 + 0) * M * kBH;
+        if ((rc = gemm_tn(b.DLAT + (size_t)s * M * C, C, h_prev, 128, g->pool_encoding_weight, 128, Mi, C, 128,
+                          b.scratch, b.scratch_floats, st)))
+            return rc;
+    }
+    if ((rc = colsum(b.DLAT, C, S * Mi, C, g->pool_encoding_bias, nullptr, b.scratch, b.scratch_floats, st))) return rc;
+    return TB2_OK;
+}
+}  // namespace tb2
+
 extern "C" {
 
-size_t tb2_lstm_backward_workspace_bytes(const tb2_lstm* m, int32_t num_active, int32_t num_steps) {
-    if (!m || num_active < 0 || num_steps < 0) return 0;
+size_t tb2_lstm_backward_workspace_bytes(const tb2_lstm* m, const tb2_layout* l, int32_t num_active,
+                                         int32_t num_steps) {
+    if (!m || !l || num_active < 0 || num_steps < 0) return 0;
+    if (m->cfg.pool_type == TB2_POOL_SOCIAL)
+        return carve_social(m, l, (size_t)(num_steps > 0 ? num_steps : 1), nullptr, nullptr);
     return carve_bwd(m, (size_t)(num_active > 0 ? num_active : 1), (size_t)(num_steps > 0 ? num_steps : 1),
                      nullptr, nullptr);
 }
@@ -684,23 +1219,27 @@ int tb2_lstm_sequence_backward(const tb2_lstm* m, const tb2_layout* l, const tb2
     TB2_REQUIRE(observed && positions && states && d_normals && active_rows, "null argument");
     TB2_REQUIRE(obs_length >= 2 && n_decode >= 0, "need obs_length >= 2 and n_decode >= 0");
     TB2_REQUIRE(m->H == kBH, "hidden_dim must be 128");
-    if (m->cfg.pool_type == TB2_POOL_SOCIAL) {
-        set_error("training backward through social pooling (hidden-state scatter) is not built yet");
+    const bool social = m->cfg.pool_type == TB2_POOL_SOCIAL;
+    if (social && (m->n_mlp < 1 || m->n_mlp > 2 || !m->cfg.pool_to_input || m->cfg.constant != 0.f)) {
+        set_error("social training backward supports one_layer / two_layer embeddings with constant = 0");
         return TB2_ERR_UNSUPPORTED;
     }
-    if (m->cfg.pool_type != TB2_POOL_NONE &&
+    if (!social && m->cfg.pool_type != TB2_POOL_NONE &&
         (m->n_mlp != 1 || !m->cfg.pool_to_input || m->cfg.constant != 0.f || m->P > 1024 || m->C > 2)) {
         set_error("training backward supports one_layer grid embeddings with constant = 0 and pool_to_input");
         return TB2_ERR_UNSUPPORTED;
     }
     const int S = obs_length - 1 + n_decode;
     TB2_REQUIRE(workspace && workspace_bytes >= carve_workspace(m, l, nullptr, nullptr), "workspace too small");
-    TB2_REQUIRE(bwd_workspace && bwd_workspace_bytes >= tb2_lstm_backward_workspace_bytes(m, num_active, S),
+    TB2_REQUIRE(bwd_workspace && bwd_workspace_bytes >= tb2_lstm_backward_workspace_bytes(m, l, num_active, S),
                 "backward workspace too small");
     if (num_active == 0) return TB2_OK;
     cudaStream_t st = (cudaStream_t)stream;
     Workspace ws;
     carve_workspace(m, l, workspace, &ws);
+    if (social)      // every track of a scene receives gradient: all rows, active_rows is ignored
+        return social_backward(m, l, w, observed, obs_length, truth, n_decode, positions, states, d_normals, g, ws,
+                               bwd_workspace, st);
     const int R = num_active, K = m->K_gate, E = m->E, P = m->P, EP = E + P;
     const size_t M = (size_t)l->M;
     BwdBuffers b;
@@ -722,7 +1261,7 @@ int tb2_lstm_sequence_backward(const tb2_lstm* m, const tb2_layout* l, const tb2
             KernelTimer kt("bwd_gather", st);
             bwd_gather_kernel<<<R, 256, 0, st>>>(active_rows, R, (const float2*)o1, (const float2*)o2, m->We, m->be,
                                                  h_prev, ws.win_count, ws.win_ent, ws.win_val, m->Wt1, m->base1,
-                                                 nm1, m->C, m->cells, b.X + (size_t)s * R * K,
+                                                 nm1, m->C, m->cells, nullptr, b.X + (size_t)s * R * K,
                                                  pooled ? b.G + (size_t)s * R * CG : nullptr,
                                                  b.VEL + (size_t)s * R * 2, b.masked + (size_t)s * R, E, P, K);
         }
@@ -746,7 +1285,7 @@ int tb2_lstm_sequence_backward(const tb2_lstm* m, const tb2_layout* l, const tb2
         const float* Whh_next = next_phase == TB2_PHASE_ENCODER ? w->encoder_weight_hh : w->decoder_weight_hh;
         {
             KernelTimer kt("bwd_cell_head", st);
-            bwd_cell_head_kernel<<<R, kBH, 0, st>>>(
+            bwd_cell_head_kernel<<<R, 4 * kBH, 0, st>>>(
                 active_rows, b.masked + (size_t)s * R, b.GP + (size_t)s * R * 512, c_prev,
                 last ? nullptr : b.DG + (size_t)(s + 1) * R * 512, Whh_next, b.pass[cur ^ 1], b.pass[cur], b.dc,
                 d_normals + (size_t)s * M * 5, m->Wn, m->bn, b.DG + (size_t)s * R * 512,

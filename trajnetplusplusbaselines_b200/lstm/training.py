@@ -2,7 +2,8 @@
 
 The forward is the same fused CUDA time loop as inference (with the per-step states kept);
 the backward is tb2_lstm_sequence_backward (csrc/train.cu): BPTT restricted to the tracks that
-actually receive gradient.  Mirrors what autograd computes for the reference's
+actually receive gradient (all tracks for social pooling, whose hidden-state scatter couples the
+tracks of a scene).  Mirrors what autograd computes for the reference's
 Trainer.train_batch (trajnetbaselines/lstm/trainer.py:229-269).
 """
 import ctypes
@@ -31,10 +32,17 @@ _GRAD_FIELDS = {
 def _grad_targets(model):
     """field name -> parameter, for every parameter the backward kernel produces a gradient for."""
     out = {k: f(model) for k, f in _GRAD_FIELDS.items()}
-    if model.pool is not None and model.pool.embedding is not None:
-        lin = model.pool.embedding[0]
-        out["pool_embedding_weight0"] = lin.weight
-        out["pool_embedding_bias0"] = lin.bias
+    pool = model.pool
+    if pool is not None and pool.embedding is not None:
+        linears = [m for m in pool.embedding if isinstance(m, torch.nn.Linear)]
+        out["pool_embedding_weight0"] = linears[0].weight
+        out["pool_embedding_bias0"] = linears[0].bias
+        if len(linears) > 1:
+            out["pool_embedding_weight1"] = linears[1].weight
+            out["pool_embedding_bias1"] = linears[1].bias
+    if pool is not None and getattr(pool, 'type_', None) == 'social':
+        out["pool_encoding_weight"] = pool.hidden_dim_encoding.weight
+        out["pool_encoding_bias"] = pool.hidden_dim_encoding.bias
     return out
 
 
@@ -69,7 +77,11 @@ class _SequenceFn(torch.autograd.Function):
             dp = torch.nan_to_num(d_positions.to(device=device, dtype=torch.float32))[-S:]
             dn[:, :, :2] += dp
         dn = dn.contiguous()
-        active = (dn != 0).any(dim=2).any(dim=0).nonzero().flatten().to(torch.int32).contiguous()
+        social = model.pool is not None and getattr(model.pool, 'type_', None) == 'social'
+        if social:      # the hidden-state scatter couples all tracks of a scene: every row is active
+            active = torch.arange(M, dtype=torch.int32, device=device)
+        else:
+            active = (dn != 0).any(dim=2).any(dim=0).nonzero().flatten().to(torch.int32).contiguous()
         R = int(active.numel())
         targets = _grad_targets(model)
         grads = {k: torch.zeros_like(p, dtype=torch.float32, device=device).contiguous() for k, p in targets.items()}
@@ -79,7 +91,7 @@ class _SequenceFn(torch.autograd.Function):
                 setattr(g, k, t.data_ptr())
             w, keep = handle.weights_struct(model._weight_fields())
             ws, need = handle.workspace(layout)
-            bneed = int(lib.tb2_lstm_backward_workspace_bytes(handle.handle, R, S))
+            bneed = int(lib.tb2_lstm_backward_workspace_bytes(handle.handle, layout.handle, R, S))
             bws = torch.empty(bneed, dtype=torch.uint8, device=device)
             pos_steps = positions[-S:].contiguous()
             n_decode = S - (int(ctx.obs.shape[0]) - 1)
@@ -98,8 +110,5 @@ class _SequenceFn(torch.autograd.Function):
 
 
 def sequence_with_grad(model, observed, batch_split, prediction_truth, n_predict):
-    if model.pool is not None and getattr(model.pool, 'type_', None) == 'social':
-        raise NotImplementedError("training through social pooling is not built yet (the hidden-state scatter "
-                                  "couples all tracks of a scene); vanilla / occupancy / directional are")
     params = tuple(model.parameters())
     return _SequenceFn.apply(model, observed, batch_split, prediction_truth, n_predict, *params)
