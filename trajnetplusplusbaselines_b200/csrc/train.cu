@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(256) bwd_gather_kernel(
 __global__ void __launch_bounds__(4 * kBH) bwd_cell_head_kernel(
     const int* __restrict__ rows, const int* __restrict__ masked, const float* __restrict__ gates_pre,
     const float* __restrict__ c_prev, const float* __restrict__ dg_next, const float* __restrict__ Whh_next,
-    const float* __restrict__ pass_prev, float* __restrict__ pass_cur, float* __restrict__ dc,
+    const float* __restrict__ dh_rec, const float* __restrict__ pass_prev, float* __restrict__ pass_cur,
+    float* __restrict__ dc,
     const float* __restrict__ dnormal, const float* __restrict__ Wn, const float* __restrict__ bn,
     float* __restrict__ dgates, float* __restrict__ hs, float* __restrict__ dn_raw, int R) {
     __shared__ float red[5][kBH];
@@ -128,7 +129,9 @@ __global__ void __launch_bounds__(4 * kBH) bwd_cell_head_kernel(
     const int m = rows[r];
     float* dg = dgates + (size_t)r * 4 * kBH;
     float dh_in = 0.f;
-    if (dg_next) {      // 4 x 128 threads: each quarter of the CTA reduces one gate block of the mat-vec
+    if (dh_rec) {       // many rows: dg_next . W_hh was done as one GEMM
+        dh_in = dh_rec[(size_t)r * kBH + u] + pass_prev[(size_t)r * kBH + u];
+    } else if (dg_next) {      // 4 x 128 threads: each quarter of the CTA reduces one gate block of the mat-vec
         dgn_s[threadIdx.x] = dg_next[(size_t)r * 4 * kBH + threadIdx.x];
         __syncthreads();
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -973,7 +976,7 @@ static size_t carve_social(const tb2_lstm* m, const tb2_layout* l, size_t S, voi
     o->VEL = take(S * M * 2);
     o->DXIN = take(S * M * (E + P));
     o->H1 = take(m->n_mlp == 2 ? S * M * d1 : 4);
-    o->DH1 = take(M * d1);
+    o->DH1 = take(M * (d1 > 128 ? d1 : 128));     // also holds the [M,128] recurrent d h of a step
     o->LAT = take(S * M * C);
     o->DLAT = take(S * M * C);
     o->DGRID = take(M * nm1 * C);
@@ -1101,11 +1104,19 @@ static int social_backward(const tb2_lstm* m, const tb2_layout* l, const tb2_lst
         float* DGs = b.DG + (size_t)s * M * 512;
         float* DXs = b.DXIN + (size_t)s * M * EP;
         const float* Xs = b.X + (size_t)s * M * K;
+        // recurrent part of d h: all rows are active, so dgates(s+1) . W_hh is a GEMM (DH1 is free here)
+        float* dh_rec = nullptr;
+        if (!last) {
+            dh_rec = b.DH1;
+            if ((rc = gemm_nn(b.DG + (size_t)(s + 1) * M * 512, 512, Whh_next, 128, dh_rec, 128, Mi, 128, 512, nullptr,
+                              st)))
+                return rc;
+        }
         {
             KernelTimer kt("bwd_cell_head", st);
             bwd_cell_head_kernel<<<Mi, 4 * kBH, 0, st>>>(
-                b.rows, b.masked + (size_t)s * M, b.GP + (size_t)s * M * 512, c_prev,
-                last ? nullptr : b.DG + (size_t)(s + 1) * M * 512, Whh_next, b.pass[cur ^ 1], b.pass[cur], b.dc,
+                b.rows, b.masked + (size_t)s * M, b.GP + (size_t)s * M * 512, c_prev, nullptr, Whh_next, dh_rec,
+                b.pass[cur ^ 1], b.pass[cur], b.dc,
                 d_normals + (size_t)s * M * 5, m->Wn, m->bn, DGs, b.HS + (size_t)s * M * 128,
                 b.DN + (size_t)s * M * 8, Mi);
         }
@@ -1287,7 +1298,7 @@ int tb2_lstm_sequence_backward(const tb2_lstm* m, const tb2_layout* l, const tb2
             KernelTimer kt("bwd_cell_head", st);
             bwd_cell_head_kernel<<<R, 4 * kBH, 0, st>>>(
                 active_rows, b.masked + (size_t)s * R, b.GP + (size_t)s * R * 512, c_prev,
-                last ? nullptr : b.DG + (size_t)(s + 1) * R * 512, Whh_next, b.pass[cur ^ 1], b.pass[cur], b.dc,
+                last ? nullptr : b.DG + (size_t)(s + 1) * R * 512, Whh_next, nullptr, b.pass[cur ^ 1], b.pass[cur], b.dc,
                 d_normals + (size_t)s * M * 5, m->Wn, m->bn, b.DG + (size_t)s * R * 512,
                 b.HS + (size_t)s * R * 128, b.DN + (size_t)s * R * 8, R);
         }
