@@ -1,0 +1,58 @@
+"""ndjson boundary: reader / writer either side of the batched predictor."""
+import json
+import os
+
+import numpy as np
+
+from trajnetplusplusbaselines_b200.data import (SceneRow, TrackRow, paths_to_xy, preprocess_test,
+                                                read_ndjson_scenes, trajnet_line, write_predictions)
+
+
+def _scene(scene_id, n_peds, start, rng):
+    paths = []
+    for p in range(n_peds):
+        x0 = rng.randn(2)
+        paths.append([TrackRow(start + 10 * t, 100 * scene_id + p, float(x0[0] + 0.1 * t), float(x0[1] - 0.05 * t))
+                      for t in range(21)])
+    return paths
+
+
+def test_writer_matches_data_block_line_format():
+    # the two record kinds exactly as they appear in the reference's DATA_BLOCK/*.ndjson
+    assert json.loads(trajnet_line(SceneRow(3, 7, 10, 210, 2.5, 0))) == \
+        {"scene": {"id": 3, "p": 7, "s": 10, "e": 210, "fps": 2.5, "tag": 0}}
+    assert json.loads(trajnet_line(TrackRow(10, 7, 1.23456, -2.5))) == {"track": {"f": 10, "p": 7, "x": 1.23, "y": -2.5}}
+    assert json.loads(trajnet_line(TrackRow(10, 7, 1.0, 2.0, 0, 3)))["track"]["prediction_number"] == 0
+
+
+def test_write_then_read_round_trip(tmp_path):
+    rng = np.random.RandomState(0)
+    scenes = [("file", sid, _scene(sid, n, 1000 * sid, rng)) for sid, n in ((1, 3), (2, 1), (5, 4))]
+    preds = []
+    for _, _, paths in scenes:
+        K = len(paths) - 1
+        prim = rng.randn(12, 2)
+        neigh = rng.randn(12, K, 2) if K else []
+        preds.append({0: [prim, neigh]})
+    fn = os.path.join(tmp_path, "pred.ndjson")
+    write_predictions(preds, scenes, fn, obs_length=9, pred_length=12)
+    got = {sid: paths for sid, paths in read_ndjson_scenes(fn)}
+    assert sorted(got) == [1, 2, 5]
+    for (_, sid, paths), pred in zip(scenes, preds):
+        back = got[sid]
+        assert back[0][0].pedestrian == paths[0][0].pedestrian            # primary first
+        assert len(back) == len(paths)
+        assert [r.frame for r in back[0]] == [paths[0][8].frame + 10 * (k + 1) for k in range(12)]
+        assert np.allclose([[r.x, r.y] for r in back[0]], np.round(pred[0][0], 2))
+        by_id = {p[0].pedestrian: p for p in back[1:]}
+        for n, path in enumerate(paths[1:]):
+            assert np.allclose([[r.x, r.y] for r in by_id[path[0].pedestrian]], np.round(pred[0][1][:, n], 2))
+
+
+def test_preprocess_test_drops_late_tracks():
+    rng = np.random.RandomState(1)
+    paths = _scene(1, 3, 0, rng)
+    paths[2] = [r for r in paths[2] if r.frame >= 100]        # appears after the 9 observed frames
+    out = preprocess_test(paths, 9)
+    assert len(out) == 2 and all(r.frame <= 80 for p in out for r in p)
+    assert paths_to_xy(out).shape == (9, 2, 2)

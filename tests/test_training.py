@@ -151,3 +151,34 @@ def test_social_training_is_deterministic_and_learns():
         opt.step()
         losses.append(loss.item())
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused", [False, True])
+def test_optimizer_updates_reach_the_device_weights(fused):
+    """Fused optimizers update parameters without bumping `_version`; the device-side repack must
+    still follow (engine.weights_key): identical loss trajectories for both Adam implementations."""
+    from trajnetplusplusbaselines_b200.lstm import LSTM, GridBasedPooling, PredictionLoss
+    xy, bs = O.synthetic_scenes(16, 8, seed=3)
+    W = O.random_weights("directional", seed=2)
+    model = LSTM(pool=GridBasedPooling(**O.MODEL_SPECS["directional"]))
+    model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in W.items()})
+    model = model.cuda().train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4, fused=fused)
+    scene = torch.from_numpy(xy).cuda()
+    targets = scene[9:21] - scene[8:20]
+    crit = PredictionLoss()
+    losses = []
+    for _ in range(4):
+        rel, _ = model(scene[:9], torch.zeros(xy.shape[1], 2), torch.from_numpy(bs), scene[9:-1].clone())
+        loss = crit(rel[-12:], targets, torch.from_numpy(bs)) * 16
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert losses[1] < losses[0] and losses[3] < losses[1], losses
+    model.eval()
+    with torch.no_grad():      # the step taken after the last training forward is seen in eval mode too
+        rel, _ = model(scene[:9], torch.zeros(xy.shape[1], 2), torch.from_numpy(bs), scene[9:-1].clone())
+        after = crit(rel[-12:], targets, torch.from_numpy(bs)).item() * 16
+    assert after < losses[3], (after, losses)

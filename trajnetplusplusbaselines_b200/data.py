@@ -56,3 +56,57 @@ def read_ndjson_scenes(filename):
             continue
         paths = [by_ped[s.pedestrian]] + [p for pid, p in by_ped.items() if pid != s.pedestrian]
         yield s.scene, paths
+
+
+def preprocess_test(scene, obs_len):
+    """Drop tracks that only appear after the observation period (evaluator/write_utils.py:31-39)."""
+    obs_frames = [row.frame for row in scene[0]][:obs_len]
+    last_obs_frame = obs_frames[-1]
+    return [[row for row in ped if row.frame <= last_obs_frame]
+            for ped in scene if ped[0].frame <= last_obs_frame]
+
+
+def trajnet_line(row):
+    """One ndjson line for a SceneRow / TrackRow (the trajnetplusplustools.writers.trajnet format as it
+    appears in the reference's DATA_BLOCK files: coordinates rounded to 2 decimals)."""
+    if isinstance(row, SceneRow):
+        return json.dumps({'scene': {'id': row.scene, 'p': row.pedestrian, 's': row.start, 'e': row.end,
+                                     'fps': row.fps, 'tag': row.tag}})
+    x, y = round(float(row.x), 2), round(float(row.y), 2)
+    if row.prediction_number is None:
+        return json.dumps({'track': {'f': row.frame, 'p': row.pedestrian, 'x': x, 'y': y}})
+    return json.dumps({'track': {'f': row.frame, 'p': row.pedestrian, 'x': x, 'y': y,
+                                 'prediction_number': row.prediction_number, 'scene_id': row.scene_id}})
+
+
+def write_predictions(pred_list, scenes, filename, obs_length=9, pred_length=12):
+    """Append the predictions of a list of scenes to an ndjson file -- same records, in the same
+    order, as evaluator/write_utils.py:42-81 (which goes through trajnetplusplustools.writers).
+
+    pred_list : per scene {mode: [primary [pred_length, 2], neighbours [pred_length, K, 2] or []]}
+    scenes    : per scene (anything, scene_id, paths) as the reference evaluator holds them
+    """
+    seq_length = obs_length + pred_length
+    with open(filename, "a") as out:
+        for predictions, (_, scene_id, paths) in zip(pred_list, scenes):
+            observed_path = paths[0]
+            frame_diff = observed_path[1].frame - observed_path[0].frame
+            first_frame = observed_path[obs_length - 1].frame + frame_diff
+            ped_id = observed_path[0].pedestrian
+            neigh_ids = [p[0].pedestrian for p in paths[1:]]
+            out.write(trajnet_line(SceneRow(scene_id, ped_id, observed_path[0].frame,
+                                            observed_path[0].frame + (seq_length - 1) * frame_diff, 2.5, 0)))
+            out.write('\n')
+            for m in range(len(predictions)):
+                prediction, neigh_predictions = predictions[m]
+                for i in range(len(prediction)):
+                    out.write(trajnet_line(TrackRow(first_frame + i * frame_diff, ped_id, prediction[i][0],
+                                                    prediction[i][1], m, scene_id)))
+                    out.write('\n')
+                if len(neigh_predictions):
+                    for n in range(neigh_predictions.shape[1]):
+                        for j in range(neigh_predictions.shape[0]):
+                            out.write(trajnet_line(TrackRow(first_frame + j * frame_diff, neigh_ids[n],
+                                                            neigh_predictions[j, n, 0], neigh_predictions[j, n, 1],
+                                                            m, scene_id)))
+                            out.write('\n')

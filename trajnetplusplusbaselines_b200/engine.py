@@ -12,6 +12,28 @@ import torch
 from . import _lib
 
 
+# Parameter changes are detected through (data_ptr, _version) of every parameter.  Fused / foreach
+# optimizers (torch.optim.Adam(fused=True)) update parameters without bumping `_version`, so every
+# optimizer step additionally advances this epoch, which is part of the weight key.
+_optimizer_epoch = [0]
+
+
+def _on_optimizer_step(optimizer, args, kwargs):
+    _optimizer_epoch[0] += 1
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook
+    register_optimizer_step_post_hook(_on_optimizer_step)
+except Exception:      # very old torch: training forwards re-upload unconditionally (see LSTM._engine)
+    pass
+
+
+def weights_key(module):
+    """Changes whenever a parameter of `module` may have changed."""
+    return (_optimizer_epoch[0],) + tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 

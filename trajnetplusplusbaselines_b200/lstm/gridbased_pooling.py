@@ -9,7 +9,7 @@ pool is not even called -- the fused sequence entry point consumes its parameter
 import torch
 
 from .. import _lib
-from ..engine import LayoutCache, ModelHandle
+from ..engine import LayoutCache, ModelHandle, weights_key
 
 _TYPES = {'occupancy': _lib.POOL_OCCUPANCY, 'directional': _lib.POOL_DIRECTIONAL,
           'social': _lib.POOL_SOCIAL}
@@ -106,7 +106,7 @@ class GridBasedPooling(torch.nn.Module):
         return fields
 
     def weights_version(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return weights_key(self)
 
     # -- the plug --------------------------------------------------------------------------------
     def reset(self, num_tracks, max_num_neigh, device):

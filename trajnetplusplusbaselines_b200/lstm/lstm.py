@@ -12,7 +12,7 @@ import torch
 
 from .. import _lib
 from ..data import paths_to_xy
-from ..engine import LayoutCache, ModelHandle
+from ..engine import LayoutCache, ModelHandle, weights_key
 from .modules import Hidden2Normal, InputEmbedding
 
 NAN = float('nan')
@@ -110,8 +110,10 @@ class LSTM(torch.nn.Module):
                     raise NotImplementedError("only GridBasedPooling interaction modules are built")
                 self.pool.fill_config(cfg)
             self._handle = ModelHandle(cfg, device)
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
-        if key != self._handle._weights_key:
+        key = weights_key(self)
+        # under grad mode (training) the repack is redone on every forward: an update scheme that
+        # by-passes both version counters and torch.optim hooks must not train on stale weights
+        if key != self._handle._weights_key or (torch.is_grad_enabled() and self.training):
             self._handle.set_weights(self._weight_fields(), key=key)
         return self._handle
 
