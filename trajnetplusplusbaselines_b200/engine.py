@@ -111,9 +111,9 @@ class ModelHandle:
                 setattr(w, field, t.data_ptr())
         return w, keep
 
-    def set_weights(self, named, key=None):
+    def set_weights(self, named, key=None, force=False):
         """named: dict field name -> CUDA fp32 contiguous tensor (or list of 3 for the MLP)."""
-        if key is not None and key == self._weights_key:
+        if not force and key is not None and key == self._weights_key:
             return
         lib = _lib.load()
         w = _lib.LstmWeights()

@@ -113,8 +113,9 @@ class LSTM(torch.nn.Module):
         key = weights_key(self)
         # under grad mode (training) the repack is redone on every forward: an update scheme that
         # by-passes both version counters and torch.optim hooks must not train on stale weights
-        if key != self._handle._weights_key or (torch.is_grad_enabled() and self.training):
-            self._handle.set_weights(self._weight_fields(), key=key)
+        force = torch.is_grad_enabled() and self.training
+        if force or key != self._handle._weights_key:
+            self._handle.set_weights(self._weight_fields(), key=key, force=force)
         return self._handle
 
     def _weight_fields(self):
