@@ -231,13 +231,26 @@ def main():
     for _ in range(args.warmup):
         step_e2e()
     barrier()
-    e2e_ms = 0.0
-    for i in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize(device)
-        t0 = time.perf_counter()
-        rel, pred = step_e2e()             # returns host tensors after a stream sync
-        e2e_ms += 1e3 * (time.perf_counter() - t0)
+    def e2e_pass():
+        per_step = []
+        for i in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize(device)
+            t0 = time.perf_counter()
+            out = step_e2e()               # returns host tensors after a stream sync
+            per_step.append(1e3 * (time.perf_counter() - t0))
+        return per_step, out
+
+    import gc
+    gc.collect()
+    per_step, (rel, pred) = e2e_pass()
+    e2e_remeasured = False
+    if max(per_step) > 5.0 * sorted(per_step)[len(per_step) // 2]:
+        # a host-side stall (another tenant on the box, a descheduled process) hit one wall-clock
+        # timed step: the whole pass is measured again, once, and that second pass is what counts
+        per_step, (rel, pred) = e2e_pass()
+        e2e_remeasured = True
+    e2e_ms = sum(per_step)
     barrier()
     h2d = observed_host.numel() * 4 + bs_t.numel() * 8
     d2h = (rel.numel() + pred.numel()) * 4
@@ -312,7 +325,7 @@ def main():
                        "recurrence_steps_per_step": STEPS_PER_FORWARD, "parallelism": "scenes sharded x%d, no collective" % world,
                        "l2": "256 MiB memset between timed iterations (untimed); inputs are smaller than L2"},
             "e2e": {"value": e2e_value, "unit": "ped-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms_max / args.steps},
+                    "ms_per_step": e2e_ms_max / args.steps, "remeasured_after_host_stall": e2e_remeasured},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,

@@ -37,6 +37,39 @@ extern std::atomic<uint64_t> g_launch_count;
         TB2_CHECK_CUDA(cudaGetLastError());                                               \
     } while (0)
 
+// Programmatic dependent launch: the kernels of a recurrence step are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's CTAs become resident
+// and run their prologue (barrier init, TMEM allocation, tensor-map prefetch) while the previous
+// kernel drains.  Every thread executes grid_dep_wait() before its first access to global memory
+// (it returns once the preceding grid has completed and its writes are visible), then
+// grid_dep_launch() lets the following kernel start its own prologue.  TB2_PDL=0 switches the
+// launch attribute off (the two instructions are then no-ops).
+#ifdef __CUDACC__
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("TB2_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // Optional per-kernel timing (tb2_profile_begin / tb2_profile_end): CUDA events recorded on the
 // launching stream around every kernel of the library.  Off by default (zero overhead).
 struct KernelTimer {

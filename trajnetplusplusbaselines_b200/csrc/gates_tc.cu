@@ -160,6 +160,8 @@ lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap map_emb_hi, const __gri
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
+    grid_dep_wait();          // embedding / pooled / state operands come from the previous kernels
+    grid_dep_launch();
     if (dbg && threadIdx.x == 0) dbg[0] = clock64() - t_begin;
     // cluster barrier phase 1 (arrive now, wait before the first DSMEM access): a CTA may only
     // touch its peer's shared memory once the peer is known to be resident
@@ -376,6 +378,8 @@ lstm_gates_tc_kernel(const __grid_constant__ CUtensorMap map_emb_hi, const __gri
 __global__ void embed_split_kernel(const float2* __restrict__ obs1, const float2* __restrict__ obs2,
                                    const float* __restrict__ We, const float* __restrict__ be,
                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int M, int E) {
+    grid_dep_wait();
+    grid_dep_launch();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * E) return;
     const int m = idx / E, k = idx - m * E;
@@ -440,8 +444,9 @@ int launch_embed_split(const tb2_lstm* m, int M, const float* obs1, const float*
     const int total = M * m->E;
     {
         KernelTimer kt("embed_split", st);
-        embed_split_kernel<<<(total + 255) / 256, 256, 0, st>>>((const float2*)obs1, (const float2*)obs2, m->We, m->be,
-                                                               (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, M, m->E);
+        launch_pdl(embed_split_kernel, dim3((total + 255) / 256), dim3(256), 0, st, (const float2*)obs1,
+                   (const float2*)obs2, (const float*)m->We, (const float*)m->be, (__nv_bfloat16*)hi,
+                   (__nv_bfloat16*)lo, M, m->E);
     }
     TB2_LAUNCH_CHECK();
     return TB2_OK;
@@ -507,7 +512,8 @@ int launch_gates_tc(const tb2_lstm* m, const tb2_layout* l, int phase, const flo
     dim3 grid(2, (M + kGtBM - 1) / kGtBM);
     {
         KernelTimer kt("lstm_gates_tc", st);
-        lstm_gates_tc_kernel<<<grid, kGtThreads, smem, st>>>(me_hi, me_lo, mp_hi, mp_lo, mh_hi, mh_lo, mw_hi, mw_lo, p);
+        launch_pdl(lstm_gates_tc_kernel, grid, dim3(kGtThreads), smem, st, me_hi, me_lo, mp_hi, mp_lo, mh_hi, mh_lo,
+                   mw_hi, mw_lo, p);
     }
     TB2_LAUNCH_CHECK();
     if (p.dbg && ++dbg_calls == 60) {

@@ -132,6 +132,8 @@ dense_layer_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
+    grid_dep_wait();          // the A operand is the previous kernel's output
+    grid_dep_launch();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -293,7 +295,7 @@ static int launch_dense_tc_t(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo,
     dim3 grid(p.N / BN, (p.M + kTcBM - 1) / kTcBM);
     {
         KernelTimer kt("dense_layer_tc", st);
-        dense_layer_tc_kernel<BN><<<grid, kTcThreads, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+        launch_pdl(dense_layer_tc_kernel<BN>, grid, dim3(kTcThreads), smem, st, ma_hi, ma_lo, mb_hi, mb_lo, p);
     }
     TB2_LAUNCH_CHECK();
     return TB2_OK;

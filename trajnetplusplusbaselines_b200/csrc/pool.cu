@@ -26,6 +26,8 @@ namespace tb2 {
 __global__ void resolve_obs_kernel(const float2* __restrict__ base, const float2* __restrict__ pred,
                                    const int* __restrict__ row_scene,
                                    const int* __restrict__ scene_off, float2* __restrict__ out, int M) {
+    grid_dep_wait();
+    grid_dep_launch();
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
     bool primary = (scene_off[row_scene[m]] == m);
@@ -37,8 +39,8 @@ int launch_resolve_obs(const tb2_layout* l, const float* base, const float* pred
     int threads = 256, blocks = (l->M + threads - 1) / threads;
     {
         KernelTimer kt("resolve_obs", st);
-        resolve_obs_kernel<<<blocks, threads, 0, st>>>((const float2*)base, (const float2*)pred,
-                                                       l->row_scene, l->scene_off, (float2*)out, l->M);
+        launch_pdl(resolve_obs_kernel, dim3(blocks), dim3(threads), 0, st, (const float2*)base, (const float2*)pred,
+                   (const int*)l->row_scene, (const int*)l->scene_off, (float2*)out, l->M);
     }
     TB2_LAUNCH_CHECK();
     return TB2_OK;
@@ -100,6 +102,8 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
     float* Ws = reinterpret_cast<float*>(cellrow + kPrepWarps * (nm1 > 0 ? nm1 : 1));   // [H][C]   (social)
     float* hs = Ws + (p.H + 4) * p.C;                                   // [n_s][H] (social); Ws rows padded by 4
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    grid_dep_wait();          // obs / hidden state come from the previous kernels of the stream
+    grid_dep_launch();
     long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 8 : nullptr;
     const long long t_begin = clock64();
 
@@ -291,7 +295,7 @@ int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hid
     }
     {
         KernelTimer kt("pool_prepare", st);
-        pool_prepare_kernel<<<l->B, kPrepThreads, smem, st>>>(p);
+        launch_pdl(pool_prepare_kernel, dim3(l->B), dim3(kPrepThreads), smem, st, p);
     }
     TB2_LAUNCH_CHECK();
     if (p.dbg && ++dbg_calls == 60) {
@@ -924,6 +928,8 @@ __global__ void __launch_bounds__(kRowsThreads, 1) pool_rows_kernel(RowsParams p
     uint32_t* ent_s = reinterpret_cast<uint32_t*>(cnt_s + p.rows_per_cta);      // [rows_per_cta][nm1]
     float* val_s = reinterpret_cast<float*>(ent_s + (size_t)p.rows_per_cta * p.nm1);   // [rows_per_cta][nm1][2]
     const int tid = threadIdx.x;
+    grid_dep_wait();
+    grid_dep_launch();
     const int col0 = blockIdx.y * p.CH;
     const int r0 = blockIdx.x * p.rows_per_cta;
     const int nrows = min(p.rows_per_cta, p.M - r0);
@@ -1015,7 +1021,7 @@ static int launch_pool_rows(const tb2_lstm* m, const tb2_layout* l, const Worksp
     }
     {
         KernelTimer kt("pool_rows", st);
-        pool_rows_kernel<<<dim3(groups, chunks), kRowsThreads, smem, st>>>(p);
+        launch_pdl(pool_rows_kernel, dim3(groups, chunks), dim3(kRowsThreads), smem, st, p);
     }
     TB2_LAUNCH_CHECK();
     return TB2_OK;

@@ -166,6 +166,8 @@ sparse_layer1_tc_kernel(const __grid_constant__ CUtensorMap map_w_hi, const __gr
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
     const int n_items = p.cells;          // every cell is one pipeline item (empty buckets multiply zeros)
+    grid_dep_wait();          // winners / latent vectors (and, after a weight update, the slabs) come from earlier kernels
+    grid_dep_launch();
 
     // ---- phase 1 (warps 1..13, 416 threads): zeroed L tiles, split latent vectors, per-cell buckets,
     //      while warp 0 already streams the first weight slabs -------------------------------------------
@@ -460,7 +462,7 @@ int launch_sparse_tc(const tb2_lstm* m, const tb2_layout* l, int gsel, Workspace
     dim3 grid(l->num_groups[gsel], d1 / kScCols);
     {
         KernelTimer kt("sparse_layer1_tc", st);
-        sparse_layer1_tc_kernel<<<grid, kScThreads, smem, st>>>(mh, ml, p);
+        launch_pdl(sparse_layer1_tc_kernel, grid, dim3(kScThreads), smem, st, mh, ml, p);
     }
     TB2_LAUNCH_CHECK();
     if (p.dbg && ++dbg_calls == 60) {

@@ -147,7 +147,9 @@ class LSTM(torch.nn.Module):
         if buf is None:
             buf = torch.empty(t.shape, dtype=torch.float32, pin_memory=True)
             self._pinned[key] = buf
-        buf.copy_(t)
+        # plain single-threaded memcpy: torch's CPU copy_ may go through the intra-op thread pool,
+        # whose wake-up latency showed rare 10-50 ms tails on the (virtualised) GPU hosts
+        np.copyto(buf.numpy(), t.numpy())
         return buf.to(device, non_blocking=True)
 
     # -- reference API -----------------------------------------------------------------------
