@@ -161,6 +161,25 @@ int tb2_lstm_forward_sequence(const tb2_lstm* model, const tb2_layout* layout,
                               float* h_dev, float* c_dev, float* states_out_dev,
                               void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Steps [first_step, last_step) of the same time loop (S = obs_length - 1 + n_decode steps in all).
+ * first_step = 0 starts from the zero state; otherwise h_dev / c_dev hold the state after step
+ * first_step - 1 -- possibly edited by the caller in between, which is how the S-GAN generator
+ * injects noise between encoder and decoder (sgan/sgan.py:200-221,373) -- and positions_out_dev
+ * holds the positions of the earlier steps.  tb2_lstm_forward_sequence == steps [0, S). */
+int tb2_lstm_forward_steps(const tb2_lstm* model, const tb2_layout* layout,
+                           const float* observed_dev, int32_t obs_length,
+                           const float* truth_dev, int32_t n_decode, int32_t first_step, int32_t last_step,
+                           float* normals_out_dev, float* positions_out_dev,
+                           float* h_dev, float* c_dev, float* states_out_dev,
+                           void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* LSTMGenerator.adding_noise (sgan/sgan.py:200-221), in place on the hidden state of all tracks:
+ *   h[m] <- cat(ReLU(weight . h[m] + bias), noise)   weight [H - noise_dim, H] (mlp_decoder_context.0),
+ * noise [noise_dim] is one vector shared by all tracks.  Called between the encoder steps and the
+ * decoder steps of tb2_lstm_forward_steps. */
+int tb2_sgan_add_noise(const float* weight_dev, const float* bias_dev, const float* noise_dev, float* h_dev,
+                       int32_t M, int32_t H, int32_t noise_dim, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Training: backward of the whole time loop (what autograd does for Trainer.train_batch,
  * lstm/trainer.py:229-269, through LSTM.forward).  Gradient accumulators are fp32 device

@@ -273,7 +273,7 @@ def step(weights, pool_cfg, phase, h, c, obs1, obs2, batch_split, pool_to_input=
 
 
 def forward(weights, pool_cfg, observed, batch_split, prediction_truth=None, n_predict=None,
-            hidden_dim=128, pool_to_input=True, return_states=False):
+            hidden_dim=128, pool_to_input=True, return_states=False, between=None):
     """LSTM.forward (lstm.py:170-264), goals off (goal_flag=False in all BASELINE configs).
 
     Returns rel_pred_scene [S, M, 5], pred_scene [S(+1), M, 2].
@@ -297,6 +297,8 @@ def forward(weights, pool_cfg, observed, batch_split, prediction_truth=None, n_p
         normals.append(normal)
         positions.append((obs2 + normal[:, :2]).astype(F32))
         states.append((h, c))
+    if between is not None:      # hook between encoder and decoder (S-GAN noise injection, sgan.py:373)
+        h, c = between(h, c)
     seq = [observed[-1].copy()] + truth                                     # :235-237
     for k in range(len(seq) - 1):                                           # :240-255
         obs1, obs2 = seq[k], seq[k + 1]

@@ -447,29 +447,38 @@ int tb2_lstm_step_forward(const tb2_lstm* m, const tb2_layout* l, int32_t phase,
     return step_impl(m, l, phase, obs1, obs2, h_in, c_in, h_out, c_out, normal_out, pos_out, &ws, 0, st);
 }
 
-int tb2_lstm_forward_sequence(const tb2_lstm* m, const tb2_layout* l, const float* observed,
-                              int32_t obs_length, const float* truth, int32_t n_decode,
-                              float* normals_out, float* positions_out, float* h, float* c,
-                              float* states_out, void* workspace, size_t workspace_bytes, void* stream) {
+// Steps [first_step, last_step) of the time loop.  first_step == 0 starts from the zero state
+// (lstm.py:207-210); otherwise h / c hold the state after step first_step - 1 (possibly edited by
+// the caller, e.g. the noise injection of the S-GAN generator between encoder and decoder,
+// sgan/sgan.py:200-221,373) and positions_out holds the positions of the earlier steps.
+int tb2_lstm_forward_steps(const tb2_lstm* m, const tb2_layout* l, const float* observed,
+                           int32_t obs_length, const float* truth, int32_t n_decode, int32_t first_step,
+                           int32_t last_step, float* normals_out, float* positions_out, float* h, float* c,
+                           float* states_out, void* workspace, size_t workspace_bytes, void* stream) {
     int rc = check_ready(m, l, workspace, workspace_bytes);
     if (rc) return rc;
     TB2_REQUIRE(observed && normals_out && positions_out && h && c, "null argument");
     TB2_REQUIRE(obs_length >= 2 && n_decode >= 0, "need obs_length >= 2 and n_decode >= 0");
+    const int S = obs_length - 1 + n_decode;
+    TB2_REQUIRE(first_step >= 0 && first_step <= last_step && last_step <= S, "bad step range");
     Workspace ws;
     carve_workspace(m, l, workspace, &ws);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t M = (size_t)l->M, H = (size_t)m->H;
     const size_t frame = M * 2;
-    TB2_CHECK_CUDA(cudaMemsetAsync(h, 0, M * H * sizeof(float), st));     // lstm.py:207-210
-    TB2_CHECK_CUDA(cudaMemsetAsync(c, 0, M * H * sizeof(float), st));
-    if (m->Wg_hi[0]) {
-        TB2_CHECK_CUDA(cudaMemsetAsync(ws.hs_hi[0], 0, M * H * 2, st));
-        TB2_CHECK_CUDA(cudaMemsetAsync(ws.hs_lo[0], 0, M * H * 2, st));
+    if (first_step == 0) {
+        TB2_CHECK_CUDA(cudaMemsetAsync(h, 0, M * H * sizeof(float), st));     // lstm.py:207-210
+        TB2_CHECK_CUDA(cudaMemsetAsync(c, 0, M * H * sizeof(float), st));
+        if (m->Wg_hi[0]) {
+            TB2_CHECK_CUDA(cudaMemsetAsync(ws.hs_hi[0], 0, M * H * 2, st));
+            TB2_CHECK_CUDA(cudaMemsetAsync(ws.hs_lo[0], 0, M * H * 2, st));
+        }
+    } else if (m->Wg_hi[0]) {      // bf16 split of the incoming state for the tensor-core gate kernel
+        if ((rc = launch_split_rows(h, ws.hs_hi[first_step & 1], ws.hs_lo[first_step & 1], M * H, st))) return rc;
     }
-    const int S = obs_length - 1 + n_decode;
     const float* h_prev = h;
     const float* c_prev = c;
-    for (int s = 0; s < S; ++s) {
+    for (int s = first_step; s < last_step; ++s) {
         const float* o1;
         const float* o2;
         int phase;
@@ -483,11 +492,20 @@ int tb2_lstm_forward_sequence(const tb2_lstm* m, const tb2_layout* l, const floa
         h_prev = h_next;
         c_prev = c_next;
     }
-    if (states_out && S > 0) {
+    if (states_out && last_step > first_step) {
         TB2_CHECK_CUDA(cudaMemcpyAsync(h, h_prev, M * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
         TB2_CHECK_CUDA(cudaMemcpyAsync(c, c_prev, M * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     return TB2_OK;
+}
+
+int tb2_lstm_forward_sequence(const tb2_lstm* m, const tb2_layout* l, const float* observed,
+                              int32_t obs_length, const float* truth, int32_t n_decode,
+                              float* normals_out, float* positions_out, float* h, float* c,
+                              float* states_out, void* workspace, size_t workspace_bytes, void* stream) {
+    TB2_REQUIRE(obs_length >= 2 && n_decode >= 0, "need obs_length >= 2 and n_decode >= 0");
+    return tb2_lstm_forward_steps(m, l, observed, obs_length, truth, n_decode, 0, obs_length - 1 + n_decode,
+                                  normals_out, positions_out, h, c, states_out, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -183,6 +183,16 @@ class ModelHandle:
                                                  _ptr(pos), _ptr(ws), need, _stream(self.device)))
         return normal, pos
 
+    def forward_steps(self, layout, observed, truth, n_decode, first_step, last_step, normals, positions, h, c):
+        """Steps [first_step, last_step) of the time loop on caller-owned state (tb2_lstm_forward_steps)."""
+        lib = _lib.load()
+        ws, need = self.workspace(layout)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.tb2_lstm_forward_steps(
+                self.handle, layout.handle, _ptr(observed), int(observed.shape[0]), _ptr(truth),
+                int(n_decode), int(first_step), int(last_step), _ptr(normals), _ptr(positions), _ptr(h), _ptr(c),
+                _ptr(None), _ptr(ws), need, _stream(self.device)))
+
     def forward_sequence(self, layout, observed, truth, n_decode, normals, positions, h, c, states=None):
         lib = _lib.load()
         ws, need = self.workspace(layout)
