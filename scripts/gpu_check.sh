@@ -29,6 +29,10 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"sparse_layer1_tc|lstm_gates_tc|dense_layer_tc|pool_prepare" \
     -s 40 -c 8 -o $out/${tag}_prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/${tag}_ncu_full.log 2>&1
 timeout 600 python scripts/classical_bench.py > $out/${tag}_classical_bench.log 2>&1
+timeout 300 python scripts/configs_bench.py > $out/${tag}_configs_bench.log 2>&1
+timeout 300 python scripts/train_bench_social.py > $out/${tag}_train_social.log 2>&1
+timeout 300 python scripts/evaluator_bench.py social > $out/${tag}_evaluator.log 2>&1
+timeout 300 python scripts/sgan_bench.py social > $out/${tag}_sgan.log 2>&1
 tail -4 $out/${tag}_canary.log
 grep -E "passed|failed|FAILED|ADE mean|teacher-forced" $out/${tag}_pytest.log | tail -30
 [ -f $out/${tag}_pytest_notc.log ] && tail -3 $out/${tag}_pytest_notc.log
@@ -37,3 +41,5 @@ cat $out/parity_report.txt 2>/dev/null | tail -20; head -3 $out/${tag}_e2e_profi
 
 tail -2 $out/${tag}_train_bench.log
 cat $out/${tag}_classical_bench.log
+tail -4 $out/${tag}_configs_bench.log | cut -c1-160
+tail -1 $out/${tag}_train_social.log; tail -1 $out/${tag}_evaluator.log; tail -1 $out/${tag}_sgan.log
