@@ -180,6 +180,11 @@ int tb2_lstm_forward_steps(const tb2_lstm* model, const tb2_layout* layout,
 int tb2_sgan_add_noise(const float* weight_dev, const float* bias_dev, const float* noise_dev, float* h_dev,
                        int32_t M, int32_t H, int32_t noise_dim, void* stream);
 
+/* VAE.add_noise at test time (vae/vae.py:87-106), in place: h[m] <- h[m] * ReLU(weight . z[m] + bias),
+ * weight [H, latent_dim] (vae_decoder.fc), z [M, latent_dim] one latent sample per track. */
+int tb2_vae_scale_hidden(const float* weight_dev, const float* bias_dev, const float* z_dev, float* h_dev,
+                         int32_t M, int32_t H, int32_t latent_dim, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Training: backward of the whole time loop (what autograd does for Trainer.train_batch,
  * lstm/trainer.py:229-269, through LSTM.forward).  Gradient accumulators are fp32 device

@@ -65,3 +65,43 @@ def sgan_weights(kind, seed):
         dis["real_classifier.%d.weight" % (2 * i)] = rng.uniform(0, kk, size=(b, a)).astype(F32)
         dis["real_classifier.%d.bias" % (2 * i)] = rng.uniform(0, kk, size=(b,)).astype(F32)
     return gen, dis
+
+
+# ----------------------------------------------------------------------------------------
+# VAE at test time (trajnetbaselines/vae/vae.py:188-315, add_noise :87-106)
+# ----------------------------------------------------------------------------------------
+def vae_forward(weights, pool_cfg, observed, batch_split, prediction_truth=None, n_predict=None, z=None):
+    """One mode: h <- h * ReLU(fc z) between the observation encoder and the decoder."""
+    W = dict(weights)
+    for k in list(W):
+        if k.startswith("obs_encoder."):
+            W["encoder." + k[len("obs_encoder."):]] = W[k]
+
+    def between(h, c):
+        dec = np.maximum(np.asarray(z, F32) @ W["vae_decoder.fc.weight"].T + W["vae_decoder.fc.bias"], 0).astype(F32)
+        return (h * dec).astype(F32), c
+    return O.forward(W, pool_cfg, observed, batch_split, prediction_truth=prediction_truth, n_predict=n_predict,
+                     between=between)
+
+
+def vae_weights(kind, seed, latent_dim=128):
+    import math
+    base = O.random_weights(kind, seed=seed)
+    rng = np.random.RandomState(2000 + seed)
+    W = {}
+    for k, v in base.items():
+        W[("obs_encoder." + k[len("encoder."):]) if k.startswith("encoder.") else k] = v
+    H = base["encoder.weight_hh"].shape[1]
+    for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+        W["pred_encoder." + k] = rng.uniform(-0.08, 0.08, size=base["encoder." + k].shape).astype(F32)
+
+    def lin(name, out_f, in_f, lo=None):
+        kk = 1.0 / math.sqrt(in_f)
+        W[name + ".weight"] = rng.uniform(-kk if lo is None else lo, kk, size=(out_f, in_f)).astype(F32)
+        W[name + ".bias"] = rng.uniform(-kk if lo is None else lo, kk, size=(out_f,)).astype(F32)
+    lin("vae_encoder_xy.fc_mu", latent_dim, 2 * H)
+    lin("vae_encoder_xy.fc_var", latent_dim, 2 * H)
+    lin("vae_encoder_x.fc_mu", latent_dim, H)
+    lin("vae_encoder_x.fc_var", latent_dim, H)
+    lin("vae_decoder.fc", H, latent_dim, lo=-0.02)          # mostly positive: the ReLU gate stays open
+    return W
