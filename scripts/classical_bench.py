@@ -59,3 +59,25 @@ for b in range(ns * 10):
 t_orca = time.perf_counter() - t0
 print(json.dumps({"cpu_restatement": {"sf_numpy_ped_steps_per_s": ns * N * 96 / t_sf,
                                       "orca_c_ped_steps_per_s": ns * 10 * N * 97 / t_orca, "cores": 1}}))
+
+# BASELINE configs[0]: Kalman predictor, 64 scenes x 5 pedestrians, 9 observed -> 12 predicted; CPU only
+# (host C++ EM + RTS smoother behind tb2_kalman_predict vs the numpy restatement, one thread each)
+from trajnetplusplusbaselines_b200.classical import kalman
+krng = np.random.RandomState(5)
+tracks = []
+for _ in range(64 * 5):
+    p0, v = krng.randn(2) * 2.0, krng.randn(2) * 0.3
+    tracks.append(p0 + np.arange(9)[:, None] * v + krng.randn(9, 2) * 0.05)
+kalman.predict_tracks(tracks[:8], n_predict=12, n_samples=0)
+t0 = time.perf_counter()
+reps = 20
+for _ in range(reps):
+    pred = kalman.predict_tracks(tracks, n_predict=12, n_samples=0)
+t_kf = (time.perf_counter() - t0) / reps
+t0 = time.perf_counter()
+for t in tracks[:32]:
+    C.kalman_predict_track(t, n_predict=12, n_iter=10)
+t_kf_np = (time.perf_counter() - t0) / 32 * len(tracks)
+print(json.dumps({"sim": "kalman_host_cpp", "scenes": 64, "tracks": len(tracks), "ms": 1e3 * t_kf,
+                  "ped_steps_per_s": len(tracks) * 12 / t_kf, "numpy_restatement_ped_steps_per_s": len(tracks) * 12 / t_kf_np,
+                  "cores": 1, "finite": bool(np.isfinite(pred).all())}))

@@ -327,3 +327,36 @@ def test_predictor_boundary_roundtrip(tmp_path):
     again = LSTMPredictor.load(fn)
     out2 = again(paths, np.zeros((3, 2)), n_predict=12, obs_length=9, modes=1, args=args)
     assert np.array_equal(out2[0][0], prim)
+
+
+def _large_scenes(sizes, seed=0):
+    rng = np.random.RandomState(seed)
+    xs = []
+    for n in sizes:
+        p0 = rng.randn(n, 2) * 3.0
+        xs.append(p0[None] + np.cumsum(rng.randn(21, n, 2) * 0.3, axis=0))
+    xy = np.concatenate(xs, axis=1).astype(np.float32)
+    xy[:4, 5] = np.nan                      # a late entry and an early exit inside the big scene
+    xy[12:, 7] = np.nan
+    return xy, np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["social", "directional"])
+def test_large_scenes_take_the_fallback_kernels(kind):
+    """Scenes far beyond the BASELINE size (90 and 40 pedestrians next to a 3-pedestrian one): the
+    grouping / shared-memory budgets of the tensor-core kernels no longer fit and the warp-level /
+    FFMA kernels take over; results still match the oracle within the 1e-4 m gate."""
+    from trajnetplusplusbaselines_b200.lstm import LSTM, GridBasedPooling
+    xy, bs = _large_scenes([90, 3, 40])
+    W = O.random_weights(kind, seed=4)
+    rel_o, pred_o = O.forward(W, O.pool_config(kind), xy[:9], bs, n_predict=12)
+    model = LSTM(pool=GridBasedPooling(**O.MODEL_SPECS[kind]))
+    model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in W.items()})
+    model = model.cuda().eval()
+    with torch.no_grad():
+        rel, pred = model(torch.from_numpy(xy[:9]), torch.zeros(xy.shape[1], 2), torch.from_numpy(bs), n_predict=12)
+    rel, pred = rel.numpy(), pred.numpy()
+    assert (np.isnan(pred) == np.isnan(pred_o)).all()
+    assert np.nanmax(np.abs(pred - pred_o)) < 1e-4
+    assert np.nanmax(np.abs(rel - rel_o)) < 1e-4

@@ -182,3 +182,27 @@ def test_optimizer_updates_reach_the_device_weights(fused):
         rel, _ = model(scene[:9], torch.zeros(xy.shape[1], 2), torch.from_numpy(bs), scene[9:-1].clone())
         after = crit(rel[-12:], targets, torch.from_numpy(bs)).item() * 16
     assert after < losses[3], (after, losses)
+
+
+@pytest.mark.gpu
+def test_social_training_large_scene():
+    """BPTT through social pooling with a 70-pedestrian scene next to small ones: finite, repeatable,
+    and the primaries' loss matches the value the oracle computes for the same forward."""
+    from trajnetplusplusbaselines_b200.lstm import PredictionLoss
+    rng = np.random.RandomState(3)
+    sizes = [70, 2, 25]
+    xs = [rng.randn(n, 2)[None] * 3.0 + np.cumsum(rng.randn(21, n, 2) * 0.3, axis=0) for n in sizes]
+    xy = np.concatenate(xs, axis=1).astype(np.float32)
+    bs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    W = O.random_weights("social", seed=6)
+    m1, loss1 = _cuda_train_step("social", W, xy, bs)
+    m2, loss2 = _cuda_train_step("social", W, xy, bs)
+    rel_o, _ = O.forward(W, O.pool_config("social"), xy[:9], bs, prediction_truth=xy[9:-1])
+    loss_o = float(O.prediction_loss(rel_o[-12:], xy[9:21] - xy[8:20], bs)) * (len(bs) - 1)
+    assert abs(loss1 - loss_o) < 1e-3 * max(1.0, abs(loss_o))
+    assert loss1 == loss2
+    for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        if p1.grad is None:
+            continue
+        assert torch.isfinite(p1.grad).all(), n1
+        assert torch.equal(p1.grad, p2.grad), n1
