@@ -894,11 +894,6 @@ static int launch_dense(const float* X, const float* WT, const float* b, float* 
     return TB2_OK;
 }
 
-int launch_dense_plain(const float* X, const float* WT, const float* b, float* Y, int M, int K, int N, int relu,
-                       cudaStream_t st) {
-    return launch_dense(X, WT, b, Y, M, K, N, relu, st);
-}
-
 // ------------------------------------------------------------------------------------------
 // First Linear for occupancy / directional grids (C <= 2 payload channels): the whole weight
 // chunk [cells * C][CH output columns] fits in shared memory, so a CTA loads it once and then

@@ -7,15 +7,18 @@
 // pooled vector does not depend on any hidden state, so a track's gradient never leaves its own
 // LSTM chain.  The caller passes the list of ACTIVE rows (tracks that receive a non-zero upstream
 // gradient: the scene primaries for PredictionLoss, loss.py:57,67) and the whole backward runs
-// on those R rows only.  Per step (reverse time): winners of the step (pool_prepare), gather of
-// X = [emb | pooled | h_prev] with the pooled rows recomputed from the winner list, recompute of
-// the gate pre-activations (R x K x 512), pointwise cell / head backward, one input-gradient GEMM
-// dX = dgates . [W_ih | W_hh], sparse scatter into dW1.  X, dgates, h, d(normal), velocity and
-// dX_emb of every (step, row) are kept, so each dense parameter gradient is ONE reduction over all
-// S * R records after the loop (a tile of the output is owned by one CTA: deterministic).
-// Social pooling couples the tracks of a scene through W_enc h_j and is not built yet (fails
-// loudly).  No floating-point atomics anywhere: the first grid-embedding layer's weight gradient is
-// dz^T . grid with the (R-row) grid of each step written out densely by the gather kernel.
+// on those R rows only, in phases:
+//   (A) per step: winners (pool_prepare) and the gather of X = [emb | pooled | h_prev], the pooled
+//       rows recomputed from the winner list, plus the dense grid row of each active track;
+//   (B) gate pre-activations of all steps in one GEMM per cell (encoder / decoder weights);
+//   (C) the sequential chain, ONE kernel per step: cell + head backward with the recurrent
+//       dgates(s+1) . W_hh mat-vec fused in;
+//   (D) input gradients of all steps in one GEMM;  (E) every parameter gradient as one reduction
+//       over all S * R (step, row) records, rows split over CTAs with the partial sums added in a
+//       fixed order.  No floating-point atomics: results are bit-identical from run to run.
+// Social pooling couples the tracks of a scene through lat_j = W_enc h_j: every track receives
+// gradient, so social_backward (further down) runs the same phases on all M rows and adds the
+// backward of the grid MLP and of the hidden-state scatter to the chain.
 #include <cuda_bf16.h>
 #include <math_constants.h>
 
