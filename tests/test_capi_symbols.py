@@ -61,3 +61,43 @@ def test_state_dict_keys_match_reference_layout():
     }
     for k, shape in expect.items():
         assert tuple(sd[k].shape) == shape, k
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """The boundary is a C ABI: a C translation unit (gcc, not nvcc / g++) includes the header, takes the
+    address of every entry point and links against the shared library."""
+    import re
+    import subprocess
+    header = open(os.path.join(ROOT, "include", "trajnet_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(tb2_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) >= 20
+    src = os.path.join(tmp_path, "abi.c")
+    with open(src, "w") as f:
+        f.write('#include "trajnet_b200.h"\n#include <stdio.h>\ntypedef void (*fn_t)(void);\n'
+                'int main(void) {\n    fn_t fns[] = {\n')
+        f.write("".join("        (fn_t)%s,\n" % n for n in names))
+        f.write('    };\n    printf("%d %d\\n", (int)(sizeof(fns) / sizeof(fns[0])), tb2_version());\n    return 0;\n}\n')
+    libdir = os.path.join(ROOT, "trajnetplusplusbaselines_b200")
+    exe = os.path.join(tmp_path, "abi")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                    "-L", libdir, "-l:libtrajnet_b200.so", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == len(names) and int(out[1]) > 0
+
+
+def test_weight_key_follows_optimizer_steps():
+    """engine.weights_key must change after ANY optimizer step (fused optimizers do not bump the
+    parameters' version counters) and stay put otherwise."""
+    import torch
+    from trajnetplusplusbaselines_b200.engine import weights_key
+    lin = torch.nn.Linear(4, 3)
+    k0 = weights_key(lin)
+    assert weights_key(lin) == k0
+    opt = torch.optim.SGD(lin.parameters(), lr=0.1)
+    lin(torch.ones(2, 4)).sum().backward()
+    opt.step()
+    k1 = weights_key(lin)
+    assert k1 != k0
+    with torch.no_grad():
+        lin.weight.add_(1.0)            # plain in-place update: version counter
+    assert weights_key(lin) != k1
