@@ -56,3 +56,41 @@ def test_preprocess_test_drops_late_tracks():
     out = preprocess_test(paths, 9)
     assert len(out) == 2 and all(r.frame <= 80 for p in out for r in p)
     assert paths_to_xy(out).shape == (9, 2, 2)
+
+
+class _ConstantVelocity:
+    """Stand-in with the reference's predictor call signature (CPU, no CUDA)."""
+
+    def __call__(self, paths, scene_goal, n_predict=12, modes=1, predict_all=True, obs_length=9, start_length=0,
+                 args=None):
+        xy = paths_to_xy(paths)
+        v = xy[obs_length - 1] - xy[obs_length - 2]
+        pred = xy[obs_length - 1][None] + np.arange(1, n_predict + 1)[:, None, None] * v[None]
+        return {0: [pred[:, 0], pred[:, 1:]]}
+
+
+def test_evaluate_file_ndjson_in_ndjson_out(tmp_path):
+    """load_test_scenes -> predict_scenes -> write_predictions on a file written in the DATA_BLOCK format."""
+    from trajnetplusplusbaselines_b200.evaluator import evaluate_file, load_test_scenes
+    rng = np.random.RandomState(2)
+    infile, outfile = os.path.join(tmp_path, "in.ndjson"), os.path.join(tmp_path, "out.ndjson")
+    truth = {}
+    with open(infile, "w") as f:
+        for sid, n in ((0, 3), (1, 2)):
+            paths = _scene(sid, n, 5000 * sid, rng)
+            late = [TrackRow(5000 * sid + 10 * t, 100 * sid + 50, 0.0, 0.1 * t) for t in range(12, 21)]   # enters after obs
+            f.write(trajnet_line(SceneRow(sid, paths[0][0].pedestrian, paths[0][0].frame, paths[0][-1].frame, 2.5, 0)) + "\n")
+            for p in paths + [late]:
+                for r in p:
+                    f.write(trajnet_line(r) + "\n")
+            truth[sid] = paths
+    scenes = load_test_scenes(infile, obs_length=9)
+    assert [len(paths) for _, _, paths in scenes] == [3, 2]              # the late track is dropped
+    assert all(len(p) == 9 for _, _, paths in scenes for p in paths)     # only the observed frames remain
+    assert evaluate_file(_ConstantVelocity(), infile, outfile) == 2
+    got = {sid: paths for sid, paths in read_ndjson_scenes(outfile)}
+    for sid, paths in truth.items():
+        xy = paths_to_xy(paths)
+        v = xy[8, 0] - xy[7, 0]
+        want = np.round(xy[8, 0][None] + np.arange(1, 13)[:, None] * v[None], 2)
+        assert np.allclose([[r.x, r.y] for r in got[sid][0]], want, atol=0.011)

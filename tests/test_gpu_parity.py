@@ -360,3 +360,31 @@ def test_large_scenes_take_the_fallback_kernels(kind):
     assert (np.isnan(pred) == np.isnan(pred_o)).all()
     assert np.nanmax(np.abs(pred - pred_o)) < 1e-4
     assert np.nanmax(np.abs(rel - rel_o)) < 1e-4
+
+
+@pytest.mark.gpu
+def test_evaluate_file_batched_equals_per_scene(tmp_path):
+    """ndjson -> chunks of scenes through one forward each -> ndjson; same numbers as calling the
+    predictor scene by scene like lstm/trajnet_evaluator.py:15-19."""
+    import types
+    from trajnetplusplusbaselines_b200.data import SceneRow, TrackRow, read_ndjson_scenes, trajnet_line
+    from trajnetplusplusbaselines_b200.evaluator import evaluate_file, load_test_scenes
+    from trajnetplusplusbaselines_b200.lstm import LSTM, GridBasedPooling, LSTMPredictor
+    xy, bs = O.synthetic_scenes(12, 6, seed=31, ragged=True)
+    infile, outfile = os.path.join(tmp_path, "in.ndjson"), os.path.join(tmp_path, "out.ndjson")
+    with open(infile, "w") as f:
+        for b in range(len(bs) - 1):
+            f.write(trajnet_line(SceneRow(b, 100 * b, 0, 200, 2.5, 0)) + "\n")
+            for p in range(bs[b], bs[b + 1]):
+                for t in range(21):
+                    f.write(trajnet_line(TrackRow(10 * t, 100 * b + int(p - bs[b]), float(xy[t, p, 0]), float(xy[t, p, 1]))) + "\n")
+    W = O.random_weights("directional", seed=8)
+    model = LSTM(pool=GridBasedPooling(**O.MODEL_SPECS["directional"]))
+    model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in W.items()})
+    predictor = LSTMPredictor(model.cuda())
+    args = types.SimpleNamespace(normalize_scene=False)
+    assert evaluate_file(predictor, infile, outfile, chunk=5, args=args) == len(bs) - 1
+    got = {sid: paths for sid, paths in read_ndjson_scenes(outfile)}
+    for _, sid, paths in load_test_scenes(infile):
+        single = predictor(paths, np.zeros((len(paths), 2)), n_predict=12, obs_length=9, args=args)[0]
+        assert np.allclose([[r.x, r.y] for r in got[sid][0]], np.round(single[0], 2), atol=0.011)
