@@ -370,7 +370,9 @@ def test_evaluate_file_batched_equals_per_scene(tmp_path):
     from trajnetplusplusbaselines_b200.data import SceneRow, TrackRow, read_ndjson_scenes, trajnet_line
     from trajnetplusplusbaselines_b200.evaluator import evaluate_file, load_test_scenes
     from trajnetplusplusbaselines_b200.lstm import LSTM, GridBasedPooling, LSTMPredictor
-    xy, bs = O.synthetic_scenes(12, 6, seed=31, ragged=True)
+    # equal scene sizes: batching ragged scenes pads them, and padded slots clobber grid cell 0 exactly as
+    # in the reference trainer (gridbased_pooling.py:281-293), which a single-scene call does not see
+    xy, bs = O.synthetic_scenes(12, 6, seed=31)
     infile, outfile = os.path.join(tmp_path, "in.ndjson"), os.path.join(tmp_path, "out.ndjson")
     with open(infile, "w") as f:
         for b in range(len(bs) - 1):
