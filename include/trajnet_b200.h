@@ -111,6 +111,12 @@ int tb2_layout_create(const int64_t* scene_offsets_host, int32_t num_scenes, tb2
 int tb2_layout_destroy(tb2_layout* layout);
 int32_t tb2_layout_num_tracks(const tb2_layout* layout);
 int32_t tb2_layout_max_scene(const tb2_layout* layout);
+/* 1 (default): scenes behave as in ONE batched call of the reference, i.e. padded to the largest scene
+ * of the batch; the NaN-padded slots count as out-of-range neighbours and clobber grid cell 0
+ * (gridbased_pooling.py:248-249,281-293) -- what the trainer sees.  0: every scene behaves as if the
+ * reference had been called on it alone (what the evaluator does, lstm/trajnet_evaluator.py:15-19), so a
+ * batch of scenes reproduces per-scene calls exactly. */
+int tb2_layout_set_padding(tb2_layout* layout, int32_t pad_to_batch_max);
 
 /* Bytes of caller-provided scratch needed by the step / sequence / pool calls below. */
 size_t tb2_lstm_workspace_bytes(const tb2_lstm* model, const tb2_layout* layout);

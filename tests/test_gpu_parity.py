@@ -4,6 +4,8 @@ fixtures.  Run on the B200 box: `pytest -m gpu`.
 Bars (BASELINE.json north_star): grid cell indices bit-exact; predicted positions within 1e-4 m
 (ADE/FDE vs the reference), tolerance written at each assert.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -370,9 +372,9 @@ def test_evaluate_file_batched_equals_per_scene(tmp_path):
     from trajnetplusplusbaselines_b200.data import SceneRow, TrackRow, read_ndjson_scenes, trajnet_line
     from trajnetplusplusbaselines_b200.evaluator import evaluate_file, load_test_scenes
     from trajnetplusplusbaselines_b200.lstm import LSTM, GridBasedPooling, LSTMPredictor
-    # equal scene sizes: batching ragged scenes pads them, and padded slots clobber grid cell 0 exactly as
-    # in the reference trainer (gridbased_pooling.py:281-293), which a single-scene call does not see
-    xy, bs = O.synthetic_scenes(12, 6, seed=31)
+    # ragged scenes: predict_batch uses the per-scene layout (tb2_layout_set_padding(0)), so the padded slots
+    # of a batched reference call (which clobber grid cell 0, gridbased_pooling.py:281-293) do not appear
+    xy, bs = O.synthetic_scenes(12, 6, seed=31, ragged=True)
     infile, outfile = os.path.join(tmp_path, "in.ndjson"), os.path.join(tmp_path, "out.ndjson")
     with open(infile, "w") as f:
         for b in range(len(bs) - 1):
@@ -390,3 +392,33 @@ def test_evaluate_file_batched_equals_per_scene(tmp_path):
     for _, sid, paths in load_test_scenes(infile):
         single = predictor(paths, np.zeros((len(paths), 2)), n_predict=12, obs_length=9, args=args)[0]
         assert np.allclose([[r.x, r.y] for r in got[sid][0]], np.round(single[0], 2), atol=0.011)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["social", "occupancy"])
+def test_per_scene_layout_equals_single_scene_calls(kind):
+    """Ragged batch with tb2_layout_set_padding(0) == every scene forwarded alone, bit for bit; with the
+    default (trainer) padding the small scenes see the padded slots, as in the reference's batched call."""
+    from trajnetplusplusbaselines_b200.lstm import LSTM, GridBasedPooling
+    xy, bs = O.synthetic_scenes(10, 9, seed=77, ragged=True, nan_tracks=True)
+    xy[:, :, :] = xy * 1.6                 # spread: more neighbours out of range / in the corner cell
+    W = O.random_weights(kind, seed=12)
+    model = LSTM(pool=GridBasedPooling(**O.MODEL_SPECS[kind]))
+    model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in W.items()})
+    model = model.cuda().eval()
+    obs = torch.from_numpy(xy[:9]).cuda()
+    with torch.no_grad():
+        _, batched = model._forward_nograd(obs, torch.from_numpy(bs), None, 12, pad_to_batch_max=False)
+        batched = batched.cpu().numpy()
+        for b in range(len(bs) - 1):
+            sl = slice(int(bs[b]), int(bs[b + 1]))
+            _, single = model(obs[:, sl].contiguous(), torch.zeros(sl.stop - sl.start, 2),
+                              torch.tensor([0, sl.stop - sl.start]), n_predict=12)
+            a, c = batched[:, sl], single.cpu().numpy()
+            assert (np.isnan(a) == np.isnan(c)).all()
+            assert np.array_equal(np.nan_to_num(a), np.nan_to_num(c)), b
+    # and the oracle agrees scene by scene
+    b = int(np.argmin(np.diff(bs)))
+    sl = slice(int(bs[b]), int(bs[b + 1]))
+    _, pred_o = O.forward(W, O.pool_config(kind), xy[:9, sl], np.array([0, sl.stop - sl.start]), n_predict=12)
+    assert np.nanmax(np.abs(batched[:, sl] - pred_o)) < 1e-4

@@ -108,6 +108,7 @@ PROTOTYPES = {
     "tb2_layout_destroy": (ctypes.c_int, [_vp]),
     "tb2_layout_num_tracks": (_i32, [_vp]),
     "tb2_layout_max_scene": (_i32, [_vp]),
+    "tb2_layout_set_padding": (ctypes.c_int, [_vp, _i32]),
     "tb2_lstm_workspace_bytes": (_sz, [_vp, _vp]),
     "tb2_grid_indices": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "tb2_pool_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -349,6 +349,11 @@ int tb2_layout_destroy(tb2_layout* l) {
 
 int32_t tb2_layout_num_tracks(const tb2_layout* l) { return l ? l->M : -1; }
 int32_t tb2_layout_max_scene(const tb2_layout* l) { return l ? l->n_max : -1; }
+int tb2_layout_set_padding(tb2_layout* l, int32_t pad_to_batch_max) {
+    TB2_REQUIRE(l, "null layout");
+    l->pad_to_max = pad_to_batch_max ? 1 : 0;
+    return TB2_OK;
+}
 
 size_t tb2_lstm_workspace_bytes(const tb2_lstm* m, const tb2_layout* l) {
     if (!m || !l) return 0;

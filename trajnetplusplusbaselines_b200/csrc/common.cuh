@@ -119,6 +119,8 @@ struct tb2_lstm {
 
 struct tb2_layout {
     int B, M, n_max;
+    int pad_to_max = 1;    // 1: scenes padded to the batch maximum like the reference's batched call (padded
+                           // slots clobber grid cell 0); 0: every scene as if it were called on its own
     std::vector<int> scene_off_host;
     int* scene_off;        // [B+1] device
     int* row_scene;        // [M]   device

@@ -79,7 +79,7 @@ struct PrepParams {
     __nv_bfloat16* emb_hi;    // [M, E] bf16 split or null
     __nv_bfloat16* emb_lo;
     int E;
-    int n_max, H, C, n, pool_type, front, skip_masked, write_pairs;
+    int n_max, H, C, n, pool_type, front, skip_masked, write_pairs, pad_to_max;
     float side, width;
     long long* dbg;           // optional [B, 8] clock64 stamps (TB2_PREP_DEBUG=1)
 };
@@ -179,6 +179,14 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
         for (int jj = lane; jj < nm1; jj += 32) {
             int j = jj + (jj >= i);
             int cell = 0, inr = 0;
+            if (!p.pad_to_max && j >= n_s) {      // per-scene semantics: the slot does not exist at all
+                myrow[jj] = -100;
+                if (p.write_pairs) {
+                    p.pair_cell[gi + jj] = 0;
+                    p.pair_flag[gi + jj] = 0;
+                }
+                continue;
+            }
             {
                 // padded slots (j >= n_s) are NaN rows in the reference's padded batch -> -500
                 const float2 pj = (j < n_s) ? pos[j] : make_float2(-500.f, -500.f);
@@ -216,7 +224,7 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
                 win = jj < nm1 && cell >= 0 && (same & later) == 0u && !(cell == 0 && (oor & later) != 0u);
                 for (int k = base + 32; win && k < nm1; ++k) {
                     int ck = myrow[k];
-                    if (ck == cell || (cell == 0 && ck < 0)) win = false;
+                    if (ck == cell || (cell == 0 && ck == -1)) win = false;
                 }
                 unsigned ball = __ballot_sync(0xffffffffu, win);
                 if (win) {
@@ -265,6 +273,7 @@ int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hid
     p.pool_type = m->cfg.pool_type;
     p.front = m->cfg.front;
     p.skip_masked = skip_masked;
+    p.pad_to_max = l->pad_to_max;
     p.write_pairs = write_pairs;
     p.We = m->We;
     p.be = m->be;

@@ -45,7 +45,7 @@ def _stream(device):
 class SceneLayout:
     """tb2_layout wrapper: the `batch_split` partition of tracks into scenes."""
 
-    def __init__(self, batch_split):
+    def __init__(self, batch_split, pad_to_batch_max=True):
         lib = _lib.load()
         offs = [int(v) for v in batch_split]
         self.offsets = offs
@@ -56,6 +56,9 @@ class SceneLayout:
         self.num_scenes = len(offs) - 1
         self.num_tracks = offs[-1]
         self.max_scene = int(lib.tb2_layout_max_scene(handle))
+        self.pad_to_batch_max = bool(pad_to_batch_max)
+        if not pad_to_batch_max:     # evaluator semantics: every scene as if called on its own
+            _lib.check(lib.tb2_layout_set_padding(handle, 0))
         self._finalizer = weakref.finalize(self, lib.tb2_layout_destroy, handle)
 
 
@@ -64,11 +67,11 @@ class LayoutCache:
         self.capacity = capacity
         self._items = OrderedDict()
 
-    def get(self, batch_split):
-        key = tuple(int(v) for v in batch_split)
+    def get(self, batch_split, pad_to_batch_max=True):
+        key = tuple(int(v) for v in batch_split) + (bool(pad_to_batch_max),)
         item = self._items.get(key)
         if item is None:
-            item = SceneLayout(key)
+            item = SceneLayout(key[:-1], pad_to_batch_max)
             self._items[key] = item
             if len(self._items) > self.capacity:
                 self._items.popitem(last=False)

@@ -186,11 +186,13 @@ class LSTM(torch.nn.Module):
             return sequence_with_grad(self, observed, batch_split, prediction_truth, n_predict)
         return self._forward_nograd(observed, batch_split, prediction_truth, n_predict)
 
-    def _forward_nograd(self, observed, batch_split, prediction_truth, n_predict, want_states=False):
+    def _forward_nograd(self, observed, batch_split, prediction_truth, n_predict, want_states=False,
+                        pad_to_batch_max=True):
         handle = self._engine()
         device = handle.device
         out_device = observed.device
-        layout = self._layouts.get(batch_split.tolist() if torch.is_tensor(batch_split) else batch_split)
+        layout = self._layouts.get(batch_split.tolist() if torch.is_tensor(batch_split) else batch_split,
+                                   pad_to_batch_max)
         M = layout.num_tracks
         if observed.shape[1] != M:
             raise ValueError("batch_split[-1] != number of tracks")
@@ -300,9 +302,9 @@ class LSTMPredictor(object):
         joblib.Parallel(n_jobs=12) over predict_scene, lstm/trajnet_evaluator.py:61).
 
         scenes: list of `paths` (each as for __call__).  Returns a list of {0: [primary, neighbours]}
-        in the same order.  Scenes never interact; the only batch effect is the reference's own:
-        scenes are padded to the batch maximum and padded slots clobber grid cell 0
-        (gridbased_pooling.py:281-293), exactly as when the reference trainer batches scenes."""
+        in the same order, equal to calling the predictor scene by scene: the scene layout is created
+        with tb2_layout_set_padding(0), so a scene does not see the padding slots a batched call of
+        the reference would add (those clobber grid cell 0, gridbased_pooling.py:281-293)."""
         self.model.eval()
         normalize = bool(getattr(args, 'normalize_scene', False))
         xys, frames, split = [], [], [0]
@@ -316,7 +318,8 @@ class LSTMPredictor(object):
         with torch.no_grad():
             observed = torch.Tensor(np.concatenate(xys, axis=1))
             goals = torch.zeros(observed.shape[1], 2)
-            _, output_scenes = self.model(observed, goals, torch.tensor(split).long(), n_predict=n_predict)
+            _, output_scenes = self.model._forward_nograd(observed, torch.tensor(split).long(), None, n_predict,
+                                                          pad_to_batch_max=False)
             output_scenes = output_scenes.cpu().numpy()
         results = []
         for i in range(len(scenes)):
