@@ -27,21 +27,20 @@ class InputEmbedding(torch.nn.Module):
     def forward(self, vel):
         raise NotImplementedError(_FUSED % "InputEmbedding")
 
-    def start_enc(self, vel):
-        """Start tag (modules.py:32-39): one-hot on the second-to-last channel."""
+    def _tag(self, vel, channel):
+        # the two tag channels at the end of the embedding are reserved for start markers
+        # (modules.py:32-48); the recurrence itself never uses them (they stay zero, A5)
         if not self.use_tags:
             raise Exception('Input embedding does not support start tag')
-        v = torch.zeros(vel.size(0), self.embedding_dim, device=vel.device)
-        v[:, -2] = 1
-        return v
+        tag = vel.new_zeros((vel.size(0), self.embedding_dim))
+        tag[:, channel] = 1
+        return tag
+
+    def start_enc(self, vel):
+        return self._tag(vel, -2)
 
     def start_dec(self, vel):
-        """Start tag (modules.py:41-48): one-hot on the last channel."""
-        if not self.use_tags:
-            raise Exception('Input embedding does not support start tag')
-        v = torch.zeros(vel.size(0), self.embedding_dim, device=vel.device)
-        v[:, -1] = 1
-        return v
+        return self._tag(vel, -1)
 
 
 class Hidden2Normal(torch.nn.Module):
