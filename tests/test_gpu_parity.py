@@ -378,10 +378,12 @@ def test_evaluate_file_batched_equals_per_scene(tmp_path):
     infile, outfile = os.path.join(tmp_path, "in.ndjson"), os.path.join(tmp_path, "out.ndjson")
     with open(infile, "w") as f:
         for b in range(len(bs) - 1):
-            f.write(trajnet_line(SceneRow(b, 100 * b, 0, 200, 2.5, 0)) + "\n")
+            f0 = 1000 * b                  # scenes are told apart by their frame range, as in DATA_BLOCK
+            f.write(trajnet_line(SceneRow(b, 100 * b, f0, f0 + 200, 2.5, 0)) + "\n")
             for p in range(bs[b], bs[b + 1]):
                 for t in range(21):
-                    f.write(trajnet_line(TrackRow(10 * t, 100 * b + int(p - bs[b]), float(xy[t, p, 0]), float(xy[t, p, 1]))) + "\n")
+                    f.write(trajnet_line(TrackRow(f0 + 10 * t, 100 * b + int(p - bs[b]), float(xy[t, p, 0]),
+                                                  float(xy[t, p, 1]))) + "\n")
     W = O.random_weights("directional", seed=8)
     model = LSTM(pool=GridBasedPooling(**O.MODEL_SPECS["directional"]))
     model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in W.items()})
