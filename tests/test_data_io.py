@@ -94,3 +94,29 @@ def test_evaluate_file_ndjson_in_ndjson_out(tmp_path):
         v = xy[8, 0] - xy[7, 0]
         want = np.round(xy[8, 0][None] + np.arange(1, 13)[:, None] * v[None], 2)
         assert np.allclose([[r.x, r.y] for r in got[sid][0]], want, atol=0.011)
+
+
+def test_get_predictions_writes_one_file_per_dataset(tmp_path):
+    """Directory layout of lstm/trajnet_evaluator.get_predictions: <root>/test/*.ndjson ->
+    <root>/test_pred/<model>_modes<k>/<dataset>.ndjson; an existing model folder is skipped."""
+    import types
+    from trajnetplusplusbaselines_b200.evaluator import get_predictions
+    rng = np.random.RandomState(4)
+    test_dir = os.path.join(tmp_path, "test")
+    os.makedirs(test_dir)
+    for name, sids in (("a.ndjson", (0, 1)), ("b.ndjson", (2,))):
+        with open(os.path.join(test_dir, name), "w") as f:
+            for sid in sids:
+                paths = _scene(sid, 3, 3000 * sid, rng)
+                f.write(trajnet_line(SceneRow(sid, paths[0][0].pedestrian, paths[0][0].frame, paths[0][-1].frame, 2.5, 0)) + "\n")
+                for p in paths:
+                    for r in p:
+                        f.write(trajnet_line(r) + "\n")
+    args = types.SimpleNamespace(path=os.path.join(tmp_path, "test_pred") + os.sep, output=["models/cv.pkl"], modes=1,
+                                 obs_length=9, pred_length=12, chunk=2, normalize_scene=False)
+    os.makedirs(args.path)
+    assert get_predictions(args, load_predictor=lambda fn: _ConstantVelocity()) == {"cv_modes1": 3}
+    out_dir = os.path.join(args.path, "cv_modes1")
+    assert sorted(os.listdir(out_dir)) == ["a.ndjson", "b.ndjson"]
+    assert len(list(read_ndjson_scenes(os.path.join(out_dir, "a.ndjson")))) == 2
+    assert get_predictions(args, load_predictor=lambda fn: _ConstantVelocity()) == {}      # skipped: already there

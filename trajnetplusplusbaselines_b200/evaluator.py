@@ -42,3 +42,57 @@ def evaluate_file(predictor, infile, outfile, obs_length=9, pred_length=12, mode
         os.remove(outfile)
     write_predictions(preds, scenes, outfile, obs_length=obs_length, pred_length=pred_length)
     return len(scenes)
+
+
+def get_predictions(args, load_predictor=None):
+    """The write side of lstm/trajnet_evaluator.get_predictions (:28-64): for every model in args.output
+    and every `*.ndjson` of the test folder, write `<path>/test_pred/<model>_modes<k>/<dataset>.ndjson`.
+    Existing model folders are skipped, like the reference does.  Returns {model_name: scenes written}."""
+    if load_predictor is None:
+        def load_predictor(filename):
+            from .lstm import LSTMPredictor
+            predictor = LSTMPredictor.load(filename)
+            predictor.model.to('cuda')
+            return predictor
+    pred_dir = args.path.rstrip(os.sep)       # .../test_pred -> the scenes are in .../test (trajnet_evaluator.py:31)
+    test_dir = pred_dir[:-len('_pred')] if pred_dir.endswith('_pred') else pred_dir
+    datasets = sorted(f for f in os.listdir(test_dir) if not f.startswith('.') and f.endswith('.ndjson'))
+    written = {}
+    for model in args.output:
+        model_name = os.path.basename(model).replace('.pkl', '') + '_modes' + str(args.modes)
+        out_dir = os.path.join(args.path, model_name)
+        if os.path.exists(out_dir):
+            print('Predictions corresponding to {} already exist.'.format(model_name))
+            continue
+        os.makedirs(out_dir)
+        predictor = load_predictor(model)
+        written[model_name] = sum(
+            evaluate_file(predictor, os.path.join(test_dir, dataset), os.path.join(out_dir, dataset),
+                          obs_length=args.obs_length, pred_length=args.pred_length, modes=args.modes,
+                          chunk=args.chunk, args=args)
+            for dataset in datasets)
+    return written
+
+
+def main(argv=None):
+    """`python -m trajnetplusplusbaselines_b200.evaluator --path <dataset> --output model.pkl ...`: the
+    prediction-writing half of `python -m trajnetbaselines.lstm.trajnet_evaluator` (same flags); the
+    metric half (`evaluator.trajnet_evaluator.trajnet_evaluate`) reads the files it writes."""
+    import argparse
+    parser = argparse.ArgumentParser()
+    parser.add_argument('--path', default='trajdata', help='directory of data to test')
+    parser.add_argument('--output', nargs='+', help='relative path to saved model')
+    parser.add_argument('--obs_length', default=9, type=int)
+    parser.add_argument('--pred_length', default=12, type=int)
+    parser.add_argument('--normalize_scene', action='store_true')
+    parser.add_argument('--modes', default=1, type=int)
+    parser.add_argument('--chunk', default=1024, type=int, help='scenes per batched forward')
+    args = parser.parse_args(argv)
+    args.output = args.output if args.output is not None else []
+    args.path = os.path.join('DATA_BLOCK', args.path, 'test_pred') + os.sep
+    for name, n in get_predictions(args).items():
+        print('{}: {} scenes written'.format(name, n))
+
+
+if __name__ == '__main__':
+    main()
