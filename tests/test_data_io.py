@@ -120,3 +120,26 @@ def test_get_predictions_writes_one_file_per_dataset(tmp_path):
     assert sorted(os.listdir(out_dir)) == ["a.ndjson", "b.ndjson"]
     assert len(list(read_ndjson_scenes(os.path.join(out_dir, "a.ndjson")))) == 2
     assert get_predictions(args, load_predictor=lambda fn: _ConstantVelocity()) == {}      # skipped: already there
+
+
+def test_fast_writer_is_byte_identical_to_the_line_writer(tmp_path):
+    """write_predictions formats track rows directly; the text must equal trajnet_line row by row, also for
+    negative zero, integral values, rounding ties and NaN neighbours."""
+    rng = np.random.RandomState(7)
+    scenes = [("f", 3, _scene(3, 4, 700, rng))]
+    prim = rng.randn(12, 2) * 30
+    prim[0] = (-0.0, 2.0)
+    prim[1] = (0.125, -0.375)
+    prim[2] = (1e-9, 123456.789)
+    neigh = rng.randn(12, 3, 2)
+    neigh[5:, 1] = np.nan
+    fn = os.path.join(tmp_path, "p.ndjson")
+    write_predictions([{0: [prim, neigh]}], scenes, fn)
+    lines = open(fn).read().splitlines()
+    first = scenes[0][2][0][8].frame + 10
+    want = [trajnet_line(SceneRow(3, scenes[0][2][0][0].pedestrian, 700, 700 + 200, 2.5, 0))]
+    want += [trajnet_line(TrackRow(first + 10 * i, scenes[0][2][0][0].pedestrian, prim[i, 0], prim[i, 1], 0, 3)) for i in range(12)]
+    for n in range(3):
+        want += [trajnet_line(TrackRow(first + 10 * j, scenes[0][2][n + 1][0].pedestrian, neigh[j, n, 0], neigh[j, n, 1], 0, 3))
+                 for j in range(12)]
+    assert lines == want

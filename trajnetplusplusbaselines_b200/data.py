@@ -36,17 +36,16 @@ def read_ndjson_scenes(filename):
     tracks_by_frame = defaultdict(list)
     scenes = []
     with open(filename) as f:
-        for line in f:
-            if not line.strip():
-                continue
-            d = json.loads(line)
-            if 'track' in d:
-                t = d['track']
-                row = TrackRow(t['f'], t['p'], t['x'], t['y'], t.get('prediction_number'), t.get('scene_id'))
-                tracks_by_frame[row.frame].append(row)
-            elif 'scene' in d:
-                s = d['scene']
-                scenes.append(SceneRow(s['id'], s['p'], s['s'], s['e'], s.get('fps'), s.get('tag')))
+        lines = [line for line in f if line.strip()]
+    # one C-level parse of the whole file instead of a json.loads call per line
+    for d in json.loads('[' + ','.join(lines) + ']') if lines else ():
+        if 'track' in d:
+            t = d['track']
+            row = TrackRow(t['f'], t['p'], t['x'], t['y'], t.get('prediction_number'), t.get('scene_id'))
+            tracks_by_frame[row.frame].append(row)
+        elif 'scene' in d:
+            s = d['scene']
+            scenes.append(SceneRow(s['id'], s['p'], s['s'], s['e'], s.get('fps'), s.get('tag')))
     for s in scenes:
         by_ped = defaultdict(list)
         for frame in range(s.start, s.end + 1):
@@ -87,6 +86,16 @@ def write_predictions(pred_list, scenes, filename, obs_length=9, pred_length=12)
     scenes    : per scene (anything, scene_id, paths) as the reference evaluator holds them
     """
     seq_length = obs_length + pred_length
+
+    def track_line(frame, ped, x, y, mode, scene_id):
+        # same text as trajnet_line(TrackRow(...)) without building the dict / calling json.dumps per row
+        x, y = round(float(x), 2), round(float(y), 2)
+        if (type(frame) is int and type(ped) is int and type(mode) is int and type(scene_id) is int
+                and x - x == 0.0 and y - y == 0.0):          # finite
+            return '{"track": {"f": %d, "p": %d, "x": %r, "y": %r, "prediction_number": %d, "scene_id": %d}}\n' % (
+                frame, ped, x, y, mode, scene_id)
+        return trajnet_line(TrackRow(frame, ped, x, y, mode, scene_id)) + '\n'
+
     with open(filename, "a") as out:
         for predictions, (_, scene_id, paths) in zip(pred_list, scenes):
             observed_path = paths[0]
@@ -99,14 +108,11 @@ def write_predictions(pred_list, scenes, filename, obs_length=9, pred_length=12)
             out.write('\n')
             for m in range(len(predictions)):
                 prediction, neigh_predictions = predictions[m]
-                for i in range(len(prediction)):
-                    out.write(trajnet_line(TrackRow(first_frame + i * frame_diff, ped_id, prediction[i][0],
-                                                    prediction[i][1], m, scene_id)))
-                    out.write('\n')
+                rows = [track_line(first_frame + i * frame_diff, ped_id, prediction[i][0], prediction[i][1], m, scene_id)
+                        for i in range(len(prediction))]
                 if len(neigh_predictions):
-                    for n in range(neigh_predictions.shape[1]):
-                        for j in range(neigh_predictions.shape[0]):
-                            out.write(trajnet_line(TrackRow(first_frame + j * frame_diff, neigh_ids[n],
-                                                            neigh_predictions[j, n, 0], neigh_predictions[j, n, 1],
-                                                            m, scene_id)))
-                            out.write('\n')
+                    neigh = np.asarray(neigh_predictions).tolist()          # python floats once, not per element
+                    for n in range(len(neigh[0])):
+                        rows.extend(track_line(first_frame + j * frame_diff, neigh_ids[n], neigh[j][n][0], neigh[j][n][1],
+                                               m, scene_id) for j in range(len(neigh)))
+                out.write(''.join(rows))
