@@ -250,6 +250,12 @@ int tb2_prediction_loss(const float* inputs_dev, const float* targets_dev, const
                         int32_t T, int32_t M, int32_t B, float background_rate, float* values_out_dev,
                         float* dinputs_out_dev, void* stream);
 
+/* L2Loss (lstm/loss.py:93-135): per (frame, scene) 0.5 * |mu - target|^2 of the primary (= the mean over
+ * the two coordinates); dinputs_out [T, B, 5] = (dx, dy, 0, 0, 0) (optional).  The x100 multiplier and the
+ * mean reductions stay with the caller.  Same argument layout as tb2_prediction_loss. */
+int tb2_l2_loss(const float* inputs_dev, const float* targets_dev, const int32_t* primary_rows_dev, int32_t T,
+                int32_t M, int32_t B, float* values_out_dev, float* dinputs_out_dev, void* stream);
+
 /* CollisionLoss (lstm/loss.py:138-162): per (frame, scene) col_wt * sum over neighbours closer
  * than col_distance to the primary of (1 - dist / col_distance); NaN coordinates read as -1000;
  * neighbours are constants.  positions [T, M, 2]; loss_out [T, B]; dprimary_out [T, B, 2]

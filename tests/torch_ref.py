@@ -121,12 +121,37 @@ def gaussian_2d(p, x):
     return torch.exp(-z / (2 * (1 - rho ** 2))) / (2 * math.pi * s1 * s2 * torch.sqrt(1 - rho ** 2))
 
 
-def prediction_loss(inputs, targets, batch_split, background_rate=0.2):
+def prediction_loss_values(inputs, targets, batch_split, background_rate=0.2):
+    """[pred_length, batch_size] values of the primaries (reference lstm/loss.py:52-91 before the mean)."""
     prim = torch.tensor([int(v) for v in batch_split[:-1]])
     t = targets[:, prim].reshape(-1, 2)
     p = inputs[:, prim].reshape(-1, 5)
     bg = torch.cat([p[:, :2], torch.full_like(p[:, 2:4], 3.0), torch.zeros_like(p[:, 4:5])], dim=1)
-    return (-torch.log(0.01 + background_rate * gaussian_2d(bg, t) + (0.99 - background_rate) * gaussian_2d(p, t))).mean()
+    v = -torch.log(0.01 + background_rate * gaussian_2d(bg, t) + (0.99 - background_rate) * gaussian_2d(p, t))
+    return v.reshape(targets.shape[0], len(prim))
+
+
+def prediction_loss(inputs, targets, batch_split, background_rate=0.2):
+    return prediction_loss_values(inputs, targets, batch_split, background_rate).mean()
+
+
+def l2_loss(inputs, targets, batch_split):
+    """Reference lstm/loss.py:93-135 without the collision term: 100 x MSE of the primaries' means."""
+    prim = torch.tensor([int(v) for v in batch_split[:-1]])
+    return ((inputs[:, prim][:, :, :2] - targets[:, prim]) ** 2).mean() * 100
+
+
+def collision_loss(positions, batch_split, col_wt=10.0, col_distance=0.2):
+    """Reference lstm/loss.py:138-162: the primary is penalised for neighbours within col_distance."""
+    batch_split = [int(v) for v in batch_split]
+    pos = torch.where(torch.isnan(positions[..., :2]), torch.full_like(positions[..., :2], -1000.0), positions[..., :2])
+    sizes = torch.as_tensor([b - a for a, b in zip(batch_split[:-1], batch_split[1:])])
+    prim_of_row = torch.repeat_interleave(torch.as_tensor(batch_split[:-1]), sizes)
+    is_neigh = torch.ones(batch_split[-1], dtype=torch.bool)
+    is_neigh[torch.as_tensor(batch_split[:-1])] = False
+    dist = torch.norm(pos[:, prim_of_row] - pos.detach(), dim=-1)[:, is_neigh]
+    hit = (dist <= col_distance).detach()
+    return col_wt * (1 - dist[hit] / col_distance).sum()
 
 
 def train_loss_and_grads(W_np, pool_cfg, xy, batch_split, obs_length=9, pred_length=12):

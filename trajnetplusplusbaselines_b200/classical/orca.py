@@ -27,7 +27,7 @@ def simulate_batch(pos, vel, goals, speeds, batch_split, orca_params=(1.5, 1.5, 
     vel_t = torch.as_tensor(np.asarray(vel), dtype=torch.float32).to(device).contiguous()
     goal_t = torch.as_tensor(np.asarray(goals), dtype=torch.float64).to(device).contiguous()
     speed_t = torch.as_tensor(np.asarray(speeds), dtype=torch.float64).to(device).contiguous()
-    layout = SceneLayout(batch_split)
+    layout = SceneLayout(batch_split, device=device)
     if layout.num_tracks != pos_t.shape[0]:
         raise ValueError("batch_split[-1] != number of agents")
     p = _lib.OrcaParams()

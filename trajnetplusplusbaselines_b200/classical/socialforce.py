@@ -23,7 +23,7 @@ def simulate_batch(states, batch_split, sf_params=(0.5, 2.1, 0.3), n_steps=96, s
     lib = _lib.load()
     device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
     st = torch.as_tensor(states, dtype=torch.float64).to(device).contiguous()
-    layout = SceneLayout(batch_split)
+    layout = SceneLayout(batch_split, device=device)
     if layout.num_tracks != st.shape[0]:
         raise ValueError("batch_split[-1] != number of pedestrians")
     p = _lib.SfParams()

@@ -177,7 +177,7 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
     m->weights_set = false;
     m->C = 0; m->cells = 0; m->n_mlp = 0; m->P = 0; m->pool_out = 0;
     m->We = m->be = m->Wn = m->bn = m->WencT = m->benc = m->Wt1 = m->base1 = nullptr;
-    m->Wt1_hi = m->Wt1_lo = m->Wt1_nat_hi = m->Wt1_nat_lo = nullptr;
+    m->Wt1_hi = m->Wt1_lo = m->Wt1_nat_hi = m->Wt1_nat_lo = m->Wt1_sw_hi = m->Wt1_sw_lo = nullptr;
     for (int i = 0; i < 2; ++i) { m->WgT[i] = m->bg[i] = nullptr; m->Wg_hi[i] = m->Wg_lo[i] = nullptr; }
     for (int i = 0; i < kMaxMlpLayers; ++i) { m->WT[i] = m->bl[i] = nullptr; m->W_hi[i] = m->W_lo[i] = nullptr; }
     auto fail = [&](int rc) { tb2_lstm_destroy(m); return rc; };
@@ -250,6 +250,11 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
                 ALLOC(nl, half);
                 m->Wt1_nat_hi = nh;
                 m->Wt1_nat_lo = nl;
+                float *sh, *sl;
+                ALLOC(sh, half);
+                ALLOC(sl, half);
+                m->Wt1_sw_hi = sh;
+                m->Wt1_sw_lo = sl;
             }
         }
         for (int layer = 1; layer < m->n_mlp; ++layer) {

@@ -70,6 +70,25 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 }
 #endif
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device: the size a launch
+// site has configured is remembered per device, so a second model on another GPU of the same
+// process configures its own copy of the kernel.
+struct DynSmemConfig {
+    size_t bytes[64];      // zero-initialised (function-local static)
+    template <typename K>
+    cudaError_t ensure(K kernel, size_t smem, size_t preset = 0) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        size_t& have = bytes[dev & 63];
+        if (have < preset) have = preset;          // e.g. the 48 KB every kernel may use without opting in
+        if (smem <= have) return cudaSuccess;
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) have = smem;
+        return e;
+    }
+};
+
 // Optional per-kernel timing (tb2_profile_begin / tb2_profile_end): CUDA events recorded on the
 // launching stream around every kernel of the library.  Off by default (zero overhead).
 struct KernelTimer {
@@ -108,6 +127,8 @@ struct tb2_lstm {
     void* Wt1_lo;
     void* Wt1_nat_hi;      // social, C == 16: bf16 [cells, d1, 16] natural k order (TMA source of sparse_layer1_tc)
     void* Wt1_nat_lo;
+    void* Wt1_sw_hi;       // social, C == 16: the same slabs as a SWIZZLE_32B shared-memory image (bulk-copy source of
+    void* Wt1_sw_lo;       // sparse_layer1_ts)
     float* WT[tb2::kMaxMlpLayers];   // layers >= 2: [K, N] transposed
     float* bl[tb2::kMaxMlpLayers];   // biases of layers >= 2
     void* W_hi[tb2::kMaxMlpLayers];  // bf16 [N, K] (hi, lo) split for the tcgen05 path (null: FFMA path)
@@ -173,6 +194,11 @@ int launch_repack_layer1_nat(const float* W1, void* hi, void* lo, int OUT, int c
 bool sparse_tc_supported(const tb2_lstm* m, const tb2_layout* l, int gsel);
 int launch_sparse_tc(const tb2_lstm* m, const tb2_layout* l, int gsel, Workspace* ws, float* out, void* out_hi,
                      void* out_lo, cudaStream_t st);
+// TS form of the same layer (A operand in tensor memory; mode 1 = one CTA, 2 = CTA pair with cta_group::2)
+bool sparse_ts_supported(const tb2_lstm* m, const tb2_layout* l);
+int launch_sparse_ts(const tb2_lstm* m, const tb2_layout* l, int mode, Workspace* ws, float* out, void* out_hi,
+                     void* out_lo, cudaStream_t st);
+int launch_repack_layer1_sw(const float* W1, void* hi, void* lo, int OUT, int cells, cudaStream_t st);
 bool dense_tc_supported(int K, int N);
 int launch_dense_tc(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                     float* Y, void* Y_hi, void* Y_lo, int M, int K, int N, int relu, cudaStream_t st);

@@ -504,11 +504,8 @@ int launch_gates_tc(const tb2_lstm* m, const tb2_layout* l, int phase, const flo
         }
     }
     const size_t smem = (size_t)kGtStages * kGtStageBytes + 1024;
-    static bool configured = false;
-    if (!configured) {
-        TB2_CHECK_CUDA(cudaFuncSetAttribute(lstm_gates_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static DynSmemConfig configured;
+    TB2_CHECK_CUDA(configured.ensure(lstm_gates_tc_kernel, smem));
     dim3 grid(2, (M + kGtBM - 1) / kGtBM);
     {
         KernelTimer kt("lstm_gates_tc", st);

@@ -287,11 +287,8 @@ template <int BN>
 static int launch_dense_tc_t(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
                              const CUtensorMap& mb_lo, const TcParams& p, cudaStream_t st) {
     const size_t smem = (size_t)TcCfg<BN>::kStages * TcCfg<BN>::kStageBytes + 1024;
-    static bool configured = false;
-    if (!configured) {
-        TB2_CHECK_CUDA(cudaFuncSetAttribute(dense_layer_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static DynSmemConfig configured;
+    TB2_CHECK_CUDA(configured.ensure(dense_layer_tc_kernel<BN>, smem));
     dim3 grid(p.N / BN, (p.M + kTcBM - 1) / kTcBM);
     {
         KernelTimer kt("dense_layer_tc", st);

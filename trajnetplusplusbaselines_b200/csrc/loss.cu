@@ -47,6 +47,23 @@ __global__ void prediction_loss_kernel(const float* __restrict__ inputs, const f
     }
 }
 
+// L2Loss (loss.py:93-135): per (frame, scene) mean over the two coordinates of the squared error of the
+// primary's predicted mean; the x100 multiplier and the mean reductions stay with the caller.
+__global__ void l2_loss_kernel(const float* __restrict__ inputs, const float* __restrict__ targets,
+                               const int* __restrict__ prim, int T, int M, int B, float* __restrict__ values,
+                               float* __restrict__ dinputs) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= T * B) return;
+    const int t = idx / B, b = idx - t * B;
+    const size_t row = (size_t)t * M + prim[b];
+    const float dx = inputs[row * 5] - targets[row * 2], dy = inputs[row * 5 + 1] - targets[row * 2 + 1];
+    values[idx] = 0.5f * (dx * dx + dy * dy);
+    if (dinputs) {
+        float* d = dinputs + (size_t)idx * 5;
+        d[0] = dx; d[1] = dy; d[2] = 0.f; d[3] = 0.f; d[4] = 0.f;
+    }
+}
+
 // col_wt * sum over frames and neighbours within col_distance of (1 - dist / col_distance); the
 // neighbours are constants (detached), NaN coordinates count as -1000 (loss.py:148-161).
 __global__ void collision_loss_kernel(const float2* __restrict__ pos, const int* __restrict__ scene_off, int T,
@@ -95,6 +112,21 @@ int tb2_prediction_loss(const float* inputs, const float* targets, const int32_t
         KernelTimer kt("prediction_loss", st);
         prediction_loss_kernel<<<(T * B + 127) / 128, 128, 0, st>>>(inputs, targets, primary_rows, T, M, B,
                                                                     background_rate, values_out, dinputs_out);
+    }
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
+}
+
+int tb2_l2_loss(const float* inputs, const float* targets, const int32_t* primary_rows, int32_t T, int32_t M,
+                int32_t B, float* values_out, float* dinputs_out, void* stream) {
+    TB2_REQUIRE(inputs && targets && primary_rows && values_out, "null argument");
+    TB2_REQUIRE(T >= 0 && M >= 0 && B >= 0, "negative size");
+    if (T * B == 0) return TB2_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        KernelTimer kt("l2_loss", st);
+        l2_loss_kernel<<<(T * B + 127) / 128, 128, 0, st>>>(inputs, targets, primary_rows, T, M, B, values_out,
+                                                            dinputs_out);
     }
     TB2_LAUNCH_CHECK();
     return TB2_OK;

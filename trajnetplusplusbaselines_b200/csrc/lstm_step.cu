@@ -250,11 +250,8 @@ int launch_gates(const tb2_lstm* m, const tb2_layout* l, int phase, const float*
     p.K_pad = m->K_gate_pad;
     p.add_pooled_to_h = (m->cfg.pool_type != TB2_POOL_NONE && !m->cfg.pool_to_input) ? 1 : 0;
     const size_t smem = (size_t)2 * kGateBK * (kGN + kGM) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        TB2_CHECK_CUDA(cudaFuncSetAttribute(lstm_gates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static DynSmemConfig configured;
+    TB2_CHECK_CUDA(configured.ensure(lstm_gates_kernel, smem));
     int blocks = (l->M + kGM - 1) / kGM;
     {
         KernelTimer kt("lstm_gates", st);
@@ -371,6 +368,9 @@ int launch_repack(tb2_lstm* m, const tb2_lstm_weights* w, cudaStream_t st) {
             return rc;
         if (m->Wt1_nat_hi &&
             (rc = launch_repack_layer1_nat(w->pool_embedding_weight[0], m->Wt1_nat_hi, m->Wt1_nat_lo, m->mlp_dims[1], m->cells, st)))
+            return rc;
+        if (m->Wt1_sw_hi &&
+            (rc = launch_repack_layer1_sw(w->pool_embedding_weight[0], m->Wt1_sw_hi, m->Wt1_sw_lo, m->mlp_dims[1], m->cells, st)))
             return rc;
         for (int layer = 1; layer < m->n_mlp; ++layer) {
             TB2_REQUIRE(w->pool_embedding_weight[layer] && w->pool_embedding_bias[layer], "pool.embedding layer missing");

@@ -296,12 +296,9 @@ int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hid
     size_t smem = (size_t)l->n_max * 2 * sizeof(float2) + (size_t)kPrepWarps * nm1 * sizeof(int);
     if (m->cfg.pool_type == TB2_POOL_SOCIAL) smem += ((size_t)(m->H + 4) * m->C + (size_t)l->n_max * m->H) * sizeof(float);
     smem = (smem + 15) & ~(size_t)15;
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        TB2_REQUIRE(smem <= 227 * 1024, "scene too large for pool_prepare shared memory");
-        TB2_CHECK_CUDA(cudaFuncSetAttribute(pool_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static DynSmemConfig configured;
+    TB2_REQUIRE(smem <= 227 * 1024, "scene too large for pool_prepare shared memory");
+    TB2_CHECK_CUDA(configured.ensure(pool_prepare_kernel, smem, 48 * 1024));
     {
         KernelTimer kt("pool_prepare", st);
         launch_pdl(pool_prepare_kernel, dim3(l->B), dim3(kPrepThreads), smem, st, p);
@@ -1018,11 +1015,8 @@ static int launch_pool_rows(const tb2_lstm* m, const tb2_layout* l, const Worksp
     groups = (l->M + rows - 1) / rows;
     p.rows_per_cta = rows;
     const size_t smem = wbytes + (size_t)rows * per_row;
-    static size_t configured = 0;
-    if (smem > configured) {
-        TB2_CHECK_CUDA(cudaFuncSetAttribute(pool_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static DynSmemConfig configured;
+    TB2_CHECK_CUDA(configured.ensure(pool_rows_kernel, smem));
     {
         KernelTimer kt("pool_rows", st);
         launch_pdl(pool_rows_kernel, dim3(groups, chunks), dim3(kRowsThreads), smem, st, p);
@@ -1033,12 +1027,8 @@ static int launch_pool_rows(const tb2_lstm* m, const tb2_layout* l, const Worksp
 
 template <int C, bool SOCIAL>
 static int launch_l1_t(const L1Params& p, int groups, size_t smem, cudaStream_t st) {
-    static size_t configured = 0;
-    if (smem > configured) {
-        TB2_CHECK_CUDA(cudaFuncSetAttribute(sparse_layer1_kernel<C, SOCIAL>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static DynSmemConfig configured;
+    TB2_CHECK_CUDA(configured.ensure(sparse_layer1_kernel<C, SOCIAL>, smem));
     dim3 grid(groups, (p.OUT + kL1Cols - 1) / kL1Cols);
     {
         KernelTimer kt("sparse_layer1", st);
@@ -1107,10 +1097,15 @@ int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float
     }
     int rc;
     const char* sp_env = getenv("TB2_SPARSE");       // debug knob: "mma" forces the warp-level MMA kernel,
-    const bool allow_tc = !(sp_env && sp_env[0] == 'm');     // "bucket" the per-cell bucket kernel
-    const bool allow_rows = !(sp_env && sp_env[0] == 'b');
+    const bool allow_tc = !(sp_env && sp_env[0] == 'm');     // "bucket" the per-cell bucket kernel, "tc" the SS-form
+    const bool allow_rows = !(sp_env && sp_env[0] == 'b');   // tcgen05 kernel, "ts1" / "ts2" the TS-form (one CTA / pair)
+    int ts_mode = 0;
+    if (sp_env && sp_env[0] == 't' && sp_env[1] == 's') ts_mode = sp_env[2] == '1' ? 1 : 2;
     if (allow_rows && pool_rows_chunk(m, d1) > 0) {   // occupancy / directional: weights resident in smem
         rc = launch_pool_rows(m, l, ws, d1, nm1, p.out, p.out_hi, p.out_lo, st);
+    } else
+    if (ts_mode && allow_tc && sparse_ts_supported(m, l)) {   // social, 16 latent channels: A operand in tensor memory
+        rc = launch_sparse_ts(m, l, ts_mode, ws, p.out, p.out_hi, p.out_lo, st);
     } else
     if (allow_tc && sparse_tc_supported(m, l, 0)) {  // social, 16 latent channels: tcgen05 path
         rc = launch_sparse_tc(m, l, 0, ws, p.out, p.out_hi, p.out_lo, st);
@@ -1136,11 +1131,8 @@ int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float
             if (!dbg_buf) cudaMalloc(&dbg_buf, (size_t)n_cta * 8 * sizeof(long long));
             q.dbg = dbg_buf;
         }
-        static size_t configured = 0;
-        if (sm > configured) {
-            TB2_CHECK_CUDA(cudaFuncSetAttribute(sparse_layer1_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            configured = sm;
-        }
+        static DynSmemConfig configured;
+        TB2_CHECK_CUDA(configured.ensure(sparse_layer1_mma_kernel, sm));
         dim3 grid(l->num_groups[gm], (d1 + kL1Cols - 1) / kL1Cols);
         {
             KernelTimer kt("sparse_layer1_mma", st);

@@ -454,11 +454,8 @@ int launch_sparse_tc(const tb2_lstm* m, const tb2_layout* l, int gsel, Workspace
         }
     }
     const size_t smem = sparse_tc_smem_bytes(p.cap, m->cells, nm1);
-    static size_t configured = 0;
-    if (smem > configured) {
-        TB2_CHECK_CUDA(cudaFuncSetAttribute(sparse_layer1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static DynSmemConfig configured;
+    TB2_CHECK_CUDA(configured.ensure(sparse_layer1_tc_kernel, smem));
     dim3 grid(l->num_groups[gsel], d1 / kScCols);
     {
         KernelTimer kt("sparse_layer1_tc", st);

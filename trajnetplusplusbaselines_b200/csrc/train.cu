@@ -1089,12 +1089,8 @@ static int social_backward(const tb2_lstm* m, const tb2_layout* l, const tb2_lst
     const size_t place_smem = (size_t)l->n_max * nm1 * sizeof(short);
     TB2_REQUIRE(place_smem <= 200 * 1024 && cells < 32768, "scene too large for the social backward");
     {
-        static size_t configured = 48 * 1024;
-        if (place_smem > configured) {
-            TB2_CHECK_CUDA(cudaFuncSetAttribute(pair_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)place_smem));
-            configured = place_smem;
-        }
+        static DynSmemConfig configured;
+        TB2_CHECK_CUDA(configured.ensure(pair_place_kernel, place_smem, 48 * 1024));
     }
     int cur = 0;
     for (int s = S - 1; s >= 0; --s, cur ^= 1) {

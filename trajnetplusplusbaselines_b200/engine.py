@@ -42,16 +42,31 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-class SceneLayout:
-    """tb2_layout wrapper: the `batch_split` partition of tracks into scenes."""
+def _device_of(device):
+    """Resolved CUDA device (the current one when `device` is None or an index-less 'cuda')."""
+    device = torch.device('cuda' if device is None else device)
+    if device.type != 'cuda':
+        raise RuntimeError("scene layouts live in device memory: got device %s" % device)
+    if device.index is None:
+        device = torch.device('cuda', torch.cuda.current_device())
+    return device
 
-    def __init__(self, batch_split, pad_to_batch_max=True):
+
+class SceneLayout:
+    """tb2_layout wrapper: the `batch_split` partition of tracks into scenes.  The handle owns device
+    buffers, allocated on `device` (default: the current CUDA device); a layout must only be used with
+    models / tensors of that device."""
+
+    def __init__(self, batch_split, pad_to_batch_max=True, device=None):
+        _lib.require_cuda()
         lib = _lib.load()
+        self.device = _device_of(device)
         offs = [int(v) for v in batch_split]
         self.offsets = offs
         arr = (ctypes.c_int64 * len(offs))(*offs)
         handle = ctypes.c_void_p()
-        _lib.check(lib.tb2_layout_create(arr, len(offs) - 1, ctypes.byref(handle)))
+        with torch.cuda.device(self.device):
+            _lib.check(lib.tb2_layout_create(arr, len(offs) - 1, ctypes.byref(handle)))
         self.handle = handle
         self.num_scenes = len(offs) - 1
         self.num_tracks = offs[-1]
@@ -67,11 +82,12 @@ class LayoutCache:
         self.capacity = capacity
         self._items = OrderedDict()
 
-    def get(self, batch_split, pad_to_batch_max=True):
-        key = tuple(int(v) for v in batch_split) + (bool(pad_to_batch_max),)
+    def get(self, batch_split, pad_to_batch_max=True, device=None):
+        device = _device_of(device)
+        key = tuple(int(v) for v in batch_split) + (bool(pad_to_batch_max), device.index)
         item = self._items.get(key)
         if item is None:
-            item = SceneLayout(key[:-1], pad_to_batch_max)
+            item = SceneLayout(key[:-2], pad_to_batch_max, device)
             self._items[key] = item
             if len(self._items) > self.capacity:
                 self._items.popitem(last=False)

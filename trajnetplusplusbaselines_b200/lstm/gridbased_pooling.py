@@ -135,7 +135,7 @@ class GridBasedPooling(torch.nn.Module):
             self._handle = ModelHandle(cfg, device)
             self._standalone_dummy = None
         self._set_plug_weights(device)
-        layout = self._layouts.get(range(0, batch_size * num_tracks + 1, num_tracks))
+        layout = self._layouts.get(range(0, batch_size * num_tracks + 1, num_tracks), device=device)
         f32 = dict(device=device, dtype=torch.float32)
         o1 = obs1.detach().to(**f32).reshape(-1, 2).contiguous()
         o2 = obs2.detach().to(**f32).reshape(-1, 2).contiguous()

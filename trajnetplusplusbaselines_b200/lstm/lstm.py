@@ -90,7 +90,10 @@ class LSTM(torch.nn.Module):
     def _device(self):
         return self.hidden2normal.linear.weight.device
 
-    def _engine(self):
+    def _engine(self, force_repack=False):
+        """force_repack: re-upload / repack the weights even if (data_ptr, _version, optimizer epoch) did
+        not change.  The training forward passes True: updates through `p.data` (manual SGD, EMA,
+        `.data.clamp_`) change none of the three."""
         if self.goal_flag:
             raise NotImplementedError("goal_flag=True is not built (off in every BASELINE config)")
         device = self._device()
@@ -111,11 +114,8 @@ class LSTM(torch.nn.Module):
                 self.pool.fill_config(cfg)
             self._handle = ModelHandle(cfg, device)
         key = weights_key(self)
-        # under grad mode (training) the repack is redone on every forward: an update scheme that
-        # by-passes both version counters and torch.optim hooks must not train on stale weights
-        force = torch.is_grad_enabled() and self.training
-        if force or key != self._handle._weights_key:
-            self._handle.set_weights(self._weight_fields(), key=key, force=force)
+        if force_repack or key != self._handle._weights_key:
+            self._handle.set_weights(self._weight_fields(), key=key, force=force_repack)
         return self._handle
 
     def _weight_fields(self):
@@ -165,7 +165,7 @@ class LSTM(torch.nn.Module):
             h, c = torch.stack(list(h)), torch.stack(list(c))
         h = h.detach().to(device=device, dtype=torch.float32).contiguous().clone()
         c = c.detach().to(device=device, dtype=torch.float32).contiguous().clone()
-        layout = self._layouts.get(batch_split.tolist() if torch.is_tensor(batch_split) else batch_split)
+        layout = self._layouts.get(batch_split.tolist() if torch.is_tensor(batch_split) else batch_split, device=device)
         o1 = self._to_device(obs1, device)
         o2 = self._to_device(obs2, device)
         normal, _ = handle.step_forward(layout, phase, o1, o2, h, c)
@@ -187,12 +187,12 @@ class LSTM(torch.nn.Module):
         return self._forward_nograd(observed, batch_split, prediction_truth, n_predict)
 
     def _forward_nograd(self, observed, batch_split, prediction_truth, n_predict, want_states=False,
-                        pad_to_batch_max=True):
-        handle = self._engine()
+                        pad_to_batch_max=True, force_repack=False):
+        handle = self._engine(force_repack)
         device = handle.device
         out_device = observed.device
         layout = self._layouts.get(batch_split.tolist() if torch.is_tensor(batch_split) else batch_split,
-                                   pad_to_batch_max)
+                                   pad_to_batch_max, device=device)
         M = layout.num_tracks
         if observed.shape[1] != M:
             raise ValueError("batch_split[-1] != number of tracks")

@@ -49,8 +49,11 @@ def _grad_targets(model):
 class _SequenceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, observed, batch_split, prediction_truth, n_predict, *params):
+        # grad mode is off inside autograd.Function.forward, so "is this a training forward" cannot be asked
+        # in LSTM._engine: every forward that records a graph repacks the weights (a few tens of
+        # microseconds), which also covers parameter updates that bypass version counters and optimizer hooks
         normals, positions, states, (obs, truth, layout) = model._forward_nograd(
-            observed, batch_split, prediction_truth, n_predict, want_states=True)
+            observed, batch_split, prediction_truth, n_predict, want_states=True, force_repack=True)
         ctx.model = model
         ctx.layout = layout
         ctx.obs = obs

@@ -66,7 +66,8 @@ class LSTMGenerator(LSTM):
         """Encoder steps only; returns the context every mode's decoder starts from."""
         handle = self._engine()
         device = handle.device
-        layout = self._layouts.get(batch_split.tolist() if torch.is_tensor(batch_split) else batch_split)
+        layout = self._layouts.get(batch_split.tolist() if torch.is_tensor(batch_split) else batch_split,
+                                   device=self._device())
         M = layout.num_tracks
         if observed.shape[1] != M:
             raise ValueError("batch_split[-1] != number of tracks")
@@ -159,7 +160,8 @@ class LSTMDiscriminator(torch.nn.Module):
         handle = body._engine()
         device = handle.device
         seq = torch.cat([body._to_device(observed, device), body._to_device(prediction, device)], dim=0)
-        layout = body._layouts.get(batch_split.tolist() if torch.is_tensor(batch_split) else batch_split)
+        layout = body._layouts.get(batch_split.tolist() if torch.is_tensor(batch_split) else batch_split,
+                                   device=body._device())
         M = layout.num_tracks
         S = int(seq.shape[0]) - 1
         f32 = dict(dtype=torch.float32, device=device)

@@ -96,7 +96,8 @@ class VAE(torch.nn.Module):
         body = self._body[0]
         handle = body._engine()
         device = handle.device
-        layout = body._layouts.get(batch_split.tolist() if torch.is_tensor(batch_split) else batch_split)
+        layout = body._layouts.get(batch_split.tolist() if torch.is_tensor(batch_split) else batch_split,
+                                   device=body._device())
         M = layout.num_tracks
         obs = body._to_device(observed, device)
         obs_length = int(obs.shape[0])
