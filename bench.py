@@ -36,6 +36,8 @@ DENSE_FLOP_PER_PED_STEP = {                       # SURVEY.md 8d, dense-equivale
     "sparse_layer1": 2 * 4096 * 1024,             # first Linear of the grid embedding (4096 -> 1024)
     "sparse_layer1_mma": 2 * 4096 * 1024,
     "sparse_layer1_tc": 2 * 4096 * 1024,
+    "sparse_layer1_pair": 2 * 4096 * 1024,
+    "sparse_layer1_solo": 2 * 4096 * 1024,
     "dense_layer": 2 * 1024 * 256,
     "dense_layer_tc": 2 * 1024 * 256,
     "lstm_gates": 2 * (64 + 256 + 128) * 512 + 2 * 128 * 5,

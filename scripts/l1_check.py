@@ -1,8 +1,8 @@
-"""A/B check of the first grid-embedding Linear of the social pool: TB2_SPARSE = tc (SS-form tcgen05
-kernel of round 1) / ts1 (TS form, one CTA) / ts2 (TS form, CTA pair) against the numpy oracle (small
+"""A/B check of the first grid-embedding Linear of the social pool: TB2_SPARSE = tc (round-1 tcgen05
+kernel) / solo (round-2 kernel, one CTA) / pair (round-2 kernel, CTA pair) against the numpy oracle (small
 case) and against each other (BASELINE-size case), with CUDA-event timing of the pool call.
 
-    python scripts/ts_check.py --mode ts2 [--big-only]
+    python scripts/l1_check.py --mode pair
 """
 import argparse
 import os
@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--mode", default="ts2")
+    ap.add_argument("--mode", default="pair")
     ap.add_argument("--scenes", type=int, default=256)
     ap.add_argument("--iters", type=int, default=70)
     args = ap.parse_args()

@@ -60,6 +60,8 @@ size_t carve_workspace(const tb2_lstm* m, const tb2_layout* l, void* base, Works
     w.win_val = (float*)take(M * nm1 * 2 * sizeof(float));
     w.pair_cell = (int*)take(M * nm1 * sizeof(int));
     w.pair_flag = (uint8_t*)take(M * nm1);
+    w.cell_row = nullptr;
+    if (m->Wt1_sw_hi != nullptr && m->cells <= 256) w.cell_row = (uint8_t*)take(M * (size_t)m->cells);
     size_t wmax = 1;
     for (int i = 1; i <= m->n_mlp; ++i) wmax = std::max(wmax, (size_t)m->mlp_dims[i]);
     w.act[0] = (float*)take(M * wmax * sizeof(float));
@@ -251,8 +253,8 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
                 m->Wt1_nat_hi = nh;
                 m->Wt1_nat_lo = nl;
                 float *sh, *sl;
-                ALLOC(sh, half);
-                ALLOC(sl, half);
+                ALLOC(sh, 2 * half);      // hi and lo interleaved by 8-row group (one bulk copy per slab)
+                ALLOC(sl, 4);
                 m->Wt1_sw_hi = sh;
                 m->Wt1_sw_lo = sl;
             }

@@ -128,7 +128,7 @@ struct tb2_lstm {
     void* Wt1_nat_hi;      // social, C == 16: bf16 [cells, d1, 16] natural k order (TMA source of sparse_layer1_tc)
     void* Wt1_nat_lo;
     void* Wt1_sw_hi;       // social, C == 16: the same slabs as a SWIZZLE_32B shared-memory image (bulk-copy source of
-    void* Wt1_sw_lo;       // sparse_layer1_ts)
+    void* Wt1_sw_lo;       // sparse_layer1_pair)
     float* WT[tb2::kMaxMlpLayers];   // layers >= 2: [K, N] transposed
     float* bl[tb2::kMaxMlpLayers];   // biases of layers >= 2
     void* W_hi[tb2::kMaxMlpLayers];  // bf16 [N, K] (hi, lo) split for the tcgen05 path (null: FFMA path)
@@ -149,6 +149,9 @@ struct tb2_layout {
     int group_cap[2];
     int num_groups[2];
     int* group_off[2];     // [G+1] scene indices, device
+    // round tables of sparse_layer1_pair (one per (layer width, unit count, CTAs per unit)), built on first use
+    struct PairPlan { int OUT, units_max, nC, units, rounds_per_unit; void* dev; };
+    std::vector<PairPlan> pair_plans;
     std::vector<void*> owned;
 };
 
@@ -163,6 +166,8 @@ struct Workspace {
     float* win_val;        // [M, nm1, 2]
     int* pair_cell;        // [M, nm1]
     uint8_t* pair_flag;    // [M, nm1]
+    uint8_t* cell_row;     // [M, cells] social, cells <= 256: per-row cell map (scene-local winner index, 0xFF none,
+                           // 0xFE NaN-padded slot) read by sparse_layer1_pair; null otherwise
     float* act[2];         // ping-pong MLP activations [M, max width]
     float* act2;           // third scratch (three_layer with a tensor-core second layer)
     float* pooled;         // [M, pool_out]
@@ -194,10 +199,10 @@ int launch_repack_layer1_nat(const float* W1, void* hi, void* lo, int OUT, int c
 bool sparse_tc_supported(const tb2_lstm* m, const tb2_layout* l, int gsel);
 int launch_sparse_tc(const tb2_lstm* m, const tb2_layout* l, int gsel, Workspace* ws, float* out, void* out_hi,
                      void* out_lo, cudaStream_t st);
-// TS form of the same layer (A operand in tensor memory; mode 1 = one CTA, 2 = CTA pair with cta_group::2)
-bool sparse_ts_supported(const tb2_lstm* m, const tb2_layout* l);
-int launch_sparse_ts(const tb2_lstm* m, const tb2_layout* l, int mode, Workspace* ws, float* out, void* out_hi,
-                     void* out_lo, cudaStream_t st);
+// round-2 kernel of the same layer (pedestrians on the M side; mode 1 = one CTA, 2 = CTA pair with cta_group::2)
+bool sparse_pair_supported(const tb2_lstm* m, const tb2_layout* l);
+int launch_sparse_pair(const tb2_lstm* m, const tb2_layout* l, int mode, Workspace* ws, float* out, void* out_hi,
+                       void* out_lo, cudaStream_t st);
 int launch_repack_layer1_sw(const float* W1, void* hi, void* lo, int OUT, int cells, cudaStream_t st);
 bool dense_tc_supported(int K, int N);
 int launch_dense_tc(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,

@@ -74,6 +74,7 @@ struct PrepParams {
     float* win_val;
     int* pair_cell;
     uint8_t* pair_flag;
+    uint8_t* cell_row;        // [M, n * n] per-row cell map for sparse_layer1_pair (or null)
     const float* We;          // input embedding (fused producer of the gate kernel's emb operand)
     const float* be;
     __nv_bfloat16* emb_hi;    // [M, E] bf16 split or null
@@ -163,6 +164,8 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
     }
     if (nm1 <= 0) {   // single-pedestrian batch: constant grid (gridbased_pooling.py:252-253)
         for (int i = tid; i < n_s; i += kPrepThreads) p.win_count[row0 + i] = 0;
+        if (p.cell_row)
+            for (int idx = tid; idx < n_s * p.n * p.n; idx += kPrepThreads) p.cell_row[(size_t)row0 * p.n * p.n + idx] = 0xffu;
         return;
     }
 
@@ -209,6 +212,11 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
         // pass 2: winners, compacted in ascending jj
         const bool masked = isnan(vi.x);      // obs2 - obs1 is NaN iff the track is absent at either frame
         int count = 0;
+        uint8_t* crow = p.cell_row ? p.cell_row + (size_t)(row0 + i) * (p.n * p.n) : nullptr;
+        if (crow) {       // all cells empty, winners marked below (same warp: ordered by the __syncwarp)
+            for (int c = lane * 4; c < p.n * p.n; c += 128) *reinterpret_cast<uint32_t*>(crow + c) = 0xffffffffu;
+            __syncwarp();
+        }
         if (!(p.skip_masked && masked)) {
             for (int base = 0; base < nm1; base += 32) {
                 int jj = base + lane;
@@ -232,6 +240,7 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
                     int j = jj + (jj >= i);
                     // a padded slot can only win in the (discarded) row of an absent pedestrian
                     p.win_ent[gi + slot] = ((uint32_t)cell << 16) | (uint32_t)(j < n_s ? j : 0xffff);
+                    if (crow) crow[cell] = (uint8_t)(j < n_s ? j : 0xfe);
                     if (p.pool_type == TB2_POOL_DIRECTIONAL) {
                         const float2 vj = (j < n_s) ? vel[j] : make_float2(CUDART_NAN_F, CUDART_NAN_F);
                         p.win_val[(gi + slot) * 2 + 0] = nan_to_num_f(vj.x - vi.x);      // :131-140
@@ -266,6 +275,8 @@ int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hid
     p.win_val = ws->win_val;
     p.pair_cell = ws->pair_cell;
     p.pair_flag = ws->pair_flag;
+    // the cell map is written as 32-bit words: n * n must be a multiple of 4 (the pair kernel asks for 16)
+    p.cell_row = (m->cfg.pool_type == TB2_POOL_SOCIAL && (m->cfg.n * m->cfg.n) % 16 == 0 && l->n_max <= 0xFD) ? ws->cell_row : nullptr;
     p.n_max = l->n_max;
     p.H = m->H;
     p.C = m->C;
@@ -1097,15 +1108,16 @@ int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float
     }
     int rc;
     const char* sp_env = getenv("TB2_SPARSE");       // debug knob: "mma" forces the warp-level MMA kernel,
-    const bool allow_tc = !(sp_env && sp_env[0] == 'm');     // "bucket" the per-cell bucket kernel, "tc" the SS-form
+    const bool allow_tc = !(sp_env && sp_env[0] == 'm');     // "bucket" the per-cell bucket kernel, "tc" round 1's
     const bool allow_rows = !(sp_env && sp_env[0] == 'b');   // tcgen05 kernel, "ts1" / "ts2" the TS-form (one CTA / pair)
-    int ts_mode = 0;
-    if (sp_env && sp_env[0] == 't' && sp_env[1] == 's') ts_mode = sp_env[2] == '1' ? 1 : 2;
+    int pair_mode = 2;                                       // default: the round-2 CTA-pair kernel; "solo": the same kernel
+    if (sp_env && sp_env[0] == 's' && sp_env[1] == 'o') pair_mode = 1;       // with one CTA per unit; "tc" / "mma" / "bucket":
+    if (sp_env && (sp_env[0] == 't' || sp_env[0] == 'm' || sp_env[0] == 'b')) pair_mode = 0;     // the round-1 kernels
     if (allow_rows && pool_rows_chunk(m, d1) > 0) {   // occupancy / directional: weights resident in smem
         rc = launch_pool_rows(m, l, ws, d1, nm1, p.out, p.out_hi, p.out_lo, st);
     } else
-    if (ts_mode && allow_tc && sparse_ts_supported(m, l)) {   // social, 16 latent channels: A operand in tensor memory
-        rc = launch_sparse_ts(m, l, ts_mode, ws, p.out, p.out_hi, p.out_lo, st);
+    if (pair_mode && ws->cell_row && sparse_pair_supported(m, l)) {   // social, 16 latent channels: CTA-pair tcgen05 kernel
+        rc = launch_sparse_pair(m, l, pair_mode, ws, p.out, p.out_hi, p.out_lo, st);
     } else
     if (allow_tc && sparse_tc_supported(m, l, 0)) {  // social, 16 latent channels: tcgen05 path
         rc = launch_sparse_tc(m, l, 0, ws, p.out, p.out_hi, p.out_lo, st);

@@ -1,0 +1,831 @@
+// First Linear of the SOCIAL grid embedding on tcgen05, CTA-pair kernel (round 2).
+//
+//   hidden1[p, :] = relu(b1 + sum_{winning (cell, j) of p} W1[:, cell-slab] . lat_j)
+//   (reference: GridBasedPooling.social + the first Linear of two_layer,
+//    trajnetbaselines/lstm/gridbased_pooling.py:145-170,227-305,316-323)
+//
+// Orientation (the transpose of round 1's sparse_layer1_tc_kernel): D[p, col] with the pedestrians on
+// the M side -- 128 TMEM lanes per CTA, one pedestrian per lane -- and the output columns on the N
+// side.  Per grid cell c one K = 16 product
+//     D[p, col] += L_c[p, 0:16] . W_c[col, 0:16]
+// where L_c[p, :] is the latent vector of p's winning neighbour in cell c, or zero.
+//   * kPair: two CTAs (one TPC) run tcgen05.mma.cta_group::2 with M = 256: each CTA owns 128
+//     pedestrians (its own A tiles) and HALF of the weight columns of the tile (B is shared by the
+//     pair), so every weight byte fetched from L2 serves 256 pedestrians and each SM's shared memory
+//     holds, and its tensor core reads, only half of B.  Per cell and CTA: 9 KB of weights written,
+//     14 KB read by the three passes, 8 KB of A written and 12 KB read = 43 KB against a 415-cycle
+//     tensor floor (81 % of the 128 B/clk port); round 1's kernel needed 70 KB for 480 cycles.
+//   * A tiles (L_c, bf16 hi and lo, SWIZZLE_32B K-major) are written by four builder warps, one
+//     thread per pedestrian row, every row every cell (no re-zeroing, no buckets): the thread reads
+//     "which neighbour of mine sits in cell c" from the per-row cell map pool_prepare leaves in
+//     global memory (16 cells per 16-byte load, prefetched) and copies the neighbour's split latent
+//     vector from a per-tile table in shared memory.  (With the A operand in tensor memory instead,
+//     the 8 KB of tcgen05.st per cell were the bottleneck: profiles/round2_ts_experiment.txt.)
+//   * The weight slabs W_c are stored pre-swizzled (SWIZZLE_32B image) in global memory, so one
+//     plain bulk copy (cp.async.bulk) of any multiple of 16 rows lands the tile the UMMA
+//     descriptor expects.
+//   * Work decomposition: the (pedestrian tile, 32-column block) space is linearised and cut into
+//     equal contiguous ranges, one per CTA pair; a range is processed in rounds of at most two
+//     contexts (tile, column range) with at most 288 accumulator columns, so a range that straddles a
+//     tile boundary still keeps all SMs equally loaded (5120 pedestrians x 1024 columns on 74 pairs:
+//     8.65 blocks each, against 128 of 148 SMs busy in round 1).
+//   * Pipeline item = 4 grid cells (K = 64; 2 when a round spans two pedestrian tiles), 3 items in
+//     flight: one barrier round trip builders -> MMA issuers -> tcgen05.commit per item.
+//   * Precision: 3-pass bf16 (hi, lo) split, fp32 accumulation in TMEM, like the other kernels;
+//     results are bit-identical to sparse_layer1_tc_kernel (same products, same order per column).
+//
+// Warp roles (512 threads): 0 = weight producer, 1 / 2 = MMA issuers of context 0 / 1 (leader CTA
+// only; 1 also owns the TMEM allocation), 4..7 = builders of A slot 0, 8..11 = builders of A slot 1
+// (second pedestrian tile of a round); warps 4..15 run the epilogue (3 per TMEM lane quarter).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cstdio>
+#include <cstdlib>
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace tb2 {
+
+constexpr int kSpThreads = 512;
+constexpr int kSpSA = 3;                 // ring of A stages (built on the fly, short turn-around)
+constexpr int kSpSBMax = 5;              // ring of weight stages (bulk copies from L2: ~1500 cycles from request to landing)
+constexpr int kSpMaxBlocks = 9;          // 32-column blocks per round (288 accumulator columns)
+constexpr int kSpDCols = kSpMaxBlocks * 32;
+constexpr int kSpMaxCells = 256;
+constexpr int kSpLatRows = 256;          // local latent table (rows of the scenes a 128-row tile touches) + 1
+constexpr uint32_t kSpATile = 128 * 32;  // one A tile: 128 pedestrian rows x 16 k bf16
+// Pipeline item: one-tile round = 4 grid cells (K = 64) of the tile; two-tile round = 2 cells of BOTH tiles (the
+// two accumulator chains are interleaved MMA by MMA).  Either way an A stage is 4 x (hi | lo) tiles = 32 KB and
+// the weights of an item are at most 4 x 9 KB (one tile: 3 stages) or 2 x 9 KB (two tiles: 5 stages).
+constexpr uint32_t kSpAStage = 4u * 2u * kSpATile;
+constexpr uint32_t kSpBCell = (uint32_t)(kSpDCols / 2) * 64u;          // bytes of weights per cell and CTA of a pair (288 columns)
+constexpr uint32_t kSpBRing = 3u * 4u * kSpBCell;
+// dynamic shared memory behind the 1024-byte alignment: [A ring | weight ring | latent table 0]; the second
+// latent table of a two-tile round sits in the unused tail of the weight ring (5 x 2 cells < 3 x 4 cells)
+constexpr size_t kSpDynBytes = (size_t)kSpSA * kSpAStage + kSpBRing + (size_t)kSpLatRows * 64;
+static_assert((size_t)kSpSBMax * 2 * kSpBCell + (size_t)kSpLatRows * 64 <= kSpBRing, "two-tile rounds: second latent table");
+static_assert(1024 + kSpDynBytes + 64 <= 227 * 1024 - 1024, "shared memory budget");
+
+__device__ __forceinline__ uint32_t sp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sp_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void sp_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// arrive on a barrier of the leader CTA (cluster address).  Default semantics (.release.cta) like CUTLASS'
+// ClusterBarrier::arrive: a .release.cluster arrive per builder warp and item cost ~2000 cycles of serial
+// latency per item (measured), and the data this signal publishes is read by THIS SM's tensor core, behind
+// the fence.proxy.async each builder thread executed.
+__device__ __forceinline__ void sp_mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void sp_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SP_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SP_WAIT_DONE;\n"
+        "bra SP_WAIT_LOOP;\n"
+        "SP_WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// the leader's "A and B of this item are ready" barrier (also arrived on from the peer CTA)
+__device__ __forceinline__ void sp_mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SPC_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SPC_WAIT_DONE;\n"
+        "bra SPC_WAIT_LOOP;\n"
+        "SPC_WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void sp_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// completion of all earlier tcgen05.mma of this thread -> arrive on `bar` (pair: in both CTAs)
+template <bool kPair>
+__device__ __forceinline__ void sp_commit(uint32_t bar) {
+    if (kPair) {
+        const uint16_t mask = 3;
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(bar), "h"(mask) : "memory");
+    } else {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    }
+}
+__device__ __forceinline__ void sp_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+
+
+// One round of a unit: `n0` 32-column blocks of pedestrian tile `tile` starting at block `blk0`, then (n1 > 0) the
+// first `n1` blocks of tile + 1.  Planned on the host (plan_rounds) so that no piece is narrower than 3 blocks.
+struct SpRound { int tile, blk0, n0, n1; };
+
+__device__ __forceinline__ void sp_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+struct SpParams {
+    const int* scene_off;
+    const int* row_scene;
+    const unsigned char* cell_row;   // [M, cells]: scene-local index of the winning neighbour (0xFF none, 0xFE NaN-padded slot)
+    const float* lat;                // [M, 16] fp32
+    const float* benc;               // [16]
+    const float* base;               // [OUT]
+    const unsigned char* w;          // bf16 [cells][OUT / 8][hi: 8 rows x 16 | lo: 8 rows x 16], 16-byte chunks swizzled by ((col >> 2) & 1)
+    float* out;                      // fp32 [M, OUT] or null
+    __nv_bfloat16* out_hi;           // bf16 split [M, OUT] or null
+    __nv_bfloat16* out_lo;
+    const SpRound* rounds;           // [units * rounds_per_unit] (plan_rounds)
+    int M, OUT, cells, rounds_per_unit;
+    float constant;
+    long long* dbg;                  // optional [units * nC, 8] cycle counters (TB2_L1_DEBUG=1)
+};
+
+// SS-form MMA with 64-bit shared-memory descriptors kept in registers (the issuing thread is a single
+// thread: every instruction between two MMAs counts)
+template <bool kPair>
+__device__ __forceinline__ void sp_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if (kPair)
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+    else
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
+// byte offset of (row r, 16-byte chunk c) inside a SWIZZLE_32B K-major tile
+__device__ __forceinline__ uint32_t sp_sw32(uint32_t r, uint32_t c) { return r * 32u + ((c ^ ((r >> 2) & 1u)) << 4); }
+
+// Builder body for one pipeline item of KC cells; `bytes` holds the KC cell-map bytes of this row (LSB first).
+template <int KC>
+__device__ __forceinline__ void sp_build_item(unsigned char* a_item, uint32_t a_stride, uint32_t bytes, int kcn, uint32_t r,
+                                              int off_r, int nlat, const uint4* lh, const uint4* ll) {
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) {
+        if (kc < kcn) {
+            const uint32_t j = (bytes >> (8 * kc)) & 0xffu;
+            uint4 h0 = make_uint4(0u, 0u, 0u, 0u), h1 = h0, l0 = h0, l1 = h0;
+            if (j != 0xffu) {
+                const int li = j == 0xfeu ? nlat : (int)j + off_r;
+                h0 = lh[li * 2]; h1 = lh[li * 2 + 1];
+                l0 = ll[li * 2]; l1 = ll[li * 2 + 1];
+            }
+            unsigned char* t = a_item + (size_t)kc * a_stride;
+            *reinterpret_cast<uint4*>(t + sp_sw32(r, 0)) = h0;
+            *reinterpret_cast<uint4*>(t + sp_sw32(r, 1)) = h1;
+            *reinterpret_cast<uint4*>(t + kSpATile + sp_sw32(r, 0)) = l0;
+            *reinterpret_cast<uint4*>(t + kSpATile + sp_sw32(r, 1)) = l1;
+        }
+    }
+}
+
+// Builder role of one warp for one round: thread = pedestrian row r; `cr` = the row's cell map (16 cells per
+// uint4) or null for rows past the end.  One-tile round: the two builder groups (warps 4..7 / 8..11) take the even
+// / odd items.  Two-tile round (kTwo): group bg builds the tiles of pedestrian tile bg inside EVERY item.
+template <int KC, bool kTwo>
+__device__ __forceinline__ void sp_builder(const uint4* cr, int groups, uint32_t SB, unsigned char* a_ring, int bg,
+                                           bool wait_weights, uint32_t r, int off_r, int nlat, const uint4* lh, const uint4* ll,
+                                           uint64_t* empty_a, uint64_t* full_b, const uint32_t (&full_remote)[kSpSA], int lane,
+                                           long long& wait_e, long long& wait_b) {
+    const uint4 none = make_uint4(~0u, ~0u, ~0u, ~0u);
+    constexpr int ipg = 16 / KC;                       // items per 16-cell load of the row's cell map
+    constexpr int step = kTwo ? 1 : 2;
+    constexpr uint32_t a_stride = kTwo ? 4u * kSpATile : 2u * kSpATile;       // bytes between the cells of an item
+    uint4 cur = cr ? __ldg(cr) : none;
+    for (int g16 = 0; g16 < groups; ++g16) {
+        const uint4 next = (cr && g16 + 1 < groups) ? __ldg(cr + g16 + 1) : none;     // prefetched one group ahead
+#pragma unroll
+        for (int jj = 0; jj < ipg / step; ++jj) {
+            uint32_t g, bytes;                          // item index inside the round, its KC cell-map bytes
+            if (kTwo) {
+                g = (uint32_t)(g16 * ipg + jj);
+                const int c = jj * KC;                  // first cell of the item inside the 16-cell load (compile time)
+                const uint32_t w = (c >> 2) == 0 ? cur.x : (c >> 2) == 1 ? cur.y : (c >> 2) == 2 ? cur.z : cur.w;
+                bytes = KC == 4 ? w : (w >> (8 * (c & 3))) & ((1u << (8 * (KC & 3))) - 1u);
+            } else {
+                g = (uint32_t)(g16 * ipg + 2 * jj + bg);
+                if (KC == 4) bytes = jj == 0 ? (bg ? cur.y : cur.x) : (bg ? cur.w : cur.z);
+                else bytes = ((jj == 0 ? cur.x : jj == 1 ? cur.y : jj == 2 ? cur.z : cur.w) >> (16 * bg)) & 0xffffu;
+            }
+            const uint32_t sa = g % kSpSA, pa = (g / kSpSA) & 1u;
+            const long long tw0 = clock64();
+            sp_mbar_wait(sp_smem_u32(&empty_a[sa]), pa ^ 1u);
+            wait_e += clock64() - tw0;
+            sp_build_item<KC>(a_ring + (size_t)sa * kSpAStage, a_stride, bytes, KC, r, off_r, nlat, lh, ll);
+            // generic-proxy writes of the tiles -> visible to the tensor core's async-proxy reads
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (wait_weights) {   // the weights of this item have landed in THIS CTA (chained into the arrive below)
+                const long long tw1 = clock64();
+                sp_mbar_wait(sp_smem_u32(&full_b[g % SB]), (g / SB) & 1u);
+                wait_b += clock64() - tw1;
+            }
+            __syncwarp();
+            if (lane == 0) sp_mbar_arrive_cluster(full_remote[sa]);
+        }
+        cur = next;
+    }
+}
+
+template <bool kPair>
+__global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpParams p) {
+    constexpr int nC = kPair ? 2 : 1;
+    extern __shared__ __align__(1024) unsigned char smem_sp[];
+    __shared__ __align__(8) uint64_t full_a[kSpSA];       // leader: A tiles (both CTAs) built AND weights (both CTAs) landed
+    __shared__ __align__(8) uint64_t empty_a[kSpSA];      // MMAs that read the A stage done
+    __shared__ __align__(8) uint64_t full_b[kSpSBMax];    // local weight slabs landed
+    __shared__ __align__(8) uint64_t empty_b[kSpSBMax];   // MMAs that read the weight stage done
+    __shared__ __align__(8) uint64_t acc_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint32_t rank = 0;
+    if (kPair) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 8 : nullptr;
+    const long long t_begin = clock64();
+
+    const uint32_t ring = (sp_smem_u32(smem_sp) + 1023u) & ~1023u;          // A ring
+    unsigned char* ring_ptr = smem_sp + (ring - sp_smem_u32(smem_sp));
+    const uint32_t bring = ring + (uint32_t)kSpSA * kSpAStage;              // weight ring
+    uint4* latH[2];
+    uint4* latL[2];
+    latH[0] = reinterpret_cast<uint4*>(ring_ptr + kSpDynBytes - (size_t)kSpLatRows * 64);
+    latL[0] = latH[0] + kSpLatRows * 2;
+    latH[1] = reinterpret_cast<uint4*>(ring_ptr + kSpDynBytes - (size_t)2 * kSpLatRows * 64);
+    latL[1] = latH[1] + kSpLatRows * 2;
+
+    // ---- prologue: TMEM (the barriers are initialised per round) ----------------------------------
+    if (warp == 1) {
+        uint32_t ncols = 512;
+        if (kPair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"(sp_smem_u32(&tmem_base_slot)), "r"(ncols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"(sp_smem_u32(&tmem_base_slot)), "r"(ncols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+    grid_dep_wait();          // cell map / latent vectors come from pool_prepare
+    grid_dep_launch();
+    const long long t_start = clock64();
+
+    // leader's full barrier as seen from this CTA (cluster address space)
+    uint32_t full_remote[kSpSA];
+#pragma unroll
+    for (int s = 0; s < kSpSA; ++s) {
+        uint32_t local = sp_smem_u32(&full_a[s]);
+        if (kPair) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(full_remote[s]) : "r"(local), "r"(0));
+        else full_remote[s] = local;
+    }
+
+    const int R = 128 * nC;                               // pedestrian rows per tile
+    uint32_t round_idx = 0;
+    long long t_setup_sum = 0, t_loop_sum = 0, t_epi_sum = 0, wait_full = 0, wait_b = 0, wait_e = 0;
+    SpRound rd = {0, 0, 0, 0};
+    for (int ri = 0; ri < p.rounds_per_unit; ++ri) {
+        rd = p.rounds[(size_t)unit * p.rounds_per_unit + ri];
+        if (rd.n0 == 0) continue;                         // padding round (uniform for the whole cluster)
+        const long long t_r0 = clock64();
+        const int nsub = rd.n1 > 0 ? 2 : 1;
+        // pipeline shape of the round (the barriers are re-initialised for it)
+        const int KC = nsub == 2 ? (kPair ? 2 : 1) : (kPair ? 4 : 2);     // grid cells per pipeline item
+        const uint32_t SB = nsub == 2 ? (uint32_t)kSpSBMax : 3u;             // weight stages
+        const int n_items = p.cells / KC;                    // cells is a multiple of 16
+        const uint32_t n_issuers = 2u;
+        if (tid == 0) {
+            for (int s2 = 0; s2 < kSpSA; ++s2) {
+                if (round_idx > 0) {
+                    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(sp_smem_u32(&full_a[s2])) : "memory");
+                    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(sp_smem_u32(&empty_a[s2])) : "memory");
+                }
+                // builders per item and CTA: one group of 4 warps (one tile) or both groups (two tiles)
+                sp_mbar_init(sp_smem_u32(&full_a[s2]), (nsub == 2 ? 8 : 4) * nC);
+                sp_mbar_init(sp_smem_u32(&empty_a[s2]), n_issuers);      // one tcgen05.commit per active MMA issuer
+            }
+            for (int s2 = 0; s2 < kSpSBMax; ++s2) {
+                if (round_idx > 0) {
+                    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(sp_smem_u32(&full_b[s2])) : "memory");
+                    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(sp_smem_u32(&empty_b[s2])) : "memory");
+                }
+                sp_mbar_init(sp_smem_u32(&full_b[s2]), 1);
+                sp_mbar_init(sp_smem_u32(&empty_b[s2]), n_issuers);
+            }
+            if (round_idx > 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(sp_smem_u32(&acc_full_bar)) : "memory");
+            sp_mbar_init(sp_smem_u32(&acc_full_bar), n_issuers);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        // piece x: columns [col0[x], col0[x] + ncols[x]) of tile[x]; accumulators of piece 1 behind those of piece 0
+        const int tile[2] = {rd.tile, rd.tile + 1};
+        const int col0[2] = {rd.blk0 * 32, 0};
+        const uint32_t ncols[2] = {(uint32_t)rd.n0 * 32u, (uint32_t)rd.n1 * 32u};
+        const uint32_t nr[2] = {ncols[0] / nC, ncols[1] / nC};              // rows of each piece's slab held by this CTA
+        const uint32_t b_cell = 64u * (nr[0] + nr[1]);                       // weight bytes per cell: piece 0 rows | piece 1 rows
+        const uint32_t b_stage = (uint32_t)KC * b_cell;
+        // ---- round setup (all warps): split latent tables of the one / two tiles ---------------------
+        int rbase[2], nrows[2], lbase[2], nlat[2];
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+            rbase[x] = tile[x] * R + (int)rank * 128;
+            int nrw = p.M - rbase[x];
+            nrw = nrw < 0 ? 0 : (nrw > 128 ? 128 : nrw);
+            if (x >= nsub) nrw = 0;
+            nrows[x] = nrw;
+            lbase[x] = 0; nlat[x] = 0;
+            if (nrw > 0) {
+                const int s_lo = p.row_scene[rbase[x]], s_hi = p.row_scene[rbase[x] + nrw - 1];
+                lbase[x] = p.scene_off[s_lo];
+                nlat[x] = p.scene_off[s_hi + 1] - lbase[x];
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+            if (nrows[x] == 0) continue;
+            for (int idx = tid; idx < (nlat[x] + 1) * 8; idx += kSpThreads) {       // 2 values per thread
+                const int r = idx >> 3, k = (idx & 7) * 2;
+                const float* src = r < nlat[x] ? p.lat + (size_t)(lbase[x] + r) * 16 : p.benc;
+                const float v0 = src[k] - p.constant, v1 = src[k + 1] - p.constant;
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+                reinterpret_cast<uint32_t*>(latH[x])[idx] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                reinterpret_cast<uint32_t*>(latL[x])[idx] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+        }
+        __syncthreads();
+        if (kPair) {      // the peer's barriers must be initialised before the first remote arrive / multicast commit
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
+        const long long t_r1 = clock64();
+        t_setup_sum += t_r1 - t_r0;
+
+        // MMA groups of a one-tile round: a 9-block piece is issued as N = 160 + 128 over the same A tiles
+        const bool split = ncols[0] > 256u;
+
+        if (warp == 0) {
+            // ===== weight producer: one bulk copy per cell and piece, up to SB items ahead =====
+            if (lane == 0) {
+                for (int it = 0; it < n_items; ++it) {
+                    const uint32_t sb = (uint32_t)it % SB, pb = ((uint32_t)it / SB) & 1u;
+                    sp_mbar_wait(sp_smem_u32(&empty_b[sb]), pb ^ 1u);
+                    const uint32_t bar = sp_smem_u32(&full_b[sb]);
+                    const uint32_t st = bring + sb * b_stage;
+                    sp_mbar_expect_tx(bar, b_stage);
+                    for (int kc = 0; kc < KC; ++kc) {
+                        const size_t cellsrc = (size_t)(it * KC + kc) * p.OUT;
+                        sp_bulk_load(st + kc * b_cell, p.w + (cellsrc + col0[0] + rank * nr[0]) * 64, nr[0] * 64u, bar);
+                        if (nsub == 2)
+                            sp_bulk_load(st + kc * b_cell + nr[0] * 64u, p.w + (cellsrc + col0[1] + rank * nr[1]) * 64,
+                                         nr[1] * 64u, bar);
+                    }
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1 || warp == 2) {
+            // ===== MMA issuers (leader CTA of a pair), one thread each; everything that does not change per cell is
+            // hoisted (a single thread retires ~1 instruction per 4 cycles, ~80 cycles per MMA all in all).  The
+            // tensor core must see two independent accumulator chains interleaved: a chain of dependent MMAs
+            // narrower than ~200 columns runs at the ~100-cycle accumulate latency, not at N / 2 cycles.  (Measured
+            // alternatives: one thread issuing both chains in turn 87 cycles per MMA = issue-bound; two threads on
+            // DIFFERENT items did not interleave, 800 cycles per cell instead of 432.) =====
+            if (lane == 0 && rank == 0) {
+                const int gq = warp - 1;
+                const uint32_t a_desc_hi = (uint32_t)(256 >> 4) | (1u << 14) | (6u << 29);    // SBO 256 | version 1 | SWIZZLE_32B
+                const uint32_t b_desc_hi = (uint32_t)(512 >> 4) | (1u << 14) | (6u << 29);    // row groups alternate hi / lo
+                const uint64_t a_base = ((uint64_t)a_desc_hi << 32) | (uint64_t)((ring & 0x3FFFFu) >> 4);
+                const uint64_t b_base = ((uint64_t)b_desc_hi << 32) | (uint64_t)((bring & 0x3FFFFu) >> 4);
+                const uint64_t bcell16 = b_cell >> 4;
+                const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(R >> 4) << 24);
+                // MMA group of this issuer.  One tile: a 9-block piece is issued as N = 160 + 128 over the same A
+                // tiles by the two issuers, anything narrower by issuer 0 alone.  Two tiles: issuer gq owns piece gq
+                // (its own A tiles inside the stage).  Both issuers wake on the same barrier and issue the same
+                // number of MMAs per item, so their two accumulator chains interleave in the tensor core's queue.
+                uint32_t gn, d;
+                uint64_t a_off16, a_cell16, b_off16;
+                if (nsub == 2) {
+                    gn = ncols[gq];
+                    d = tmem_base + (gq ? ncols[0] : 0u);
+                    a_off16 = (uint64_t)((uint32_t)gq * 2u * kSpATile >> 4);
+                    a_cell16 = (4u * kSpATile) >> 4;
+                    b_off16 = gq ? (uint64_t)(nr[0] * 4u) : 0u;                      // piece 1's rows behind piece 0's
+                } else {
+                    gn = split ? (gq == 0 ? 160u : ncols[0] - 160u) : (gq == 0 ? ncols[0] : 0u);
+                    d = tmem_base + ((split && gq == 1) ? 160u : 0u);
+                    a_off16 = 0u;
+                    a_cell16 = (2u * kSpATile) >> 4;
+                    b_off16 = (split && gq == 1) ? (uint64_t)((160u / nC) * 4u) : 0u;   // the group's rows inside a cell
+                }
+                const bool have = gn > 0;
+                const uint32_t idesc = idesc_base | ((gn >> 3) << 17);
+                for (int it = 0; it < n_items; ++it) {
+                    const uint32_t sa = (uint32_t)it % kSpSA, pa = ((uint32_t)it / kSpSA) & 1u;
+                    const uint32_t sb = (uint32_t)it % SB;
+                    const long long t0 = clock64();
+                    sp_mbar_wait_cluster(sp_smem_u32(&full_a[sa]), pa);
+                    wait_full += clock64() - t0;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (have) {
+                        // the start-address field never carries into the next field (addresses < 256 KB)
+                        uint64_t ad = a_base + (uint64_t)(sa * (kSpAStage >> 4)) + a_off16;
+                        uint64_t bd = b_base + (uint64_t)(sb * (b_stage >> 4)) + b_off16;
+                        sp_umma<kPair>(d, ad, bd, idesc, it > 0 ? 1u : 0u);                     // hi . hi
+                        sp_umma<kPair>(d, ad + (kSpATile >> 4), bd, idesc, 1u);                 // lo . hi
+                        sp_umma<kPair>(d, ad, bd + (256u >> 4), idesc, 1u);                     // hi . lo
+#pragma unroll 3
+                        for (int kc = 1; kc < KC; ++kc) {
+                            ad += a_cell16; bd += bcell16;
+                            sp_umma<kPair>(d, ad, bd, idesc, 1u);
+                            sp_umma<kPair>(d, ad + (kSpATile >> 4), bd, idesc, 1u);
+                            sp_umma<kPair>(d, ad, bd + (256u >> 4), idesc, 1u);
+                        }
+                    }
+                    sp_commit<kPair>(sp_smem_u32(&empty_a[sa]));
+                    sp_commit<kPair>(sp_smem_u32(&empty_b[sb]));
+                }
+                sp_commit<kPair>(sp_smem_u32(&acc_full_bar));
+            }
+            __syncwarp();
+        } else if (warp >= 4 && warp < 12) {
+            // ===== A builders: thread = pedestrian row; every row of every cell's (hi, lo) tile is written =====
+            const int bg = (warp - 4) >> 2;
+            const uint32_t r = (uint32_t)((warp & 3) * 32 + lane);
+            const int x = nsub == 2 ? bg : 0;                       // two tiles: builder group bg owns tile bg
+            const int row = rbase[x] + (int)r;
+            const bool row_ok = (int)r < nrows[x];
+            const uint4* cr = row_ok ? reinterpret_cast<const uint4*>(p.cell_row + (size_t)row * p.cells) : nullptr;
+            const int off_r = row_ok ? p.scene_off[p.row_scene[row]] - lbase[x] : 0;
+            // A stage of a two-tile round: [cell][tile][hi | lo]
+            unsigned char* a_ring = ring_ptr + (nsub == 2 ? (size_t)bg * 2u * kSpATile : 0u);
+#define TB2_SP_BUILD(KCV, TWO)                                                                                          \
+    sp_builder<KCV, TWO>(cr, p.cells >> 4, SB, a_ring, bg, (warp & 3) == 0, r, off_r, nlat[x], latH[x], latL[x], empty_a,  \
+                         full_b, full_remote, lane, wait_e, wait_b)
+            if (nsub == 2) { if (kPair) TB2_SP_BUILD(2, true); else TB2_SP_BUILD(1, true); }
+            else { if (kPair) TB2_SP_BUILD(4, false); else TB2_SP_BUILD(2, false); }
+#undef TB2_SP_BUILD
+        }
+        {
+            // ===== epilogue (all 16 warps, 4 per TMEM lane quarter): thread = pedestrian row, 16 columns per tcgen05.ld =====
+            const int q = warp & 3, sub = warp >> 2;
+            sp_mbar_wait(sp_smem_u32(&acc_full_bar), 0u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long t_e0 = clock64();
+            if (warp == 12 && lane == 0) t_loop_sum += t_e0 - t_r1;
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+            // accumulator column d of an MMA group = row (d mod n/2) of the slab of CTA (d div n/2): 16-column
+            // chunks never straddle the two halves (n/2 is a multiple of 16)
+            const int nchunk0 = (int)ncols[0] >> 4, nchunk = (int)(ncols[0] + ncols[1]) >> 4;
+            for (int ch = sub; ch < nchunk; ch += 4) {
+                const int x = ch >= nchunk0 ? 1 : 0;                             // sub-round
+                int dx = (x ? ch - nchunk0 : ch) * 16;                           // column inside the sub-round's accumulators
+                const int nrx = (int)ncols[x] / nC;                              // rows per CTA of the piece
+                int gn = (int)ncols[x], goff = 0;                                // MMA group of this column
+                if (split) {
+                    if (dx >= 160) { dx -= 160; gn = (int)ncols[0] - 160; goff = 160 / nC; }
+                    else gn = 160;
+                }
+                const int half = gn / nC;                                        // rows per CTA of the group
+                const int hsel = dx >= half ? 1 : 0;                             // which CTA's rows (pair only)
+                const int col = col0[x] + hsel * nrx + goff + (dx - hsel * half);
+                const int row = tile[x] * R + (int)rank * 128 + q * 32 + lane;
+                uint32_t v[16];
+                sp_tmem_ld16(trow + (uint32_t)(ch * 16), v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < p.M) {
+                    const size_t o = (size_t)row * p.OUT + col;
+                    float bias[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.base + col) + i);
+                        bias[4 * i] = b4.x; bias[4 * i + 1] = b4.y; bias[4 * i + 2] = b4.z; bias[4 * i + 3] = b4.w;
+                    }
+                    if (p.out_hi) {
+                        uint32_t ph[8], pl[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float x0 = fmaxf(__uint_as_float(v[2 * i]) + bias[2 * i], 0.f);
+                            const float x1 = fmaxf(__uint_as_float(v[2 * i + 1]) + bias[2 * i + 1], 0.f);
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                            const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+                            const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                            ph[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            pl[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+                        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
+                        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
+                        dh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]); dh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+                        dl[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]); dl[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+                    } else {
+                        float4* d4 = reinterpret_cast<float4*>(p.out + o);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float4 y;
+                            y.x = fmaxf(__uint_as_float(v[4 * i]) + bias[4 * i], 0.f);
+                            y.y = fmaxf(__uint_as_float(v[4 * i + 1]) + bias[4 * i + 1], 0.f);
+                            y.z = fmaxf(__uint_as_float(v[4 * i + 2]) + bias[4 * i + 2], 0.f);
+                            y.w = fmaxf(__uint_as_float(v[4 * i + 3]) + bias[4 * i + 3], 0.f);
+                            d4[i] = y;
+                        }
+                    }
+                }
+            }
+            if (warp == 12 && lane == 0) t_epi_sum += clock64() - t_e0;
+        }
+        ++round_idx;
+        // the next round overwrites the latent tables, the TMEM accumulators and (pair) the peer's accumulators
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (kPair) {
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (dbg) {
+        if (tid == 0) {
+            dbg[0] = t_setup_sum; dbg[6] = clock64() - t_start;
+            dbg[5] = (long long)rd.n0 | ((long long)rd.n1 << 12) | ((long long)(t_start - t_begin) << 24);
+        }
+        if (warp == 1 && lane == 0) dbg[2] = wait_full;
+        if (warp == 4 && lane == 0) { dbg[4] = wait_e; dbg[7] = wait_b; }
+        if (warp == 12 && lane == 0) { dbg[1] = t_loop_sum; dbg[3] = t_epi_sum; }
+    }
+    if (warp == 1) {
+        uint32_t ncols = 512;
+        if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+bool sparse_pair_supported(const tb2_lstm* m, const tb2_layout* l) {
+    if (m->cfg.pool_type != TB2_POOL_SOCIAL || m->C != 16 || m->Wt1_sw_hi == nullptr) return false;
+    if (m->mlp_dims[1] % 32 != 0 || m->mlp_dims[1] / 32 < kSpMaxBlocks) return false;
+    if (m->cells > kSpMaxCells || m->cells % 16 != 0) return false;
+    // local latent table of a 128-row tile: the scenes it touches, <= 128 + 2 (n_max - 1) rows, + 1;
+    // cell-map bytes hold scene-local indices (0xFE / 0xFF reserved)
+    return 128 + 2 * (l->n_max - 1) + 1 <= kSpLatRows - 1 && l->n_max <= 0xFD;
+}
+
+// Cut the linearised (tile, 32-column block) space [0, tiles * nb) into n_rounds consecutive rounds of 1..cap
+// blocks, such that a round lies inside one tile or straddles exactly one tile boundary with both pieces at
+// least `minpiece` blocks (a 32- or 64-column MMA costs ~50 cycles, not 16 / 32), at most 8, and at most cap2
+// together.  Reachability
+// DP over (round, end position) inside a window around the even split.
+static bool plan_rounds_dp(long long total, int nb, int n_rounds, int cap, int cap2, int minpiece, std::vector<SpRound>& out) {
+    const int W = 24;                                      // positions considered: even split +- W
+    std::vector<std::vector<signed char>> from((size_t)n_rounds + 1, std::vector<signed char>(2 * W + 1, -1));
+    auto base = [&](int k) { return (long long)k * total / n_rounds; };
+    from[0][W] = 0;
+    for (int k = 0; k < n_rounds; ++k) {
+        for (int o = 0; o <= 2 * W; ++o) {
+            if (from[k][o] < 0) continue;
+            const long long pos = base(k) + o - W;
+            for (int sz = 1; sz <= cap; ++sz) {
+                const long long end = pos + sz;
+                if (end > total) break;
+                const long long t0 = pos / nb, t1 = (end - 1) / nb;
+                if (t1 > t0 + 1) continue;
+                if (t1 == t0 + 1) {
+                    const long long a = (t0 + 1) * nb - pos, b = end - (t0 + 1) * nb;
+                    if (a < minpiece || b < minpiece || a > 8 || b > 8 || sz > cap2) continue;
+                }
+                const long long off = end - base(k + 1) + W;
+                if (off < 0 || off > 2 * W) continue;
+                if (from[k + 1][(size_t)off] < 0) from[k + 1][(size_t)off] = (signed char)sz;
+            }
+        }
+    }
+    const long long off_end = total - base(n_rounds) + W;
+    if (off_end < 0 || off_end > 2 * W || from[n_rounds][(size_t)off_end] < 0) return false;
+    out.assign((size_t)n_rounds, SpRound{0, 0, 0, 0});
+    long long end = total;
+    for (int k = n_rounds; k > 0; --k) {
+        const int sz = from[k][(size_t)(end - base(k) + W)];
+        const long long pos = end - sz;
+        const long long t0 = pos / nb;
+        const long long in0 = std::min<long long>(sz, (t0 + 1) * nb - pos);
+        out[(size_t)k - 1] = SpRound{(int)t0, (int)(pos - t0 * nb), (int)in0, (int)(sz - in0)};
+        end = pos;
+    }
+    return end == 0;
+}
+
+struct SpPlan {
+    int M, OUT, units, nC, rounds_per_unit;
+    SpRound* dev;
+};
+
+// the round table of a (layout, OUT, units) combination lives with the layout (device memory of its device)
+static int get_plan(const tb2_layout* l, int OUT, int units_max, int nC, const SpRound** dev_out, int* units_out,
+                    int* rpu_out, cudaStream_t st) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    tb2_layout* lm = const_cast<tb2_layout*>(l);
+    for (const auto& e : lm->pair_plans)
+        if (e.OUT == OUT && e.units_max == units_max && e.nC == nC) {
+            *dev_out = (const SpRound*)e.dev; *units_out = e.units; *rpu_out = e.rounds_per_unit;
+            return TB2_OK;
+        }
+    const int R = 128 * nC, nb = OUT / 32;
+    const long long tiles = (l->M + R - 1) / R, total = tiles * nb;
+    int units = units_max;
+    if ((long long)units > total) units = (int)total;
+    const int rpu = (int)((total + (long long)units * kSpMaxBlocks - 1) / ((long long)units * kSpMaxBlocks));
+    const int n_rounds = units * rpu;
+    std::vector<SpRound> rounds;
+    bool ok = false;       // smallest maximum round first (the kernel's time is the largest round), then the widest narrow piece
+    // a two-tile round moves twice the A tiles through shared memory (63 KB per cell against 43 KB: bound by the
+    // 128 B/clk port at ~490 cycles per cell instead of the 432-cycle tensor floor; measured 141-148 k cycles for 9
+    // blocks against 115 k): it gets one block less than the cap when the split allows it
+    for (int cap = (int)((total + n_rounds - 1) / n_rounds); cap <= kSpMaxBlocks && !ok; ++cap)
+        for (int relax = 0; relax < 2 && !ok; ++relax)
+            for (int minpiece = 3; minpiece >= 1 && !ok; --minpiece)
+                ok = plan_rounds_dp(total, nb, n_rounds, cap, relax ? cap : std::max(cap - 1, 1), minpiece, rounds);
+    if (!ok) { set_error("sparse_layer1_pair: no round plan (internal)"); return TB2_ERR_INVALID; }
+    SpRound* dev = nullptr;
+    TB2_CHECK_CUDA(cudaMalloc(&dev, rounds.size() * sizeof(SpRound)));
+    lm->owned.push_back(dev);
+    TB2_CHECK_CUDA(cudaMemcpyAsync(dev, rounds.data(), rounds.size() * sizeof(SpRound), cudaMemcpyHostToDevice, st));
+    TB2_CHECK_CUDA(cudaStreamSynchronize(st));       // one-time (per layout): `rounds` is a host temporary
+    tb2_layout::PairPlan e;
+    e.OUT = OUT; e.units_max = units_max; e.nC = nC; e.units = units; e.rounds_per_unit = rpu; e.dev = dev;
+    lm->pair_plans.push_back(e);
+    *dev_out = dev; *units_out = units; *rpu_out = rpu;
+    return TB2_OK;
+}
+
+template <bool kPair>
+static int launch_sparse_pair_t(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float* out, void* out_hi,
+                                void* out_lo, cudaStream_t st) {
+    constexpr int nC = kPair ? 2 : 1;
+    static int sm_count[64] = {0};
+    int dev = 0;
+    TB2_CHECK_CUDA(cudaGetDevice(&dev));
+    if (sm_count[dev & 63] == 0)
+        TB2_CHECK_CUDA(cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+    const int d1 = m->mlp_dims[1];
+    int units_max = sm_count[dev & 63] / nC;
+    {
+        const char* e = getenv("TB2_PAIR_UNITS");      // debug knob
+        if (e && atoi(e) > 0) units_max = atoi(e);
+    }
+    SpParams p;
+    int units = 0, rpu = 0, rc;
+    if ((rc = get_plan(l, d1, units_max, nC, &p.rounds, &units, &rpu, st))) return rc;
+    p.rounds_per_unit = rpu;
+    p.scene_off = l->scene_off;
+    p.row_scene = l->row_scene;
+    p.cell_row = ws->cell_row;
+    p.lat = ws->lat;
+    p.benc = m->benc;
+    p.base = m->base1;
+    p.w = (const unsigned char*)m->Wt1_sw_hi;
+    p.out = out;
+    p.out_hi = (__nv_bfloat16*)out_hi;
+    p.out_lo = (__nv_bfloat16*)out_lo;
+    p.M = l->M;
+    p.OUT = d1;
+    p.cells = m->cells;
+    p.constant = m->cfg.constant;
+    p.dbg = nullptr;
+    static long long* dbg_buf = nullptr;
+    static int dbg_calls = 0;
+    const int n_cta = units * nC;
+    {
+        const char* e = getenv("TB2_L1_DEBUG");
+        if (e && e[0] == '1') {
+            if (!dbg_buf) { cudaMalloc(&dbg_buf, (size_t)1024 * 8 * sizeof(long long)); cudaMemset(dbg_buf, 0, (size_t)1024 * 8 * sizeof(long long)); }
+            if (n_cta <= 1024) p.dbg = dbg_buf;
+        }
+    }
+    const size_t smem = 1024 + kSpDynBytes + 64;
+    static_assert(1024 + kSpDynBytes + 64 <= 227 * 1024 - 512, "shared memory budget");
+    static DynSmemConfig configured;
+    TB2_CHECK_CUDA(configured.ensure(sparse_layer1_pair_kernel<kPair>, smem));
+    {
+        KernelTimer kt(kPair ? "sparse_layer1_pair" : "sparse_layer1_solo", st);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(n_cta);
+        cfg.blockDim = dim3(kSpThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        if (pdl_enabled()) {
+            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        if (kPair) {
+            attr[na].id = cudaLaunchAttributeClusterDimension;
+            attr[na].val.clusterDim.x = 2;
+            attr[na].val.clusterDim.y = 1;
+            attr[na].val.clusterDim.z = 1;
+            ++na;
+        }
+        cfg.attrs = attr;
+        cfg.numAttrs = na;
+        TB2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, sparse_layer1_pair_kernel<kPair>, p));
+    }
+    TB2_LAUNCH_CHECK();
+    if (p.dbg && ++dbg_calls == 60) {
+        std::vector<long long> h((size_t)n_cta * 8);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        double mx = 0, pdl = 0;
+        for (int c = 0; c < n_cta; ++c) {
+            for (int k = 0; k < 8; ++k) a[k] += (double)h[(size_t)c * 8 + k] / n_cta;
+            if ((double)h[(size_t)c * 8 + 6] > mx) mx = (double)h[(size_t)c * 8 + 6];
+            pdl += (double)(h[(size_t)c * 8 + 5] >> 24) / n_cta;
+        }
+        if (getenv("TB2_L1_DEBUG_ALL")) {
+            for (int c = 0; c < n_cta; c += nC) {
+                const long long* d = &h[(size_t)c * 8];
+                fprintf(stderr, "  unit %3d  last round blocks %2d + %2d | setup %6lld loop %7lld mma-wait %7lld epi %6lld total %7lld | builder: wait-empty %7lld wait-weights %7lld\n",
+                        c / nC, (int)(d[5] & 0xfff), (int)((d[5] >> 12) & 0xfff), d[0], d[1], d[2], d[3], d[6], d[4], d[7]);
+            }
+        }
+        fprintf(stderr, "[tb2 sparse_pair x%d debug] per-CTA cycles: prologue + wait for the previous kernel %.0f | setup %.0f | cells loop until "
+                        "accumulators ready %.0f | MMA thread waiting for A/B (leader CTAs, averaged over all) %.0f | epilogue %.0f | builder "
+                        "warp 4: waiting for a free stage %.0f, for the weights %.0f | total after the wait %.0f (max %.0f)\n",
+                nC, pdl, a[0], a[1], a[2], a[3], a[4], a[7], a[6], mx);
+    }
+    return TB2_OK;
+}
+
+// mode: 1 = one CTA per unit (cta_group::1), 2 = CTA pair (cta_group::2)
+int launch_sparse_pair(const tb2_lstm* m, const tb2_layout* l, int mode, Workspace* ws, float* out, void* out_hi,
+                       void* out_lo, cudaStream_t st) {
+    if (mode == 2) return launch_sparse_pair_t<true>(m, l, ws, out, out_hi, out_lo, st);
+    return launch_sparse_pair_t<false>(m, l, ws, out, out_hi, out_lo, st);
+}
+
+// weight repack: W1[o][c * cells + cell] -> bf16 [cell][o / 8][hi | lo][o % 8][16] with the two 16-byte halves
+// of a row exchanged where ((o >> 2) & 1): the SWIZZLE_32B shared-memory image (8-row atoms of 256 bytes,
+// hi and lo atoms alternating, SBO = 512) of any slab whose first row is a multiple of 8, so ONE plain bulk
+// copy per cell lands both operand tiles the UMMA descriptors expect
+__global__ void repack_layer1_sw_kernel(const float* __restrict__ W1, __nv_bfloat16* __restrict__ dst, int OUT, int cells) {
+    size_t total = (size_t)cells * OUT * 16;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx & 15);
+        const size_t co = idx >> 4;
+        const int o = (int)(co % OUT), cell = (int)(co / OUT);
+        const float v = W1[(size_t)o * 16 * cells + (size_t)c * cells + cell];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const int chunk = (c >> 3) ^ ((o >> 2) & 1);
+        const size_t atom = ((size_t)cell * OUT + (size_t)(o & ~7)) * 32;          // bf16 elements: 8 rows x (hi 16 + lo 16)
+        const size_t e = atom + (size_t)(o & 7) * 16 + (size_t)(chunk * 8 + (c & 7));
+        dst[e] = h;
+        dst[e + 128] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+int launch_repack_layer1_sw(const float* W1, void* hi, void* lo, int OUT, int cells, cudaStream_t st) {
+    (void)lo;     // one interleaved image of 2 x cells x OUT x 16 bf16 behind `hi`
+    repack_layer1_sw_kernel<<<1024, 256, 0, st>>>(W1, (__nv_bfloat16*)hi, OUT, cells);
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
+}
+
+}  // namespace tb2

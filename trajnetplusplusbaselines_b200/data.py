@@ -18,10 +18,13 @@ SceneRow.__new__.__defaults__ = (None, None, None, None, None, None)
 def paths_to_xy(paths):
     """list of paths (primary first) -> xy [n_frames, n_peds, 2] float64, NaN where absent.
 
-    Frames are those of the primary pedestrian, like trajnetplusplustools.Reader.paths_to_xy.
+    Same contract as trajnetplusplustools.Reader.paths_to_xy: the frames are the SORTED set of the
+    primary pedestrian's frames, and a pedestrian without a single row in those frames is dropped (it
+    would be an all-NaN column that the writer later emits as NaN track rows).
     """
-    frames = [r.frame for r in paths[0]]
+    frames = sorted(set(r.frame for r in paths[0]))
     frame_index = {f: i for i, f in enumerate(frames)}
+    paths = [path for path in paths if any(r.frame in frame_index for r in path)]
     xy = np.full((len(frames), len(paths), 2), np.nan)
     for p, path in enumerate(paths):
         for r in path:

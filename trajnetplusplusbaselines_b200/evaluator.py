@@ -87,6 +87,11 @@ def main(argv=None):
     parser.add_argument('--normalize_scene', action='store_true')
     parser.add_argument('--modes', default=1, type=int)
     parser.add_argument('--chunk', default=1024, type=int, help='scenes per batched forward')
+    # flags of the reference's evaluator CLI that only steer its scoring / plotting stage (not built here):
+    # accepted and ignored so that the documented commands (e.g. `--write_only`) keep working
+    parser.add_argument('--write_only', action='store_true', help='accepted for compatibility: this tool only writes')
+    parser.add_argument('--disable-collision', action='store_true', help='accepted for compatibility (scoring option)')
+    parser.add_argument('--labels', nargs='+', help='accepted for compatibility (table labels)')
     args = parser.parse_args(argv)
     args.output = args.output if args.output is not None else []
     args.path = os.path.join('DATA_BLOCK', args.path, 'test_pred') + os.sep
