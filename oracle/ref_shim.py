@@ -61,8 +61,14 @@ def import_reference(root=None):
 
     _stub("trajnetplusplustools", Reader=_Reader, TrackRow=_data.TrackRow, SceneRow=_data.SceneRow)
     _stub("trajnetplusplustools.show")
+    _stub("trajnetplusplustools.reader", Reader=_Reader)
     _stub("matplotlib")
     _stub("matplotlib.pyplot")
+    _stub("matplotlib.font_manager", FontProperties=object)
+    _stub("matplotlib.animation")
+    _stub("mpl_toolkits")
+    _stub("mpl_toolkits.mplot3d")
+    _stub("mpl_toolkits.mplot3d.axes3d")
     _stub("pykalman")
     _stub("socialforce")
     _stub("socialforce.potentials", PedPedPotential=object)

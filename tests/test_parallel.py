@@ -47,7 +47,16 @@ def _worker(rank, world, port, out):
     x = torch.arange(24, dtype=torch.float32).reshape(4, 6) * (rank + 1)
     model(x).sum().backward()
     n = allreduce_gradients(list(model.parameters()) + list(frozen.parameters()))
-    out[rank] = (n, [p.grad.clone() for p in model.parameters()])
+    assert all(p.grad is None for p in frozen.parameters())        # no gradient on any rank -> stays None
+    first = [p.grad.clone() for p in model.parameters()]
+    # second step: rank 1 has an empty shard (runs no backward at all) and must still enter the collective
+    model.zero_grad(set_to_none=True)
+    if rank == 0:
+        model(x).sum().backward()
+    allreduce_gradients(list(model.parameters()) + list(frozen.parameters()))
+    second = [p.grad.clone() for p in model.parameters()]
+    assert all(p.grad is None for p in frozen.parameters())
+    out[rank] = (n, first, second)
     dist.destroy_process_group()
 
 
@@ -66,8 +75,14 @@ def test_gradient_allreduce_world2_gloo():
         model(x).sum().backward()
         g = [p.grad.clone() for p in model.parameters()]
         expect = g if expect is None else [a + b for a, b in zip(expect, g)]
+    model.zero_grad()
+    model(torch.arange(24, dtype=torch.float32).reshape(4, 6)).sum().backward()
+    only_rank0 = [p.grad.clone() for p in model.parameters()]
+    n_params = sum(p.numel() for p in model.parameters()) + 2 * 2 + 2          # + the unused Linear(2, 2)
     for rank in range(world):
-        n, grads = out[rank]
-        assert n == sum(p.numel() for p in model.parameters())
+        n, grads, second = out[rank]
+        assert n == n_params + 6                    # fixed layout: every parameter + one "has a gradient" flag each
         for a, b in zip(grads, expect):
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)
+        for a, b in zip(second, only_rank0):        # the idle rank received rank 0's gradients
             assert torch.allclose(a, b, rtol=1e-6, atol=1e-6)

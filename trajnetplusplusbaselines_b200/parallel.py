@@ -31,21 +31,37 @@ def shard_scenes(batch_split, world_size, rank):
     return lo, hi, t_lo, t_hi, (bs[lo:hi + 1] - bs[lo]).tolist()
 
 
-def allreduce_gradients(parameters, group=None, local_scenes=None, global_scenes=None):
-    """One all-reduce(SUM) over a flat fp32 bucket of every existing gradient (parameters whose
-    grad is None, e.g. goal_embedding.*, are skipped identically on all ranks).
+def allreduce_gradients(parameters, group=None):
+    """One all-reduce(SUM) per step over a single flat fp32 bucket.
 
-    The reference multiplies the mean loss by batch_size (trainer.py:263); with each rank scaling
-    by its LOCAL scene count the summed gradient equals the single-process one for equal shards."""
-    params = [p for p in parameters if p.grad is not None]
+    The bucket is laid out over the FIXED list of parameters that require grad, so every rank enters the
+    collective with the same size whatever happened locally: a rank whose shard was empty (more ranks than
+    scenes) or that ran no backward contributes zeros instead of skipping the call (which would leave the other
+    ranks blocked).  One extra float per parameter says "some rank has a gradient for it": parameters without a
+    gradient on ANY rank (e.g. goal_embedding.*) keep `grad is None`, exactly as in a single process, so the
+    optimizer (weight decay) still skips them.
+
+    The reference multiplies the mean loss by batch_size (trainer.py:263); with each rank scaling by its LOCAL
+    scene count the summed gradient equals the single-process one."""
+    params = [p for p in parameters if p.requires_grad]
     if not params:
         return 0
-    flat = torch.cat([p.grad.reshape(-1).to(torch.float32) for p in params])
+    device = params[0].device
+    pieces = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(torch.float32) for p in params]
+    flags = torch.tensor([0.0 if p.grad is None else 1.0 for p in params], dtype=torch.float32, device=device)
+    flat = torch.cat(pieces + [flags])
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    # a rank that ran a backward keeps `None` where it had none (every rank runs the same graph); only a rank
+    # without any local gradient reads the flags (one small device-to-host copy) to learn which parameters exist
+    local_any = any(p.grad is not None for p in params)
+    have = None if local_any else flat[-len(params):].tolist()
     off = 0
-    for p in params:
-        n = p.grad.numel()
-        p.grad.copy_(flat[off:off + n].view_as(p.grad))
+    for i, p in enumerate(params):
+        n = p.numel()
+        if p.grad is not None:
+            p.grad.copy_(flat[off:off + n].view_as(p))
+        elif have is not None and have[i] > 0:
+            p.grad = flat[off:off + n].view_as(p).to(p.dtype).clone()
         off += n
     return flat.numel()
