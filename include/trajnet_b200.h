@@ -35,6 +35,7 @@ extern "C" {
 #define TB2_POOL_OCCUPANCY 1      /* GridBasedPooling(type_='occupancy')   gridbased_pooling.py:112-116 */
 #define TB2_POOL_DIRECTIONAL 2    /* GridBasedPooling(type_='directional') gridbased_pooling.py:118-143 */
 #define TB2_POOL_SOCIAL 3         /* GridBasedPooling(type_='social')      gridbased_pooling.py:145-170 */
+#define TB2_POOL_HIDDEN_MLP 4     /* HiddenStateMLPPooling (--type hiddenstatemlp) non_gridbased_pooling.py:150-239 */
 
 #define TB2_PHASE_ENCODER 0
 #define TB2_PHASE_DECODER 1
@@ -69,6 +70,11 @@ typedef struct tb2_lstm_config {
     int32_t num_layers;      /* grid-embedding MLP: 0 ('None'), 1, 2 or 3 layers   */
     int32_t layer_dims[2];   /* hidden widths of the two/three_layer MLP           */
     int32_t out_dim;         /* pool.out_dim                                       */
+    /* TB2_POOL_HIDDEN_MLP only (0 otherwise): widths of the three per-neighbour embeddings whose
+     * concatenation (mlp_dim = their sum) is max-pooled over the scene and projected to out_dim */
+    int32_t mlp_dim_spatial; /* Linear(2, .) on pos_j - pos_i                      */
+    int32_t mlp_dim_vel;     /* Linear(2, .) on 4 (v_j - v_i); may be 0            */
+    int32_t mlp_dim_hidden;  /* Linear(H, .) on h_j; may be 0                      */
 } tb2_lstm_config;
 
 /* Device pointers to the parameters in the reference's state_dict layout (row-major
@@ -90,6 +96,15 @@ typedef struct tb2_lstm_weights {
     const float* pool_encoding_bias;      /* [latent] */
     const float* pool_embedding_weight[3];/* pool.embedding.{0,2,4}.weight */
     const float* pool_embedding_bias[3];  /* pool.embedding.{0,2,4}.bias   */
+    /* TB2_POOL_HIDDEN_MLP (NULL otherwise) */
+    const float* pool_spatial_weight;     /* pool.spatial_embedding.0.weight [mlp_dim_spatial, 2] */
+    const float* pool_spatial_bias;
+    const float* pool_vel_weight;         /* pool.vel_embedding.0.weight [mlp_dim_vel, 2] */
+    const float* pool_vel_bias;
+    const float* pool_hidden_weight;      /* pool.hidden_embedding.0.weight [mlp_dim_hidden, H] */
+    const float* pool_hidden_bias;
+    const float* pool_out_weight;         /* pool.out_projection.weight [out_dim, mlp_dim] */
+    const float* pool_out_bias;
 } tb2_lstm_weights;
 
 typedef struct tb2_lstm tb2_lstm;          /* opaque: config + repacked weights on the device */
@@ -166,6 +181,21 @@ int tb2_lstm_forward_sequence(const tb2_lstm* model, const tb2_layout* layout,
                               float* normals_out_dev, float* positions_out_dev,
                               float* h_dev, float* c_dev, float* states_out_dev,
                               void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* The same time loop for callers whose results live in HOST memory (the reference's predictor / evaluator
+ * boundary hands numpy arrays back): after every recurrence step the step's slices of normals / positions are
+ * copied to the pinned host buffers on `copy_stream`, ordered behind the step by an event, while the later
+ * steps compute -- the device-to-host traffic (S x M x 28 bytes) hides under the forward instead of following
+ * it.  The call does not synchronise: results are complete once `copy_stream` is.  normals_host / positions_host
+ * [S, M, 5] / [S, M, 2] must be page-locked; the device outputs are written as well. */
+int tb2_lstm_forward_sequence_host(tb2_lstm* model, const tb2_layout* layout,
+                                   const float* observed_dev, int32_t obs_length,
+                                   const float* truth_dev, int32_t n_decode,
+                                   float* normals_out_dev, float* positions_out_dev,
+                                   float* h_dev, float* c_dev,
+                                   void* workspace_dev, size_t workspace_bytes,
+                                   float* normals_host, float* positions_host,
+                                   void* stream, void* copy_stream);
 
 /* Steps [first_step, last_step) of the same time loop (S = obs_length - 1 + n_decode steps in all).
  * first_step = 0 starts from the zero state; otherwise h_dev / c_dev hold the state after step

@@ -50,6 +50,19 @@ class PoolConfig:
                             "dir_social": latent_dim + 2}[type_]
 
 
+class MlpPoolConfig:
+    """Constructor arguments of HiddenStateMLPPooling (non_gridbased_pooling.py:166-193)."""
+
+    def __init__(self, hidden_dim=128, mlp_dim=128, mlp_dim_spatial=32, mlp_dim_vel=32, out_dim=None):
+        self.type_ = "hiddenstatemlp"
+        self.hidden_dim = hidden_dim
+        self.mlp_dim = mlp_dim
+        self.mlp_dim_spatial = mlp_dim_spatial
+        self.mlp_dim_vel = mlp_dim_vel
+        self.mlp_dim_hidden = mlp_dim - mlp_dim_spatial - mlp_dim_vel
+        self.out_dim = hidden_dim if out_dim is None else out_dim
+
+
 def _sigmoid(x):
     x = np.asarray(x, dtype=F32)
     return (F32(1.0) / (F32(1.0) + np.exp(-x, dtype=F32))).astype(F32)
@@ -174,8 +187,40 @@ def embed_grid(cfg, weights, grid, prefix="pool."):
     return x
 
 
+def _embed_with_masking(x, w, b, fill=-100.0):
+    """embed_with_masking (non_gridbased_pooling.py:49-58): relu(Linear) where no input is NaN, else `fill`."""
+    bad = np.isnan(x).any(axis=-1)
+    out = np.full(x.shape[:-1] + (w.shape[0],), F32(fill), dtype=F32)
+    out[~bad] = np.maximum(_linear(x[~bad].astype(F32), w, b), F32(0.0))
+    return out
+
+
+def hidden_mlp_pool_forward(cfg, weights, hidden, obs1, obs2, prefix="pool."):
+    """HiddenStateMLPPooling.forward (non_gridbased_pooling.py:197-239) -> [B*N, out_dim]: max over ALL tracks j of
+    the scene (the track itself included) of [spatial(pos_j - pos_i) | hidden(h_j) | vel(4 (v_j - v_i))]."""
+    obs1 = np.asarray(obs1, dtype=F32)
+    obs2 = np.asarray(obs2, dtype=F32)
+    hidden = np.asarray(hidden, dtype=F32)
+    B, N, _ = obs2.shape
+    rel = obs2[:, None, :, :] - obs2[:, :, None, :]                         # rel_obs :13-23: [b, i, j] = pos_j - pos_i
+    parts = [_embed_with_masking(rel, weights[prefix + "spatial_embedding.0.weight"], weights[prefix + "spatial_embedding.0.bias"])]
+    if cfg.mlp_dim_hidden:
+        hid = _embed_with_masking(hidden, weights[prefix + "hidden_embedding.0.weight"], weights[prefix + "hidden_embedding.0.bias"])
+        parts.append(np.broadcast_to(hid[:, None, :, :], (B, N, N, hid.shape[-1])))
+    if cfg.mlp_dim_vel:
+        vel = obs2 - obs1
+        relv = (vel[:, None, :, :] - vel[:, :, None, :]) * F32(4.0)        # rel_directional :26-39, x 4 :233
+        parts.append(_embed_with_masking(relv, weights[prefix + "vel_embedding.0.weight"], weights[prefix + "vel_embedding.0.bias"]))
+    emb = np.concatenate(parts, axis=-1)
+    pooled = emb.max(axis=2)                                                # :237
+    return _linear(pooled.reshape(B * N, -1).astype(F32), weights[prefix + "out_projection.weight"],
+                   weights[prefix + "out_projection.bias"])
+
+
 def pool_forward(cfg, weights, hidden, obs1, obs2, prefix="pool."):
     """GridBasedPooling.forward (gridbased_pooling.py:94-110) -> [B*N, out_dim]."""
+    if getattr(cfg, "type_", None) == "hiddenstatemlp":
+        return hidden_mlp_pool_forward(cfg, weights, hidden, obs1, obs2, prefix)
     obs1 = np.asarray(obs1, dtype=F32)
     obs2 = np.asarray(obs2, dtype=F32)
     B, N, _ = obs2.shape
@@ -411,7 +456,17 @@ MODEL_SPECS = {
 }
 
 
+# non-grid interaction modules (reference lstm/non_gridbased_pooling.py); trainer.py builds
+# HiddenStateMLPPooling(hidden_dim, out_dim=args.pool_dim (256), mlp_dim_vel=args.vel_dim (32))
+NONGRID_SPECS = {
+    "hiddenstatemlp": dict(hidden_dim=128, mlp_dim=128, mlp_dim_spatial=32, mlp_dim_vel=32, out_dim=256),
+    "hiddenstatemlp_small": dict(hidden_dim=128, mlp_dim=48, mlp_dim_spatial=16, mlp_dim_vel=8, out_dim=40),
+}
+
+
 def pool_config(kind):
+    if kind in NONGRID_SPECS:
+        return MlpPoolConfig(**NONGRID_SPECS[kind])
     spec = MODEL_SPECS[kind]
     return None if spec is None else PoolConfig(**spec)
 
@@ -430,7 +485,15 @@ def random_weights(kind, seed=0, scale=1.0, embedding_dim=64, hidden_dim=128):
 
     E, H = embedding_dim, hidden_dim
     pool_dim = 0
-    if cfg is not None:
+    if cfg is not None and cfg.type_ == "hiddenstatemlp":
+        lin("pool.spatial_embedding.0.weight", "pool.spatial_embedding.0.bias", cfg.mlp_dim_spatial, 2)
+        if cfg.mlp_dim_vel:
+            lin("pool.vel_embedding.0.weight", "pool.vel_embedding.0.bias", cfg.mlp_dim_vel, 2)
+        if cfg.mlp_dim_hidden:
+            lin("pool.hidden_embedding.0.weight", "pool.hidden_embedding.0.bias", cfg.mlp_dim_hidden, H)
+        lin("pool.out_projection.weight", "pool.out_projection.bias", cfg.out_dim, cfg.mlp_dim)
+        pool_dim = cfg.out_dim
+    elif cfg is not None:
         if cfg.type_ in ("social", "dir_social"):
             lin("pool.hidden_dim_encoding.weight", "pool.hidden_dim_encoding.bias", cfg.latent_dim, H)
         n_layers = {"None": 0, None: 0, "one_layer": 1, "two_layer": 2, "three_layer": 3}[cfg.embedding_arch]

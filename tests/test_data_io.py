@@ -93,7 +93,10 @@ def test_evaluate_file_ndjson_in_ndjson_out(tmp_path):
         xy = paths_to_xy(paths)
         v = xy[8, 0] - xy[7, 0]
         want = np.round(xy[8, 0][None] + np.arange(1, 13)[:, None] * v[None], 2)
-        assert np.allclose([[r.x, r.y] for r in got[sid][0]], want, atol=0.011)
+        # the ndjson rows carry two decimals: compare in hundredths; a value within float rounding of x.xx5 may
+        # round the other way, those entries are counted
+        units = np.rint(np.abs(np.array([[r.x, r.y] for r in got[sid][0]]) - want) * 100).astype(int)
+        assert units.max() <= 1 and int((units > 0).sum()) <= 1, units
 
 
 def test_get_predictions_writes_one_file_per_dataset(tmp_path):

@@ -295,6 +295,34 @@ def test_full_size_properties_social():
     assert np.nanmedian(d) < TOL_POS
 
 
+def test_full_size_social_vs_oracle():
+    """BASELINE configs[2] at its FULL size (256 scenes x 20 pedestrians, T = 9 + 12) against the numpy oracle:
+    every track of every scene, not a slice.  Gate: ADE / FDE of the primaries and the worst track within
+    1e-4 m; tracks that land in a different grid cell than the oracle (a boundary hit within float
+    rounding) would show up as outliers and are counted."""
+    kind = "social"
+    B, N = 256, 20
+    xy, bs = O.synthetic_scenes(B, N, seed=41, nan_tracks=True)
+    W = O.random_weights(kind, seed=8)
+    model = build_model(kind, W)
+    M = xy.shape[1]
+    with torch.no_grad():
+        rel, pred = model(torch.from_numpy(xy[:9]).cuda(), torch.zeros(M, 2), torch.from_numpy(bs), n_predict=12)
+    rel_o, pred_o = O.forward(W, O.pool_config(kind), xy[:9], bs, n_predict=12)
+    pred = pred.cpu().numpy()
+    assert (np.isnan(pred) == np.isnan(pred_o)).all()
+    d = np.where(np.isnan(pred_o), 0.0, np.abs(pred - pred_o))
+    per_track = d.max(axis=(0, 2))
+    outliers = int((per_track > 1e-4).sum())
+    prim = bs[:-1]
+    err = np.linalg.norm((pred - pred_o)[-12:, prim], axis=2)          # [12, B] displacement error vs the oracle
+    ade, fde = float(err.mean()), float(err[-1].mean())
+    print("full-size social vs oracle: max %.2e m, tracks beyond 1e-4 m: %d of %d, ADE diff %.2e, FDE diff %.2e"
+          % (float(d.max()), outliers, M, ade, fde))
+    assert outliers == 0
+    assert ade < 1e-4 and fde < 1e-4 and float(err.max()) < 1e-4
+
+
 def test_predictor_boundary_roundtrip(tmp_path):
     """LSTMPredictor.__call__ / save / load (lstm.py:266-313) on the collision-test style scene."""
     from types import SimpleNamespace

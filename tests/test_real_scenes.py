@@ -50,6 +50,10 @@ def test_cuda_on_real_scenes(real, kind, wseed):
         got = got.numpy()
         assert (np.isnan(got) == np.isnan(ref)).all()
         d = np.abs(got - ref)
-        # free-running rollouts may flip a cell in a rare track; gate like ADE/FDE
+        # a pedestrian sitting within float rounding of a cell boundary can land in the neighbouring cell in a
+        # free-running rollout; such tracks are COUNTED, everything else must agree to 1e-4
+        per_track = np.nanmax(np.where(np.isnan(d), 0.0, d), axis=(0, 2))
+        flipped = int((per_track > 1e-4).sum())
+        print("%s%s: %d of %d tracks beyond 1e-4 (max %.2e), median %.2e" % (kind, key, flipped, M, float(np.nanmax(d)), float(np.nanmedian(d))))
         assert np.nanmedian(d) < 1e-5
-        assert (np.nanmax(d, axis=(0, 2)) > 1e-4).sum() <= max(1, M // 100), float(np.nanmax(d))
+        assert flipped == 0, (kind, key, flipped, float(np.nanmax(d)))

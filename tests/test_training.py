@@ -39,6 +39,20 @@ def test_torch_restatement_matches_reference_gradients(train_golden, case):
         check_summary(name + "/" + pname, g, train_golden, rtol=2e-3, atol=2e-5)
 
 
+def _rel_to_max(name, grad, golden):
+    """max |grad - reference| / max |reference| over the stored entries of a gradient tensor."""
+    from oracle.make_train_golden import N_SAMPLES
+    g = np.asarray(grad, dtype=np.float32)
+    if name + "/full" in golden:
+        ref = golden[name + "/full"]
+        got = g
+    else:
+        idx = np.random.RandomState(12345).randint(0, g.size, size=N_SAMPLES)
+        ref = golden[name + "/samples"]
+        got = g.reshape(-1)[idx]
+    return float(np.abs(got - ref).max()) / max(float(np.abs(ref).max()), 1e-12)
+
+
 def _cuda_train_step(kind, W, xy, bs):
     from trajnetplusplusbaselines_b200.lstm import LSTM, GridBasedPooling, PredictionLoss
     spec = O.MODEL_SPECS[kind]
@@ -65,15 +79,23 @@ def test_cuda_backward_matches_reference_gradients(train_golden, case):
     W = O.random_weights(kind, seed=wseed)
     model, loss = _cuda_train_step(kind, W, xy, bs)
     # forward runs the 3-pass bf16 tensor-core path: loss agrees to ~1e-5 relative
-    assert abs(loss - float(train_golden[name + "/loss"][0])) < 2e-4
-    worst = 0.0
+    ref_loss = float(train_golden[name + "/loss"][0])
+    assert abs(loss - ref_loss) < 1e-4 * max(1.0, abs(ref_loss))
+    worst, worst_name = 0.0, ""
     for pname, p in model.named_parameters():
         if pname.startswith("goal_embedding"):
             assert p.grad is None
             continue
         assert p.grad is not None, pname
-        worst = max(worst, check_summary(name + "/" + pname, p.grad.cpu().numpy(), train_golden, rtol=5e-3, atol=5e-5))
-    print(name, "max |grad - reference| =", worst)
+        g = p.grad.cpu().numpy()
+        rel = _rel_to_max(name + "/" + pname, g, train_golden)
+        if rel > worst:
+            worst, worst_name = rel, pname
+        # every parameter tensor within 1e-4 of its largest reference entry (measured: a few 1e-6, the fp32
+        # summation order of the backward), plus the sum / |sum| checks of the stored summaries
+        assert rel < 1e-4, (name, pname, rel)
+        check_summary(name + "/" + pname, g, train_golden, rtol=1e-3, atol=1e-5)
+    print("%s: worst max|grad - reference| / max|reference| = %.2e (%s)" % (name, worst, worst_name))
 
 
 @pytest.mark.gpu
@@ -93,7 +115,7 @@ def test_cuda_backward_baseline_shape_vs_torch(kind):
             continue
         g = p.grad.cpu().numpy()
         scale = max(np.abs(g_ref).max(), 1e-6)
-        assert np.abs(g - g_ref).max() < 5e-3 * scale + 5e-5, pname
+        assert np.abs(g - g_ref).max() < 1e-4 * scale + 1e-7, (pname, float(np.abs(g - g_ref).max() / scale))
 
 
 @pytest.mark.gpu

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtrajnet_b200.so")
 
-POOL_NONE, POOL_OCCUPANCY, POOL_DIRECTIONAL, POOL_SOCIAL = 0, 1, 2, 3
+POOL_NONE, POOL_OCCUPANCY, POOL_DIRECTIONAL, POOL_SOCIAL, POOL_HIDDEN_MLP = 0, 1, 2, 3, 4
 PHASE_ENCODER, PHASE_DECODER = 0, 1
 
 _c_float_p = ctypes.c_void_p   # device pointers travel as integers
@@ -32,6 +32,9 @@ class LstmConfig(ctypes.Structure):
         ("num_layers", ctypes.c_int32),
         ("layer_dims", ctypes.c_int32 * 2),
         ("out_dim", ctypes.c_int32),
+        ("mlp_dim_spatial", ctypes.c_int32),
+        ("mlp_dim_vel", ctypes.c_int32),
+        ("mlp_dim_hidden", ctypes.c_int32),
     ]
 
 
@@ -53,6 +56,14 @@ class LstmWeights(ctypes.Structure):
         ("pool_encoding_bias", ctypes.c_void_p),
         ("pool_embedding_weight", ctypes.c_void_p * 3),
         ("pool_embedding_bias", ctypes.c_void_p * 3),
+        ("pool_spatial_weight", ctypes.c_void_p),
+        ("pool_spatial_bias", ctypes.c_void_p),
+        ("pool_vel_weight", ctypes.c_void_p),
+        ("pool_vel_bias", ctypes.c_void_p),
+        ("pool_hidden_weight", ctypes.c_void_p),
+        ("pool_hidden_bias", ctypes.c_void_p),
+        ("pool_out_weight", ctypes.c_void_p),
+        ("pool_out_bias", ctypes.c_void_p),
     ]
 
 
@@ -114,6 +125,7 @@ PROTOTYPES = {
     "tb2_pool_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "tb2_lstm_step_forward": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "tb2_lstm_forward_sequence": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "tb2_lstm_forward_sequence_host": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
     "tb2_lstm_forward_steps": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "tb2_lstm_backward_workspace_bytes": (_sz, [_vp, _vp, _i32, _i32]),
     "tb2_lstm_sequence_backward": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(LstmWeights), _vp, _i32, _vp, _i32,

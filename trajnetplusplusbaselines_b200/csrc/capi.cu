@@ -170,7 +170,7 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
     *out = nullptr;
     TB2_REQUIRE(cfg->hidden_dim == 128, "hidden_dim must be 128 (kernel specialisation)");
     TB2_REQUIRE(cfg->embedding_dim >= 4 && cfg->embedding_dim <= 1024, "embedding_dim out of range");
-    TB2_REQUIRE(cfg->pool_type >= TB2_POOL_NONE && cfg->pool_type <= TB2_POOL_SOCIAL, "bad pool_type");
+    TB2_REQUIRE(cfg->pool_type >= TB2_POOL_NONE && cfg->pool_type <= TB2_POOL_HIDDEN_MLP, "bad pool_type");
     tb2_lstm* m = new (std::nothrow) tb2_lstm();
     TB2_REQUIRE(m, "out of host memory");
     m->cfg = *cfg;
@@ -182,7 +182,18 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
     m->Wt1_hi = m->Wt1_lo = m->Wt1_nat_hi = m->Wt1_nat_lo = m->Wt1_sw_hi = m->Wt1_sw_lo = nullptr;
     for (int i = 0; i < 2; ++i) { m->WgT[i] = m->bg[i] = nullptr; m->Wg_hi[i] = m->Wg_lo[i] = nullptr; }
     for (int i = 0; i < kMaxMlpLayers; ++i) { m->WT[i] = m->bl[i] = nullptr; m->W_hi[i] = m->W_lo[i] = nullptr; }
+    m->mp_Ws = m->mp_bs = m->mp_Wv = m->mp_bv = m->mp_WhT = m->mp_bh = m->mp_WoT = m->mp_bo = nullptr;
     auto fail = [&](int rc) { tb2_lstm_destroy(m); return rc; };
+    if (cfg->pool_type == TB2_POOL_HIDDEN_MLP) {
+        if (!(cfg->mlp_dim_spatial >= 1 && cfg->mlp_dim_vel >= 0 && cfg->mlp_dim_hidden >= 0 && cfg->out_dim >= 1 &&
+              cfg->mlp_dim_spatial + cfg->mlp_dim_vel + cfg->mlp_dim_hidden <= 4096)) {
+            set_error("invalid argument: hidden-state MLP pooling widths");
+            return fail(TB2_ERR_INVALID);
+        }
+        m->pool_out = cfg->out_dim;
+        if (cfg->pool_to_input) m->P = m->pool_out;
+        else if (m->pool_out != m->H) { set_error("invalid argument: pool_to_input=0 needs out_dim == hidden_dim"); return fail(TB2_ERR_INVALID); }
+    } else
     if (cfg->pool_type != TB2_POOL_NONE) {
         if (cfg->pool_size != 1 || cfg->blur_size != 1) {
             set_error("pool_size / blur_size != 1 are not built (the reference CLI never sets them)");
@@ -235,6 +246,17 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
         ALLOC(m->WencT, m->H * m->C);
         ALLOC(m->benc, m->C);
     }
+    if (cfg->pool_type == TB2_POOL_HIDDEN_MLP) {
+        const int D = cfg->mlp_dim_spatial + cfg->mlp_dim_vel + cfg->mlp_dim_hidden;
+        ALLOC(m->mp_Ws, cfg->mlp_dim_spatial * 2);
+        ALLOC(m->mp_bs, cfg->mlp_dim_spatial);
+        ALLOC(m->mp_Wv, std::max(cfg->mlp_dim_vel, 1) * 2);
+        ALLOC(m->mp_bv, std::max(cfg->mlp_dim_vel, 1));
+        ALLOC(m->mp_WhT, (size_t)m->H * std::max(cfg->mlp_dim_hidden, 1));
+        ALLOC(m->mp_bh, std::max(cfg->mlp_dim_hidden, 1));
+        ALLOC(m->mp_WoT, (size_t)D * cfg->out_dim);
+        ALLOC(m->mp_bo, cfg->out_dim);
+    }
     if (m->n_mlp >= 1) {
         ALLOC(m->Wt1, (size_t)m->cells * m->C * m->mlp_dims[1]);
         ALLOC(m->base1, m->mlp_dims[1]);
@@ -281,6 +303,7 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
 
 int tb2_lstm_destroy(tb2_lstm* m) {
     if (!m) return TB2_OK;
+    for (cudaEvent_t ev : m->step_events) cudaEventDestroy(ev);
     for (void* p : m->owned) cudaFree(p);
     delete m;
     return TB2_OK;
@@ -378,7 +401,7 @@ static int check_ready(const tb2_lstm* m, const tb2_layout* l, void* ws, size_t 
 int tb2_grid_indices(const tb2_lstm* m, const tb2_layout* l, const float* obs, int32_t* cell_out,
                      uint8_t* in_range_out, void* stream) {
     TB2_REQUIRE(m && l && obs && cell_out && in_range_out, "null argument");
-    TB2_REQUIRE(m->cfg.pool_type != TB2_POOL_NONE, "model has no grid pooling");
+    TB2_REQUIRE(m->cfg.pool_type >= TB2_POOL_OCCUPANCY && m->cfg.pool_type <= TB2_POOL_SOCIAL, "model has no grid pooling");
     // The pair tables are produced straight into the caller's buffers: no workspace needed.
     Workspace ws;
     std::memset(&ws, 0, sizeof(ws));
@@ -406,12 +429,14 @@ int tb2_pool_forward(const tb2_lstm* m, const tb2_layout* l, const float* hidden
                      void* stream) {
     int rc = check_ready(m, l, workspace, workspace_bytes);
     if (rc) return rc;
-    TB2_REQUIRE(m->cfg.pool_type != TB2_POOL_NONE, "model has no grid pooling");
+    TB2_REQUIRE(m->cfg.pool_type != TB2_POOL_NONE, "model has no interaction pooling");
     TB2_REQUIRE(obs1 && obs2 && pooled_out, "null argument");
-    TB2_REQUIRE(m->cfg.pool_type != TB2_POOL_SOCIAL || hidden, "social pooling needs hidden states");
+    TB2_REQUIRE((m->cfg.pool_type != TB2_POOL_SOCIAL && m->cfg.pool_type != TB2_POOL_HIDDEN_MLP) || hidden,
+                "this pooling needs hidden states");
     Workspace ws;
     carve_workspace(m, l, workspace, &ws);
     cudaStream_t st = (cudaStream_t)stream;
+    if (m->cfg.pool_type == TB2_POOL_HIDDEN_MLP) return launch_hidden_mlp_pool(m, l, hidden, obs1, obs2, pooled_out, st);
     if ((rc = launch_pool_prepare(m, l, hidden, obs1, obs2, 0, 0, 0, &ws, st))) return rc;
     return launch_pool_mlp(m, l, &ws, pooled_out, nullptr, nullptr, st);
 }
@@ -424,6 +449,12 @@ static int step_impl(const tb2_lstm* m, const tb2_layout* l, int phase, const fl
     int rc;
     const bool tc = m->Wg_hi[0] != nullptr;
     const float* pooled = nullptr;
+    if (m->cfg.pool_type == TB2_POOL_HIDDEN_MLP) {
+        // non-grid interaction module: one kernel per scene -> pooled fp32, split for the tensor-core gate kernel
+        if ((rc = launch_hidden_mlp_pool(m, l, h_in, obs1, obs2, ws->pooled, st))) return rc;
+        if (tc && (rc = launch_split_rows(ws->pooled, ws->pool_hi, ws->pool_lo, (size_t)l->M * m->P, st))) return rc;
+        pooled = ws->pooled;
+    } else
     if (m->cfg.pool_type != TB2_POOL_NONE) {
         if ((rc = launch_pool_prepare(m, l, h_in, obs1, obs2, 1, 0, tc ? 1 : 0, ws, st))) return rc;
         if (tc) rc = launch_pool_mlp(m, l, ws, nullptr, ws->pool_hi, ws->pool_lo, st);
@@ -432,7 +463,7 @@ static int step_impl(const tb2_lstm* m, const tb2_layout* l, int phase, const fl
         pooled = ws->pooled;
     }
     if (tc) {
-        if (m->cfg.pool_type == TB2_POOL_NONE &&     // pooled models: pool_prepare already wrote emb
+        if ((m->cfg.pool_type == TB2_POOL_NONE || m->cfg.pool_type == TB2_POOL_HIDDEN_MLP) &&     // grid pools: pool_prepare already wrote emb
             (rc = launch_embed_split(m, l->M, obs1, obs2, ws->emb_hi, ws->emb_lo, st)))
             return rc;
         return launch_gates_tc(m, l, phase, obs1, obs2, ws->emb_hi, ws->emb_lo, ws->pool_hi, ws->pool_lo,
@@ -463,10 +494,18 @@ int tb2_lstm_step_forward(const tb2_lstm* m, const tb2_layout* l, int32_t phase,
 // (lstm.py:207-210); otherwise h / c hold the state after step first_step - 1 (possibly edited by
 // the caller, e.g. the noise injection of the S-GAN generator between encoder and decoder,
 // sgan/sgan.py:200-221,373) and positions_out holds the positions of the earlier steps.
-int tb2_lstm_forward_steps(const tb2_lstm* m, const tb2_layout* l, const float* observed,
-                           int32_t obs_length, const float* truth, int32_t n_decode, int32_t first_step,
-                           int32_t last_step, float* normals_out, float* positions_out, float* h, float* c,
-                           float* states_out, void* workspace, size_t workspace_bytes, void* stream) {
+struct HostSink {              // optional: per-step device-to-host streaming of the outputs
+    float* normals_host;
+    float* positions_host;
+    cudaStream_t copy_stream;
+    std::vector<cudaEvent_t>* events;
+};
+
+static int forward_steps_impl(const tb2_lstm* m, const tb2_layout* l, const float* observed,
+                              int32_t obs_length, const float* truth, int32_t n_decode, int32_t first_step,
+                              int32_t last_step, float* normals_out, float* positions_out, float* h, float* c,
+                              float* states_out, void* workspace, size_t workspace_bytes, void* stream,
+                              const HostSink* sink) {
     int rc = check_ready(m, l, workspace, workspace_bytes);
     if (rc) return rc;
     TB2_REQUIRE(observed && normals_out && positions_out && h && c, "null argument");
@@ -503,12 +542,46 @@ int tb2_lstm_forward_steps(const tb2_lstm* m, const tb2_layout* l, const float* 
             return rc;
         h_prev = h_next;
         c_prev = c_next;
+        if (sink) {     // this step's results -> host, behind the step, beside the following steps
+            cudaEvent_t ev = (*sink->events)[(size_t)s];
+            TB2_CHECK_CUDA(cudaEventRecord(ev, st));
+            TB2_CHECK_CUDA(cudaStreamWaitEvent(sink->copy_stream, ev, 0));
+            TB2_CHECK_CUDA(cudaMemcpyAsync(sink->normals_host + (size_t)s * M * 5, normals_out + (size_t)s * M * 5,
+                                           M * 5 * sizeof(float), cudaMemcpyDeviceToHost, sink->copy_stream));
+            TB2_CHECK_CUDA(cudaMemcpyAsync(sink->positions_host + (size_t)s * frame, positions_out + (size_t)s * frame,
+                                           frame * sizeof(float), cudaMemcpyDeviceToHost, sink->copy_stream));
+        }
     }
     if (states_out && last_step > first_step) {
         TB2_CHECK_CUDA(cudaMemcpyAsync(h, h_prev, M * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
         TB2_CHECK_CUDA(cudaMemcpyAsync(c, c_prev, M * H * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
     return TB2_OK;
+}
+
+int tb2_lstm_forward_steps(const tb2_lstm* m, const tb2_layout* l, const float* observed,
+                           int32_t obs_length, const float* truth, int32_t n_decode, int32_t first_step,
+                           int32_t last_step, float* normals_out, float* positions_out, float* h, float* c,
+                           float* states_out, void* workspace, size_t workspace_bytes, void* stream) {
+    return forward_steps_impl(m, l, observed, obs_length, truth, n_decode, first_step, last_step, normals_out,
+                              positions_out, h, c, states_out, workspace, workspace_bytes, stream, nullptr);
+}
+
+int tb2_lstm_forward_sequence_host(tb2_lstm* m, const tb2_layout* l, const float* observed, int32_t obs_length,
+                                   const float* truth, int32_t n_decode, float* normals_out, float* positions_out,
+                                   float* h, float* c, void* workspace, size_t workspace_bytes,
+                                   float* normals_host, float* positions_host, void* stream, void* copy_stream) {
+    TB2_REQUIRE(m && normals_host && positions_host && copy_stream, "null argument");
+    TB2_REQUIRE(obs_length >= 2 && n_decode >= 0, "need obs_length >= 2 and n_decode >= 0");
+    const int S = obs_length - 1 + n_decode;
+    while ((int)m->step_events.size() < S) {
+        cudaEvent_t ev;
+        TB2_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        m->step_events.push_back(ev);
+    }
+    HostSink sink{normals_host, positions_host, (cudaStream_t)copy_stream, &m->step_events};
+    return forward_steps_impl(m, l, observed, obs_length, truth, n_decode, 0, S, normals_out, positions_out, h, c,
+                              nullptr, workspace, workspace_bytes, stream, &sink);
 }
 
 int tb2_lstm_forward_sequence(const tb2_lstm* m, const tb2_layout* l, const float* observed,

@@ -133,6 +133,9 @@ struct tb2_lstm {
     float* bl[tb2::kMaxMlpLayers];   // biases of layers >= 2
     void* W_hi[tb2::kMaxMlpLayers];  // bf16 [N, K] (hi, lo) split for the tcgen05 path (null: FFMA path)
     void* W_lo[tb2::kMaxMlpLayers];
+    std::vector<cudaEvent_t> step_events;     // tb2_lstm_forward_sequence_host: one event per recurrence step
+    // HiddenStateMLPPooling (TB2_POOL_HIDDEN_MLP)
+    float *mp_Ws, *mp_bs, *mp_Wv, *mp_bv, *mp_WhT, *mp_bh, *mp_WoT, *mp_bo;
     void* Wg_hi[2];        // gate weights [4H (rank, gate, unit), K_gate] bf16 split (null: FFMA gates)
     void* Wg_lo[2];
     std::vector<void*> owned;
@@ -204,6 +207,8 @@ bool sparse_pair_supported(const tb2_lstm* m, const tb2_layout* l);
 int launch_sparse_pair(const tb2_lstm* m, const tb2_layout* l, int mode, Workspace* ws, float* out, void* out_hi,
                        void* out_lo, cudaStream_t st);
 int launch_repack_layer1_sw(const float* W1, void* hi, void* lo, int OUT, int cells, cudaStream_t st);
+int launch_hidden_mlp_pool(const tb2_lstm* m, const tb2_layout* l, const float* hidden, const float* obs1,
+                           const float* obs2, float* out, cudaStream_t st);
 bool dense_tc_supported(int K, int N);
 int launch_dense_tc(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                     float* Y, void* Y_hi, void* Y_lo, int M, int K, int N, int relu, cudaStream_t st);

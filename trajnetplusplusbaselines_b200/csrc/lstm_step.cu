@@ -351,13 +351,35 @@ int launch_repack(tb2_lstm* m, const tb2_lstm_weights* w, cudaStream_t st) {
             (rc = launch_repack_gates_tc(wih[ph], whh[ph], m->Wg_hi[ph], m->Wg_lo[ph], m->E + m->P, m->H, st)))
             return rc;
     }
+    if (m->cfg.pool_type == TB2_POOL_HIDDEN_MLP) {
+        const tb2_lstm_config& c = m->cfg;
+        const int D = c.mlp_dim_spatial + c.mlp_dim_vel + c.mlp_dim_hidden;
+        TB2_REQUIRE(w->pool_spatial_weight && w->pool_spatial_bias && w->pool_out_weight && w->pool_out_bias,
+                    "pool.spatial_embedding / pool.out_projection missing");
+        TB2_REQUIRE(c.mlp_dim_vel == 0 || (w->pool_vel_weight && w->pool_vel_bias), "pool.vel_embedding missing");
+        TB2_REQUIRE(c.mlp_dim_hidden == 0 || (w->pool_hidden_weight && w->pool_hidden_bias), "pool.hidden_embedding missing");
+        if ((rc = copy_dev(w->pool_spatial_weight, m->mp_Ws, (size_t)c.mlp_dim_spatial * 2, st))) return rc;
+        if ((rc = copy_dev(w->pool_spatial_bias, m->mp_bs, (size_t)c.mlp_dim_spatial, st))) return rc;
+        if (c.mlp_dim_vel) {
+            if ((rc = copy_dev(w->pool_vel_weight, m->mp_Wv, (size_t)c.mlp_dim_vel * 2, st))) return rc;
+            if ((rc = copy_dev(w->pool_vel_bias, m->mp_bv, (size_t)c.mlp_dim_vel, st))) return rc;
+        }
+        if (c.mlp_dim_hidden) {
+            transpose_kernel<<<64, 256, 0, st>>>(w->pool_hidden_weight, m->mp_WhT, c.mlp_dim_hidden, m->H);
+            TB2_LAUNCH_CHECK();
+            if ((rc = copy_dev(w->pool_hidden_bias, m->mp_bh, (size_t)c.mlp_dim_hidden, st))) return rc;
+        }
+        transpose_kernel<<<128, 256, 0, st>>>(w->pool_out_weight, m->mp_WoT, c.out_dim, D);
+        TB2_LAUNCH_CHECK();
+        if ((rc = copy_dev(w->pool_out_bias, m->mp_bo, (size_t)c.out_dim, st))) return rc;
+    }
     if (m->cfg.pool_type == TB2_POOL_SOCIAL) {
         TB2_REQUIRE(w->pool_encoding_weight && w->pool_encoding_bias, "pool.hidden_dim_encoding missing");
         transpose_kernel<<<64, 256, 0, st>>>(w->pool_encoding_weight, m->WencT, m->C, m->H);
         TB2_LAUNCH_CHECK();
         if ((rc = copy_dev(w->pool_encoding_bias, m->benc, (size_t)m->C, st))) return rc;
     }
-    if (m->cfg.pool_type != TB2_POOL_NONE && m->n_mlp >= 1) {
+    if (m->cfg.pool_type != TB2_POOL_NONE && m->cfg.pool_type != TB2_POOL_HIDDEN_MLP && m->n_mlp >= 1) {
         TB2_REQUIRE(w->pool_embedding_weight[0] && w->pool_embedding_bias[0], "pool.embedding.0 missing");
         repack_layer1_kernel<<<1024, 256, 0, st>>>(w->pool_embedding_weight[0], w->pool_embedding_bias[0],
                                                    m->Wt1, m->base1, m->mlp_dims[1], m->C, m->cells,

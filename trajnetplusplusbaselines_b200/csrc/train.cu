@@ -614,12 +614,18 @@ __global__ void pair_offsets_kernel(const int* __restrict__ counts, int B, int c
 }
 
 // sorted[start[c] + base[b][c] + rank] = slot id, bit 31 set when the pair is NOT the winner of its
-// cell (it then takes part in d lat but not in d W1); rank = earlier slots of the scene in cell c
+// cell (it then takes part in d lat but not in d W1); rank = earlier slots of the scene in cell c.
+// Bit 30 ("dead"): an in-range pair of cell 0 whose observer's LAST writer of cell 0 is an out-of-range
+// neighbour (or a padding slot).  The cell then holds the constant 0, and the reference's
+// lp_pool2d(occ, 1, pool_size = 1) = sign(x) relu(|x|) has derivative sign(0)^2 = 0 at exactly 0
+// (gridbased_pooling.py:304): no gradient reaches any writer of that cell.  (Found by the drop-in test
+// against the unmodified Trainer.train_batch; a cell overwritten by a later IN-RANGE writer holds a non-zero
+// latent vector and all its writers do receive gradient.)
 __global__ void pair_place_kernel(const int* __restrict__ scene_off, const int* __restrict__ masked,
                                   const int* __restrict__ pair_cell, const uint8_t* __restrict__ pair_flag,
                                   const int* __restrict__ win_count, const uint32_t* __restrict__ win_ent, int nm1,
                                   int cells, const int* __restrict__ base, const int* __restrict__ start,
-                                  unsigned* __restrict__ sorted) {
+                                  int pad_to_max, unsigned* __restrict__ sorted) {
     extern __shared__ short cell_s[];         // [n_s * nm1] cell of the in-range pairs, -1 otherwise
     const int b = blockIdx.x, row0 = scene_off[b], n_s = scene_off[b + 1] - row0;
     for (int idx = threadIdx.x; idx < n_s * nm1; idx += blockDim.x) {
@@ -627,6 +633,7 @@ __global__ void pair_place_kernel(const int* __restrict__ scene_off, const int* 
         cell_s[idx] = (short)((pair_flag[slot] && !masked[row0 + idx / nm1]) ? pair_cell[slot] : -1);
     }
     __syncthreads();
+    const int n_slots = pad_to_max ? nm1 : n_s - 1;      // neighbour slots that write at all
     for (int idx = threadIdx.x; idx < n_s * nm1; idx += blockDim.x) {
         const int cell = cell_s[idx];
         if (cell < 0) continue;
@@ -637,8 +644,17 @@ __global__ void pair_place_kernel(const int* __restrict__ scene_off, const int* 
         bool winner = false;
         const int cnt = win_count[row0 + r];
         for (int e = 0; e < cnt; ++e) winner |= win_ent[(size_t)(row0 + r) * nm1 + e] == want;
+        bool dead = false;
+        if (cell == 0) {
+            // last writer of cell 0 for this observer: in-range pairs of cell 0 and every out-of-range slot write it
+            for (int q = n_slots - 1; q >= 0; --q) {
+                const int cq = cell_s[r * nm1 + q];
+                if (cq == 0) break;                                   // an in-range pair wrote last: the cell is alive
+                if (cq < 0) { dead = true; break; }                   // out of range (or padding): constant
+            }
+        }
         sorted[start[cell] + base[(size_t)b * cells + cell] + rank] =
-            (unsigned)((size_t)row0 * nm1 + idx) | (winner ? 0u : 0x80000000u);
+            (unsigned)((size_t)row0 * nm1 + idx) | (winner ? 0u : 0x80000000u) | (dead ? 0x40000000u : 0u);
     }
 }
 
@@ -657,12 +673,16 @@ __global__ void __launch_bounds__(256) social_dgrid_kernel(const unsigned* __res
     __shared__ __align__(16) float Bs[C][kDgK + 4];
     __shared__ int slot_s[kDgPairs];
     const int cell = blockIdx.x;
-    const int p0 = start[cell] + blockIdx.y * kDgPairs, p1 = min(start[cell + 1], p0 + kDgPairs);
-    if (p0 >= p1) return;
-    const int np = p1 - p0, tid = threadIdx.x;
-    if (tid < kDgPairs) slot_s[tid] = tid < np ? (int)(sorted[p0 + tid] & 0x7fffffffu) : -1;
-    __syncthreads();
+    const int tid = threadIdx.x;
     const int pr = tid >> 2, cq = tid & 3;
+    // a cell can hold more pairs than gridDim.y * 64 (several neighbours of one observer in the same cell, all
+    // scenes of the batch): every CTA walks its chunks with stride gridDim.y
+    for (int p0 = start[cell] + blockIdx.y * kDgPairs; p0 < start[cell + 1]; p0 += gridDim.y * kDgPairs) {
+    const int p1 = min(start[cell + 1], p0 + kDgPairs);
+    const int np = p1 - p0;
+    __syncthreads();
+    if (tid < kDgPairs) slot_s[tid] = tid < np ? (int)(sorted[p0 + tid] & 0x7fffffffu) : -1;       // bit 30 (dead) kept
+    __syncthreads();
     float acc[CQ];
 #pragma unroll
     for (int q = 0; q < CQ; ++q) acc[q] = 0.f;
@@ -671,7 +691,7 @@ __global__ void __launch_bounds__(256) social_dgrid_kernel(const unsigned* __res
         for (int idx = tid; idx < kDgPairs * (kDgK / 4); idx += 256) {
             const int r = idx / (kDgK / 4), c4 = (idx % (kDgK / 4)) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int slot = slot_s[r];
+            const int slot = slot_s[r] < 0 ? -1 : (slot_s[r] & 0x3fffffff);
             if (slot >= 0) {
                 const float* src = dz1 + (size_t)(slot / nm1) * d1 + k0 + c4;
                 if (k0 + c4 + 3 < d1) v = *reinterpret_cast<const float4*>(src);
@@ -708,9 +728,11 @@ __global__ void __launch_bounds__(256) social_dgrid_kernel(const unsigned* __res
         __syncthreads();
     }
     if (pr < np) {
-        float* out = dgrid + (size_t)slot_s[pr] * C + cq * CQ;
+        const bool dead = (slot_s[pr] & 0x40000000) != 0;             // its cell holds the constant: zero gradient
+        float* out = dgrid + (size_t)(slot_s[pr] & 0x3fffffff) * C + cq * CQ;
 #pragma unroll
-        for (int q = 0; q < CQ; ++q) out[q] = acc[q];
+        for (int q = 0; q < CQ; ++q) out[q] = dead ? 0.f : acc[q];
+    }
     }
 }
 
@@ -768,7 +790,7 @@ __global__ void __launch_bounds__(256) social_dw1_kernel(const unsigned* __restr
         for (int idx = threadIdx.x; idx < nb * C; idx += 256) {
             const int t = idx / C, ch = idx - t * C;
             const unsigned sv = sorted[pb + t];
-            const int slot = (int)(sv & 0x7fffffffu);
+            const int slot = (int)(sv & 0x3fffffffu);
             const int i = slot / nm1, jj = slot - i * nm1;
             const int s0 = scene_off[row_scene[i]];
             const int j = jj + (jj >= i - s0);
@@ -1152,7 +1174,7 @@ static int social_backward(const tb2_lstm* m, const tb2_layout* l, const tb2_lst
                                                                        b.counts);
             pair_offsets_kernel<<<1, 1024, cells * sizeof(int), st>>>(b.counts, l->B, cells, b.base, b.start);
             pair_place_kernel<<<l->B, 256, place_smem, st>>>(
-                l->scene_off, msk, pcell, pflag, winc, wine, nm1, cells, b.base, b.start, b.sorted);
+                l->scene_off, msk, pcell, pflag, winc, wine, nm1, cells, b.base, b.start, l->pad_to_max, b.sorted);
         }
         TB2_LAUNCH_CHECK();
         switch (C) {
@@ -1203,6 +1225,12 @@ static int social_backward(const tb2_lstm* m, const tb2_layout* l, const tb2_lst
             return rc;
     }
     if ((rc = colsum(b.DLAT, C, S * Mi, C, g->pool_encoding_bias, nullptr, b.scratch, b.scratch_floats, st))) return rc;
+    if (const char* dump = getenv("TB2_DUMP_DLAT")) {       // debug: d lat of every (step, track) as raw fp32 [S, M, C]
+        std::vector<float> host((size_t)S * M * C);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(host.data(), b.DLAT, host.size() * sizeof(float), cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(dump, "wb")) { fwrite(host.data(), sizeof(float), host.size(), f); fclose(f); }
+    }
     return TB2_OK;
 }
 }  // namespace tb2

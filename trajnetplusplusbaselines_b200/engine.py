@@ -212,6 +212,18 @@ class ModelHandle:
                 int(n_decode), int(first_step), int(last_step), _ptr(normals), _ptr(positions), _ptr(h), _ptr(c),
                 _ptr(None), _ptr(ws), need, _stream(self.device)))
 
+    def forward_sequence_host(self, layout, observed, truth, n_decode, normals, positions, h, c, normals_host,
+                              positions_host, copy_stream):
+        """tb2_lstm_forward_sequence_host: per-step device-to-host copies on `copy_stream`; the caller
+        synchronises that stream before reading the pinned host tensors."""
+        lib = _lib.load()
+        ws, need = self.workspace(layout)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.tb2_lstm_forward_sequence_host(
+                self.handle, layout.handle, _ptr(observed), int(observed.shape[0]), _ptr(truth), int(n_decode),
+                _ptr(normals), _ptr(positions), _ptr(h), _ptr(c), _ptr(ws), need, _ptr(normals_host),
+                _ptr(positions_host), _stream(self.device), ctypes.c_void_p(copy_stream.cuda_stream)))
+
     def forward_sequence(self, layout, observed, truth, n_decode, normals, positions, h, c, states=None):
         lib = _lib.load()
         ws, need = self.workspace(layout)

@@ -110,7 +110,7 @@ class LSTM(torch.nn.Module):
             cfg.pool_size = cfg.blur_size = 1
             if self.pool is not None:
                 if not hasattr(self.pool, 'fill_config'):
-                    raise NotImplementedError("only GridBasedPooling interaction modules are built")
+                    raise NotImplementedError("only GridBasedPooling and HiddenStateMLPPooling interaction modules are built")
                 self.pool.fill_config(cfg)
             self._handle = ModelHandle(cfg, device)
         key = weights_key(self)
@@ -215,6 +215,15 @@ class LSTM(torch.nn.Module):
         h = torch.empty((M, self.hidden_dim), **f32)
         c = torch.empty((M, self.hidden_dim), **f32)
         states = torch.empty((S, 2, M, self.hidden_dim), **f32) if want_states else None
+        if out_device != device and not want_states and obs_length > 2:
+            # host caller: every step's slice of the results is copied to pinned host memory on a second stream
+            # while the later steps compute; one synchronisation of that stream at the end
+            normals_h, positions_h = self._host_buffers(normals, positions)
+            copy_stream = self._copy_stream(device)
+            handle.forward_sequence_host(layout, obs, truth, n_decode, normals, positions, h, c, normals_h, positions_h,
+                                         copy_stream)
+            copy_stream.synchronize()
+            return normals_h.view(normals_h.shape), positions_h.view(positions_h.shape)
         handle.forward_sequence(layout, obs, truth, n_decode, normals, positions, h, c, states)
         if obs_length == 2:                      # lstm.py:222-223: positions seeded with observed[-1]
             positions = torch.cat([obs[-1:].clone(), positions], dim=0)
@@ -224,11 +233,11 @@ class LSTM(torch.nn.Module):
             normals, positions = self._to_host(normals, positions)
         return normals, positions
 
-    def _to_host(self, *tensors):
-        """D2H into a pool of pinned buffers and hand out VIEWS of them (no per-call allocation:
-        fresh host pages cost ~2 ms per result under the box's virtualisation).  A buffer is
-        reused only once nothing derived from an earlier result (views, .numpy() arrays) is
-        alive any more, which the storage use-count tells."""
+    def _host_buffers(self, *tensors):
+        """Pinned host buffers shaped like `tensors`, from a pool (no per-call allocation: fresh host
+        pages cost ~2 ms per result under the box's virtualisation).  A buffer is reused only once
+        nothing derived from an earlier result (views, .numpy() arrays) is alive any more, which the
+        storage use-count tells."""
         outs = []
         for i, t in enumerate(tensors):
             key = (tuple(t.shape), 'out', i)
@@ -241,6 +250,20 @@ class LSTM(torch.nn.Module):
             if buf is None:
                 buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
                 pool.append(buf)
+            outs.append(buf)
+        return outs
+
+    def _copy_stream(self, device):
+        st = self._pinned.get(('copy_stream', device.index))
+        if st is None:
+            st = torch.cuda.Stream(device=device)
+            self._pinned[('copy_stream', device.index)] = st
+        return st
+
+    def _to_host(self, *tensors):
+        """D2H into pooled pinned buffers; VIEWS of them are handed out."""
+        outs = []
+        for buf, t in zip(self._host_buffers(*tensors), tensors):
             buf.copy_(t, non_blocking=True)
             outs.append(buf.view(buf.shape))
         torch.cuda.current_stream(tensors[0].device).synchronize()

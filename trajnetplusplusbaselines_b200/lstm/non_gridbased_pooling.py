@@ -1,0 +1,116 @@
+"""Non-grid interaction modules with the reference's constructors, parameters and plug signature
+(trajnetbaselines/lstm/non_gridbased_pooling.py).
+
+Built: HiddenStateMLPPooling (:150-239, `--type hiddenstatemlp`, the Social-GAN pooling): max over the
+scene of per-neighbour embeddings of relative position, hidden state and relative velocity, then a linear
+projection.  One kernel per step (csrc/mlp_pool.cu); same plug contract as GridBasedPooling (attribute
+`out_dim`, `reset(...)`, `__call__(hidden [B, N, H], obs1, obs2) -> [B * N, out_dim]`).  Inside
+`LSTM.forward` the module is not called -- the fused sequence entry point reads its parameters.
+
+NearestNeighborMLP (:64-147), AttentionMLPPooling (:242-351), NearestNeighborLSTM, TrajectronPooling and
+NMMP are not built (their constructors raise).
+"""
+import torch
+
+from .. import _lib
+from ..engine import LayoutCache, ModelHandle, weights_key
+
+
+class HiddenStateMLPPooling(torch.nn.Module):
+    def __init__(self, hidden_dim=128, mlp_dim=128, mlp_dim_spatial=32, mlp_dim_vel=32, out_dim=None):
+        """Same arguments and sub-module names as the reference (non_gridbased_pooling.py:166-193)."""
+        super().__init__()
+        self.out_dim = out_dim or hidden_dim
+        self.hidden_dim = hidden_dim
+        self.mlp_dim = mlp_dim
+        self.mlp_dim_spatial = mlp_dim_spatial
+        self.mlp_dim_vel = mlp_dim_vel
+        self.mlp_dim_hidden = mlp_dim - mlp_dim_spatial - mlp_dim_vel
+        if self.mlp_dim_spatial < 1 or self.mlp_dim_vel < 0 or self.mlp_dim_hidden < 0:
+            raise ValueError("mlp_dim must cover mlp_dim_spatial (>= 1) + mlp_dim_vel")
+        self.spatial_embedding = torch.nn.Sequential(torch.nn.Linear(2, self.mlp_dim_spatial), torch.nn.ReLU())
+        if self.mlp_dim_vel:
+            self.vel_embedding = torch.nn.Sequential(torch.nn.Linear(2, self.mlp_dim_vel), torch.nn.ReLU())
+        if self.mlp_dim_hidden:
+            self.hidden_embedding = torch.nn.Sequential(torch.nn.Linear(self.hidden_dim, self.mlp_dim_hidden), torch.nn.ReLU())
+        self.out_projection = torch.nn.Linear(self.mlp_dim, self.out_dim)
+        self._handle = None
+        self._layouts = LayoutCache()
+
+    # -- configuration shared with LSTM ---------------------------------------------------------
+    def fill_config(self, cfg):
+        cfg.pool_type = _lib.POOL_HIDDEN_MLP
+        cfg.out_dim = int(self.out_dim)
+        cfg.mlp_dim_spatial = int(self.mlp_dim_spatial)
+        cfg.mlp_dim_vel = int(self.mlp_dim_vel)
+        cfg.mlp_dim_hidden = int(self.mlp_dim_hidden)
+        cfg.pool_size = cfg.blur_size = 1
+
+    def weight_fields(self):
+        fields = dict(pool_spatial_weight=self.spatial_embedding[0].weight, pool_spatial_bias=self.spatial_embedding[0].bias,
+                      pool_out_weight=self.out_projection.weight, pool_out_bias=self.out_projection.bias)
+        if self.mlp_dim_vel:
+            fields.update(pool_vel_weight=self.vel_embedding[0].weight, pool_vel_bias=self.vel_embedding[0].bias)
+        if self.mlp_dim_hidden:
+            fields.update(pool_hidden_weight=self.hidden_embedding[0].weight, pool_hidden_bias=self.hidden_embedding[0].bias)
+        return fields
+
+    def weights_version(self):
+        return weights_key(self)
+
+    # -- the plug --------------------------------------------------------------------------------
+    def reset(self, num_tracks, max_num_neigh, device):
+        self.track_mask = None
+
+    def forward(self, hidden_states, obs1, obs2):
+        """[B, N, H], [B, N, 2], [B, N, 2] -> [B * N, out_dim] (non_gridbased_pooling.py:197-239)."""
+        _lib.require_cuda()
+        batch_size, num_tracks = obs2.size(0), obs2.size(1)
+        device = self.out_projection.weight.device
+        if device.type != 'cuda':
+            raise RuntimeError("HiddenStateMLPPooling runs on CUDA only: move the module to a B200 (module.cuda())")
+        if hidden_states.size(-1) != self.hidden_dim:
+            raise ValueError("hidden_states width != hidden_dim")
+        if self._handle is None or self._handle.device != device:
+            cfg = _lib.LstmConfig()
+            cfg.hidden_dim = 128            # the stand-alone plug does not touch the LSTM cell
+            cfg.embedding_dim = 64
+            cfg.pool_to_input = 1
+            self.fill_config(cfg)
+            self._handle = ModelHandle(cfg, device)
+            self._standalone_dummy = None
+        if getattr(self, '_standalone_dummy', None) is None:
+            z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
+            in_dim = 64 + self.out_dim
+            self._standalone_dummy = dict(
+                input_embedding_weight=z(62, 2), input_embedding_bias=z(62),
+                encoder_weight_ih=z(512, in_dim), encoder_weight_hh=z(512, 128),
+                encoder_bias_ih=z(512), encoder_bias_hh=z(512),
+                decoder_weight_ih=z(512, in_dim), decoder_weight_hh=z(512, 128),
+                decoder_bias_ih=z(512), decoder_bias_hh=z(512),
+                hidden2normal_weight=z(5, 128), hidden2normal_bias=z(5))
+        fields = dict(self._standalone_dummy)
+        fields.update(self.weight_fields())
+        self._handle.set_weights(fields, key=self.weights_version())
+        layout = self._layouts.get(range(0, batch_size * num_tracks + 1, num_tracks), device=device)
+        f32 = dict(device=device, dtype=torch.float32)
+        o1 = obs1.detach().to(**f32).reshape(-1, 2).contiguous()
+        o2 = obs2.detach().to(**f32).reshape(-1, 2).contiguous()
+        hid = hidden_states.detach().to(**f32).reshape(batch_size * num_tracks, -1).contiguous()
+        out = self._handle.pool_forward(layout, hid, o1, o2, self.out_dim)
+        return out.to(obs2.device) if obs2.device != device else out
+
+
+def _not_built(name, lines):
+    class _NotBuilt(torch.nn.Module):
+        def __init__(self, *args, **kwargs):
+            raise NotImplementedError("%s (reference non_gridbased_pooling.py:%s) is not built; HiddenStateMLPPooling "
+                                      "and GridBasedPooling are" % (name, lines))
+    _NotBuilt.__name__ = name
+    return _NotBuilt
+
+
+NearestNeighborMLP = _not_built("NearestNeighborMLP", "64-147")
+AttentionMLPPooling = _not_built("AttentionMLPPooling", "242-351")
+NearestNeighborLSTM = _not_built("NearestNeighborLSTM", "354-")
+TrajectronPooling = _not_built("TrajectronPooling", "")

@@ -33,6 +33,8 @@ def _grad_targets(model):
     """field name -> parameter, for every parameter the backward kernel produces a gradient for."""
     out = {k: f(model) for k, f in _GRAD_FIELDS.items()}
     pool = model.pool
+    if pool is not None and not hasattr(pool, 'embedding'):
+        raise NotImplementedError("training of %s is not built (inference only); use torch.no_grad()" % type(pool).__name__)
     if pool is not None and pool.embedding is not None:
         linears = [m for m in pool.embedding if isinstance(m, torch.nn.Linear)]
         out["pool_embedding_weight0"] = linears[0].weight
