@@ -36,14 +36,27 @@ __device__ __forceinline__ double sf_potential(double rx, double ry, double sb, 
     return v0 * exp(-b / sigma);
 }
 
+// kWarpScenes: every scene has at most 32 pedestrians -> one WARP per scene, 4 scenes per CTA, __syncwarp instead
+// of __syncthreads (a CTA of one warp caps an SM at 32 resident warps; the arithmetic per pedestrian is unchanged,
+// results are bit-identical to the one-scene-per-CTA form).
+constexpr int kScenesPerCta = 4;
+
+template <bool kWarpScenes>
+__device__ __forceinline__ void scene_sync() {
+    if (kWarpScenes) __syncwarp();
+    else __syncthreads();
+}
+
+template <bool kWarpScenes>
 __global__ void sf_simulate_kernel(const int* __restrict__ scene_off, const double* __restrict__ state,
-                                   double* __restrict__ out, int A, tb2_sf_params p) {
+                                   double* __restrict__ out, int A, int B, int n_max, tb2_sf_params p) {
     extern __shared__ double smem_sf[];
-    const int scene = blockIdx.x;
+    const int scene = kWarpScenes ? blockIdx.x * kScenesPerCta + (int)(threadIdx.x >> 5) : (int)blockIdx.x;
+    if (scene >= B) return;                                  // whole warp (kWarpScenes): no block-wide barrier below
     const int row0 = scene_off[scene];
     const int n = scene_off[scene + 1] - row0;
-    const int a = threadIdx.x;
-    double* px = smem_sf;
+    const int a = kWarpScenes ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+    double* px = smem_sf + (kWarpScenes ? (size_t)(threadIdx.x >> 5) * n_max * 7 : 0);
     double* py = px + n;
     double* vx = py + n;
     double* vy = vx + n;
@@ -71,7 +84,7 @@ __global__ void sf_simulate_kernel(const int* __restrict__ scene_off, const doub
             px[a] = x; py[a] = y; vx[a] = ux; vy[a] = uy; ex[a] = eax; ey[a] = eay;
             sp[a] = sqrt(ux * ux + uy * uy);
         }
-        __syncthreads();
+        scene_sync<kWarpScenes>();
         if (a < n) {
             double Fx = 1.0 / tau * (s0 * eax - ux);
             double Fy = 1.0 / tau * (s0 * eay - uy);
@@ -105,7 +118,7 @@ __global__ void sf_simulate_kernel(const int* __restrict__ scene_off, const doub
             }
         }
         if (k % p.sample_every == 0) ++sample;
-        __syncthreads();
+        scene_sync<kWarpScenes>();
     }
 }
 
@@ -200,16 +213,18 @@ __device__ void orca_lp3(const Line* lines, int n, int begin, float radius, floa
     }
 }
 
+template <bool kWarpScenes>
 __global__ void orca_simulate_kernel(const int* __restrict__ scene_off, const float2* __restrict__ pos_in,
                                      const float2* __restrict__ vel_in, const double2* __restrict__ goal_in,
-                                     const double* __restrict__ speed_in, float2* __restrict__ out, int A,
-                                     tb2_orca_params p) {
+                                     const double* __restrict__ speed_in, float2* __restrict__ out, int A, int B,
+                                     int n_max, tb2_orca_params p) {
     extern __shared__ float2 smem_orca[];
-    const int scene = blockIdx.x;
+    const int scene = kWarpScenes ? blockIdx.x * kScenesPerCta + (int)(threadIdx.x >> 5) : (int)blockIdx.x;
+    if (scene >= B) return;
     const int row0 = scene_off[scene];
     const int n = scene_off[scene + 1] - row0;
-    const int a = threadIdx.x;
-    float2* pos = smem_orca;
+    const int a = kWarpScenes ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+    float2* pos = smem_orca + (kWarpScenes ? (size_t)(threadIdx.x >> 5) * n_max * 2 : 0);
     float2* vel = pos + n;
 
     float2 mypos = f2(0.f, 0.f), myvel = f2(0.f, 0.f), pref = f2(0.f, 0.f);
@@ -225,7 +240,7 @@ __global__ void orca_simulate_kernel(const int* __restrict__ scene_off, const fl
         pos[a] = mypos;
         vel[a] = myvel;
     }
-    __syncthreads();
+    scene_sync<kWarpScenes>();
     const float inv_th = 1.0f / p.time_horizon;
     const float inv_ts = 1.0f / p.time_step;
     const float cr = p.radius + p.radius;
@@ -292,7 +307,7 @@ __global__ void orca_simulate_kernel(const int* __restrict__ scene_off, const fl
             if (fail < nn) orca_lp3(lines, nn, fail, maxsp, res);
             newv = res;
         }
-        __syncthreads();                       // every agent has read the old positions / velocities
+        scene_sync<kWarpScenes>();                       // every agent has read the old positions / velocities
         if (a < n) {
             myvel = newv;
             mypos = vadd(mypos, vmul(p.time_step, myvel));
@@ -307,7 +322,7 @@ __global__ void orca_simulate_kernel(const int* __restrict__ scene_off, const fl
             else pref = f2((float)gx, (float)gy);
         }
         if (count % p.sample_every == 0) ++sample;
-        __syncthreads();
+        scene_sync<kWarpScenes>();
     }
 }
 
@@ -326,7 +341,14 @@ int tb2_sf_simulate(const tb2_layout* l, const tb2_sf_params* p, const double* s
     size_t smem = (size_t)l->n_max * 7 * sizeof(double);
     {
         KernelTimer kt("sf_simulate", st);
-        sf_simulate_kernel<<<l->B, threads, smem, st>>>(l->scene_off, state, out, l->M, *p);
+        if (l->n_max <= 32)
+            sf_simulate_kernel<true><<<(l->B + kScenesPerCta - 1) / kScenesPerCta, 32 * kScenesPerCta, smem * kScenesPerCta, st>>>(
+                l->scene_off, state, out, l->M, l->B, l->n_max, *p);
+        else {
+            static DynSmemConfig configured;
+            TB2_CHECK_CUDA(configured.ensure(sf_simulate_kernel<false>, smem, 48 * 1024));
+            sf_simulate_kernel<false><<<l->B, threads, smem, st>>>(l->scene_off, state, out, l->M, l->B, l->n_max, *p);
+        }
     }
     TB2_LAUNCH_CHECK();
     return TB2_OK;
@@ -343,8 +365,14 @@ int tb2_orca_simulate(const tb2_layout* l, const tb2_orca_params* p, const float
     size_t smem = (size_t)l->n_max * 2 * sizeof(float2);
     {
         KernelTimer kt("orca_simulate", st);
-        orca_simulate_kernel<<<l->B, threads, smem, st>>>(l->scene_off, (const float2*)pos, (const float2*)vel,
-                                                         (const double2*)goal, speed, (float2*)out, l->M, *p);
+        if (l->n_max <= 32)
+            orca_simulate_kernel<true><<<(l->B + kScenesPerCta - 1) / kScenesPerCta, 32 * kScenesPerCta, smem * kScenesPerCta, st>>>(
+                l->scene_off, (const float2*)pos, (const float2*)vel, (const double2*)goal, speed, (float2*)out, l->M, l->B,
+                l->n_max, *p);
+        else
+            orca_simulate_kernel<false><<<l->B, threads, smem, st>>>(l->scene_off, (const float2*)pos, (const float2*)vel,
+                                                                    (const double2*)goal, speed, (float2*)out, l->M, l->B,
+                                                                    l->n_max, *p);
     }
     TB2_LAUNCH_CHECK();
     return TB2_OK;
