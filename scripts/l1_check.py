@@ -97,6 +97,18 @@ def main():
             bad = np.argwhere(d > 1e-4)
             print("   bad count", len(bad), "of", d.size, " rows", np.unique(bad[:, 0])[:20].tolist(),
                   " n bad rows", len(np.unique(bad[:, 0])), " n bad cols", len(np.unique(bad[:, 1])))
+        # the full two_layer pool (with the round-2 kernel the 1024 -> 256 Linear runs inside it): vs the round-1 path
+        W2_ = O.random_weights("social", seed=21)
+        pool2_ = make_pool("social", W2_)
+        os.environ["TB2_SPARSE"] = "tc"
+        ref2 = pool2_(*t_in).cpu().numpy()
+        os.environ["TB2_SPARSE"] = args.mode
+        out2 = pool2_(*t_in)
+        torch.cuda.synchronize()
+        d2 = np.abs(out2.cpu().numpy() - ref2)
+        print("[%s] big ragged=%d two_layer pooled  max|mode - tc| = %.3e  mean %.3e  (ref max %.3f)  fuse2=%s" % (
+            args.mode, ragged, float(np.nanmax(d2)), float(np.nanmean(d2)), float(np.nanmax(np.abs(ref2))),
+            "on" if os.environ.get("TB2_FUSE2") == "1" else "off"), flush=True)
         if not ragged:
             # timing of the whole pool call (prepare + layer 1) with the cycle counters of the kernel
             os.environ["TB2_L1_DEBUG"] = "1"

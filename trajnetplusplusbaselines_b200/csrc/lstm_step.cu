@@ -400,6 +400,9 @@ int launch_repack(tb2_lstm* m, const tb2_lstm_weights* w, cudaStream_t st) {
                                                   m->mlp_dims[layer + 1], m->mlp_dims[layer]);
             TB2_LAUNCH_CHECK();
             if ((rc = copy_dev(w->pool_embedding_bias[layer], m->bl[layer], (size_t)m->mlp_dims[layer + 1], st))) return rc;
+            if (layer == 1 && m->W2_sw &&
+                (rc = launch_repack_layer2_sw(w->pool_embedding_weight[1], m->W2_sw, m->mlp_dims[2], m->mlp_dims[1], st)))
+                return rc;
             if (m->W_hi[layer] &&
                 (rc = launch_split_bf16(w->pool_embedding_weight[layer], m->W_hi[layer], m->W_lo[layer],
                                         (size_t)m->mlp_dims[layer] * m->mlp_dims[layer + 1], st)))

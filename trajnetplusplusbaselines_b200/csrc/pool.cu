@@ -1051,7 +1051,7 @@ static int launch_l1_t(const L1Params& p, int groups, size_t smem, cudaStream_t 
 
 // Grid -> pooled vector (GridBasedPooling.forward after the grid is known, :106-110).
 int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float* pooled_out,
-                    void* pool_hi, void* pool_lo, cudaStream_t st) {
+                    void* pool_hi, void* pool_lo, cudaStream_t st, bool keep_hidden) {
     const int nm1 = l->n_max > 1 ? l->n_max - 1 : 1;
     // producers that cannot write the bf16 split themselves go through fp32 scratch + split_rows
     const bool want_split = pool_hi != nullptr;
@@ -1117,7 +1117,14 @@ int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float
         rc = launch_pool_rows(m, l, ws, d1, nm1, p.out, p.out_hi, p.out_lo, st);
     } else
     if (pair_mode && ws->cell_row && sparse_pair_supported(m, l)) {   // social, 16 latent channels: CTA-pair tcgen05 kernel
-        rc = launch_sparse_pair(m, l, pair_mode, ws, p.out, p.out_hi, p.out_lo, st);
+        // TB2_FUSE2=1: also run the 1024 -> 256 Linear inside the kernel (hidden1 never leaves the SM).  Built, parity-
+        // green (2.9e-7 vs the separate layer) and measured: it LOSES 1.3 % per forward at the BASELINE shape and the
+        // per-piece partial sums make results depend on the batch decomposition -- off by default
+        // (profiles/round2_fuse2_experiment.txt).
+        const char* f2 = getenv("TB2_FUSE2");
+        if (!keep_hidden && sparse_pair_can_fuse(m) && f2 && f2[0] == '1')
+            return launch_sparse_pair(m, l, pair_mode, ws, pooled_out, pool_hi, pool_lo, true, st);
+        rc = launch_sparse_pair(m, l, pair_mode, ws, p.out, p.out_hi, p.out_lo, false, st);
     } else
     if (allow_tc && sparse_tc_supported(m, l, 0)) {  // social, 16 latent channels: tcgen05 path
         rc = launch_sparse_tc(m, l, 0, ws, p.out, p.out_hi, p.out_lo, st);

@@ -68,6 +68,12 @@ constexpr uint32_t kSpBRing = 3u * 4u * kSpBCell;
 constexpr size_t kSpDynBytes = (size_t)kSpSA * kSpAStage + kSpBRing + (size_t)kSpLatRows * 64;
 static_assert((size_t)kSpSBMax * 2 * kSpBCell + (size_t)kSpLatRows * 64 <= kSpBRing, "two-tile rounds: second latent table");
 static_assert(1024 + kSpDynBytes + 64 <= 227 * 1024 - 1024, "shared memory budget");
+// fused layer-2 tail: hidden1 of the round as A tiles (one (hi | lo) tile pair per 16 columns) + a ring of W2 k-step tiles
+constexpr int kSpN2 = 256;
+constexpr int kSpTailStages = 6;
+constexpr uint32_t kSpA2Bytes = (uint32_t)(kSpDCols / 16) * 2u * kSpATile;
+static_assert(kSpA2Bytes + 4u * (uint32_t)kSpN2 * 64u <= kSpDynBytes, "tail: one CTA per unit, 4 stages");
+static_assert(kSpA2Bytes + (uint32_t)kSpTailStages * (uint32_t)(kSpN2 / 2) * 64u <= kSpDynBytes, "tail: pair, 6 stages");
 
 __device__ __forceinline__ uint32_t sp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sp_mbar_init(uint32_t bar, uint32_t count) {
@@ -136,7 +142,7 @@ __device__ __forceinline__ void sp_tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) 
 
 // One round of a unit: `n0` 32-column blocks of pedestrian tile `tile` starting at block `blk0`, then (n1 > 0) the
 // first `n1` blocks of tile + 1.  Planned on the host (plan_rounds) so that no piece is narrower than 3 blocks.
-struct SpRound { int tile, blk0, n0, n1; };
+struct SpRound { int tile, blk0, n0, n1, slot0, slot1; };      // slot: index of the piece among the pieces of its tile (fused layer 2)
 
 __device__ __forceinline__ void sp_tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
@@ -159,6 +165,10 @@ struct SpParams {
     __nv_bfloat16* out_hi;           // bf16 split [M, OUT] or null
     __nv_bfloat16* out_lo;
     const SpRound* rounds;           // [units * rounds_per_unit] (plan_rounds)
+    // fused second Linear (two_layer, 256 outputs): hidden1 stays on chip; every piece writes its K-slice partial sums
+    const unsigned char* w2;         // bf16 [OUT / 16][N2 / 8][hi: 8 rows x 16 | lo: 8 rows x 16] of pool.embedding.2.weight, or null
+    float* partials;                 // [tiles][max_slots][R][N2] fp32
+    int N2, max_slots;
     int M, OUT, cells, rounds_per_unit;
     float constant;
     long long* dbg;                  // optional [units * nC, 8] cycle counters (TB2_L1_DEBUG=1)
@@ -266,6 +276,10 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
     __shared__ __align__(8) uint64_t full_b[kSpSBMax];    // local weight slabs landed
     __shared__ __align__(8) uint64_t empty_b[kSpSBMax];   // MMAs that read the weight stage done
     __shared__ __align__(8) uint64_t acc_full_bar;
+    __shared__ __align__(8) uint64_t full_w[kSpTailStages];      // tail: W2 k-step tile landed (local)
+    __shared__ __align__(8) uint64_t empty_w[kSpTailStages];     // tail: MMAs that read the stage done
+    __shared__ __align__(8) uint64_t peer_w[kSpTailStages];      // tail, leader: the peer CTA's tile landed
+    __shared__ __align__(8) uint64_t acc2_full_bar;
     __shared__ uint32_t tmem_base_slot;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -318,7 +332,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
     const int R = 128 * nC;                               // pedestrian rows per tile
     uint32_t round_idx = 0;
     long long t_setup_sum = 0, t_loop_sum = 0, t_epi_sum = 0, wait_full = 0, wait_b = 0, wait_e = 0;
-    SpRound rd = {0, 0, 0, 0};
+    SpRound rd = {0, 0, 0, 0, 0, 0};
     for (int ri = 0; ri < p.rounds_per_unit; ++ri) {
         rd = p.rounds[(size_t)unit * p.rounds_per_unit + ri];
         if (rd.n0 == 0) continue;                         // padding round (uniform for the whole cluster)
@@ -349,6 +363,18 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
             }
             if (round_idx > 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(sp_smem_u32(&acc_full_bar)) : "memory");
             sp_mbar_init(sp_smem_u32(&acc_full_bar), n_issuers);
+            for (int s2 = 0; s2 < kSpTailStages; ++s2) {
+                if (round_idx > 0) {
+                    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(sp_smem_u32(&full_w[s2])) : "memory");
+                    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(sp_smem_u32(&empty_w[s2])) : "memory");
+                    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(sp_smem_u32(&peer_w[s2])) : "memory");
+                }
+                sp_mbar_init(sp_smem_u32(&full_w[s2]), 1);
+                sp_mbar_init(sp_smem_u32(&empty_w[s2]), 1);
+                sp_mbar_init(sp_smem_u32(&peer_w[s2]), 1);
+            }
+            if (round_idx > 0) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(sp_smem_u32(&acc2_full_bar)) : "memory");
+            sp_mbar_init(sp_smem_u32(&acc2_full_bar), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         // piece x: columns [col0[x], col0[x] + ncols[x]) of tile[x]; accumulators of piece 1 behind those of piece 0
@@ -511,9 +537,9 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
             // accumulator column d of an MMA group = row (d mod n/2) of the slab of CTA (d div n/2): 16-column
             // chunks never straddle the two halves (n/2 is a multiple of 16)
             const int nchunk0 = (int)ncols[0] >> 4, nchunk = (int)(ncols[0] + ncols[1]) >> 4;
-            for (int ch = sub; ch < nchunk; ch += 4) {
-                const int x = ch >= nchunk0 ? 1 : 0;                             // sub-round
-                int dx = (x ? ch - nchunk0 : ch) * 16;                           // column inside the sub-round's accumulators
+            auto chunk_col = [&](int ch, int& x) {           // first global hidden1 column of 16-column chunk ch, its piece
+                x = ch >= nchunk0 ? 1 : 0;
+                int dx = (x ? ch - nchunk0 : ch) * 16;                           // column inside the piece's accumulators
                 const int nrx = (int)ncols[x] / nC;                              // rows per CTA of the piece
                 int gn = (int)ncols[x], goff = 0;                                // MMA group of this column
                 if (split) {
@@ -522,7 +548,12 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
                 }
                 const int half = gn / nC;                                        // rows per CTA of the group
                 const int hsel = dx >= half ? 1 : 0;                             // which CTA's rows (pair only)
-                const int col = col0[x] + hsel * nrx + goff + (dx - hsel * half);
+                return col0[x] + hsel * nrx + goff + (dx - hsel * half);
+            };
+            if (p.w2 == nullptr) {
+            for (int ch = sub; ch < nchunk; ch += 4) {
+                int x;
+                const int col = chunk_col(ch, x);
                 const int row = tile[x] * R + (int)rank * 128 + q * 32 + lane;
                 uint32_t v[16];
                 sp_tmem_ld16(trow + (uint32_t)(ch * 16), v);
@@ -566,6 +597,127 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
                 }
             }
             if (warp == 12 && lane == 0) t_epi_sum += clock64() - t_e0;
+            } else {
+            // ===== fused second Linear (reference gridbased_pooling.py:316-323, the 1024 -> 256 layer of two_layer):
+            // hidden1 = relu(b1 + D) never leaves the SM.  T1: the accumulators become A tiles (bf16 hi | lo, one tile
+            // pair per 16 columns = one k-step of layer 2) in the shared memory the rings used.  T2: the weight producer
+            // streams the matching k-step tiles of W2 (same pre-swizzled bulk-copy format as the layer-1 slabs), one
+            // thread issues D2[rows, 256] += A2_k . W2_k (3 passes) per k-step.  T3: D2, the piece's K-slice partial sum of
+            // the layer-2 pre-activation, goes to the partial buffer slot of the piece; pooled_reduce_kernel adds the
+            // slots of a tile in a fixed order, applies bias + ReLU and writes the gate kernel's operand. =====
+            unsigned char* a2 = ring_ptr;                                        // [chunk][hi tile | lo tile]
+            const uint32_t w_ring = ring + kSpA2Bytes;
+            const int TS = kPair ? kSpTailStages : 4;
+            const uint32_t w_stage = (uint32_t)(kSpN2 / nC) * 64u;               // this CTA's rows of one k-step tile
+            const uint32_t r_cta = (uint32_t)(q * 32 + lane);
+            for (int ch = sub; ch < nchunk; ch += 4) {
+                int x;
+                const int col = chunk_col(ch, x);
+                uint32_t v[16];
+                sp_tmem_ld16(trow + (uint32_t)(ch * 16), v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                uint32_t ph[8], pl[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.base + col) + i);
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const float x0 = fmaxf(__uint_as_float(v[4 * i + 2 * j]) + bb[2 * j], 0.f);
+                        const float x1 = fmaxf(__uint_as_float(v[4 * i + 2 * j + 1]) + bb[2 * j + 1], 0.f);
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                        const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+                        const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                        ph[2 * i + j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                        pl[2 * i + j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                    }
+                }
+                unsigned char* t = a2 + (size_t)ch * 2u * kSpATile;
+                *reinterpret_cast<uint4*>(t + sp_sw32(r_cta, 0)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                *reinterpret_cast<uint4*>(t + sp_sw32(r_cta, 1)) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+                *reinterpret_cast<uint4*>(t + kSpATile + sp_sw32(r_cta, 0)) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                *reinterpret_cast<uint4*>(t + kSpATile + sp_sw32(r_cta, 1)) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (kPair) {      // both CTAs' A2 tiles are complete and their accumulators drained before the leader issues
+                asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+                asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (warp == 0) {
+                if (lane == 0) {
+                    for (int ch = 0; ch < nchunk; ++ch) {
+                        int x;
+                        const int kstep = chunk_col(ch, x) >> 4;
+                        const uint32_t sw = (uint32_t)(ch % TS), pw = (uint32_t)((ch / TS) & 1);
+                        sp_mbar_wait(sp_smem_u32(&empty_w[sw]), pw ^ 1u);
+                        const uint32_t bar = sp_smem_u32(&full_w[sw]);
+                        sp_mbar_expect_tx(bar, w_stage);
+                        sp_bulk_load(w_ring + sw * w_stage, p.w2 + ((size_t)kstep * kSpN2 + rank * (uint32_t)(kSpN2 / nC)) * 64,
+                                     w_stage, bar);
+                    }
+                }
+                __syncwarp();
+            } else if (warp == 2) {
+                if (kPair && lane == 0 && rank != 0) {           // relay: "my tile of k-step ch has landed" -> leader
+                    for (int ch = 0; ch < nchunk; ++ch) {
+                        const uint32_t sw = (uint32_t)(ch % TS), pw = (uint32_t)((ch / TS) & 1);
+                        sp_mbar_wait(sp_smem_u32(&full_w[sw]), pw);
+                        uint32_t remote;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(sp_smem_u32(&peer_w[sw])), "r"(0));
+                        sp_mbar_arrive_cluster(remote);
+                    }
+                }
+                __syncwarp();
+            } else if (warp == 1) {
+                if (lane == 0 && rank == 0) {
+                    const uint32_t a_desc_hi = (uint32_t)(256 >> 4) | (1u << 14) | (6u << 29);
+                    const uint32_t b_desc_hi = (uint32_t)(512 >> 4) | (1u << 14) | (6u << 29);
+                    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kSpN2 >> 3) << 17) | ((uint32_t)(R >> 4) << 24);
+                    for (int ch = 0; ch < nchunk; ++ch) {
+                        const uint32_t sw = (uint32_t)(ch % TS), pw = (uint32_t)((ch / TS) & 1);
+                        sp_mbar_wait(sp_smem_u32(&full_w[sw]), pw);
+                        if (kPair) sp_mbar_wait_cluster(sp_smem_u32(&peer_w[sw]), pw);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const int x = ch >= nchunk0 ? 1 : 0;
+                        const uint32_t d = tmem_base + (x ? (uint32_t)kSpN2 : 0u);
+                        const uint64_t ad = ((uint64_t)a_desc_hi << 32) | (uint64_t)(((ring + (uint32_t)ch * 2u * kSpATile) & 0x3FFFFu) >> 4);
+                        const uint64_t bd = ((uint64_t)b_desc_hi << 32) | (uint64_t)(((w_ring + sw * w_stage) & 0x3FFFFu) >> 4);
+                        const uint32_t first = (ch == 0 || ch == nchunk0) ? 0u : 1u;
+                        sp_umma<kPair>(d, ad, bd, idesc, first);                                // hi . hi
+                        sp_umma<kPair>(d, ad + (kSpATile >> 4), bd, idesc, 1u);                 // lo . hi
+                        sp_umma<kPair>(d, ad, bd + (256u >> 4), idesc, 1u);                     // hi . lo
+                        sp_commit<kPair>(sp_smem_u32(&empty_w[sw]));
+                    }
+                    sp_commit<kPair>(sp_smem_u32(&acc2_full_bar));
+                }
+                __syncwarp();
+            }
+            // T3: partial sums of the layer-2 pre-activation -> the slot of this piece
+            sp_mbar_wait(sp_smem_u32(&acc2_full_bar), 0u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int x = 0; x < nsub; ++x) {
+                const int row_t = (int)rank * 128 + q * 32 + lane;                // row inside the tile
+                const int slot = x ? rd.slot1 : rd.slot0;
+                float* dst = p.partials + (((size_t)tile[x] * p.max_slots + slot) * R + row_t) * kSpN2;
+                const bool row_ok = tile[x] * R + row_t < p.M;
+                for (int c16 = sub; c16 < kSpN2 / 16; c16 += 4) {
+                    uint32_t v[16];
+                    sp_tmem_ld16(trow + (uint32_t)(x * kSpN2 + c16 * 16), v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (row_ok) {
+                        float4* d4 = reinterpret_cast<float4*>(dst + c16 * 16);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            d4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                                __uint_as_float(v[4 * i + 3]));
+                    }
+                }
+            }
+            if (warp == 12 && lane == 0) t_epi_sum += clock64() - t_e0;
+            }
         }
         ++round_idx;
         // the next round overwrites the latent tables, the TMEM accumulators and (pair) the peer's accumulators
@@ -636,35 +788,27 @@ static bool plan_rounds_dp(long long total, int nb, int n_rounds, int cap, int c
     }
     const long long off_end = total - base(n_rounds) + W;
     if (off_end < 0 || off_end > 2 * W || from[n_rounds][(size_t)off_end] < 0) return false;
-    out.assign((size_t)n_rounds, SpRound{0, 0, 0, 0});
+    out.assign((size_t)n_rounds, SpRound{0, 0, 0, 0, 0, 0});
     long long end = total;
     for (int k = n_rounds; k > 0; --k) {
         const int sz = from[k][(size_t)(end - base(k) + W)];
         const long long pos = end - sz;
         const long long t0 = pos / nb;
         const long long in0 = std::min<long long>(sz, (t0 + 1) * nb - pos);
-        out[(size_t)k - 1] = SpRound{(int)t0, (int)(pos - t0 * nb), (int)in0, (int)(sz - in0)};
+        out[(size_t)k - 1] = SpRound{(int)t0, (int)(pos - t0 * nb), (int)in0, (int)(sz - in0), 0, 0};
         end = pos;
     }
     return end == 0;
 }
 
-struct SpPlan {
-    int M, OUT, units, nC, rounds_per_unit;
-    SpRound* dev;
-};
-
-// the round table of a (layout, OUT, units) combination lives with the layout (device memory of its device)
-static int get_plan(const tb2_layout* l, int OUT, int units_max, int nC, const SpRound** dev_out, int* units_out,
-                    int* rpu_out, cudaStream_t st) {
+// the round table of a (layout, OUT, units) combination lives with the layout (device memory of its device),
+// together with the partial-sum buffer of the fused second Linear and the number of pieces per tile
+static int get_plan(const tb2_layout* l, int OUT, int units_max, int nC, const tb2_layout::PairPlan** out, cudaStream_t st) {
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
     tb2_layout* lm = const_cast<tb2_layout*>(l);
     for (const auto& e : lm->pair_plans)
-        if (e.OUT == OUT && e.units_max == units_max && e.nC == nC) {
-            *dev_out = (const SpRound*)e.dev; *units_out = e.units; *rpu_out = e.rounds_per_unit;
-            return TB2_OK;
-        }
+        if (e.OUT == OUT && e.units_max == units_max && e.nC == nC) { *out = &e; return TB2_OK; }
     const int R = 128 * nC, nb = OUT / 32;
     const long long tiles = (l->M + R - 1) / R, total = tiles * nb;
     int units = units_max;
@@ -681,21 +825,76 @@ static int get_plan(const tb2_layout* l, int OUT, int units_max, int nC, const S
             for (int minpiece = 3; minpiece >= 1 && !ok; --minpiece)
                 ok = plan_rounds_dp(total, nb, n_rounds, cap, relax ? cap : std::max(cap - 1, 1), minpiece, rounds);
     if (!ok) { set_error("sparse_layer1_pair: no round plan (internal)"); return TB2_ERR_INVALID; }
+    // slot of every piece among the pieces of its tile (order of the rounds): pooled_reduce_kernel sums them in this order
+    std::vector<int> nslots((size_t)tiles, 0);
+    for (auto& r : rounds) {
+        if (r.n0 > 0) r.slot0 = nslots[(size_t)r.tile]++;
+        if (r.n1 > 0) r.slot1 = nslots[(size_t)r.tile + 1]++;
+    }
+    int max_slots = 1;
+    for (int v : nslots) max_slots = std::max(max_slots, v);
     SpRound* dev = nullptr;
+    int* dev_slots = nullptr;
+    float* partials = nullptr;
     TB2_CHECK_CUDA(cudaMalloc(&dev, rounds.size() * sizeof(SpRound)));
     lm->owned.push_back(dev);
+    TB2_CHECK_CUDA(cudaMalloc(&dev_slots, (size_t)tiles * sizeof(int)));
+    lm->owned.push_back(dev_slots);
+    TB2_CHECK_CUDA(cudaMalloc(&partials, (size_t)tiles * max_slots * R * kSpN2 * sizeof(float)));
+    lm->owned.push_back(partials);
     TB2_CHECK_CUDA(cudaMemcpyAsync(dev, rounds.data(), rounds.size() * sizeof(SpRound), cudaMemcpyHostToDevice, st));
-    TB2_CHECK_CUDA(cudaStreamSynchronize(st));       // one-time (per layout): `rounds` is a host temporary
+    TB2_CHECK_CUDA(cudaMemcpyAsync(dev_slots, nslots.data(), (size_t)tiles * sizeof(int), cudaMemcpyHostToDevice, st));
+    TB2_CHECK_CUDA(cudaStreamSynchronize(st));       // one-time (per layout): the host vectors are temporaries
     tb2_layout::PairPlan e;
     e.OUT = OUT; e.units_max = units_max; e.nC = nC; e.units = units; e.rounds_per_unit = rpu; e.dev = dev;
+    e.tile_slots = dev_slots; e.partials = partials; e.max_slots = max_slots; e.R = R;
     lm->pair_plans.push_back(e);
-    *dev_out = dev; *units_out = units; *rpu_out = rpu;
+    *out = &lm->pair_plans.back();
     return TB2_OK;
 }
 
+// pooled[row, :] = relu(b2 + sum over the tile's pieces (slot order) of partial[tile][slot][row, :]) -- the second Linear of
+// two_layer after the fused kernel; written as fp32 and / or as the bf16 (hi, lo) operand of the gate kernel
+__global__ void __launch_bounds__(256) pooled_reduce_kernel(const float* __restrict__ partials, const int* __restrict__ tile_slots,
+                                                            int max_slots, int R, int M, const float* __restrict__ bias,
+                                                            float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
+                                                            __nv_bfloat16* __restrict__ out_lo) {
+    grid_dep_wait();
+    grid_dep_launch();
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;            // one float4 of one row
+    if (idx >= (size_t)M * (kSpN2 / 4)) return;
+    const int row = (int)(idx / (kSpN2 / 4)), c4 = (int)(idx % (kSpN2 / 4)) * 4;
+    const int tile = row / R, rr = row - tile * R;
+    const int ns = tile_slots[tile];
+    const float4 b = *reinterpret_cast<const float4*>(bias + c4);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < ns; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(partials + (((size_t)tile * max_slots + s) * R + rr) * kSpN2 + c4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const float y[4] = {fmaxf(acc.x + b.x, 0.f), fmaxf(acc.y + b.y, 0.f), fmaxf(acc.z + b.z, 0.f), fmaxf(acc.w + b.w, 0.f)};
+    const size_t o = (size_t)row * kSpN2 + c4;
+    if (out) *reinterpret_cast<float4*>(out + o) = make_float4(y[0], y[1], y[2], y[3]);
+    if (out_hi) {
+        uint32_t ph[2], pl[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(y[2 * i]), h1 = __float2bfloat16_rn(y[2 * i + 1]);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(y[2 * i] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(y[2 * i + 1] - __bfloat162float(h1));
+            ph[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            pl[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(ph[0], ph[1]);
+        *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(pl[0], pl[1]);
+    }
+}
+
+// fuse2: also run the second Linear (pool.embedding.2, 256 outputs) inside the kernel; `out*` then receive the POOLED
+// vector [M, 256] (fp32 and / or bf16 split) instead of hidden1
 template <bool kPair>
 static int launch_sparse_pair_t(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float* out, void* out_hi,
-                                void* out_lo, cudaStream_t st) {
+                                void* out_lo, bool fuse2, cudaStream_t st) {
     constexpr int nC = kPair ? 2 : 1;
     static int sm_count[64] = {0};
     int dev = 0;
@@ -709,9 +908,16 @@ static int launch_sparse_pair_t(const tb2_lstm* m, const tb2_layout* l, Workspac
         if (e && atoi(e) > 0) units_max = atoi(e);
     }
     SpParams p;
-    int units = 0, rpu = 0, rc;
-    if ((rc = get_plan(l, d1, units_max, nC, &p.rounds, &units, &rpu, st))) return rc;
-    p.rounds_per_unit = rpu;
+    const tb2_layout::PairPlan* plan = nullptr;
+    int rc;
+    if ((rc = get_plan(l, d1, units_max, nC, &plan, st))) return rc;
+    const int units = plan->units;
+    p.rounds = (const SpRound*)plan->dev;
+    p.rounds_per_unit = plan->rounds_per_unit;
+    p.w2 = fuse2 ? (const unsigned char*)m->W2_sw : nullptr;
+    p.partials = plan->partials;
+    p.N2 = kSpN2;
+    p.max_slots = plan->max_slots;
     p.scene_off = l->scene_off;
     p.row_scene = l->row_scene;
     p.cell_row = ws->cell_row;
@@ -719,9 +925,9 @@ static int launch_sparse_pair_t(const tb2_lstm* m, const tb2_layout* l, Workspac
     p.benc = m->benc;
     p.base = m->base1;
     p.w = (const unsigned char*)m->Wt1_sw_hi;
-    p.out = out;
-    p.out_hi = (__nv_bfloat16*)out_hi;
-    p.out_lo = (__nv_bfloat16*)out_lo;
+    p.out = fuse2 ? nullptr : out;
+    p.out_hi = fuse2 ? nullptr : (__nv_bfloat16*)out_hi;
+    p.out_lo = fuse2 ? nullptr : (__nv_bfloat16*)out_lo;
     p.M = l->M;
     p.OUT = d1;
     p.cells = m->cells;
@@ -767,6 +973,13 @@ static int launch_sparse_pair_t(const tb2_lstm* m, const tb2_layout* l, Workspac
         TB2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, sparse_layer1_pair_kernel<kPair>, p));
     }
     TB2_LAUNCH_CHECK();
+    if (fuse2) {
+        KernelTimer kt("pooled_reduce", st);
+        const unsigned blocks = (unsigned)(((size_t)l->M * (kSpN2 / 4) + 255) / 256);
+        launch_pdl(pooled_reduce_kernel, dim3(blocks), dim3(256), 0, st, (const float*)plan->partials, (const int*)plan->tile_slots,
+                   plan->max_slots, plan->R, l->M, (const float*)m->bl[1], out, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo);
+        TB2_LAUNCH_CHECK();
+    }
     if (p.dbg && ++dbg_calls == 60) {
         std::vector<long long> h((size_t)n_cta * 8);
         cudaStreamSynchronize(st);
@@ -795,9 +1008,38 @@ static int launch_sparse_pair_t(const tb2_lstm* m, const tb2_layout* l, Workspac
 
 // mode: 1 = one CTA per unit (cta_group::1), 2 = CTA pair (cta_group::2)
 int launch_sparse_pair(const tb2_lstm* m, const tb2_layout* l, int mode, Workspace* ws, float* out, void* out_hi,
-                       void* out_lo, cudaStream_t st) {
-    if (mode == 2) return launch_sparse_pair_t<true>(m, l, ws, out, out_hi, out_lo, st);
-    return launch_sparse_pair_t<false>(m, l, ws, out, out_hi, out_lo, st);
+                       void* out_lo, bool fuse2, cudaStream_t st) {
+    if (fuse2 && !(m->W2_sw != nullptr && m->n_mlp == 2 && m->mlp_dims[2] == kSpN2)) {
+        set_error("fused second Linear needs a two_layer embedding with 256 outputs");
+        return TB2_ERR_INVALID;
+    }
+    if (mode == 2) return launch_sparse_pair_t<true>(m, l, ws, out, out_hi, out_lo, fuse2, st);
+    return launch_sparse_pair_t<false>(m, l, ws, out, out_hi, out_lo, fuse2, st);
+}
+
+bool sparse_pair_can_fuse(const tb2_lstm* m) { return m->W2_sw != nullptr && m->n_mlp == 2 && m->mlp_dims[2] == kSpN2; }
+
+// pool.embedding.2.weight [N2, K] -> bf16 [K / 16][N2 / 8][hi: 8 rows x 16 | lo: 8 rows x 16], 16-byte halves of a row
+// exchanged where ((n >> 2) & 1): the same bulk-copy image as the layer-1 slabs, one "slab" per k-step of layer 2
+__global__ void repack_layer2_sw_kernel(const float* __restrict__ W2, __nv_bfloat16* __restrict__ dst, int N2, int K) {
+    const size_t total = (size_t)N2 * K;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int n = (int)(idx / K), k = (int)(idx - (size_t)n * K);
+        const int kstep = k >> 4, c = k & 15;
+        const float v = W2[idx];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const int chunk = (c >> 3) ^ ((n >> 2) & 1);
+        const size_t atom = ((size_t)kstep * N2 + (size_t)(n & ~7)) * 32;          // bf16 elements: 8 rows x (hi 16 + lo 16)
+        const size_t e = atom + (size_t)(n & 7) * 16 + (size_t)(chunk * 8 + (c & 7));
+        dst[e] = h;
+        dst[e + 128] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+int launch_repack_layer2_sw(const float* W2, void* dst, int N2, int K, cudaStream_t st) {
+    repack_layer2_sw_kernel<<<512, 256, 0, st>>>(W2, (__nv_bfloat16*)dst, N2, K);
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
 }
 
 // weight repack: W1[o][c * cells + cell] -> bf16 [cell][o / 8][hi | lo][o % 8][16] with the two 16-byte halves

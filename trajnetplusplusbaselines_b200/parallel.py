@@ -57,11 +57,15 @@ def allreduce_gradients(parameters, group=None):
     local_any = any(p.grad is not None for p in params)
     have = None if local_any else flat[-len(params):].tolist()
     off = 0
+    dst, src = [], []
     for i, p in enumerate(params):
         n = p.numel()
         if p.grad is not None:
-            p.grad.copy_(flat[off:off + n].view_as(p))
+            dst.append(p.grad)
+            src.append(flat[off:off + n].view_as(p))
         elif have is not None and have[i] > 0:
             p.grad = flat[off:off + n].view_as(p).to(p.dtype).clone()
         off += n
+    if dst:
+        torch._foreach_copy_(dst, src)           # one fused launch instead of one copy kernel per parameter
     return flat.numel()
