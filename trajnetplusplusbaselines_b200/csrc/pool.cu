@@ -85,6 +85,12 @@ struct PrepParams {
     long long* dbg;           // optional [B, 8] clock64 stamps (TB2_PREP_DEBUG=1)
 };
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ float nan_to_num_f(float x) {
     if (isnan(x)) return 0.f;
     if (isinf(x)) return x > 0 ? 3.402823466e+38f : -3.402823466e+38f;
@@ -101,21 +107,43 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
     float2* vel = pos + n_s;                                            // [n_s] obs2 - obs1 (may be NaN)
     int* cellrow = reinterpret_cast<int*>(vel + n_s);                   // [kPrepWarps][nm1]
     float* Ws = reinterpret_cast<float*>(cellrow + kPrepWarps * (nm1 > 0 ? nm1 : 1));   // [H][C]   (social)
-    float* hs = Ws + (p.H + 4) * p.C;                                   // [n_s][H] (social); Ws rows padded by 4
+    float* hs = Ws + (p.H + 8) * p.C;                                   // [n_s][H] (social); Ws: see the two layouts below
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // social, 16 latent channels of a 128-wide state (the BASELINE configuration): lat on a (4 channels x 16 k) register
+    // tile per lane, weights [k][c] staged once (they do not depend on the previous kernel: requested before the wait)
+    const bool social = p.pool_type == TB2_POOL_SOCIAL;
+    const bool fast_lat = social && p.C == 16 && p.H == 128;
+    if (fast_lat) {
+        // Ws: 8 blocks of 16 k rows x 16 channels, block stride 272 floats (staggers the banks of the 8 k-slices)
+        for (int idx = tid; idx < 128 * 4; idx += kPrepThreads) {
+            const int k = idx >> 2, q4 = idx & 3;
+            cp_async16(Ws + (k >> 4) * 272 + (k & 15) * 16 + q4 * 4, p.WencT + k * 16 + q4 * 4);
+        }
+    } else if (social) {
+        // W_enc in [C][H] order (k contiguous) so the dot products below run on float4 pairs
+        for (int idx = tid; idx < p.H * p.C; idx += kPrepThreads) {
+            const int k = idx / p.C, c = idx - k * p.C;          // WencT is [H][C]: coalesced read
+            Ws[c * (p.H + 4) + k] = p.WencT[idx];                // row stride H + 4: 2-way instead of 16-way conflicts
+        }
+    }
     grid_dep_wait();          // obs / hidden state come from the previous kernels of the stream
     grid_dep_launch();
     long long* dbg = p.dbg ? p.dbg + (size_t)blockIdx.x * 8 : nullptr;
     const long long t_begin = clock64();
 
+    if (fast_lat) {           // raw rows (nan_to_num is applied where they are read), asynchronously
+        const float* hsrc = p.hidden + (size_t)row0 * 128;
+        for (int idx = tid; idx < n_s * 32; idx += kPrepThreads) cp_async16(hs + idx * 4, hsrc + idx * 4);
+    }
+    cp_async_commit();
     for (int j = tid; j < n_s; j += kPrepThreads) {
         float2 a = p.obs1[row0 + j], b = p.obs2[row0 + j];
         vel[j] = make_float2(b.x - a.x, b.y - a.y);
         if (isnan(b.x) || isnan(b.y)) b = make_float2(-500.f, -500.f);
         pos[j] = b;
     }
-    if (p.pool_type == TB2_POOL_SOCIAL) {
-        // stage nan_to_num(h) of the scene and W_enc^T in shared memory (coalesced float4 loads)
+    if (social && !fast_lat) {
+        // stage nan_to_num(h) of the scene in shared memory (coalesced float4 loads)
         const float4* hsrc = reinterpret_cast<const float4*>(p.hidden + (size_t)row0 * p.H);
         float4* hdst = reinterpret_cast<float4*>(hs);
         for (int idx = tid; idx < n_s * p.H / 4; idx += kPrepThreads) {
@@ -123,12 +151,8 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
             v.x = nan_to_num_f(v.x); v.y = nan_to_num_f(v.y); v.z = nan_to_num_f(v.z); v.w = nan_to_num_f(v.w);
             hdst[idx] = v;
         }
-        // W_enc in [C][H] order (k contiguous) so the dot products below run on float4 pairs
-        for (int idx = tid; idx < p.H * p.C; idx += kPrepThreads) {
-            const int k = idx / p.C, c = idx - k * p.C;          // WencT is [H][C]: coalesced read
-            Ws[c * (p.H + 4) + k] = p.WencT[idx];                // row stride H + 4: 2-way instead of 16-way conflicts
-        }
     }
+    cp_async_wait_all();
     __syncthreads();
     if (dbg && tid == 0) dbg[0] = clock64() - t_begin;
     if (p.emb_hi != nullptr) {
@@ -145,7 +169,40 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
         }
     }
     if (dbg && tid == 0) dbg[1] = clock64() - t_begin;
-    if (p.pool_type == TB2_POOL_SOCIAL) {
+    if (fast_lat) {
+        // lat[j][c] = sum_k nan_to_num(h[j][k]) * WencT[k][c] + benc[c]: one warp per pedestrian, lane = (4 channels,
+        // 16-wide k slice); the slice sums are added across the 8 slices by an xor tree (fixed order)
+        const int c4 = lane & 3, kq = lane >> 2;
+        float4 w[16];
+        const float4* wp = reinterpret_cast<const float4*>(Ws + kq * 272) + c4;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = wp[i * 4];
+        const float4 bc = *reinterpret_cast<const float4*>(p.benc + c4 * 4);
+        if (dbg && tid == 0) dbg[7] = clock64() - t_begin + (long long)(w[15].x == 123.f) + (long long)(bc.x == 123.f);
+        for (int j = warp; j < n_s; j += kPrepWarps) {
+            const float4* hp = reinterpret_cast<const float4*>(hs + j * 128 + kq * 16);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 hv = hp[q];
+                const float hk[4] = {nan_to_num_f(hv.x), nan_to_num_f(hv.y), nan_to_num_f(hv.z), nan_to_num_f(hv.w)};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc.x = fmaf(hk[i], w[4 * q + i].x, acc.x); acc.y = fmaf(hk[i], w[4 * q + i].y, acc.y);
+                    acc.z = fmaf(hk[i], w[4 * q + i].z, acc.z); acc.w = fmaf(hk[i], w[4 * q + i].w, acc.w);
+                }
+            }
+#pragma unroll
+            for (int off = 4; off < 32; off <<= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+                acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+            }
+            if (kq == 0)
+                *reinterpret_cast<float4*>(p.lat + (size_t)(row0 + j) * 16 + c4 * 4) =
+                    make_float4(acc.x + bc.x, acc.y + bc.y, acc.z + bc.z, acc.w + bc.w);
+            if (dbg && tid == 0 && j == 0) dbg[4] = clock64() - t_begin;
+        }
+    } else if (social) {
         // lat[j][c] = sum_k nan_to_num(h[j][k]) * WencT[k][c] + benc[c]
         const int total = n_s * p.C;
         for (int idx = tid; idx < total; idx += kPrepThreads) {
@@ -209,6 +266,7 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
             }
         }
         __syncwarp();
+        if (dbg && warp == 0 && lane == 0 && i == 0) dbg[5] = clock64() - t_begin;
         // pass 2: winners, compacted in ascending jj
         const bool masked = isnan(vi.x);      // obs2 - obs1 is NaN iff the track is absent at either frame
         int count = 0;
@@ -254,6 +312,7 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
         }
         if (lane == 0) p.win_count[row0 + i] = count;
         __syncwarp();
+        if (dbg && warp == 0 && lane == 0 && i == 0) dbg[6] = clock64() - t_begin;
     }
     if (dbg && lane == 0 && warp == 0) dbg[3] = clock64() - t_begin;
 }
@@ -297,15 +356,15 @@ int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hid
     {
         const char* e = getenv("TB2_PREP_DEBUG");
         if (e && e[0] == '1') {
-            if (!dbg_buf) cudaMalloc(&dbg_buf, (size_t)l->B * 8 * sizeof(long long));
-            p.dbg = dbg_buf;
+            if (!dbg_buf) cudaMalloc(&dbg_buf, (size_t)4096 * 8 * sizeof(long long));
+            if (l->B <= 4096 && l->B >= 64) p.dbg = dbg_buf;        // the BASELINE-size batches only
         }
     }
     p.side = m->cfg.cell_side;        // pool_size == 1
     p.width = (float)m->cfg.n;
     int nm1 = l->n_max > 1 ? l->n_max - 1 : 1;
     size_t smem = (size_t)l->n_max * 2 * sizeof(float2) + (size_t)kPrepWarps * nm1 * sizeof(int);
-    if (m->cfg.pool_type == TB2_POOL_SOCIAL) smem += ((size_t)(m->H + 4) * m->C + (size_t)l->n_max * m->H) * sizeof(float);
+    if (m->cfg.pool_type == TB2_POOL_SOCIAL) smem += ((size_t)(m->H + 8) * m->C + (size_t)l->n_max * m->H) * sizeof(float);
     smem = (smem + 15) & ~(size_t)15;
     static DynSmemConfig configured;
     TB2_REQUIRE(smem <= 227 * 1024, "scene too large for pool_prepare shared memory");
@@ -319,10 +378,11 @@ int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hid
         std::vector<long long> h((size_t)l->B * 8);
         cudaStreamSynchronize(st);
         cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        double a[4] = {0, 0, 0, 0};
-        for (int c = 0; c < l->B; ++c) for (int k = 0; k < 4; ++k) a[k] += (double)h[(size_t)c * 8 + k] / l->B;
-        fprintf(stderr, "[tb2 pool_prepare debug] per-CTA cycles since start: staged %.0f | emb %.0f | lat %.0f | "
-                        "winners (warp 0) %.0f\n", a[0], a[1], a[2], a[3]);
+        double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < l->B; ++c) for (int k = 0; k < 8; ++k) a[k] += (double)h[(size_t)c * 8 + k] / l->B;
+        fprintf(stderr, "[tb2 pool_prepare debug] per-CTA cycles since start (after the dependency wait): staged %.0f | emb %.0f | "
+                        "lat: weights in registers %.0f, first pedestrian %.0f, all %.0f | winners: row 0 binned %.0f, row 0 done %.0f, warp 0 done %.0f\n",
+                a[0], a[1], a[7], a[4], a[2], a[5], a[6], a[3]);
     }
     return TB2_OK;
 }
@@ -1109,10 +1169,12 @@ int launch_pool_mlp(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float
     int rc;
     const char* sp_env = getenv("TB2_SPARSE");       // debug knob: "mma" forces the warp-level MMA kernel,
     const bool allow_tc = !(sp_env && sp_env[0] == 'm');     // "bucket" the per-cell bucket kernel, "tc" round 1's
-    const bool allow_rows = !(sp_env && sp_env[0] == 'b');   // tcgen05 kernel, "ts1" / "ts2" the TS-form (one CTA / pair)
-    int pair_mode = 2;                                       // default: the round-2 CTA-pair kernel; "solo": the same kernel
-    if (sp_env && sp_env[0] == 's' && sp_env[1] == 'o') pair_mode = 1;       // with one CTA per unit; "tc" / "mma" / "bucket":
-    if (sp_env && (sp_env[0] == 't' || sp_env[0] == 'm' || sp_env[0] == 'b')) pair_mode = 0;     // the round-1 kernels
+    const bool allow_rows = !(sp_env && sp_env[0] == 'b');   // tcgen05 kernel
+    int pair_mode = 3;                                       // default: the round-2 CTA-pair kernel with the A operand in tensor
+    if (sp_env && sp_env[0] == 'p') pair_mode = 2;           // memory; "pair": A in shared memory; "solo": one CTA per unit;
+    if (sp_env && sp_env[0] == 's' && sp_env[1] == 'o') pair_mode = 1;       // "tc" / "mma" / "bucket": the round-1 kernels
+    if (sp_env && (sp_env[0] == 't' || sp_env[0] == 'm' || sp_env[0] == 'b')) pair_mode = 0;
+    if (sp_env && sp_env[0] == 't' && sp_env[1] == 's') pair_mode = 3;
     if (allow_rows && pool_rows_chunk(m, d1) > 0) {   // occupancy / directional: weights resident in smem
         rc = launch_pool_rows(m, l, ws, d1, nm1, p.out, p.out_hi, p.out_lo, st);
     } else

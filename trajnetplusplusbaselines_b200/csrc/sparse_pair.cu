@@ -51,7 +51,9 @@ namespace tb2 {
 
 constexpr int kSpThreads = 512;
 constexpr int kSpSA = 3;                 // ring of A stages (built on the fly, short turn-around)
-constexpr int kSpSBMax = 5;              // ring of weight stages (bulk copies from L2: ~1500 cycles from request to landing)
+constexpr int kSpSBMax = 8;              // ring of weight stages (bulk copies from L2: ~1500 cycles from request to landing):
+                                         // 3 x 4 cells (one tile) / 5 x 2 cells (two tiles); TS variant, whose A ring
+                                         // lives in tensor memory: 5 x 4 cells / 8 x 2 cells over the freed shared memory
 constexpr int kSpMaxBlocks = 9;          // 32-column blocks per round (288 accumulator columns)
 constexpr int kSpDCols = kSpMaxBlocks * 32;
 constexpr int kSpMaxCells = 256;
@@ -66,7 +68,9 @@ constexpr uint32_t kSpBRing = 3u * 4u * kSpBCell;
 // dynamic shared memory behind the 1024-byte alignment: [A ring | weight ring | latent table 0]; the second
 // latent table of a two-tile round sits in the unused tail of the weight ring (5 x 2 cells < 3 x 4 cells)
 constexpr size_t kSpDynBytes = (size_t)kSpSA * kSpAStage + kSpBRing + (size_t)kSpLatRows * 64;
-static_assert((size_t)kSpSBMax * 2 * kSpBCell + (size_t)kSpLatRows * 64 <= kSpBRing, "two-tile rounds: second latent table");
+static_assert((size_t)5 * 2 * kSpBCell + (size_t)kSpLatRows * 64 <= kSpBRing, "two-tile rounds: second latent table");
+static_assert((size_t)5 * 4 * kSpBCell <= kSpDynBytes - (size_t)kSpLatRows * 64, "TS: one-tile weight ring");
+static_assert((size_t)8 * 2 * kSpBCell <= kSpDynBytes - (size_t)2 * kSpLatRows * 64, "TS: two-tile weight ring");
 static_assert(1024 + kSpDynBytes + 64 <= 227 * 1024 - 1024, "shared memory budget");
 // fused layer-2 tail: hidden1 of the round as A tiles (one (hi | lo) tile pair per 16 columns) + a ring of W2 k-step tiles
 constexpr int kSpN2 = 256;
@@ -74,6 +78,12 @@ constexpr int kSpTailStages = 6;
 constexpr uint32_t kSpA2Bytes = (uint32_t)(kSpDCols / 16) * 2u * kSpATile;
 static_assert(kSpA2Bytes + 4u * (uint32_t)kSpN2 * 64u <= kSpDynBytes, "tail: one CTA per unit, 4 stages");
 static_assert(kSpA2Bytes + (uint32_t)kSpTailStages * (uint32_t)(kSpN2 / 2) * 64u <= kSpDynBytes, "tail: pair, 6 stages");
+
+// TS variant (A operand in tensor memory): accumulators in TMEM columns [0, 288), the A ring behind them: 3 stages x
+// 64 columns (one-tile item: 4 cells x (hi 8 | lo 8) columns; two-tile item: 2 cells x 2 tiles x 16 columns)
+constexpr uint32_t kSpTsACol0 = 320;
+constexpr uint32_t kSpTsAStageCols = 64;
+static_assert(kSpDCols <= (int)kSpTsACol0 && kSpTsACol0 + kSpSA * kSpTsAStageCols <= 512, "TMEM budget of the TS variant");
 
 __device__ __forceinline__ uint32_t sp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sp_mbar_init(uint32_t bar, uint32_t count) {
@@ -194,6 +204,31 @@ __device__ __forceinline__ void sp_umma(uint32_t tmem_d, uint64_t adesc, uint64_
             "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 
+// TS form: A = 128 lanes x 8 TMEM columns (16 bf16 of K per lane) of each CTA, B from shared memory
+template <bool kPair>
+__device__ __forceinline__ void sp_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if (kPair)
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+    else
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// one pedestrian row (lane) of one cell: hi (8 columns) | lo (8 columns)
+__device__ __forceinline__ void sp_tmem_st16(uint32_t taddr, const uint4& h0, const uint4& h1, const uint4& l0, const uint4& l1) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "r"(h0.x), "r"(h0.y), "r"(h0.z), "r"(h0.w), "r"(h1.x), "r"(h1.y), "r"(h1.z), "r"(h1.w),
+                   "r"(l0.x), "r"(l0.y), "r"(l0.z), "r"(l0.w), "r"(l1.x), "r"(l1.y), "r"(l1.z), "r"(l1.w) : "memory");
+}
+
 // byte offset of (row r, 16-byte chunk c) inside a SWIZZLE_32B K-major tile
 __device__ __forceinline__ uint32_t sp_sw32(uint32_t r, uint32_t c) { return r * 32u + ((c ^ ((r >> 2) & 1u)) << 4); }
 
@@ -220,14 +255,30 @@ __device__ __forceinline__ void sp_build_item(unsigned char* a_item, uint32_t a_
     }
 }
 
+// TS variant: the row's (hi | lo) vectors of the item's cells go to the lane's 16 TMEM columns per cell
+template <int KC>
+__device__ __forceinline__ void sp_build_item_ts(uint32_t a_item, uint32_t cell_cols, uint32_t bytes, int off_r, int nlat,
+                                                 const uint4* lh, const uint4* ll) {
+#pragma unroll
+    for (int kc = 0; kc < KC; ++kc) {
+        const uint32_t j = (bytes >> (8 * kc)) & 0xffu;
+        uint4 h0 = make_uint4(0u, 0u, 0u, 0u), h1 = h0, l0 = h0, l1 = h0;
+        if (j != 0xffu) {
+            const int li = j == 0xfeu ? nlat : (int)j + off_r;
+            h0 = lh[li * 2]; h1 = lh[li * 2 + 1];
+            l0 = ll[li * 2]; l1 = ll[li * 2 + 1];
+        }
+        sp_tmem_st16(a_item + (uint32_t)kc * cell_cols, h0, h1, l0, l1);
+    }
+}
+
 // Builder role of one warp for one round: thread = pedestrian row r; `cr` = the row's cell map (16 cells per
 // uint4) or null for rows past the end.  One-tile round: the two builder groups (warps 4..7 / 8..11) take the even
 // / odd items.  Two-tile round (kTwo): group bg builds the tiles of pedestrian tile bg inside EVERY item.
-template <int KC, bool kTwo>
-__device__ __forceinline__ void sp_builder(const uint4* cr, int groups, uint32_t SB, unsigned char* a_ring, int bg,
-                                           bool wait_weights, uint32_t r, int off_r, int nlat, const uint4* lh, const uint4* ll,
-                                           uint64_t* empty_a, uint64_t* full_b, const uint32_t (&full_remote)[kSpSA], int lane,
-                                           long long& wait_e, long long& wait_b) {
+template <int KC, bool kTwo, bool kTS>
+__device__ __forceinline__ void sp_builder(const uint4* cr, int groups, unsigned char* a_ring, uint32_t a_tmem, int bg,
+                                           uint32_t r, int off_r, int nlat, const uint4* lh, const uint4* ll,
+                                           uint64_t* empty_a, const uint32_t (&full_remote)[kSpSA], int lane, long long& wait_e) {
     const uint4 none = make_uint4(~0u, ~0u, ~0u, ~0u);
     constexpr int ipg = 16 / KC;                       // items per 16-cell load of the row's cell map
     constexpr int step = kTwo ? 1 : 2;
@@ -252,14 +303,16 @@ __device__ __forceinline__ void sp_builder(const uint4* cr, int groups, uint32_t
             const long long tw0 = clock64();
             sp_mbar_wait(sp_smem_u32(&empty_a[sa]), pa ^ 1u);
             wait_e += clock64() - tw0;
-            sp_build_item<KC>(a_ring + (size_t)sa * kSpAStage, a_stride, bytes, KC, r, off_r, nlat, lh, ll);
-            // generic-proxy writes of the tiles -> visible to the tensor core's async-proxy reads
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (wait_weights) {   // the weights of this item have landed in THIS CTA (chained into the arrive below)
-                const long long tw1 = clock64();
-                sp_mbar_wait(sp_smem_u32(&full_b[g % SB]), (g / SB) & 1u);
-                wait_b += clock64() - tw1;
+            if (kTS) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                sp_build_item_ts<KC>(a_tmem + sa * kSpTsAStageCols, kTwo ? 32u : 16u, bytes, off_r, nlat, lh, ll);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            } else {
+                sp_build_item<KC>(a_ring + (size_t)sa * kSpAStage, a_stride, bytes, KC, r, off_r, nlat, lh, ll);
+                // generic-proxy writes of the tiles -> visible to the tensor core's async-proxy reads
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
+            if (kTS) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) sp_mbar_arrive_cluster(full_remote[sa]);
         }
@@ -267,7 +320,7 @@ __device__ __forceinline__ void sp_builder(const uint4* cr, int groups, uint32_t
     }
 }
 
-template <bool kPair>
+template <bool kPair, bool kTS>
 __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpParams p) {
     constexpr int nC = kPair ? 2 : 1;
     extern __shared__ __align__(1024) unsigned char smem_sp[];
@@ -291,7 +344,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
 
     const uint32_t ring = (sp_smem_u32(smem_sp) + 1023u) & ~1023u;          // A ring
     unsigned char* ring_ptr = smem_sp + (ring - sp_smem_u32(smem_sp));
-    const uint32_t bring = ring + (uint32_t)kSpSA * kSpAStage;              // weight ring
+    const uint32_t bring = kTS ? ring : ring + (uint32_t)kSpSA * kSpAStage;   // weight ring (TS: no A ring in shared memory)
     uint4* latH[2];
     uint4* latL[2];
     latH[0] = reinterpret_cast<uint4*>(ring_ptr + kSpDynBytes - (size_t)kSpLatRows * 64);
@@ -316,9 +369,8 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
-    grid_dep_wait();          // cell map / latent vectors come from pool_prepare
-    grid_dep_launch();
-    const long long t_start = clock64();
+    long long t_start = 0;
+    unsigned long long ns_start = 0;
 
     // leader's full barrier as seen from this CTA (cluster address space)
     uint32_t full_remote[kSpSA];
@@ -340,7 +392,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
         const int nsub = rd.n1 > 0 ? 2 : 1;
         // pipeline shape of the round (the barriers are re-initialised for it)
         const int KC = nsub == 2 ? (kPair ? 2 : 1) : (kPair ? 4 : 2);     // grid cells per pipeline item
-        const uint32_t SB = nsub == 2 ? (uint32_t)kSpSBMax : 3u;             // weight stages
+        const uint32_t SB = nsub == 2 ? (kTS ? 8u : 5u) : (kTS ? 5u : 3u);   // weight stages
         const int n_items = p.cells / KC;                    // cells is a multiple of 16
         const uint32_t n_issuers = 2u;
         if (tid == 0) {
@@ -350,7 +402,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
                     asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(sp_smem_u32(&empty_a[s2])) : "memory");
                 }
                 // builders per item and CTA: one group of 4 warps (one tile) or both groups (two tiles)
-                sp_mbar_init(sp_smem_u32(&full_a[s2]), (nsub == 2 ? 8 : 4) * nC);
+                sp_mbar_init(sp_smem_u32(&full_a[s2]), ((nsub == 2 ? 8 : 4) + 1) * nC);        // + the weight relay
                 sp_mbar_init(sp_smem_u32(&empty_a[s2]), n_issuers);      // one tcgen05.commit per active MMA issuer
             }
             for (int s2 = 0; s2 < kSpSBMax; ++s2) {
@@ -384,6 +436,31 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
         const uint32_t nr[2] = {ncols[0] / nC, ncols[1] / nC};              // rows of each piece's slab held by this CTA
         const uint32_t b_cell = 64u * (nr[0] + nr[1]);                       // weight bytes per cell: piece 0 rows | piece 1 rows
         const uint32_t b_stage = (uint32_t)KC * b_cell;
+        // weights of item `it` of this round -> stage it % SB (the producer thread; the stage must be free)
+        auto load_item = [&](int it) {
+            const uint32_t sb = (uint32_t)it % SB;
+            const uint32_t bar = sp_smem_u32(&full_b[sb]);
+            const uint32_t st = bring + sb * b_stage;
+            sp_mbar_expect_tx(bar, b_stage);
+            for (int kc = 0; kc < KC; ++kc) {
+                const size_t cellsrc = (size_t)(it * KC + kc) * p.OUT;
+                sp_bulk_load(st + kc * b_cell, p.w + (cellsrc + col0[0] + rank * nr[0]) * 64, nr[0] * 64u, bar);
+                if (nsub == 2)
+                    sp_bulk_load(st + kc * b_cell + nr[0] * 64u, p.w + (cellsrc + col0[1] + rank * nr[1]) * 64, nr[1] * 64u, bar);
+            }
+        };
+        // The weights depend on nothing the previous kernel writes: the producer thread (which has just initialised
+        // the barriers) requests the first SB items before the round's setup -- in the first round before the wait
+        // for the previous kernel, so they land while pool_prepare is still running.
+        const int n_pre = n_items < (int)SB ? n_items : (int)SB;
+        if (tid == 0)
+            for (int it = 0; it < n_pre; ++it) load_item(it);
+        if (round_idx == 0) {
+            grid_dep_wait();          // cell map / latent vectors come from pool_prepare
+            grid_dep_launch();
+            t_start = clock64();
+            if (dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_start));
+        }
         // ---- round setup (all warps): split latent tables of the one / two tiles ---------------------
         int rbase[2], nrows[2], lbase[2], nlat[2];
 #pragma unroll
@@ -420,7 +497,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
             asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
         }
         const long long t_r1 = clock64();
-        t_setup_sum += t_r1 - t_r0;
+        t_setup_sum += t_r1 - (round_idx == 0 ? t_start : t_r0);
 
         // MMA groups of a one-tile round: a 9-block piece is issued as N = 160 + 128 over the same A tiles
         const bool split = ncols[0] > 256u;
@@ -428,19 +505,10 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
         if (warp == 0) {
             // ===== weight producer: one bulk copy per cell and piece, up to SB items ahead =====
             if (lane == 0) {
-                for (int it = 0; it < n_items; ++it) {
+                for (int it = n_pre; it < n_items; ++it) {
                     const uint32_t sb = (uint32_t)it % SB, pb = ((uint32_t)it / SB) & 1u;
                     sp_mbar_wait(sp_smem_u32(&empty_b[sb]), pb ^ 1u);
-                    const uint32_t bar = sp_smem_u32(&full_b[sb]);
-                    const uint32_t st = bring + sb * b_stage;
-                    sp_mbar_expect_tx(bar, b_stage);
-                    for (int kc = 0; kc < KC; ++kc) {
-                        const size_t cellsrc = (size_t)(it * KC + kc) * p.OUT;
-                        sp_bulk_load(st + kc * b_cell, p.w + (cellsrc + col0[0] + rank * nr[0]) * 64, nr[0] * 64u, bar);
-                        if (nsub == 2)
-                            sp_bulk_load(st + kc * b_cell + nr[0] * 64u, p.w + (cellsrc + col0[1] + rank * nr[1]) * 64,
-                                         nr[1] * 64u, bar);
-                    }
+                    load_item(it);
                 }
             }
             __syncwarp();
@@ -487,7 +555,22 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
                     sp_mbar_wait_cluster(sp_smem_u32(&full_a[sa]), pa);
                     wait_full += clock64() - t0;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (have) {
+                    if (have && kTS) {
+                        // A from tensor memory: stage sa, (two tiles: the issuer's own tile inside every cell)
+                        uint32_t at = tmem_base + kSpTsACol0 + sa * kSpTsAStageCols + (nsub == 2 ? (uint32_t)gq * 16u : 0u);
+                        const uint32_t at_cell = nsub == 2 ? 32u : 16u;
+                        uint64_t bd = b_base + (uint64_t)(sb * (b_stage >> 4)) + b_off16;
+                        sp_umma_ts<kPair>(d, at, bd, idesc, it > 0 ? 1u : 0u);                  // hi . hi
+                        sp_umma_ts<kPair>(d, at + 8u, bd, idesc, 1u);                           // lo . hi
+                        sp_umma_ts<kPair>(d, at, bd + (256u >> 4), idesc, 1u);                  // hi . lo
+#pragma unroll 3
+                        for (int kc = 1; kc < KC; ++kc) {
+                            at += at_cell; bd += bcell16;
+                            sp_umma_ts<kPair>(d, at, bd, idesc, 1u);
+                            sp_umma_ts<kPair>(d, at + 8u, bd, idesc, 1u);
+                            sp_umma_ts<kPair>(d, at, bd + (256u >> 4), idesc, 1u);
+                        }
+                    } else if (have) {
                         // the start-address field never carries into the next field (addresses < 256 KB)
                         uint64_t ad = a_base + (uint64_t)(sa * (kSpAStage >> 4)) + a_off16;
                         uint64_t bd = b_base + (uint64_t)(sb * (b_stage >> 4)) + b_off16;
@@ -508,6 +591,23 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
                 sp_commit<kPair>(sp_smem_u32(&acc_full_bar));
             }
             __syncwarp();
+        } else if (warp == 3) {
+            // ===== weight relay (one thread per CTA): "the weights of item `it` have landed in THIS CTA" joins the
+            // builders' arrivals on the leader's full barrier of the item's A stage, so that the MMA issuers wait on one
+            // barrier per item and the builders never wait for the weights (they are the critical warps of a two-tile
+            // round).  The A stage's previous phase must have completed before this phase's arrival. =====
+            if (lane == 0) {
+                for (int it = 0; it < n_items; ++it) {
+                    const uint32_t sa = (uint32_t)it % kSpSA, pa = ((uint32_t)it / kSpSA) & 1u;
+                    const uint32_t sb = (uint32_t)it % SB, pb = ((uint32_t)it / SB) & 1u;
+                    sp_mbar_wait(sp_smem_u32(&empty_a[sa]), pa ^ 1u);
+                    const long long tw1 = clock64();
+                    sp_mbar_wait(sp_smem_u32(&full_b[sb]), pb);
+                    wait_b += clock64() - tw1;
+                    sp_mbar_arrive_cluster(full_remote[sa]);
+                }
+            }
+            __syncwarp();
         } else if (warp >= 4 && warp < 12) {
             // ===== A builders: thread = pedestrian row; every row of every cell's (hi, lo) tile is written =====
             const int bg = (warp - 4) >> 2;
@@ -519,9 +619,11 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
             const int off_r = row_ok ? p.scene_off[p.row_scene[row]] - lbase[x] : 0;
             // A stage of a two-tile round: [cell][tile][hi | lo]
             unsigned char* a_ring = ring_ptr + (nsub == 2 ? (size_t)bg * 2u * kSpATile : 0u);
+            // TS: this warp's TMEM lane quarter, first column of the A ring (two tiles: [cell][tile][hi | lo])
+            const uint32_t a_tmem = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kSpTsACol0 + (nsub == 2 ? (uint32_t)bg * 16u : 0u);
 #define TB2_SP_BUILD(KCV, TWO)                                                                                          \
-    sp_builder<KCV, TWO>(cr, p.cells >> 4, SB, a_ring, bg, (warp & 3) == 0, r, off_r, nlat[x], latH[x], latL[x], empty_a,  \
-                         full_b, full_remote, lane, wait_e, wait_b)
+    sp_builder<KCV, TWO, kTS>(cr, p.cells >> 4, a_ring, a_tmem, bg, r, off_r, nlat[x], latH[x], latL[x], empty_a, full_remote,  \
+                              lane, wait_e)
             if (nsub == 2) { if (kPair) TB2_SP_BUILD(2, true); else TB2_SP_BUILD(1, true); }
             else { if (kPair) TB2_SP_BUILD(4, false); else TB2_SP_BUILD(2, false); }
 #undef TB2_SP_BUILD
@@ -731,11 +833,14 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
     }
     if (dbg) {
         if (tid == 0) {
-            dbg[0] = t_setup_sum; dbg[6] = clock64() - t_start;
+            unsigned long long ns_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_end));
+            dbg[0] = t_setup_sum | ((long long)(ns_end - ns_start) << 24); dbg[6] = clock64() - t_start;
             dbg[5] = (long long)rd.n0 | ((long long)rd.n1 << 12) | ((long long)(t_start - t_begin) << 24);
         }
         if (warp == 1 && lane == 0) dbg[2] = wait_full;
-        if (warp == 4 && lane == 0) { dbg[4] = wait_e; dbg[7] = wait_b; }
+        if (warp == 4 && lane == 0) dbg[4] = wait_e;
+        if (warp == 3 && lane == 0) dbg[7] = wait_b;
         if (warp == 12 && lane == 0) { dbg[1] = t_loop_sum; dbg[3] = t_epi_sum; }
     }
     if (warp == 1) {
@@ -892,7 +997,7 @@ __global__ void __launch_bounds__(256) pooled_reduce_kernel(const float* __restr
 
 // fuse2: also run the second Linear (pool.embedding.2, 256 outputs) inside the kernel; `out*` then receive the POOLED
 // vector [M, 256] (fp32 and / or bf16 split) instead of hidden1
-template <bool kPair>
+template <bool kPair, bool kTS>
 static int launch_sparse_pair_t(const tb2_lstm* m, const tb2_layout* l, Workspace* ws, float* out, void* out_hi,
                                 void* out_lo, bool fuse2, cudaStream_t st) {
     constexpr int nC = kPair ? 2 : 1;
@@ -946,9 +1051,9 @@ static int launch_sparse_pair_t(const tb2_lstm* m, const tb2_layout* l, Workspac
     const size_t smem = 1024 + kSpDynBytes + 64;
     static_assert(1024 + kSpDynBytes + 64 <= 227 * 1024 - 512, "shared memory budget");
     static DynSmemConfig configured;
-    TB2_CHECK_CUDA(configured.ensure(sparse_layer1_pair_kernel<kPair>, smem));
+    TB2_CHECK_CUDA(configured.ensure(sparse_layer1_pair_kernel<kPair, kTS>, smem));
     {
-        KernelTimer kt(kPair ? "sparse_layer1_pair" : "sparse_layer1_solo", st);
+        KernelTimer kt(kPair ? (kTS ? "sparse_layer1_pair_ts" : "sparse_layer1_pair") : "sparse_layer1_solo", st);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(n_cta);
         cfg.blockDim = dim3(kSpThreads);
@@ -970,7 +1075,7 @@ static int launch_sparse_pair_t(const tb2_lstm* m, const tb2_layout* l, Workspac
         }
         cfg.attrs = attr;
         cfg.numAttrs = na;
-        TB2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, sparse_layer1_pair_kernel<kPair>, p));
+        TB2_CHECK_CUDA(cudaLaunchKernelEx(&cfg, sparse_layer1_pair_kernel<kPair, kTS>, p));
     }
     TB2_LAUNCH_CHECK();
     if (fuse2) {
@@ -985,8 +1090,11 @@ static int launch_sparse_pair_t(const tb2_lstm* m, const tb2_layout* l, Workspac
         cudaStreamSynchronize(st);
         cudaMemcpy(h.data(), dbg_buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        double mx = 0, pdl = 0;
+        double mx = 0, pdl = 0, ghz = 0;
         for (int c = 0; c < n_cta; ++c) {
+            const long long ns = h[(size_t)c * 8] >> 24;
+            h[(size_t)c * 8] &= 0xffffff;
+            if (ns > 0) ghz += (double)h[(size_t)c * 8 + 6] / (double)ns / n_cta;
             for (int k = 0; k < 8; ++k) a[k] += (double)h[(size_t)c * 8 + k] / n_cta;
             if ((double)h[(size_t)c * 8 + 6] > mx) mx = (double)h[(size_t)c * 8 + 6];
             pdl += (double)(h[(size_t)c * 8 + 5] >> 24) / n_cta;
@@ -1000,21 +1108,23 @@ static int launch_sparse_pair_t(const tb2_lstm* m, const tb2_layout* l, Workspac
         }
         fprintf(stderr, "[tb2 sparse_pair x%d debug] per-CTA cycles: prologue + wait for the previous kernel %.0f | setup %.0f | cells loop until "
                         "accumulators ready %.0f | MMA thread waiting for A/B (leader CTAs, averaged over all) %.0f | epilogue %.0f | builder "
-                        "warp 4: waiting for a free stage %.0f, for the weights %.0f | total after the wait %.0f (max %.0f)\n",
-                nC, pdl, a[0], a[1], a[2], a[3], a[4], a[7], a[6], mx);
+                        "warp 4: waiting for a free stage %.0f, for the weights %.0f | total after the wait %.0f (max %.0f) | SM clock "
+                        "during the kernel (clock64 / globaltimer) %.3f GHz\n",
+                nC, pdl, a[0], a[1], a[2], a[3], a[4], a[7], a[6], mx, ghz);
     }
     return TB2_OK;
 }
 
-// mode: 1 = one CTA per unit (cta_group::1), 2 = CTA pair (cta_group::2)
+// mode: 1 = one CTA per unit (cta_group::1), 2 = CTA pair (cta_group::2), 3 = CTA pair with the A operand in tensor memory
 int launch_sparse_pair(const tb2_lstm* m, const tb2_layout* l, int mode, Workspace* ws, float* out, void* out_hi,
                        void* out_lo, bool fuse2, cudaStream_t st) {
     if (fuse2 && !(m->W2_sw != nullptr && m->n_mlp == 2 && m->mlp_dims[2] == kSpN2)) {
         set_error("fused second Linear needs a two_layer embedding with 256 outputs");
         return TB2_ERR_INVALID;
     }
-    if (mode == 2) return launch_sparse_pair_t<true>(m, l, ws, out, out_hi, out_lo, fuse2, st);
-    return launch_sparse_pair_t<false>(m, l, ws, out, out_hi, out_lo, fuse2, st);
+    if (mode == 3) return launch_sparse_pair_t<true, true>(m, l, ws, out, out_hi, out_lo, fuse2, st);
+    if (mode == 2) return launch_sparse_pair_t<true, false>(m, l, ws, out, out_hi, out_lo, fuse2, st);
+    return launch_sparse_pair_t<false, false>(m, l, ws, out, out_hi, out_lo, fuse2, st);
 }
 
 bool sparse_pair_can_fuse(const tb2_lstm* m) { return m->W2_sw != nullptr && m->n_mlp == 2 && m->mlp_dims[2] == kSpN2; }
