@@ -57,8 +57,11 @@ int launch_resolve_obs(const tb2_layout* l, const float* base, const float* pred
 //     cell"; padded slots (scene smaller than the batch maximum) are trailing out-of-range
 //     writers of cell 0 exactly like the reference's NaN padding (lstm.py:31-40).
 // ------------------------------------------------------------------------------------------
-constexpr int kPrepThreads = 256;
-constexpr int kPrepWarps = kPrepThreads / 32;
+// One warp per pedestrian of the scene (latent projection, then the row of winners), between 8 and 20 warps: two CTAs
+// of 640 threads per SM need <= 51 registers per thread.  (The kernel is instruction-issue bound: ncu round 2 showed
+// 1800 instructions per warp at 8 cycles each with 8 warps per scene.)
+constexpr int kPrepMaxThreads = 640;
+static int prep_threads(int n_max) { return 32 * std::min(std::max(n_max, 8), kPrepMaxThreads / 32); }
 constexpr int kMaxSceneForPrep = 256;   // per-warp cell row buffer
 
 struct PrepParams {
@@ -97,7 +100,8 @@ __device__ __forceinline__ float nan_to_num_f(float x) {
     return x;
 }
 
-__global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p) {
+__global__ void __launch_bounds__(kPrepMaxThreads, 2) pool_prepare_kernel(PrepParams p) {
+    const int kPrepThreads = (int)blockDim.x, kPrepWarps = kPrepThreads >> 5;
     extern __shared__ __align__(16) float smem_prep[];
     const int scene = blockIdx.x;
     const int row0 = p.scene_off[scene];
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
     float2* pos = reinterpret_cast<float2*>(smem_prep);                 // [n_s] obs2 with -500
     float2* vel = pos + n_s;                                            // [n_s] obs2 - obs1 (may be NaN)
     int* cellrow = reinterpret_cast<int*>(vel + n_s);                   // [kPrepWarps][nm1]
-    float* Ws = reinterpret_cast<float*>(cellrow + kPrepWarps * (nm1 > 0 ? nm1 : 1));   // [H][C]   (social)
+    float* Ws = reinterpret_cast<float*>(cellrow + ((kPrepWarps * (nm1 > 0 ? nm1 : 1) + 3) & ~3));   // 16-byte aligned (social)
     float* hs = Ws + (p.H + 8) * p.C;                                   // [n_s][H] (social); Ws: see the two layouts below
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // social, 16 latent channels of a 128-wide state (the BASELINE configuration): lat on a (4 channels x 16 k) register
@@ -157,8 +161,9 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
     if (dbg && tid == 0) dbg[0] = clock64() - t_begin;
     if (p.emb_hi != nullptr) {
         // emb = cat(relu(W_e . (4 v) + b_e), 0, 0) (modules.py:24-30) as bf16 (hi, lo) for the gate GEMM
+        const int e_shift = (p.E & (p.E - 1)) == 0 ? 31 - __clz(p.E) : -1;       // E = 64: no integer division per element
         for (int idx = tid; idx < n_s * p.E; idx += kPrepThreads) {
-            const int j = idx / p.E, k = idx - j * p.E;
+            const int j = e_shift >= 0 ? idx >> e_shift : idx / p.E, k = idx - j * p.E;
             const float2 v = vel[j];
             float e = 0.f;
             if (k < p.E - 2 && !isnan(v.x))
@@ -173,23 +178,26 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
         // lat[j][c] = sum_k nan_to_num(h[j][k]) * WencT[k][c] + benc[c]: one warp per pedestrian, lane = (4 channels,
         // 16-wide k slice); the slice sums are added across the 8 slices by an xor tree (fixed order)
         const int c4 = lane & 3, kq = lane >> 2;
-        float4 w[16];
         const float4* wp = reinterpret_cast<const float4*>(Ws + kq * 272) + c4;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = wp[i * 4];
         const float4 bc = *reinterpret_cast<const float4*>(p.benc + c4 * 4);
-        if (dbg && tid == 0) dbg[7] = clock64() - t_begin + (long long)(w[15].x == 123.f) + (long long)(bc.x == 123.f);
         for (int j = warp; j < n_s; j += kPrepWarps) {
             const float4* hp = reinterpret_cast<const float4*>(hs + j * 128 + kq * 16);
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float4 hv = hp[q];
-                const float hk[4] = {nan_to_num_f(hv.x), nan_to_num_f(hv.y), nan_to_num_f(hv.z), nan_to_num_f(hv.w)};
+                float4 hv = hp[q];
+                // nan_to_num only where a value is not finite (exponent all ones): one test per four values
+                const uint32_t m = max(max(__float_as_uint(hv.x) & 0x7fffffffu, __float_as_uint(hv.y) & 0x7fffffffu),
+                                       max(__float_as_uint(hv.z) & 0x7fffffffu, __float_as_uint(hv.w) & 0x7fffffffu));
+                if (m >= 0x7f800000u) {
+                    hv.x = nan_to_num_f(hv.x); hv.y = nan_to_num_f(hv.y); hv.z = nan_to_num_f(hv.z); hv.w = nan_to_num_f(hv.w);
+                }
+                const float hk[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    acc.x = fmaf(hk[i], w[4 * q + i].x, acc.x); acc.y = fmaf(hk[i], w[4 * q + i].y, acc.y);
-                    acc.z = fmaf(hk[i], w[4 * q + i].z, acc.z); acc.w = fmaf(hk[i], w[4 * q + i].w, acc.w);
+                    const float4 w = wp[(4 * q + i) * 4];
+                    acc.x = fmaf(hk[i], w.x, acc.x); acc.y = fmaf(hk[i], w.y, acc.y);
+                    acc.z = fmaf(hk[i], w.z, acc.z); acc.w = fmaf(hk[i], w.w, acc.w);
                 }
             }
 #pragma unroll
@@ -200,7 +208,6 @@ __global__ void __launch_bounds__(kPrepThreads) pool_prepare_kernel(PrepParams p
             if (kq == 0)
                 *reinterpret_cast<float4*>(p.lat + (size_t)(row0 + j) * 16 + c4 * 4) =
                     make_float4(acc.x + bc.x, acc.y + bc.y, acc.z + bc.z, acc.w + bc.w);
-            if (dbg && tid == 0 && j == 0) dbg[4] = clock64() - t_begin;
         }
     } else if (social) {
         // lat[j][c] = sum_k nan_to_num(h[j][k]) * WencT[k][c] + benc[c]
@@ -363,7 +370,8 @@ int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hid
     p.side = m->cfg.cell_side;        // pool_size == 1
     p.width = (float)m->cfg.n;
     int nm1 = l->n_max > 1 ? l->n_max - 1 : 1;
-    size_t smem = (size_t)l->n_max * 2 * sizeof(float2) + (size_t)kPrepWarps * nm1 * sizeof(int);
+    const int nthreads = prep_threads(l->n_max);
+    size_t smem = (size_t)l->n_max * 2 * sizeof(float2) + (size_t)(((nthreads / 32) * nm1 + 3) & ~3) * sizeof(int);
     if (m->cfg.pool_type == TB2_POOL_SOCIAL) smem += ((size_t)(m->H + 8) * m->C + (size_t)l->n_max * m->H) * sizeof(float);
     smem = (smem + 15) & ~(size_t)15;
     static DynSmemConfig configured;
@@ -371,7 +379,7 @@ int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hid
     TB2_CHECK_CUDA(configured.ensure(pool_prepare_kernel, smem, 48 * 1024));
     {
         KernelTimer kt("pool_prepare", st);
-        launch_pdl(pool_prepare_kernel, dim3(l->B), dim3(kPrepThreads), smem, st, p);
+        launch_pdl(pool_prepare_kernel, dim3(l->B), dim3(nthreads), smem, st, p);
     }
     TB2_LAUNCH_CHECK();
     if (p.dbg && ++dbg_calls == 60) {
@@ -381,8 +389,8 @@ int launch_pool_prepare(const tb2_lstm* m, const tb2_layout* l, const float* hid
         double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int c = 0; c < l->B; ++c) for (int k = 0; k < 8; ++k) a[k] += (double)h[(size_t)c * 8 + k] / l->B;
         fprintf(stderr, "[tb2 pool_prepare debug] per-CTA cycles since start (after the dependency wait): staged %.0f | emb %.0f | "
-                        "lat: weights in registers %.0f, first pedestrian %.0f, all %.0f | winners: row 0 binned %.0f, row 0 done %.0f, warp 0 done %.0f\n",
-                a[0], a[1], a[7], a[4], a[2], a[5], a[6], a[3]);
+                        "lat %.0f | winners: row 0 binned %.0f, row 0 done %.0f, warp 0 done %.0f\n",
+                a[0], a[1], a[2], a[5], a[6], a[3]);
     }
     return TB2_OK;
 }
