@@ -19,6 +19,9 @@
 // Social pooling couples the tracks of a scene through lat_j = W_enc h_j: every track receives
 // gradient, so social_backward (further down) runs the same phases on all M rows and adds the
 // backward of the grid MLP and of the hidden-state scatter to the chain.
+#include <cublas_v2.h>
+#include <dlfcn.h>
+#include <mutex>
 #include <cuda_bf16.h>
 #include <math_constants.h>
 
@@ -850,9 +853,112 @@ int resolve_step_inputs(const tb2_layout* l, const float* observed, int obs_leng
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+
+// ------------------------------------------------------------------------------------------
+// Large plain GEMMs of the all-row (social) backward: cuBLAS with FP32 emulation on the bf16 tensor cores
+// (CUBLAS_COMPUTE_32F_EMULATED_16BFX9: every fp32 operand is split into three bf16 values, nine products,
+// fp32-accurate) -- library code for plain library GEMMs; everything with a gather, a mask or a fused epilogue
+// stays in the kernels of this file.  TB2_CUBLAS=0 forces the FFMA kernels (A/B), =2 plain fp32 cuBLAS.
+// ------------------------------------------------------------------------------------------
+// cuBLAS is bound at run time (dlopen): inside a torch process the already loaded libcublas.so.12 is used, whatever
+// its minor version; entry points a build does not have (cublasSetEmulationStrategy) are simply skipped, and without
+// the library the FFMA kernels below do the work.
+struct CublasApi {
+    cublasStatus_t (*create)(cublasHandle_t*) = nullptr;
+    cublasStatus_t (*set_stream)(cublasHandle_t, cudaStream_t) = nullptr;
+    cublasStatus_t (*gemm_ex)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const void*, const void*,
+                              cudaDataType, int, const void*, cudaDataType, int, const void*, void*, cudaDataType, int,
+                              cublasComputeType_t, cublasGemmAlgo_t) = nullptr;
+    cublasStatus_t (*set_emulation)(cublasHandle_t, cublasEmulationStrategy_t) = nullptr;
+    bool ok = false;
+};
+static const CublasApi& cublas_api() {
+    static CublasApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* lib = dlopen("libcublas.so.12", RTLD_NOW | RTLD_GLOBAL);
+        if (!lib) lib = dlopen("libcublas.so", RTLD_NOW | RTLD_GLOBAL);
+        if (lib) {
+            api.create = reinterpret_cast<decltype(api.create)>(dlsym(lib, "cublasCreate_v2"));
+            api.set_stream = reinterpret_cast<decltype(api.set_stream)>(dlsym(lib, "cublasSetStream_v2"));
+            api.gemm_ex = reinterpret_cast<decltype(api.gemm_ex)>(dlsym(lib, "cublasGemmEx"));
+            api.set_emulation = reinterpret_cast<decltype(api.set_emulation)>(dlsym(lib, "cublasSetEmulationStrategy"));
+            api.ok = api.create && api.set_stream && api.gemm_ex;
+        }
+    }
+    return api;
+}
+
+static cublasHandle_t cublas_for_device(int* mode_out) {
+    static std::mutex mu;
+    static cublasHandle_t handles[64] = {nullptr};
+    static int mode = -1;            // 0 off, 1 emulated bf16x9, 2 fp32
+    std::lock_guard<std::mutex> lock(mu);
+    if (mode < 0) {
+        const char* e = getenv("TB2_CUBLAS");
+        mode = e ? atoi(e) : 1;
+        if (mode != 0 && !cublas_api().ok) mode = 0;
+    }
+    *mode_out = mode;
+    if (mode == 0) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    cublasHandle_t& h = handles[dev & 63];
+    if (!h) {
+        if (cublas_api().create(&h) != CUBLAS_STATUS_SUCCESS) { h = nullptr; return nullptr; }
+        if (mode == 1 && cublas_api().set_emulation) cublas_api().set_emulation(h, CUBLAS_EMULATION_STRATEGY_EAGER);
+    }
+    return h;
+}
+
+// column-major view: C(m x n) = alpha * op(A)(m x k) . op(B)(k x n) + beta * C; false = not taken (caller falls back)
+static bool cublas_gemm(cublasOperation_t ta, cublasOperation_t tb, int m, int n, int k, const float* A, int lda,
+                        const float* B, int ldb, float beta, float* C, int ldc, const char* name, cudaStream_t st) {
+    if ((double)m * n * k < 3.2e7) return false;            // small problems: the FFMA kernels (deterministic split order)
+    int mode = 0;
+    cublasHandle_t h = cublas_for_device(&mode);
+    if (!h) return false;
+    const CublasApi& api = cublas_api();
+    static bool emulation_ok = true;
+    const float alpha = 1.f;
+    KernelTimer kt(name, st);
+    if (api.set_stream(h, st) != CUBLAS_STATUS_SUCCESS) return false;
+    cublasStatus_t rc = CUBLAS_STATUS_NOT_SUPPORTED;
+    if (mode == 1 && emulation_ok) {
+        rc = api.gemm_ex(h, ta, tb, m, n, k, &alpha, A, CUDA_R_32F, lda, B, CUDA_R_32F, ldb, &beta, C, CUDA_R_32F, ldc,
+                         CUBLAS_COMPUTE_32F_EMULATED_16BFX9, CUBLAS_GEMM_DEFAULT);
+        if (rc != CUBLAS_STATUS_SUCCESS) emulation_ok = false;
+    }
+    if (rc != CUBLAS_STATUS_SUCCESS)
+        rc = api.gemm_ex(h, ta, tb, m, n, k, &alpha, A, CUDA_R_32F, lda, B, CUDA_R_32F, ldb, &beta, C, CUDA_R_32F, ldc,
+                         CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT);
+    return rc == CUBLAS_STATUS_SUCCESS;
+}
+
+__global__ void fill_bias_rows_kernel(float* __restrict__ C, int ldc, int M, int N, const float* __restrict__ bias) {
+    const size_t total = (size_t)M * (N / 4);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = idx / (N / 4);
+        const int c4 = (int)(idx - r * (N / 4)) * 4;
+        *reinterpret_cast<float4*>(C + r * ldc + c4) = *reinterpret_cast<const float4*>(bias + c4);
+    }
+}
+
 // C = A . B (+bias), B [K, N] row-major
 static int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
                    const float* bias, cudaStream_t st) {
+    {   // row-major C = A . B  <=>  column-major C^T (N x M) = B^T-view (N x K) . A^T-view (K x M)
+        const bool bias_ok = !bias || (N % 4 == 0 && ldc % 4 == 0 && aligned16(C) && aligned16(bias));
+        if (bias_ok && (double)M * N * K >= 3.2e7) {
+            if (bias) {
+                fill_bias_rows_kernel<<<1184, 256, 0, st>>>(C, ldc, M, N, bias);
+                TB2_LAUNCH_CHECK();
+            }
+            if (cublas_gemm(CUBLAS_OP_N, CUBLAS_OP_N, N, M, K, B, ldb, A, lda, bias ? 1.f : 0.f, C, ldc, "bwd_gemm_cublas", st))
+                return TB2_OK;
+        }
+    }
     const int vec = (lda % 4 == 0 && ldb % 4 == 0 && aligned16(A) && aligned16(B)) ? 1 : 0;
     const bool small = (size_t)((M + 63) / 64) * ((N + kGT - 1) / kGT) < 148;     // few tiles: halve them
     {
@@ -871,6 +977,8 @@ static int gemm_nn(const float* A, int lda, const float* B, int ldb, float* C, i
 // C = A . B^T, B [N, K] row-major
 static int gemm_nt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
                    cudaStream_t st) {
+    // row-major C = A . B^T, B [N, K]  <=>  column-major C^T (N x M) = (B-view (K x N))^T . A-view (K x M)
+    if (cublas_gemm(CUBLAS_OP_T, CUBLAS_OP_N, N, M, K, B, ldb, A, lda, 0.f, C, ldc, "bwd_gemm_cublas", st)) return TB2_OK;
     const int vec = (lda % 4 == 0 && ldb % 4 == 0 && aligned16(A) && aligned16(B)) ? 1 : 0;
     const bool small = (size_t)((M + 63) / 64) * ((N + kGT - 1) / kGT) < 148;
     {
@@ -891,6 +999,8 @@ static int gemm_nt(const float* A, int lda, const float* B, int ldb, float* C, i
 static int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int R, int N, int Kc,
                    float* scratch, size_t scratch_floats, cudaStream_t st) {
     if (R <= 0) return TB2_OK;
+    // row-major C (N x Kc) += A^T . B  <=>  column-major C^T (Kc x N) += B-view (Kc x R) . (A-view (N x R))^T
+    if (cublas_gemm(CUBLAS_OP_N, CUBLAS_OP_T, Kc, N, R, B, ldb, A, lda, 1.f, C, ldc, "bwd_gemm_tn_cublas", st)) return TB2_OK;
     const int vec = (lda % 4 == 0 && ldb % 4 == 0 && aligned16(A) && aligned16(B)) ? 1 : 0;
     const int tiles32 = ((N + 31) / 32) * ((Kc + kGT - 1) / kGT);
     int Z = (2 * 148 + tiles32 - 1) / tiles32;
