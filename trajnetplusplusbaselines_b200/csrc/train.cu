@@ -739,6 +739,120 @@ __global__ void __launch_bounds__(256) social_dgrid_kernel(const unsigned* __res
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// social_dgrid on the tensor cores (warp-level mma.sync, 3-pass bf16 split, fp32 accumulation): per grid cell the
+// pairs of the cell form a GEMM  dgrid[pairs, 16] = dz1[rows of the pairs, d1] . Wt1[cell]^T[d1, 16]  whose A rows are
+// gathered.  One CTA = one cell (its weight slab as bf16 hi | lo in shared memory, loaded once), 64 pairs per chunk:
+// warp = (16-pair tile, half of the d1 range); the A fragments come straight from global memory (a quad reads 32
+// contiguous bytes of a dz1 row per load) and are split into (hi, lo) in registers.  The FFMA version above needed
+// five shared-memory loads per 16 FMAs and ran at 8.6 TFLOP/s.
+// ------------------------------------------------------------------------------------------
+__global__ void split_bf16_flat_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = src[i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split2(const float2 v, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v.x - __low2float(h), v.y - __high2float(h));
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+constexpr int kDmPairs = 64, kDmYs = 8;
+static size_t dgrid_mma_smem(int d1) { return (size_t)2 * 16 * (d1 + 8) * sizeof(__nv_bfloat16) + 4 * 16 * 16 * sizeof(float) + kDmPairs * sizeof(int); }
+
+__global__ void __launch_bounds__(256) social_dgrid_mma_kernel(const unsigned* __restrict__ sorted, const int* __restrict__ start,
+                                                               const float* __restrict__ dz1, int d1,
+                                                               const __nv_bfloat16* __restrict__ w_hi,
+                                                               const __nv_bfloat16* __restrict__ w_lo, int nm1,
+                                                               float* __restrict__ dgrid) {
+    extern __shared__ __align__(16) unsigned char smem_dm[];
+    const int ldw = d1 + 8;                                       // bf16 elements per weight row (+8: conflict-free fragments)
+    __nv_bfloat16* Bh = reinterpret_cast<__nv_bfloat16*>(smem_dm);
+    __nv_bfloat16* Bl = Bh + 16 * ldw;
+    float* red = reinterpret_cast<float*>(Bl + 16 * ldw);         // [4 pair tiles][16 rows][16 channels]
+    int* slot_s = reinterpret_cast<int*>(red + 4 * 16 * 16);
+    const int cell = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int p_begin = start[cell] + blockIdx.y * kDmPairs, p_end = start[cell + 1];
+    if (p_begin >= p_end) return;
+    for (int idx = tid; idx < 16 * (d1 / 8); idx += 256) {
+        const int r = idx / (d1 / 8), c8 = (idx - r * (d1 / 8)) * 8;
+        *reinterpret_cast<uint4*>(Bh + r * ldw + c8) = *reinterpret_cast<const uint4*>(w_hi + ((size_t)cell * 16 + r) * d1 + c8);
+        *reinterpret_cast<uint4*>(Bl + r * ldw + c8) = *reinterpret_cast<const uint4*>(w_lo + ((size_t)cell * 16 + r) * d1 + c8);
+    }
+    const int pt = warp & 3, kh = warp >> 2, g = lane >> 2, t = lane & 3;
+    const int khalf = d1 / 2;
+    for (int p0 = p_begin; p0 < p_end; p0 += gridDim.y * kDmPairs) {
+        const int np = min(kDmPairs, p_end - p0);
+        __syncthreads();
+        if (tid < kDmPairs) slot_s[tid] = tid < np ? (int)(sorted[p0 + tid] & 0x7fffffffu) : -1;
+        __syncthreads();
+        const int s0 = slot_s[pt * 16 + g], s1 = slot_s[pt * 16 + g + 8];
+        const float* a0p = s0 < 0 ? nullptr : dz1 + (size_t)((s0 & 0x3fffffff) / nm1) * d1 + kh * khalf + 2 * t;
+        const float* a1p = s1 < 0 ? nullptr : dz1 + (size_t)((s1 & 0x3fffffff) / nm1) * d1 + kh * khalf + 2 * t;
+        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        const float2 z2 = make_float2(0.f, 0.f);
+        const uint32_t* bh0 = reinterpret_cast<const uint32_t*>(Bh + g * ldw + kh * khalf + 2 * t);
+        const uint32_t* bl0 = reinterpret_cast<const uint32_t*>(Bl + g * ldw + kh * khalf + 2 * t);
+        const int ldw2 = 8 * ldw / 2;                              // 32-bit words between channel g and g + 8
+#pragma unroll 4
+        for (int k0 = 0; k0 < khalf; k0 += 16) {
+            const float2 v00 = a0p ? *reinterpret_cast<const float2*>(a0p + k0) : z2;
+            const float2 v10 = a1p ? *reinterpret_cast<const float2*>(a1p + k0) : z2;
+            const float2 v01 = a0p ? *reinterpret_cast<const float2*>(a0p + k0 + 8) : z2;
+            const float2 v11 = a1p ? *reinterpret_cast<const float2*>(a1p + k0 + 8) : z2;
+            uint32_t ah[4], al[4];
+            split2(v00, ah[0], al[0]); split2(v10, ah[1], al[1]); split2(v01, ah[2], al[2]); split2(v11, ah[3], al[3]);
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const uint32_t h0 = bh0[nt * ldw2 + k0 / 2], h1 = bh0[nt * ldw2 + k0 / 2 + 4];
+                const uint32_t l0 = bl0[nt * ldw2 + k0 / 2], l1 = bl0[nt * ldw2 + k0 / 2 + 4];
+                mma_bf16_16816(acc[nt], ah, h0, h1);
+                mma_bf16_16816(acc[nt], al, h0, h1);
+                mma_bf16_16816(acc[nt], ah, l0, l1);
+            }
+        }
+        // the two halves of the d1 range: warps 4..7 hand their sums to warps 0..3
+        float* rp = red + pt * 256;
+        if (kh == 1) {
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                rp[g * 16 + nt * 8 + 2 * t] = acc[nt][0]; rp[g * 16 + nt * 8 + 2 * t + 1] = acc[nt][1];
+                rp[(g + 8) * 16 + nt * 8 + 2 * t] = acc[nt][2]; rp[(g + 8) * 16 + nt * 8 + 2 * t + 1] = acc[nt][3];
+            }
+        }
+        __syncthreads();
+        if (kh == 0) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int sl = half ? s1 : s0;
+                if (sl < 0) continue;
+                const bool dead = (sl & 0x40000000) != 0;          // its cell holds the constant: zero gradient
+                float* out = dgrid + (size_t)(sl & 0x3fffffff) * 16;
+                const int r = g + 8 * half;
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const float x = acc[nt][2 * half] + rp[r * 16 + nt * 8 + 2 * t];
+                    const float y = acc[nt][2 * half + 1] + rp[r * 16 + nt * 8 + 2 * t + 1];
+                    *reinterpret_cast<float2*>(out + nt * 8 + 2 * t) = dead ? make_float2(0.f, 0.f) : make_float2(x, y);
+                }
+            }
+        }
+    }
+}
+
 // per scene: dlat[j] = sum over the observers i (rows ascending) whose pair (i, j) is in range of
 // that pair's dgrid slot; then the social part of d h_prev[j] = W_enc^T dlat[j] is added to the
 // by-pass buffer that the next (earlier) step's cell kernel reads.
@@ -1089,6 +1203,7 @@ struct SocBuffers {
     unsigned* sorted;
     uint8_t* pflag;
     uint32_t* wine;
+    __nv_bfloat16 *Wt1_hi, *Wt1_lo;                       // bf16 split of the cell-major first-layer weights (dgrid on mma.sync)
 };
 
 static size_t carve_social(const tb2_lstm* m, const tb2_layout* l, size_t S, void* basep, SocBuffers* b) {
@@ -1134,13 +1249,22 @@ static size_t carve_social(const tb2_lstm* m, const tb2_layout* l, size_t S, voi
     o->counts = reinterpret_cast<int*>(take((size_t)l->B * cells));
     o->base = reinterpret_cast<int*>(take((size_t)l->B * cells));
     o->start = reinterpret_cast<int*>(take(cells + 1));
+    o->Wt1_hi = reinterpret_cast<__nv_bfloat16*>(take((cells * C * d1 + 1) / 2));
+    o->Wt1_lo = reinterpret_cast<__nv_bfloat16*>(take((cells * C * d1 + 1) / 2));
     return off * sizeof(float) + 256;
 }
 
 template <int C>
 static int social_pair_kernels(const tb2_lstm* m, const tb2_layout* l, const SocBuffers& b, const float* lat,
                                int nm1, int d1, cudaStream_t st) {
-    {
+    const char* nomma = getenv("TB2_DGRID_FFMA");               // A/B knob: the fp32 FFMA kernel
+    if (C == 16 && d1 % 32 == 0 && b.Wt1_hi != nullptr && dgrid_mma_smem(d1) <= 200 * 1024 && !(nomma && nomma[0] == '1')) {
+        static DynSmemConfig configured;
+        TB2_CHECK_CUDA(configured.ensure(social_dgrid_mma_kernel, dgrid_mma_smem(d1), 48 * 1024));
+        KernelTimer kt("social_dgrid_mma", st);
+        social_dgrid_mma_kernel<<<dim3(m->cells, kDmYs), 256, dgrid_mma_smem(d1), st>>>(
+            b.sorted, b.start, b.DH1, d1, b.Wt1_hi, b.Wt1_lo, nm1, b.DGRID);
+    } else {
         KernelTimer kt("social_dgrid", st);
         social_dgrid_kernel<C><<<dim3(m->cells, (l->M + kDgPairs - 1) / kDgPairs), 256, 0, st>>>(
             b.sorted, b.start, b.DH1, d1, m->Wt1, nm1, b.DGRID);
@@ -1176,6 +1300,8 @@ static int social_backward(const tb2_lstm* m, const tb2_layout* l, const tb2_lst
     TB2_CHECK_CUDA(cudaMemsetAsync(b.dWt1, 0, (size_t)cells * C * d1 * sizeof(float), st));
     TB2_CHECK_CUDA(cudaMemsetAsync(b.zero_h, 0, M * 128 * sizeof(float), st));      // state before step 0
     iota_kernel<<<(Mi + 255) / 256, 256, 0, st>>>(b.rows, Mi);
+    TB2_LAUNCH_CHECK();
+    split_bf16_flat_kernel<<<1184, 256, 0, st>>>(m->Wt1, b.Wt1_hi, b.Wt1_lo, (size_t)cells * C * d1);
     TB2_LAUNCH_CHECK();
     int rc;
     const bool tc2 = two && m->W_hi[1] != nullptr;
