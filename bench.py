@@ -37,6 +37,7 @@ DENSE_FLOP_PER_PED_STEP = {                       # SURVEY.md 8d, dense-equivale
     "sparse_layer1_mma": 2 * 4096 * 1024,
     "sparse_layer1_tc": 2 * 4096 * 1024,
     "sparse_layer1_pair": 2 * 4096 * 1024,
+    "sparse_layer1_pair_ts": 2 * 4096 * 1024,
     "sparse_layer1_solo": 2 * 4096 * 1024,
     "dense_layer": 2 * 1024 * 256,
     "dense_layer_tc": 2 * 1024 * 256,
@@ -432,7 +433,8 @@ def main():
         for tname in ("round2_traffic.json", "round1_traffic.json"):
             tpath = os.path.join(ROOT, "profiles", tname)
             if os.path.exists(tpath):      # dram bytes per launch from the committed ncu --set full capture
-                traffic = json.load(open(tpath))["bytes_per_launch"].get(dom)
+                per_launch = json.load(open(tpath))["bytes_per_launch"]
+                traffic = per_launch.get(dom, per_launch.get(dom[:-3]) if dom.endswith("_ts") else None)
                 if traffic is not None:
                     break
         if dom in DENSE_FLOP_PER_PED_STEP:

@@ -1195,6 +1195,43 @@ static size_t carve_bwd(const tb2_lstm* m, size_t R, size_t S, void* base, BwdBu
 
 namespace tb2 {
 
+
+// fp32 window [rows x cols] (leading dimension ld_src) -> bf16 (hi, lo) at column col_off of a [rows x ld_dst] matrix
+__global__ void split2d_kernel(const float* __restrict__ src, int ld_src, int rows, int cols, __nv_bfloat16* __restrict__ hi,
+                               __nv_bfloat16* __restrict__ lo, int ld_dst, int col_off) {
+    const size_t total = (size_t)rows * cols;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = idx / cols;
+        const int c = (int)(idx - r * cols);
+        const float v = src[r * ld_src + c];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[r * ld_dst + col_off + c] = h;
+        lo[r * ld_dst + col_off + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+// src [R x Cc] row-major -> bf16 (hi, lo) of its transpose [Cc x R] (weights: a few hundred KB, once per backward)
+__global__ void transpose_split_kernel(const float* __restrict__ src, int R, int Cc, __nv_bfloat16* __restrict__ hi,
+                                       __nv_bfloat16* __restrict__ lo) {
+    const size_t total = (size_t)R * Cc;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t c = idx / R;
+        const int r = (int)(idx - c * R);
+        const float v = src[(size_t)r * Cc + c];
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[idx] = h;
+        lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+static int split2d(const float* src, int ld_src, size_t rows, int cols, __nv_bfloat16* hi, __nv_bfloat16* lo, int ld_dst,
+                   int col_off, cudaStream_t st) {
+    KernelTimer kt("bwd_split", st);
+    const size_t total = rows * (size_t)cols;
+    const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+    split2d_kernel<<<blocks, 256, 0, st>>>(src, ld_src, (int)rows, cols, hi, lo, ld_dst, col_off);
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
+}
+
 struct SocBuffers {
     float *X, *GP, *DG, *HS, *DN, *VEL, *DXIN, *H1, *DH1, *LAT, *DLAT, *DGRID, *dWt1;
     float *pass[2], *dc, *zero_h, *scratch;
@@ -1204,6 +1241,15 @@ struct SocBuffers {
     uint8_t* pflag;
     uint32_t* wine;
     __nv_bfloat16 *Wt1_hi, *Wt1_lo;                       // bf16 split of the cell-major first-layer weights (dgrid on mma.sync)
+    // 3-pass tcgen05 versions of the row GEMMs (dense_layer_tc_kernel): bf16 (hi, lo) operands
+    __nv_bfloat16 *X_hi, *X_lo;                           // [S][M][K]
+    __nv_bfloat16 *DG_hi[2], *DG_lo[2];                   // [M][512], steps s and s + 1
+    __nv_bfloat16 *DZ2_hi, *DZ2_lo;                       // [M][P]
+    __nv_bfloat16 *Wcat_hi[2], *Wcat_lo[2];               // [512][K] = [W_ih | W_hh] per phase
+    __nv_bfloat16 *WhhT_hi[2], *WhhT_lo[2];               // [128][512]
+    __nv_bfloat16 *WihT_hi[2], *WihT_lo[2];               // [E + P][512]
+    __nv_bfloat16 *W2T_hi, *W2T_lo;                       // [d1][P]
+    float* zero_bias;                                     // [max(d1, 512)]
 };
 
 static size_t carve_social(const tb2_lstm* m, const tb2_layout* l, size_t S, void* basep, SocBuffers* b) {
@@ -1251,6 +1297,24 @@ static size_t carve_social(const tb2_lstm* m, const tb2_layout* l, size_t S, voi
     o->start = reinterpret_cast<int*>(take(cells + 1));
     o->Wt1_hi = reinterpret_cast<__nv_bfloat16*>(take((cells * C * d1 + 1) / 2));
     o->Wt1_lo = reinterpret_cast<__nv_bfloat16*>(take((cells * C * d1 + 1) / 2));
+    auto take_bf16 = [&](size_t n) { return reinterpret_cast<__nv_bfloat16*>(take((n + 1) / 2)); };
+    o->X_hi = take_bf16(S * M * K);
+    o->X_lo = take_bf16(S * M * K);
+    for (int i = 0; i < 2; ++i) {
+        o->DG_hi[i] = take_bf16(M * 512);
+        o->DG_lo[i] = take_bf16(M * 512);
+        o->Wcat_hi[i] = take_bf16(512 * K);
+        o->Wcat_lo[i] = take_bf16(512 * K);
+        o->WhhT_hi[i] = take_bf16(128 * 512);
+        o->WhhT_lo[i] = take_bf16(128 * 512);
+        o->WihT_hi[i] = take_bf16((E + P) * 512);
+        o->WihT_lo[i] = take_bf16((E + P) * 512);
+    }
+    o->DZ2_hi = take_bf16(M * P);
+    o->DZ2_lo = take_bf16(M * P);
+    o->W2T_hi = take_bf16(d1 * P);
+    o->W2T_lo = take_bf16(d1 * P);
+    o->zero_bias = take(d1 > 512 ? d1 : 512);
     return off * sizeof(float) + 256;
 }
 
@@ -1334,11 +1398,42 @@ static int social_backward(const tb2_lstm* m, const tb2_layout* l, const tb2_lst
         }
         TB2_LAUNCH_CHECK();
     }
+    // The row GEMMs (rows = all tracks) run on the 3-pass tcgen05 kernel of the forward (dense_layer_tc_kernel:
+    // Y = A . W^T + bias, bf16 (hi, lo) operands, fp32 accumulation) when the shapes allow it: A and the (transposed)
+    // weights are split once, the outputs stay fp32.  TB2_BWD_TC=0: cuBLAS / FFMA GEMMs (A/B).
+    const char* notc = getenv("TB2_BWD_TC");
+    const bool tcg = !(notc && notc[0] == '0') && K == EP + 128 && dense_tc_supported(K, 512) && dense_tc_supported(512, 128) &&
+                     dense_tc_supported(512, EP) && (!two || dense_tc_supported(P, d1));
+    if (tcg) {
+        TB2_CHECK_CUDA(cudaMemsetAsync(b.zero_bias, 0, (size_t)(d1 > 512 ? d1 : 512) * sizeof(float), st));
+        for (int phase = 0; phase < 2; ++phase) {
+            const float* Wih_p = phase == TB2_PHASE_ENCODER ? w->encoder_weight_ih : w->decoder_weight_ih;
+            const float* Whh_p = phase == TB2_PHASE_ENCODER ? w->encoder_weight_hh : w->decoder_weight_hh;
+            if ((rc = split2d(Wih_p, EP, 512, EP, b.Wcat_hi[phase], b.Wcat_lo[phase], K, 0, st))) return rc;
+            if ((rc = split2d(Whh_p, 128, 512, 128, b.Wcat_hi[phase], b.Wcat_lo[phase], K, EP, st))) return rc;
+            transpose_split_kernel<<<256, 256, 0, st>>>(Whh_p, 512, 128, b.WhhT_hi[phase], b.WhhT_lo[phase]);
+            TB2_LAUNCH_CHECK();
+            transpose_split_kernel<<<512, 256, 0, st>>>(Wih_p, 512, EP, b.WihT_hi[phase], b.WihT_lo[phase]);
+            TB2_LAUNCH_CHECK();
+        }
+        if (two) {
+            transpose_split_kernel<<<1024, 256, 0, st>>>(w->pool_embedding_weight[1], P, d1, b.W2T_hi, b.W2T_lo);
+            TB2_LAUNCH_CHECK();
+        }
+        if ((rc = split2d(b.X, K, (size_t)S * M, K, b.X_hi, b.X_lo, K, 0, st))) return rc;
+    }
     // (B) gate pre-activations of all steps
     for (int phase = 0; phase < 2; ++phase) {
         const int s0 = phase == TB2_PHASE_ENCODER ? 0 : S_enc;
         const int ns = phase == TB2_PHASE_ENCODER ? S_enc : S - S_enc;
         if (ns <= 0) continue;
+        if (tcg) {
+            if ((rc = launch_dense_tc(b.X_hi + (size_t)s0 * M * K, b.X_lo + (size_t)s0 * M * K, b.Wcat_hi[phase],
+                                      b.Wcat_lo[phase], m->bg[phase], b.GP + (size_t)s0 * M * 512, nullptr, nullptr, ns * Mi,
+                                      K, 512, 0, st)))
+                return rc;
+            continue;
+        }
         if ((rc = gemm_nn(b.X + (size_t)s0 * M * K, K, m->WgT[phase], 512, b.GP + (size_t)s0 * M * 512, 512,
                           ns * Mi, 512, K, m->bg[phase], st)))
             return rc;
@@ -1365,8 +1460,12 @@ static int social_backward(const tb2_lstm* m, const tb2_layout* l, const tb2_lst
         float* dh_rec = nullptr;
         if (!last) {
             dh_rec = b.DH1;
-            if ((rc = gemm_nn(b.DG + (size_t)(s + 1) * M * 512, 512, Whh_next, 128, dh_rec, 128, Mi, 128, 512, nullptr,
-                              st)))
+            if (tcg) {      // dgates(s + 1) was split at the end of the previous iteration
+                if ((rc = launch_dense_tc(b.DG_hi[(s + 1) & 1], b.DG_lo[(s + 1) & 1], b.WhhT_hi[next_phase], b.WhhT_lo[next_phase],
+                                          b.zero_bias, dh_rec, nullptr, nullptr, Mi, 512, 128, 0, st)))
+                    return rc;
+            } else if ((rc = gemm_nn(b.DG + (size_t)(s + 1) * M * 512, 512, Whh_next, 128, dh_rec, 128, Mi, 128, 512, nullptr,
+                                     st)))
                 return rc;
         }
         {
@@ -1378,14 +1477,24 @@ static int social_backward(const tb2_lstm* m, const tb2_layout* l, const tb2_lst
                 b.DN + (size_t)s * M * 8, Mi);
         }
         TB2_LAUNCH_CHECK();
-        if ((rc = gemm_nn(DGs, 512, Wih, EP, DXs, EP, Mi, EP, 512, nullptr, st))) return rc;
+        if (tcg) {
+            if ((rc = split2d(DGs, 512, M, 512, b.DG_hi[s & 1], b.DG_lo[s & 1], 512, 0, st))) return rc;
+            if ((rc = launch_dense_tc(b.DG_hi[s & 1], b.DG_lo[s & 1], b.WihT_hi[phase], b.WihT_lo[phase], b.zero_bias, DXs,
+                                      nullptr, nullptr, Mi, 512, EP, 0, st)))
+                return rc;
+        } else if ((rc = gemm_nn(DGs, 512, Wih, EP, DXs, EP, Mi, EP, 512, nullptr, st))) return rc;
         const unsigned eb = (unsigned)((M * d1 + 255) / 256);
         if (two) {
             const float* H1s = b.H1 + (size_t)s * M * d1;
             relu_mask_kernel<<<(unsigned)((M * P + 255) / 256), 256, 0, st>>>(Xs, K, DXs, EP, Mi, E, P);   // dz2
             TB2_LAUNCH_CHECK();
             // d hidden1 = dz2 . W2 (torch layout [P, d1] is the [K = P, N = d1] operand), then the ReLU mask
-            if ((rc = gemm_nn(DXs + E, EP, w->pool_embedding_weight[1], d1, b.DH1, d1, Mi, d1, P, nullptr, st))) return rc;
+            if (tcg) {
+                if ((rc = split2d(DXs + E, EP, M, P, b.DZ2_hi, b.DZ2_lo, P, 0, st))) return rc;
+                if ((rc = launch_dense_tc(b.DZ2_hi, b.DZ2_lo, b.W2T_hi, b.W2T_lo, b.zero_bias, b.DH1, nullptr, nullptr, Mi, P, d1,
+                                          0, st)))
+                    return rc;
+            } else if ((rc = gemm_nn(DXs + E, EP, w->pool_embedding_weight[1], d1, b.DH1, d1, Mi, d1, P, nullptr, st))) return rc;
             masked_copy_kernel<<<eb, 256, 0, st>>>(H1s, d1, b.DH1, d1, b.DH1, d1, Mi, d1);
             TB2_LAUNCH_CHECK();
             if ((rc = gemm_tn(DXs + E, EP, H1s, d1, g->pool_embedding_weight1, d1, Mi, P, d1, b.scratch,
