@@ -36,6 +36,10 @@ extern "C" {
 #define TB2_POOL_DIRECTIONAL 2    /* GridBasedPooling(type_='directional') gridbased_pooling.py:118-143 */
 #define TB2_POOL_SOCIAL 3         /* GridBasedPooling(type_='social')      gridbased_pooling.py:145-170 */
 #define TB2_POOL_HIDDEN_MLP 4     /* HiddenStateMLPPooling (--type hiddenstatemlp) non_gridbased_pooling.py:150-239 */
+#define TB2_POOL_NN_MLP 5         /* NearestNeighborMLP (--type nn) non_gridbased_pooling.py:64-147: `n` = neighbours kept,
+                                   * mlp_dim_spatial = width of one neighbour's embedding (out_dim / n), mlp_dim_vel != 0 <=>
+                                   * no_vel == False (inputs [rel pos | rel vel]); weights pool_spatial_weight
+                                   * [out_dim / n, 2 or 4] / pool_spatial_bias = pool.embedding.0.{weight, bias} */
 
 #define TB2_PHASE_ENCODER 0
 #define TB2_PHASE_DECODER 1

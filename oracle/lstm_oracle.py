@@ -63,6 +63,17 @@ class MlpPoolConfig:
         self.out_dim = hidden_dim if out_dim is None else out_dim
 
 
+class NnPoolConfig:
+    """Constructor arguments of NearestNeighborMLP (non_gridbased_pooling.py:78-91)."""
+
+    def __init__(self, n=4, out_dim=32, no_vel=False):
+        self.type_ = "nn"
+        self.n = n
+        self.out_dim = out_dim
+        self.no_vel = no_vel
+        self.input_dim = 2 if no_vel else 4
+
+
 def _sigmoid(x):
     x = np.asarray(x, dtype=F32)
     return (F32(1.0) / (F32(1.0) + np.exp(-x, dtype=F32))).astype(F32)
@@ -217,10 +228,39 @@ def hidden_mlp_pool_forward(cfg, weights, hidden, obs1, obs2, prefix="pool."):
                    weights[prefix + "out_projection.bias"])
 
 
+def nn_mlp_pool_forward(cfg, weights, obs1, obs2, prefix="pool."):
+    """NearestNeighborMLP.forward (non_gridbased_pooling.py:96-147) -> [B*N, out_dim]: features of the n nearest other
+    tracks in ascending distance (NaN distances count as 1000, :131-132; NaN features become 0, :141; fewer than n other
+    tracks: zero rows, :134-136), shared Linear + ReLU per neighbour, concatenated."""
+    obs1 = np.asarray(obs1, dtype=F32)
+    obs2 = np.asarray(obs2, dtype=F32)
+    B, N, _ = obs2.shape
+    w, b = weights[prefix + "embedding.0.weight"], weights[prefix + "embedding.0.bias"]
+    vel = obs2 - obs1
+    out = np.zeros((B, N, cfg.n, w.shape[0]), dtype=F32)
+    for bi in range(B):
+        for i in range(N):
+            others = [j for j in range(N) if j != i]
+            rel = np.stack([obs2[bi, j] - obs2[bi, i] for j in others]) if others else np.zeros((0, 2), F32)
+            relv = np.stack([vel[bi, j] - vel[bi, i] for j in others]) if others else np.zeros((0, 2), F32)
+            with np.errstate(invalid="ignore"):
+                dist = np.sqrt((rel[:, 0] * rel[:, 0] + rel[:, 1] * rel[:, 1]).astype(F32)).astype(F32)
+            dist = np.where(np.isnan(dist), F32(1000.0), dist)
+            order = np.argsort(dist, kind="stable")[:cfg.n]                  # torch.topk(-dist): ascending distance
+            feats = np.zeros((cfg.n, cfg.input_dim), dtype=F32)
+            for k, o in enumerate(order):
+                f = rel[o] if cfg.no_vel else np.concatenate([rel[o], relv[o]])
+                feats[k] = np.nan_to_num(f.astype(F32))
+            out[bi, i] = np.maximum(_linear(feats, w, b), F32(0.0))
+    return out.reshape(B * N, -1)
+
+
 def pool_forward(cfg, weights, hidden, obs1, obs2, prefix="pool."):
     """GridBasedPooling.forward (gridbased_pooling.py:94-110) -> [B*N, out_dim]."""
     if getattr(cfg, "type_", None) == "hiddenstatemlp":
         return hidden_mlp_pool_forward(cfg, weights, hidden, obs1, obs2, prefix)
+    if getattr(cfg, "type_", None) == "nn":
+        return nn_mlp_pool_forward(cfg, weights, obs1, obs2, prefix)
     obs1 = np.asarray(obs1, dtype=F32)
     obs2 = np.asarray(obs2, dtype=F32)
     B, N, _ = obs2.shape
@@ -464,9 +504,18 @@ NONGRID_SPECS = {
 }
 
 
+# NearestNeighborMLP(n=args.neigh (4), out_dim=args.pool_dim, no_vel=args.no_vel) (lstm/trainer.py:476-477)
+NN_SPECS = {
+    "nn": dict(n=4, out_dim=256, no_vel=False),
+    "nn_small": dict(n=3, out_dim=24, no_vel=True),
+}
+
+
 def pool_config(kind):
     if kind in NONGRID_SPECS:
         return MlpPoolConfig(**NONGRID_SPECS[kind])
+    if kind in NN_SPECS:
+        return NnPoolConfig(**NN_SPECS[kind])
     spec = MODEL_SPECS[kind]
     return None if spec is None else PoolConfig(**spec)
 
@@ -485,7 +534,10 @@ def random_weights(kind, seed=0, scale=1.0, embedding_dim=64, hidden_dim=128):
 
     E, H = embedding_dim, hidden_dim
     pool_dim = 0
-    if cfg is not None and cfg.type_ == "hiddenstatemlp":
+    if cfg is not None and cfg.type_ == "nn":
+        lin("pool.embedding.0.weight", "pool.embedding.0.bias", cfg.out_dim // cfg.n, cfg.input_dim)
+        pool_dim = cfg.out_dim
+    elif cfg is not None and cfg.type_ == "hiddenstatemlp":
         lin("pool.spatial_embedding.0.weight", "pool.spatial_embedding.0.bias", cfg.mlp_dim_spatial, 2)
         if cfg.mlp_dim_vel:
             lin("pool.vel_embedding.0.weight", "pool.vel_embedding.0.bias", cfg.mlp_dim_vel, 2)

@@ -1,5 +1,5 @@
-"""Non-grid interaction module HiddenStateMLPPooling (reference
-lstm/non_gridbased_pooling.py:150-239) against vectors the unmodified reference produced
+"""Non-grid interaction modules HiddenStateMLPPooling and NearestNeighborMLP (reference
+lstm/non_gridbased_pooling.py:150-239 and :64-147) against vectors the unmodified reference produced
 (oracle/make_nongrid_golden.py): the numpy oracle on CPU, the CUDA kernel behind the plug and inside
 LSTM.forward on the GPU."""
 import os
@@ -9,12 +9,17 @@ import pytest
 import torch
 
 from oracle import lstm_oracle as O
-from oracle.make_nongrid_golden import KINDS, plug_inputs, scene_inputs
+from oracle.make_nongrid_golden import KINDS, NN_KINDS, plug_inputs, scene_inputs
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "nongrid_golden.npz"))
 
 
-@pytest.mark.parametrize("kind", KINDS)
+def _pool(kind):
+    from trajnetplusplusbaselines_b200.lstm import HiddenStateMLPPooling, NearestNeighborMLP
+    return NearestNeighborMLP(**O.NN_SPECS[kind]) if kind in O.NN_SPECS else HiddenStateMLPPooling(**O.NONGRID_SPECS[kind])
+
+
+@pytest.mark.parametrize("kind", KINDS + NN_KINDS)
 def test_oracle_matches_reference_vectors(kind):
     W = O.random_weights(kind, seed=13)
     cfg = O.pool_config(kind)
@@ -30,9 +35,9 @@ def test_oracle_matches_reference_vectors(kind):
 
 
 def test_state_dict_keys_match_reference_layout():
-    from trajnetplusplusbaselines_b200.lstm import LSTM, HiddenStateMLPPooling
-    for kind in KINDS:
-        model = LSTM(pool=HiddenStateMLPPooling(**O.NONGRID_SPECS[kind]))
+    from trajnetplusplusbaselines_b200.lstm import LSTM
+    for kind in KINDS + NN_KINDS:
+        model = LSTM(pool=_pool(kind))
         W = O.random_weights(kind, seed=13)           # keys / shapes checked against the reference by the generator
         sd = model.state_dict()
         assert set(sd.keys()) == set(W.keys())
@@ -42,20 +47,20 @@ def test_state_dict_keys_match_reference_layout():
 
 def test_unbuilt_modules_raise():
     from trajnetplusplusbaselines_b200.lstm import non_gridbased_pooling as ngp
-    for name in ("NearestNeighborMLP", "AttentionMLPPooling", "NearestNeighborLSTM", "TrajectronPooling"):
+    for name in ("AttentionMLPPooling", "NearestNeighborLSTM", "TrajectronPooling"):
         with pytest.raises(NotImplementedError):
             getattr(ngp, name)()
 
 
 def _model(kind):
-    from trajnetplusplusbaselines_b200.lstm import LSTM, HiddenStateMLPPooling
-    model = LSTM(pool=HiddenStateMLPPooling(**O.NONGRID_SPECS[kind]))
+    from trajnetplusplusbaselines_b200.lstm import LSTM
+    model = LSTM(pool=_pool(kind))
     model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in O.random_weights(kind, seed=13).items()}, strict=True)
     return model.cuda().eval()
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("kind", KINDS + NN_KINDS)
 def test_cuda_plug_matches_reference_vectors(kind):
     from trajnetplusplusbaselines_b200 import _lib
     model = _model(kind)
@@ -69,7 +74,7 @@ def test_cuda_plug_matches_reference_vectors(kind):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("kind", KINDS + NN_KINDS)
 def test_cuda_forward_matches_reference_vectors(kind):
     model = _model(kind)
     xy, bs = scene_inputs()
@@ -86,9 +91,9 @@ def test_cuda_forward_matches_reference_vectors(kind):
 
 
 @pytest.mark.gpu
-def test_cuda_baseline_shape_vs_oracle_and_training_raises():
+@pytest.mark.parametrize("kind", ["hiddenstatemlp", "nn"])
+def test_cuda_baseline_shape_vs_oracle_and_training_raises(kind):
     """256-d pooling at N = 20, T = 9 + 12 on 48 scenes vs the oracle; training is inference-only."""
-    kind = "hiddenstatemlp"
     model = _model(kind)
     xy, bs = O.synthetic_scenes(48, 20, seed=3, nan_tracks=True)
     M = xy.shape[1]

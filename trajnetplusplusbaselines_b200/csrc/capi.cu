@@ -170,7 +170,7 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
     *out = nullptr;
     TB2_REQUIRE(cfg->hidden_dim == 128, "hidden_dim must be 128 (kernel specialisation)");
     TB2_REQUIRE(cfg->embedding_dim >= 4 && cfg->embedding_dim <= 1024, "embedding_dim out of range");
-    TB2_REQUIRE(cfg->pool_type >= TB2_POOL_NONE && cfg->pool_type <= TB2_POOL_HIDDEN_MLP, "bad pool_type");
+    TB2_REQUIRE(cfg->pool_type >= TB2_POOL_NONE && cfg->pool_type <= TB2_POOL_NN_MLP, "bad pool_type");
     tb2_lstm* m = new (std::nothrow) tb2_lstm();
     TB2_REQUIRE(m, "out of host memory");
     m->cfg = *cfg;
@@ -185,6 +185,15 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
     for (int i = 0; i < kMaxMlpLayers; ++i) { m->WT[i] = m->bl[i] = nullptr; m->W_hi[i] = m->W_lo[i] = nullptr; }
     m->mp_Ws = m->mp_bs = m->mp_Wv = m->mp_bv = m->mp_WhT = m->mp_bh = m->mp_WoT = m->mp_bo = nullptr;
     auto fail = [&](int rc) { tb2_lstm_destroy(m); return rc; };
+    if (cfg->pool_type == TB2_POOL_NN_MLP) {
+        if (!(cfg->n >= 1 && cfg->n <= 32 && cfg->mlp_dim_spatial >= 1 && cfg->out_dim == cfg->n * cfg->mlp_dim_spatial)) {
+            set_error("invalid argument: nearest-neighbour pooling needs 1 <= n <= 32 and out_dim == n * mlp_dim_spatial");
+            return fail(TB2_ERR_INVALID);
+        }
+        m->pool_out = cfg->out_dim;
+        if (cfg->pool_to_input) m->P = m->pool_out;
+        else if (m->pool_out != m->H) { set_error("invalid argument: pool_to_input=0 needs out_dim == hidden_dim"); return fail(TB2_ERR_INVALID); }
+    } else
     if (cfg->pool_type == TB2_POOL_HIDDEN_MLP) {
         if (!(cfg->mlp_dim_spatial >= 1 && cfg->mlp_dim_vel >= 0 && cfg->mlp_dim_hidden >= 0 && cfg->out_dim >= 1 &&
               cfg->mlp_dim_spatial + cfg->mlp_dim_vel + cfg->mlp_dim_hidden <= 4096)) {
@@ -247,6 +256,10 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
         ALLOC(m->WencT, m->H * m->C);
         ALLOC(m->benc, m->C);
     }
+    if (cfg->pool_type == TB2_POOL_NN_MLP) {
+        ALLOC(m->mp_Ws, cfg->mlp_dim_spatial * 4);
+        ALLOC(m->mp_bs, cfg->mlp_dim_spatial);
+    } else
     if (cfg->pool_type == TB2_POOL_HIDDEN_MLP) {
         const int D = cfg->mlp_dim_spatial + cfg->mlp_dim_vel + cfg->mlp_dim_hidden;
         ALLOC(m->mp_Ws, cfg->mlp_dim_spatial * 2);
@@ -443,6 +456,7 @@ int tb2_pool_forward(const tb2_lstm* m, const tb2_layout* l, const float* hidden
     carve_workspace(m, l, workspace, &ws);
     cudaStream_t st = (cudaStream_t)stream;
     if (m->cfg.pool_type == TB2_POOL_HIDDEN_MLP) return launch_hidden_mlp_pool(m, l, hidden, obs1, obs2, pooled_out, st);
+    if (m->cfg.pool_type == TB2_POOL_NN_MLP) return launch_nn_mlp_pool(m, l, obs1, obs2, pooled_out, st);
     if ((rc = launch_pool_prepare(m, l, hidden, obs1, obs2, 0, 0, 0, &ws, st))) return rc;
     return launch_pool_mlp(m, l, &ws, pooled_out, nullptr, nullptr, st);
 }
@@ -455,9 +469,11 @@ static int step_impl(const tb2_lstm* m, const tb2_layout* l, int phase, const fl
     int rc;
     const bool tc = m->Wg_hi[0] != nullptr;
     const float* pooled = nullptr;
-    if (m->cfg.pool_type == TB2_POOL_HIDDEN_MLP) {
+    if (m->cfg.pool_type == TB2_POOL_HIDDEN_MLP || m->cfg.pool_type == TB2_POOL_NN_MLP) {
         // non-grid interaction module: one kernel per scene -> pooled fp32, split for the tensor-core gate kernel
-        if ((rc = launch_hidden_mlp_pool(m, l, h_in, obs1, obs2, ws->pooled, st))) return rc;
+        if (m->cfg.pool_type == TB2_POOL_NN_MLP) rc = launch_nn_mlp_pool(m, l, obs1, obs2, ws->pooled, st);
+        else rc = launch_hidden_mlp_pool(m, l, h_in, obs1, obs2, ws->pooled, st);
+        if (rc) return rc;
         if (tc && (rc = launch_split_rows(ws->pooled, ws->pool_hi, ws->pool_lo, (size_t)l->M * m->P, st))) return rc;
         pooled = ws->pooled;
     } else
@@ -469,7 +485,7 @@ static int step_impl(const tb2_lstm* m, const tb2_layout* l, int phase, const fl
         pooled = ws->pooled;
     }
     if (tc) {
-        if ((m->cfg.pool_type == TB2_POOL_NONE || m->cfg.pool_type == TB2_POOL_HIDDEN_MLP) &&     // grid pools: pool_prepare already wrote emb
+        if ((m->cfg.pool_type == TB2_POOL_NONE || m->cfg.pool_type == TB2_POOL_HIDDEN_MLP || m->cfg.pool_type == TB2_POOL_NN_MLP) &&     // grid pools: pool_prepare already wrote emb
             (rc = launch_embed_split(m, l->M, obs1, obs2, ws->emb_hi, ws->emb_lo, st)))
             return rc;
         return launch_gates_tc(m, l, phase, obs1, obs2, ws->emb_hi, ws->emb_lo, ws->pool_hi, ws->pool_lo,

@@ -214,6 +214,8 @@ int launch_repack_layer2_sw(const float* W2, void* dst, int N2, int K, cudaStrea
 int launch_repack_layer1_sw(const float* W1, void* hi, void* lo, int OUT, int cells, cudaStream_t st);
 int launch_hidden_mlp_pool(const tb2_lstm* m, const tb2_layout* l, const float* hidden, const float* obs1,
                            const float* obs2, float* out, cudaStream_t st);
+int launch_nn_mlp_pool(const tb2_lstm* m, const tb2_layout* l, const float* obs1, const float* obs2, float* out,
+                       cudaStream_t st);
 bool dense_tc_supported(int K, int N);
 int launch_dense_tc(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                     float* Y, void* Y_hi, void* Y_lo, int M, int K, int N, int relu, cudaStream_t st);

@@ -351,6 +351,12 @@ int launch_repack(tb2_lstm* m, const tb2_lstm_weights* w, cudaStream_t st) {
             (rc = launch_repack_gates_tc(wih[ph], whh[ph], m->Wg_hi[ph], m->Wg_lo[ph], m->E + m->P, m->H, st)))
             return rc;
     }
+    if (m->cfg.pool_type == TB2_POOL_NN_MLP) {
+        const tb2_lstm_config& c = m->cfg;
+        TB2_REQUIRE(w->pool_spatial_weight && w->pool_spatial_bias, "pool.embedding.0 (nearest-neighbour pooling) missing");
+        if ((rc = copy_dev(w->pool_spatial_weight, m->mp_Ws, (size_t)c.mlp_dim_spatial * (c.mlp_dim_vel ? 4 : 2), st))) return rc;
+        if ((rc = copy_dev(w->pool_spatial_bias, m->mp_bs, (size_t)c.mlp_dim_spatial, st))) return rc;
+    }
     if (m->cfg.pool_type == TB2_POOL_HIDDEN_MLP) {
         const tb2_lstm_config& c = m->cfg;
         const int D = c.mlp_dim_spatial + c.mlp_dim_vel + c.mlp_dim_hidden;
@@ -379,7 +385,8 @@ int launch_repack(tb2_lstm* m, const tb2_lstm_weights* w, cudaStream_t st) {
         TB2_LAUNCH_CHECK();
         if ((rc = copy_dev(w->pool_encoding_bias, m->benc, (size_t)m->C, st))) return rc;
     }
-    if (m->cfg.pool_type != TB2_POOL_NONE && m->cfg.pool_type != TB2_POOL_HIDDEN_MLP && m->n_mlp >= 1) {
+    if (m->cfg.pool_type != TB2_POOL_NONE && m->cfg.pool_type != TB2_POOL_HIDDEN_MLP && m->cfg.pool_type != TB2_POOL_NN_MLP &&
+        m->n_mlp >= 1) {
         TB2_REQUIRE(w->pool_embedding_weight[0] && w->pool_embedding_bias[0], "pool.embedding.0 missing");
         repack_layer1_kernel<<<1024, 256, 0, st>>>(w->pool_embedding_weight[0], w->pool_embedding_bias[0],
                                                    m->Wt1, m->base1, m->mlp_dims[1], m->C, m->cells,

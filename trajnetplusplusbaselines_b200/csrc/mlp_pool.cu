@@ -138,4 +138,103 @@ int launch_hidden_mlp_pool(const tb2_lstm* m, const tb2_layout* l, const float* 
     return TB2_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// NearestNeighborMLP on the device (--type nn, reference non_gridbased_pooling.py:64-147).
+//
+//   for every track i: the n nearest other tracks of its scene by ||pos_j - pos_i|| (absent tracks count as 1000 m,
+//   reference :131-132), in ascending distance; per kept neighbour the features [pos_j - pos_i | v_j - v_i] (NaN -> 0,
+//   :141; missing neighbours are zero rows, :134-136) go through Linear(2 or 4 -> out_dim / n) + ReLU; the n
+//   embeddings are concatenated.  One warp per track: lane = candidate neighbour, n rounds of a warp arg-min.
+// ------------------------------------------------------------------------------------------
+struct NnPoolParams {
+    const float2* obs1;
+    const float2* obs2;
+    const int* scene_off;
+    const float* W;            // [d, 2 or 4]
+    const float* b;            // [d]
+    float* out;                // [M, n * d]
+    int n, d, with_vel;
+};
+
+__global__ void __launch_bounds__(256) nn_mlp_pool_kernel(NnPoolParams p) {
+    extern __shared__ __align__(16) float smem_nn[];
+    const int scene = blockIdx.x;
+    const int row0 = p.scene_off[scene];
+    const int ns = p.scene_off[scene + 1] - row0;
+    float2* pos = reinterpret_cast<float2*>(smem_nn);              // [ns] obs2 (NaN kept)
+    float2* vel = pos + ns;                                        // [ns] obs2 - obs1
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    grid_dep_wait();
+    grid_dep_launch();
+    for (int j = tid; j < ns; j += blockDim.x) {
+        const float2 a = p.obs1[row0 + j], b = p.obs2[row0 + j];
+        pos[j] = b;
+        vel[j] = make_float2(b.x - a.x, b.y - a.y);
+    }
+    __syncthreads();
+    for (int i = warp; i < ns; i += nwarps) {
+        const float2 pi = pos[i], vi = vel[i];
+        float* out = p.out + (size_t)(row0 + i) * p.n * p.d;
+        float last_d = -1.f;
+        int last_j = -1;
+        for (int k = 0; k < p.n; ++k) {
+            // arg-min over the candidates after (last_d, last_j) in (distance, index) order: selection without marking
+            float best = CUDART_INF_F;
+            int best_j = 0x7fffffff;
+            for (int j = lane; j < ns; j += 32) {
+                if (j == i) continue;
+                const float rx = pos[j].x - pi.x, ry = pos[j].y - pi.y;
+                float dist = sqrtf(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)));
+                if (isnan(dist)) dist = 1000.f;
+                const bool after = dist > last_d || (dist == last_d && j > last_j);
+                if (after && (dist < best || (dist == best && j < best_j))) { best = dist; best_j = j; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+                const int oj = __shfl_xor_sync(0xffffffffu, best_j, off);
+                if (ob < best || (ob == best && oj < best_j)) { best = ob; best_j = oj; }
+            }
+            float f[4] = {0.f, 0.f, 0.f, 0.f};                     // fewer than n other tracks: zero features
+            if (best_j != 0x7fffffff) {
+                last_d = best; last_j = best_j;
+                const float2 pj = pos[best_j], vj = vel[best_j];
+                f[0] = pj.x - pi.x; f[1] = pj.y - pi.y; f[2] = vj.x - vi.x; f[3] = vj.y - vi.y;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) f[c] = isnan(f[c]) ? 0.f : (isinf(f[c]) ? copysignf(3.402823466e+38f, f[c]) : f[c]);
+            } else {
+                last_d = CUDART_INF_F;
+            }
+            const int in_dim = p.with_vel ? 4 : 2;
+            for (int o = lane; o < p.d; o += 32) {
+                float acc = p.b[o];
+                for (int c = 0; c < in_dim; ++c) acc = fmaf(f[c], p.W[o * in_dim + c], acc);
+                out[k * p.d + o] = fmaxf(acc, 0.f);
+            }
+        }
+    }
+}
+
+int launch_nn_mlp_pool(const tb2_lstm* m, const tb2_layout* l, const float* obs1, const float* obs2, float* out,
+                       cudaStream_t st) {
+    NnPoolParams p;
+    p.obs1 = (const float2*)obs1;
+    p.obs2 = (const float2*)obs2;
+    p.scene_off = l->scene_off;
+    p.W = m->mp_Ws;
+    p.b = m->mp_bs;
+    p.out = out;
+    p.n = m->cfg.n;
+    p.d = m->cfg.mlp_dim_spatial;
+    p.with_vel = m->cfg.mlp_dim_vel != 0;
+    const size_t smem = (size_t)l->n_max * 4 * sizeof(float) + 16;
+    TB2_REQUIRE(smem <= 48 * 1024, "scene too large for the nearest-neighbour pooling kernel");
+    {
+        KernelTimer kt("nn_mlp_pool", st);
+        launch_pdl(nn_mlp_pool_kernel, dim3(l->B), dim3(256), smem, st, p);
+    }
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
+}
+
 }  // namespace tb2

@@ -7,8 +7,11 @@ projection.  One kernel per step (csrc/mlp_pool.cu); same plug contract as GridB
 `out_dim`, `reset(...)`, `__call__(hidden [B, N, H], obs1, obs2) -> [B * N, out_dim]`).  Inside
 `LSTM.forward` the module is not called -- the fused sequence entry point reads its parameters.
 
-NearestNeighborMLP (:64-147), AttentionMLPPooling (:242-351), NearestNeighborLSTM, TrajectronPooling and
-NMMP are not built (their constructors raise).
+NearestNeighborMLP (:64-147, `--type nn`): relative position (and velocity) of the n nearest tracks, each through a
+shared Linear + ReLU, concatenated.  One kernel per step (nn_mlp_pool_kernel in csrc/mlp_pool.cu).
+
+AttentionMLPPooling (:242-351), NearestNeighborLSTM, TrajectronPooling and NMMP are not built (their constructors
+raise).
 """
 import torch
 
@@ -101,6 +104,82 @@ class HiddenStateMLPPooling(torch.nn.Module):
         return out.to(obs2.device) if obs2.device != device else out
 
 
+class _StandalonePlug:
+    """Shared stand-alone path of the non-grid plugs: a model handle whose LSTM-cell slots hold zeros."""
+
+    def _plug_handle(self, device):
+        if self._handle is None or self._handle.device != device:
+            cfg = _lib.LstmConfig()
+            cfg.hidden_dim = 128            # the stand-alone plug does not touch the LSTM cell
+            cfg.embedding_dim = 64
+            cfg.pool_to_input = 1
+            self.fill_config(cfg)
+            self._handle = ModelHandle(cfg, device)
+            self._standalone_dummy = None
+        if getattr(self, '_standalone_dummy', None) is None:
+            z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
+            in_dim = 64 + self.out_dim
+            self._standalone_dummy = dict(
+                input_embedding_weight=z(62, 2), input_embedding_bias=z(62),
+                encoder_weight_ih=z(512, in_dim), encoder_weight_hh=z(512, 128),
+                encoder_bias_ih=z(512), encoder_bias_hh=z(512),
+                decoder_weight_ih=z(512, in_dim), decoder_weight_hh=z(512, 128),
+                decoder_bias_ih=z(512), decoder_bias_hh=z(512),
+                hidden2normal_weight=z(5, 128), hidden2normal_bias=z(5))
+        fields = dict(self._standalone_dummy)
+        fields.update(self.weight_fields())
+        self._handle.set_weights(fields, key=self.weights_version())
+        return self._handle
+
+
+class NearestNeighborMLP(torch.nn.Module, _StandalonePlug):
+    def __init__(self, n=4, out_dim=32, no_vel=False):
+        """Same arguments and sub-module names as the reference (non_gridbased_pooling.py:78-91)."""
+        super().__init__()
+        if n < 1 or n > 32 or out_dim % n != 0:
+            raise ValueError("NearestNeighborMLP needs 1 <= n <= 32 and n dividing out_dim (reference :87-88)")
+        self.n = n
+        self.out_dim = out_dim
+        self.no_velocity = no_vel
+        self.input_dim = 2 if self.no_velocity else 4
+        self.embedding = torch.nn.Sequential(torch.nn.Linear(self.input_dim, int(out_dim / self.n)), torch.nn.ReLU())
+        self._handle = None
+        self._layouts = LayoutCache()
+
+    def fill_config(self, cfg):
+        cfg.pool_type = _lib.POOL_NN_MLP
+        cfg.n = int(self.n)
+        cfg.out_dim = int(self.out_dim)
+        cfg.mlp_dim_spatial = int(self.out_dim // self.n)
+        cfg.mlp_dim_vel = 0 if self.no_velocity else 1
+        cfg.mlp_dim_hidden = 0
+        cfg.pool_size = cfg.blur_size = 1
+
+    def weight_fields(self):
+        return dict(pool_spatial_weight=self.embedding[0].weight, pool_spatial_bias=self.embedding[0].bias)
+
+    def weights_version(self):
+        return weights_key(self)
+
+    def reset(self, num_tracks, max_num_neigh, device):
+        self.track_mask = None
+
+    def forward(self, _, obs1, obs2):
+        """_, [B, N, 2], [B, N, 2] -> [B * N, out_dim] (non_gridbased_pooling.py:96-147)."""
+        _lib.require_cuda()
+        batch_size, num_tracks = obs2.size(0), obs2.size(1)
+        device = self.embedding[0].weight.device
+        if device.type != 'cuda':
+            raise RuntimeError("NearestNeighborMLP runs on CUDA only: move the module to a B200 (module.cuda())")
+        handle = self._plug_handle(device)
+        layout = self._layouts.get(range(0, batch_size * num_tracks + 1, num_tracks), device=device)
+        f32 = dict(device=device, dtype=torch.float32)
+        o1 = obs1.detach().to(**f32).reshape(-1, 2).contiguous()
+        o2 = obs2.detach().to(**f32).reshape(-1, 2).contiguous()
+        out = handle.pool_forward(layout, None, o1, o2, self.out_dim)
+        return out.to(obs2.device) if obs2.device != device else out
+
+
 def _not_built(name, lines):
     class _NotBuilt(torch.nn.Module):
         def __init__(self, *args, **kwargs):
@@ -110,7 +189,6 @@ def _not_built(name, lines):
     return _NotBuilt
 
 
-NearestNeighborMLP = _not_built("NearestNeighborMLP", "64-147")
 AttentionMLPPooling = _not_built("AttentionMLPPooling", "242-351")
 NearestNeighborLSTM = _not_built("NearestNeighborLSTM", "354-")
 TrajectronPooling = _not_built("TrajectronPooling", "")

@@ -33,7 +33,7 @@ def _grad_targets(model):
     """field name -> parameter, for every parameter the backward kernel produces a gradient for."""
     out = {k: f(model) for k, f in _GRAD_FIELDS.items()}
     pool = model.pool
-    if pool is not None and not hasattr(pool, 'embedding'):
+    if pool is not None and not hasattr(pool, 'embedding_arch'):        # only GridBasedPooling has a backward
         raise NotImplementedError("training of %s is not built (inference only); use torch.no_grad()" % type(pool).__name__)
     if pool is not None and pool.embedding is not None:
         linears = [m for m in pool.embedding if isinstance(m, torch.nn.Linear)]
