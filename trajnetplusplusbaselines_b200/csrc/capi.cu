@@ -77,7 +77,35 @@ size_t carve_workspace(const tb2_lstm* m, const tb2_layout* l, void* base, Works
         w.hs_lo[i] = take(M * 128 * 2);
     }
     w.bytes = off;
+    w.write_pairs = 0;
     if (ws) *ws = w;
+    return off;
+}
+
+size_t carve_train_cache(const tb2_lstm* m, const tb2_layout* l, size_t S, void* base, TrainCache* out) {
+    const bool two = m->n_mlp == 2;
+    if (m->cfg.pool_type != TB2_POOL_SOCIAL || m->Wg_hi[0] == nullptr || m->n_mlp < 1 || m->n_mlp > 2 || !m->cfg.pool_to_input ||
+        (two && m->W_hi[1] == nullptr))
+        return 0;
+    const size_t M = (size_t)l->M, C = (size_t)m->C, nm1 = (size_t)(l->n_max > 1 ? l->n_max - 1 : 1);
+    const size_t d1 = (size_t)m->mlp_dims[1], P = (size_t)m->P;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? (void*)((char*)base + off) : nullptr;
+        off += (bytes + 255) & ~(size_t)255;
+        return p;
+    };
+    TrainCache c;
+    c.lat = (float*)take(S * M * C * sizeof(float));
+    c.win_count = (int*)take(S * M * sizeof(int));
+    c.win_ent = (uint32_t*)take(S * M * nm1 * sizeof(uint32_t));
+    c.pair_cell = (int*)take(S * M * nm1 * sizeof(int));
+    c.pair_flag = (uint8_t*)take(S * M * nm1);
+    c.h1_hi = two ? take(S * M * d1 * 2) : nullptr;
+    c.h1_lo = two ? take(S * M * d1 * 2) : nullptr;
+    c.pool_hi = take(S * M * P * 2);
+    c.pool_lo = take(S * M * P * 2);
+    if (out) *out = c;
     return off;
 }
 
@@ -478,7 +506,7 @@ static int step_impl(const tb2_lstm* m, const tb2_layout* l, int phase, const fl
         pooled = ws->pooled;
     } else
     if (m->cfg.pool_type != TB2_POOL_NONE) {
-        if ((rc = launch_pool_prepare(m, l, h_in, obs1, obs2, 1, 0, tc ? 1 : 0, ws, st))) return rc;
+        if ((rc = launch_pool_prepare(m, l, h_in, obs1, obs2, 1, ws->write_pairs, tc ? 1 : 0, ws, st))) return rc;
         if (tc) rc = launch_pool_mlp(m, l, ws, nullptr, ws->pool_hi, ws->pool_lo, st);
         else rc = launch_pool_mlp(m, l, ws, ws->pooled, nullptr, nullptr, st);
         if (rc) return rc;
@@ -527,7 +555,7 @@ static int forward_steps_impl(const tb2_lstm* m, const tb2_layout* l, const floa
                               int32_t obs_length, const float* truth, int32_t n_decode, int32_t first_step,
                               int32_t last_step, float* normals_out, float* positions_out, float* h, float* c,
                               float* states_out, void* workspace, size_t workspace_bytes, void* stream,
-                              const HostSink* sink) {
+                              const HostSink* sink, const TrainCache* cache = nullptr) {
     int rc = check_ready(m, l, workspace, workspace_bytes);
     if (rc) return rc;
     TB2_REQUIRE(observed && normals_out && positions_out && h && c, "null argument");
@@ -559,8 +587,24 @@ static int forward_steps_impl(const tb2_lstm* m, const tb2_layout* l, const floa
             return rc;
         float* h_next = states_out ? states_out + ((size_t)s * 2 + 0) * M * H : h;
         float* c_next = states_out ? states_out + ((size_t)s * 2 + 1) * M * H : c;
+        Workspace wstep = ws;
+        if (cache) {        // this step's winners, latent vectors, hidden1 and pooled vector stay where the backward reads them
+            const size_t nm1 = (size_t)(l->n_max > 1 ? l->n_max - 1 : 1), us = (size_t)s;
+            wstep.lat = cache->lat + us * M * m->C;
+            wstep.win_count = cache->win_count + us * M;
+            wstep.win_ent = cache->win_ent + us * M * nm1;
+            wstep.pair_cell = cache->pair_cell + us * M * nm1;
+            wstep.pair_flag = cache->pair_flag + us * M * nm1;
+            if (cache->h1_hi) {
+                wstep.act[0] = (float*)((char*)cache->h1_hi + us * M * (size_t)m->mlp_dims[1] * 2);
+                wstep.act[1] = (float*)((char*)cache->h1_lo + us * M * (size_t)m->mlp_dims[1] * 2);
+            }
+            wstep.pool_hi = (char*)cache->pool_hi + us * M * (size_t)m->P * 2;
+            wstep.pool_lo = (char*)cache->pool_lo + us * M * (size_t)m->P * 2;
+            wstep.write_pairs = 1;
+        }
         if ((rc = step_impl(m, l, phase, o1, o2, h_prev, c_prev, h_next, c_next,
-                            normals_out + (size_t)s * M * 5, positions_out + (size_t)s * frame, &ws, s & 1, st)))
+                            normals_out + (size_t)s * M * 5, positions_out + (size_t)s * frame, &wstep, s & 1, st)))
             return rc;
         h_prev = h_next;
         c_prev = c_next;
@@ -604,6 +648,26 @@ int tb2_lstm_forward_sequence_host(tb2_lstm* m, const tb2_layout* l, const float
     HostSink sink{normals_host, positions_host, (cudaStream_t)copy_stream, &m->step_events};
     return forward_steps_impl(m, l, observed, obs_length, truth, n_decode, 0, S, normals_out, positions_out, h, c,
                               nullptr, workspace, workspace_bytes, stream, &sink);
+}
+
+size_t tb2_lstm_train_cache_bytes(const tb2_lstm* m, const tb2_layout* l, int32_t num_steps) {
+    if (!m || !l || num_steps < 1) return 0;
+    return carve_train_cache(m, l, (size_t)num_steps, nullptr, nullptr);
+}
+
+int tb2_lstm_forward_sequence_train(const tb2_lstm* m, const tb2_layout* l, const float* observed, int32_t obs_length,
+                                    const float* truth, int32_t n_decode, float* normals_out, float* positions_out,
+                                    float* h, float* c, float* states_out, void* cache, size_t cache_bytes,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+    TB2_REQUIRE(m && l, "null handle");
+    TB2_REQUIRE(obs_length >= 2 && n_decode >= 0, "need obs_length >= 2 and n_decode >= 0");
+    TB2_REQUIRE(states_out, "a training forward keeps the per-step states");
+    const int S = obs_length - 1 + n_decode;
+    TrainCache tc;
+    const size_t need = carve_train_cache(m, l, (size_t)S, cache, &tc);
+    TB2_REQUIRE(!cache || (need > 0 && cache_bytes >= need), "training cache too small (tb2_lstm_train_cache_bytes)");
+    return forward_steps_impl(m, l, observed, obs_length, truth, n_decode, 0, S, normals_out, positions_out, h, c,
+                              states_out, workspace, workspace_bytes, stream, nullptr, cache ? &tc : nullptr);
 }
 
 int tb2_lstm_forward_sequence(const tb2_lstm* m, const tb2_layout* l, const float* observed,

@@ -183,7 +183,25 @@ struct Workspace {
     void* hs_hi[2];        // [M, 128] ping-pong split of the hidden state
     void* hs_lo[2];
     size_t bytes;
+    int write_pairs;       // pool_prepare also exports the pair tables (training forward with a cache)
 };
+
+// Per-step forward quantities a training forward keeps for the social backward (tb2_lstm_forward_sequence_train):
+// the backward then skips its own pool_prepare / grid-embedding recomputation.  Layouts match the backward's
+// own per-step arrays ([S][M][...]).
+struct TrainCache {
+    float* lat;            // [S][M][C]
+    int* win_count;        // [S][M]
+    uint32_t* win_ent;     // [S][M][nm1]
+    int* pair_cell;        // [S][M][nm1]
+    uint8_t* pair_flag;    // [S][M * nm1]
+    void* h1_hi;           // [S][M][d1] bf16 (two_layer) or null
+    void* h1_lo;
+    void* pool_hi;         // [S][M][P] bf16
+    void* pool_lo;
+};
+// 0 when the configuration keeps no cache (anything but social pooling on the tensor-core path)
+size_t carve_train_cache(const tb2_lstm* m, const tb2_layout* l, size_t S, void* base, TrainCache* out);
 size_t carve_workspace(const tb2_lstm* m, const tb2_layout* l, void* base, Workspace* ws);
 
 // kernels.cu launchers (all asynchronous on `st`)

@@ -1348,7 +1348,8 @@ static int social_pair_kernels(const tb2_lstm* m, const tb2_layout* l, const Soc
 static int social_backward(const tb2_lstm* m, const tb2_layout* l, const tb2_lstm_weights* w,
                            const float* observed, int obs_length, const float* truth, int n_decode,
                            const float* positions, const float* states, const float* d_normals,
-                           const tb2_lstm_grads* g, Workspace& ws, void* bwd_workspace, cudaStream_t st) {
+                           const tb2_lstm_grads* g, Workspace& ws, void* bwd_workspace, cudaStream_t st,
+                           const TrainCache* cache = nullptr) {
     const int S = obs_length - 1 + n_decode, S_enc = obs_length - 1;
     const int Mi = l->M, K = m->K_gate, E = m->E, P = m->P, EP = E + P, C = m->C, cells = m->cells;
     const int d1 = m->mlp_dims[1];
@@ -1360,6 +1361,13 @@ static int social_backward(const tb2_lstm* m, const tb2_layout* l, const tb2_lst
                 "social backward needs gradient buffers for pool.hidden_dim_encoding and pool.embedding");
     SocBuffers b;
     carve_social(m, l, (size_t)S, bwd_workspace, &b);
+    if (cache) {      // the forward kept its per-step winners / latent vectors: same [S][M][...] layouts
+        b.LAT = cache->lat;
+        b.winc = cache->win_count;
+        b.wine = cache->win_ent;
+        b.pcell = cache->pair_cell;
+        b.pflag = cache->pair_flag;
+    }
     TB2_CHECK_CUDA(cudaMemsetAsync(b.dc, 0, M * 128 * sizeof(float), st));
     TB2_CHECK_CUDA(cudaMemsetAsync(b.dWt1, 0, (size_t)cells * C * d1 * sizeof(float), st));
     TB2_CHECK_CUDA(cudaMemsetAsync(b.zero_h, 0, M * 128 * sizeof(float), st));      // state before step 0
@@ -1381,6 +1389,19 @@ static int social_backward(const tb2_lstm* m, const tb2_layout* l, const tb2_lst
         w2.win_ent = b.wine + (size_t)s * M * nm1;
         w2.pair_cell = b.pcell + (size_t)s * M * nm1;
         w2.pair_flag = b.pflag + (size_t)s * M * nm1;
+        if (cache) {
+            // hidden1 and the pooled vector of the forward, as fp32 (hi + lo of the bf16 pair the next kernel consumed)
+            if (two) {
+                merge_split_kernel<<<1024, 256, 0, st>>>((const __nv_bfloat16*)cache->h1_hi + (size_t)s * M * d1,
+                                                         (const __nv_bfloat16*)cache->h1_lo + (size_t)s * M * d1, nullptr,
+                                                         b.H1 + (size_t)s * M * d1, M * d1);
+                TB2_LAUNCH_CHECK();
+            }
+            merge_split_kernel<<<512, 256, 0, st>>>((const __nv_bfloat16*)cache->pool_hi + (size_t)s * M * P,
+                                                    (const __nv_bfloat16*)cache->pool_lo + (size_t)s * M * P, nullptr, ws.pooled,
+                                                    M * P);
+            TB2_LAUNCH_CHECK();
+        } else {
         if ((rc = launch_pool_prepare(m, l, h_prev ? h_prev : b.zero_h, o1, o2, 1, 1, 0, &w2, st))) return rc;
         if ((rc = launch_pool_mlp(m, l, &w2, ws.pooled, nullptr, nullptr, st, /*keep_hidden=*/true))) return rc;
         if (two) {
@@ -1388,6 +1409,7 @@ static int social_backward(const tb2_lstm* m, const tb2_layout* l, const tb2_lst
                                                      tc2 ? (const __nv_bfloat16*)ws.act[1] : nullptr, ws.act[0],
                                                      b.H1 + (size_t)s * M * d1, M * d1);
             TB2_LAUNCH_CHECK();
+        }
         }
         {
             KernelTimer kt("bwd_gather", st);
@@ -1591,12 +1613,40 @@ size_t tb2_lstm_backward_workspace_bytes(const tb2_lstm* m, const tb2_layout* l,
                      nullptr, nullptr);
 }
 
+static int sequence_backward_impl(const tb2_lstm* m, const tb2_layout* l, const tb2_lstm_weights* w,
+                               const float* observed, int32_t obs_length, const float* truth, int32_t n_decode,
+                               const float* positions, const float* states, const float* d_normals,
+                               const int32_t* active_rows, int32_t num_active, const tb2_lstm_grads* g,
+                               void* workspace, size_t workspace_bytes, void* bwd_workspace,
+                               size_t bwd_workspace_bytes, void* stream, const void* cache, size_t cache_bytes);
+
 int tb2_lstm_sequence_backward(const tb2_lstm* m, const tb2_layout* l, const tb2_lstm_weights* w,
                                const float* observed, int32_t obs_length, const float* truth, int32_t n_decode,
                                const float* positions, const float* states, const float* d_normals,
                                const int32_t* active_rows, int32_t num_active, const tb2_lstm_grads* g,
                                void* workspace, size_t workspace_bytes, void* bwd_workspace,
                                size_t bwd_workspace_bytes, void* stream) {
+    return sequence_backward_impl(m, l, w, observed, obs_length, truth, n_decode, positions, states, d_normals, active_rows,
+                                  num_active, g, workspace, workspace_bytes, bwd_workspace, bwd_workspace_bytes, stream, nullptr, 0);
+}
+
+int tb2_lstm_sequence_backward_cached(const tb2_lstm* m, const tb2_layout* l, const tb2_lstm_weights* w,
+                                      const float* observed, int32_t obs_length, const float* truth, int32_t n_decode,
+                                      const float* positions, const float* states, const float* d_normals,
+                                      const int32_t* active_rows, int32_t num_active, const tb2_lstm_grads* g,
+                                      void* workspace, size_t workspace_bytes, void* bwd_workspace,
+                                      size_t bwd_workspace_bytes, const void* cache, size_t cache_bytes, void* stream) {
+    return sequence_backward_impl(m, l, w, observed, obs_length, truth, n_decode, positions, states, d_normals, active_rows,
+                                  num_active, g, workspace, workspace_bytes, bwd_workspace, bwd_workspace_bytes, stream, cache,
+                                  cache_bytes);
+}
+
+static int sequence_backward_impl(const tb2_lstm* m, const tb2_layout* l, const tb2_lstm_weights* w,
+                               const float* observed, int32_t obs_length, const float* truth, int32_t n_decode,
+                               const float* positions, const float* states, const float* d_normals,
+                               const int32_t* active_rows, int32_t num_active, const tb2_lstm_grads* g,
+                               void* workspace, size_t workspace_bytes, void* bwd_workspace,
+                               size_t bwd_workspace_bytes, void* stream, const void* cache, size_t cache_bytes) {
     TB2_REQUIRE(m && l && w && g, "null handle");
     TB2_REQUIRE(m->weights_set, "tb2_lstm_set_weights has not been called");
     TB2_REQUIRE(observed && positions && states && d_normals && active_rows, "null argument");
@@ -1620,9 +1670,13 @@ int tb2_lstm_sequence_backward(const tb2_lstm* m, const tb2_layout* l, const tb2
     cudaStream_t st = (cudaStream_t)stream;
     Workspace ws;
     carve_workspace(m, l, workspace, &ws);
-    if (social)      // every track of a scene receives gradient: all rows, active_rows is ignored
+    if (social) {    // every track of a scene receives gradient: all rows, active_rows is ignored
+        TrainCache tc;
+        const size_t need = cache ? carve_train_cache(m, l, (size_t)S, const_cast<void*>(cache), &tc) : 0;
+        TB2_REQUIRE(!cache || (need > 0 && cache_bytes >= need), "training cache too small (tb2_lstm_train_cache_bytes)");
         return social_backward(m, l, w, observed, obs_length, truth, n_decode, positions, states, d_normals, g, ws,
-                               bwd_workspace, st);
+                               bwd_workspace, st, cache ? &tc : nullptr);
+    }
     const int R = num_active, K = m->K_gate, E = m->E, P = m->P, EP = E + P;
     const size_t M = (size_t)l->M;
     BwdBuffers b;

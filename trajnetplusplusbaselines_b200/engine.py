@@ -224,6 +224,20 @@ class ModelHandle:
                 _ptr(normals), _ptr(positions), _ptr(h), _ptr(c), _ptr(ws), need, _ptr(normals_host),
                 _ptr(positions_host), _stream(self.device), ctypes.c_void_p(copy_stream.cuda_stream)))
 
+    def train_cache_bytes(self, layout, num_steps):
+        return int(_lib.load().tb2_lstm_train_cache_bytes(self.handle, layout.handle, int(num_steps)))
+
+    def forward_sequence_train(self, layout, observed, truth, n_decode, normals, positions, h, c, states, cache):
+        """tb2_lstm_forward_sequence_train: per-step forward quantities of the social pooling stay in `cache`
+        (uint8 device tensor of train_cache_bytes) for tb2_lstm_sequence_backward_cached."""
+        lib = _lib.load()
+        ws, need = self.workspace(layout)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.tb2_lstm_forward_sequence_train(
+                self.handle, layout.handle, _ptr(observed), int(observed.shape[0]), _ptr(truth), int(n_decode),
+                _ptr(normals), _ptr(positions), _ptr(h), _ptr(c), _ptr(states), _ptr(cache), int(cache.numel()),
+                _ptr(ws), need, _stream(self.device)))
+
     def forward_sequence(self, layout, observed, truth, n_decode, normals, positions, h, c, states=None):
         lib = _lib.load()
         ws, need = self.workspace(layout)

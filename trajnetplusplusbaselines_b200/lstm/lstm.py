@@ -215,6 +215,11 @@ class LSTM(torch.nn.Module):
         h = torch.empty((M, self.hidden_dim), **f32)
         c = torch.empty((M, self.hidden_dim), **f32)
         states = torch.empty((S, 2, M, self.hidden_dim), **f32) if want_states else None
+        cache = None
+        if want_states:        # training forward: keep what the social backward would recompute (0 bytes: no cache)
+            cache_bytes = handle.train_cache_bytes(layout, S)
+            if cache_bytes > 0:
+                cache = torch.empty(cache_bytes, dtype=torch.uint8, device=device)
         if out_device != device and not want_states and obs_length > 2:
             # host caller: every step's slice of the results is copied to pinned host memory on a second stream
             # while the later steps compute; one synchronisation of that stream at the end
@@ -224,11 +229,14 @@ class LSTM(torch.nn.Module):
                                          copy_stream)
             copy_stream.synchronize()
             return normals_h.view(normals_h.shape), positions_h.view(positions_h.shape)
-        handle.forward_sequence(layout, obs, truth, n_decode, normals, positions, h, c, states)
+        if cache is not None:
+            handle.forward_sequence_train(layout, obs, truth, n_decode, normals, positions, h, c, states, cache)
+        else:
+            handle.forward_sequence(layout, obs, truth, n_decode, normals, positions, h, c, states)
         if obs_length == 2:                      # lstm.py:222-223: positions seeded with observed[-1]
             positions = torch.cat([obs[-1:].clone(), positions], dim=0)
         if want_states:
-            return normals, positions, states, (obs, truth, layout)
+            return normals, positions, states, (obs, truth, layout, cache)
         if out_device != device:
             normals, positions = self._to_host(normals, positions)
         return normals, positions

@@ -54,13 +54,14 @@ class _SequenceFn(torch.autograd.Function):
         # grad mode is off inside autograd.Function.forward, so "is this a training forward" cannot be asked
         # in LSTM._engine: every forward that records a graph repacks the weights (a few tens of
         # microseconds), which also covers parameter updates that bypass version counters and optimizer hooks
-        normals, positions, states, (obs, truth, layout) = model._forward_nograd(
+        normals, positions, states, (obs, truth, layout, cache) = model._forward_nograd(
             observed, batch_split, prediction_truth, n_predict, want_states=True, force_repack=True)
         ctx.model = model
         ctx.layout = layout
         ctx.obs = obs
         ctx.truth = truth
         ctx.states = states
+        ctx.cache = cache
         ctx.num_steps = normals.shape[0]
         ctx.params = params
         ctx.save_for_backward(positions)
@@ -101,10 +102,17 @@ class _SequenceFn(torch.autograd.Function):
             pos_steps = positions[-S:].contiguous()
             n_decode = S - (int(ctx.obs.shape[0]) - 1)
             with torch.cuda.device(device):
-                _lib.check(lib.tb2_lstm_sequence_backward(
-                    handle.handle, layout.handle, ctypes.byref(w), _ptr(ctx.obs), int(ctx.obs.shape[0]),
-                    _ptr(ctx.truth), n_decode, _ptr(pos_steps), _ptr(ctx.states), _ptr(dn), _ptr(active), R,
-                    ctypes.byref(g), _ptr(ws), need, _ptr(bws), bneed, _stream(device)))
+                if ctx.cache is not None:
+                    _lib.check(lib.tb2_lstm_sequence_backward_cached(
+                        handle.handle, layout.handle, ctypes.byref(w), _ptr(ctx.obs), int(ctx.obs.shape[0]),
+                        _ptr(ctx.truth), n_decode, _ptr(pos_steps), _ptr(ctx.states), _ptr(dn), _ptr(active), R,
+                        ctypes.byref(g), _ptr(ws), need, _ptr(bws), bneed, _ptr(ctx.cache), int(ctx.cache.numel()),
+                        _stream(device)))
+                else:
+                    _lib.check(lib.tb2_lstm_sequence_backward(
+                        handle.handle, layout.handle, ctypes.byref(w), _ptr(ctx.obs), int(ctx.obs.shape[0]),
+                        _ptr(ctx.truth), n_decode, _ptr(pos_steps), _ptr(ctx.states), _ptr(dn), _ptr(active), R,
+                        ctypes.byref(g), _ptr(ws), need, _ptr(bws), bneed, _stream(device)))
             del keep
         by_param = {id(p): grads[k] for k, p in targets.items()}
         out = []
