@@ -278,7 +278,8 @@ __device__ __forceinline__ void sp_build_item_ts(uint32_t a_item, uint32_t cell_
 template <int KC, bool kTwo, bool kTS>
 __device__ __forceinline__ void sp_builder(const uint4* cr, int groups, unsigned char* a_ring, uint32_t a_tmem, int bg,
                                            uint32_t r, int off_r, int nlat, const uint4* lh, const uint4* ll,
-                                           uint64_t* empty_a, const uint32_t (&full_remote)[kSpSA], int lane, long long& wait_e) {
+                                           uint64_t* empty_a, const uint32_t (&full_remote)[kSpSA], int lane, long long& wait_e,
+                                           uint32_t SA = kSpSA, uint32_t ts_stage_cols = kSpTsAStageCols) {
     const uint4 none = make_uint4(~0u, ~0u, ~0u, ~0u);
     constexpr int ipg = 16 / KC;                       // items per 16-cell load of the row's cell map
     constexpr int step = kTwo ? 1 : 2;
@@ -299,13 +300,13 @@ __device__ __forceinline__ void sp_builder(const uint4* cr, int groups, unsigned
                 if (KC == 4) bytes = jj == 0 ? (bg ? cur.y : cur.x) : (bg ? cur.w : cur.z);
                 else bytes = ((jj == 0 ? cur.x : jj == 1 ? cur.y : jj == 2 ? cur.z : cur.w) >> (16 * bg)) & 0xffffu;
             }
-            const uint32_t sa = g % kSpSA, pa = (g / kSpSA) & 1u;
+            const uint32_t sa = g % SA, pa = (g / SA) & 1u;
             const long long tw0 = clock64();
             sp_mbar_wait(sp_smem_u32(&empty_a[sa]), pa ^ 1u);
             wait_e += clock64() - tw0;
             if (kTS) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                sp_build_item_ts<KC>(a_tmem + sa * kSpTsAStageCols, kTwo ? 32u : 16u, bytes, off_r, nlat, lh, ll);
+                sp_build_item_ts<KC>(a_tmem + sa * ts_stage_cols, kTwo ? 32u : 16u, bytes, off_r, nlat, lh, ll);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             } else {
                 sp_build_item<KC>(a_ring + (size_t)sa * kSpAStage, a_stride, bytes, KC, r, off_r, nlat, lh, ll);
@@ -391,8 +392,14 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
         const long long t_r0 = clock64();
         const int nsub = rd.n1 > 0 ? 2 : 1;
         // pipeline shape of the round (the barriers are re-initialised for it)
-        const int KC = nsub == 2 ? (kPair ? 2 : 1) : (kPair ? 4 : 2);     // grid cells per pipeline item
-        const uint32_t SB = nsub == 2 ? (kTS ? 8u : 5u) : (kTS ? 5u : 3u);   // weight stages
+        // TS variant, two-tile round of <= 256 accumulator columns: items of 4 cells of both tiles (one barrier round trip per
+        // 4 cells instead of 2: the issuers of a two-tile round barely run ahead of the tensor pipe), 2 A stages of 128 TMEM
+        // columns at [256, 512)
+        const bool wide_items = kTS && kPair && nsub == 2 && (rd.n0 + rd.n1) * 32 <= 256;
+        const uint32_t SA = wide_items ? 2u : (uint32_t)kSpSA;
+        const uint32_t a_col0 = wide_items ? 256u : kSpTsACol0, a_stage_cols = wide_items ? 128u : kSpTsAStageCols;
+        const int KC = nsub == 2 ? (kPair ? (wide_items ? 4 : 2) : 1) : (kPair ? 4 : 2);     // grid cells per pipeline item
+        const uint32_t SB = nsub == 2 ? (wide_items ? 5u : (kTS ? 8u : 5u)) : (kTS ? 5u : 3u);   // weight stages
         const int n_items = p.cells / KC;                    // cells is a multiple of 16
         const uint32_t n_issuers = 2u;
         if (tid == 0) {
@@ -549,7 +556,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
                 const bool have = gn > 0;
                 const uint32_t idesc = idesc_base | ((gn >> 3) << 17);
                 for (int it = 0; it < n_items; ++it) {
-                    const uint32_t sa = (uint32_t)it % kSpSA, pa = ((uint32_t)it / kSpSA) & 1u;
+                    const uint32_t sa = (uint32_t)it % SA, pa = ((uint32_t)it / SA) & 1u;
                     const uint32_t sb = (uint32_t)it % SB;
                     const long long t0 = clock64();
                     sp_mbar_wait_cluster(sp_smem_u32(&full_a[sa]), pa);
@@ -557,7 +564,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     if (have && kTS) {
                         // A from tensor memory: stage sa, (two tiles: the issuer's own tile inside every cell)
-                        uint32_t at = tmem_base + kSpTsACol0 + sa * kSpTsAStageCols + (nsub == 2 ? (uint32_t)gq * 16u : 0u);
+                        uint32_t at = tmem_base + a_col0 + sa * a_stage_cols + (nsub == 2 ? (uint32_t)gq * 16u : 0u);
                         const uint32_t at_cell = nsub == 2 ? 32u : 16u;
                         uint64_t bd = b_base + (uint64_t)(sb * (b_stage >> 4)) + b_off16;
                         sp_umma_ts<kPair>(d, at, bd, idesc, it > 0 ? 1u : 0u);                  // hi . hi
@@ -598,7 +605,7 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
             // round).  The A stage's previous phase must have completed before this phase's arrival. =====
             if (lane == 0) {
                 for (int it = 0; it < n_items; ++it) {
-                    const uint32_t sa = (uint32_t)it % kSpSA, pa = ((uint32_t)it / kSpSA) & 1u;
+                    const uint32_t sa = (uint32_t)it % SA, pa = ((uint32_t)it / SA) & 1u;
                     const uint32_t sb = (uint32_t)it % SB, pb = ((uint32_t)it / SB) & 1u;
                     sp_mbar_wait(sp_smem_u32(&empty_a[sa]), pa ^ 1u);
                     const long long tw1 = clock64();
@@ -620,11 +627,11 @@ __global__ void __launch_bounds__(kSpThreads, 1) sparse_layer1_pair_kernel(SpPar
             // A stage of a two-tile round: [cell][tile][hi | lo]
             unsigned char* a_ring = ring_ptr + (nsub == 2 ? (size_t)bg * 2u * kSpATile : 0u);
             // TS: this warp's TMEM lane quarter, first column of the A ring (two tiles: [cell][tile][hi | lo])
-            const uint32_t a_tmem = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kSpTsACol0 + (nsub == 2 ? (uint32_t)bg * 16u : 0u);
+            const uint32_t a_tmem = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + a_col0 + (nsub == 2 ? (uint32_t)bg * 16u : 0u);
 #define TB2_SP_BUILD(KCV, TWO)                                                                                          \
     sp_builder<KCV, TWO, kTS>(cr, p.cells >> 4, a_ring, a_tmem, bg, r, off_r, nlat[x], latH[x], latL[x], empty_a, full_remote,  \
-                              lane, wait_e)
-            if (nsub == 2) { if (kPair) TB2_SP_BUILD(2, true); else TB2_SP_BUILD(1, true); }
+                              lane, wait_e, SA, a_stage_cols)
+            if (nsub == 2) { if (wide_items) TB2_SP_BUILD(4, true); else if (kPair) TB2_SP_BUILD(2, true); else TB2_SP_BUILD(1, true); }
             else { if (kPair) TB2_SP_BUILD(4, false); else TB2_SP_BUILD(2, false); }
 #undef TB2_SP_BUILD
         }
