@@ -41,6 +41,10 @@ extern "C" {
                                    * no_vel == False (inputs [rel pos | rel vel]); weights pool_spatial_weight
                                    * [out_dim / n, 2 or 4] / pool_spatial_bias = pool.embedding.0.{weight, bias} */
 
+#define TB2_POOL_ATTN_MLP 6       /* AttentionMLPPooling (--type attentionmlp) non_gridbased_pooling.py:242-351: the
+                                   * embeddings of TB2_POOL_HIDDEN_MLP (fill value attn_fill instead of -100, 0 for the
+                                   * hidden part), wq / wk / wv, a one-head torch.nn.MultiheadAttention, out_projection */
+
 #define TB2_PHASE_ENCODER 0
 #define TB2_PHASE_DECODER 1
 
@@ -79,6 +83,7 @@ typedef struct tb2_lstm_config {
     int32_t mlp_dim_spatial; /* Linear(2, .) on pos_j - pos_i                      */
     int32_t mlp_dim_vel;     /* Linear(2, .) on 4 (v_j - v_i); may be 0            */
     int32_t mlp_dim_hidden;  /* Linear(H, .) on h_j; may be 0                      */
+    float attn_fill;         /* TB2_POOL_ATTN_MLP: fill_value of embed_with_masking (-10) */
 } tb2_lstm_config;
 
 /* Device pointers to the parameters in the reference's state_dict layout (row-major
@@ -109,6 +114,14 @@ typedef struct tb2_lstm_weights {
     const float* pool_hidden_bias;
     const float* pool_out_weight;         /* pool.out_projection.weight [out_dim, mlp_dim] */
     const float* pool_out_bias;
+    /* TB2_POOL_ATTN_MLP (NULL otherwise), E = mlp_dim */
+    const float* pool_attn_wq;            /* pool.wq.weight [E, E] (no bias) */
+    const float* pool_attn_wk;            /* pool.wk.weight */
+    const float* pool_attn_wv;            /* pool.wv.weight */
+    const float* pool_attn_in_proj_weight;  /* pool.multihead_attn.in_proj_weight [3E, E] */
+    const float* pool_attn_in_proj_bias;    /* pool.multihead_attn.in_proj_bias [3E] */
+    const float* pool_attn_out_proj_weight; /* pool.multihead_attn.out_proj.weight [E, E] */
+    const float* pool_attn_out_proj_bias;   /* pool.multihead_attn.out_proj.bias [E] */
 } tb2_lstm_weights;
 
 typedef struct tb2_lstm tb2_lstm;          /* opaque: config + repacked weights on the device */

@@ -63,6 +63,20 @@ class MlpPoolConfig:
         self.out_dim = hidden_dim if out_dim is None else out_dim
 
 
+class AttnPoolConfig:
+    """Constructor arguments of AttentionMLPPooling (non_gridbased_pooling.py:257-292)."""
+
+    def __init__(self, hidden_dim=128, mlp_dim=128, mlp_dim_spatial=32, mlp_dim_vel=32, out_dim=None, fill_value=-10):
+        self.type_ = "attentionmlp"
+        self.hidden_dim = hidden_dim
+        self.mlp_dim = mlp_dim
+        self.mlp_dim_spatial = mlp_dim_spatial
+        self.mlp_dim_vel = mlp_dim_vel
+        self.mlp_dim_hidden = mlp_dim - mlp_dim_spatial - mlp_dim_vel
+        self.out_dim = hidden_dim if out_dim is None else out_dim
+        self.fill_value = fill_value
+
+
 class NnPoolConfig:
     """Constructor arguments of NearestNeighborMLP (non_gridbased_pooling.py:78-91)."""
 
@@ -228,6 +242,49 @@ def hidden_mlp_pool_forward(cfg, weights, hidden, obs1, obs2, prefix="pool."):
                    weights[prefix + "out_projection.bias"])
 
 
+def attn_mlp_pool_forward(cfg, weights, hidden, obs1, obs2, prefix="pool."):
+    """AttentionMLPPooling.forward (non_gridbased_pooling.py:297-351) -> [B*N, out_dim].  For track i the sequence is
+    the embedding e_ij = [spatial(pos_j - pos_i) | hidden(h_j) | vel(4 (v_j - v_i))] of EVERY slot j of the (padded)
+    scene -- NaN inputs become the fill value (-10; 0 for the hidden part), nothing is masked in the attention --,
+    query / key / value = wq / wk / wv (no bias) followed by torch.nn.MultiheadAttention (1 head: in-projection with
+    bias, softmax(q k^T / sqrt(E)) v, out-projection); the output at sequence position i is kept (:349-350)."""
+    obs1 = np.asarray(obs1, dtype=F32)
+    obs2 = np.asarray(obs2, dtype=F32)
+    hidden = np.asarray(hidden, dtype=F32)
+    B, N, _ = obs2.shape
+    E = cfg.mlp_dim
+    rel = obs2[:, None, :, :] - obs2[:, :, None, :]
+    parts = [_embed_with_masking(rel, weights[prefix + "spatial_embedding.0.weight"], weights[prefix + "spatial_embedding.0.bias"],
+                                 fill=cfg.fill_value)]
+    if cfg.mlp_dim_hidden:
+        hid = _embed_with_masking(hidden, weights[prefix + "hidden_embedding.0.weight"], weights[prefix + "hidden_embedding.0.bias"],
+                                  fill=0.0)
+        parts.append(np.broadcast_to(hid[:, None, :, :], (B, N, N, hid.shape[-1])))
+    if cfg.mlp_dim_vel:
+        vel = obs2 - obs1
+        relv = (vel[:, None, :, :] - vel[:, :, None, :]) * F32(4.0)
+        parts.append(_embed_with_masking(relv, weights[prefix + "vel_embedding.0.weight"], weights[prefix + "vel_embedding.0.bias"],
+                                         fill=cfg.fill_value))
+    emb = np.concatenate(parts, axis=-1).astype(F32)                        # [B, i, j, E]
+    zero = np.zeros(E, dtype=F32)
+    q = _linear(emb, weights[prefix + "wq.weight"], zero)
+    k = _linear(emb, weights[prefix + "wk.weight"], zero)
+    v = _linear(emb, weights[prefix + "wv.weight"], zero)
+    w_in, b_in = weights[prefix + "multihead_attn.in_proj_weight"], weights[prefix + "multihead_attn.in_proj_bias"]
+    q = _linear(q, w_in[:E], b_in[:E]) * F32(math.sqrt(1.0 / E))
+    k = _linear(k, w_in[E:2 * E], b_in[E:2 * E])
+    v = _linear(v, w_in[2 * E:], b_in[2 * E:])
+    idx = np.arange(N)
+    qi = q[:, idx, idx, :]                                                   # the query at sequence position i
+    scores = np.einsum("bie,bije->bij", qi, k).astype(F32)
+    scores = scores - scores.max(axis=-1, keepdims=True)
+    w = np.exp(scores, dtype=F32)
+    w = (w / w.sum(axis=-1, keepdims=True)).astype(F32)
+    att = np.einsum("bij,bije->bie", w, v).astype(F32)
+    att = _linear(att, weights[prefix + "multihead_attn.out_proj.weight"], weights[prefix + "multihead_attn.out_proj.bias"])
+    return _linear(att.reshape(B * N, E), weights[prefix + "out_projection.weight"], weights[prefix + "out_projection.bias"])
+
+
 def nn_mlp_pool_forward(cfg, weights, obs1, obs2, prefix="pool."):
     """NearestNeighborMLP.forward (non_gridbased_pooling.py:96-147) -> [B*N, out_dim]: features of the n nearest other
     tracks in ascending distance (NaN distances count as 1000, :131-132; NaN features become 0, :141; fewer than n other
@@ -261,6 +318,8 @@ def pool_forward(cfg, weights, hidden, obs1, obs2, prefix="pool."):
         return hidden_mlp_pool_forward(cfg, weights, hidden, obs1, obs2, prefix)
     if getattr(cfg, "type_", None) == "nn":
         return nn_mlp_pool_forward(cfg, weights, obs1, obs2, prefix)
+    if getattr(cfg, "type_", None) == "attentionmlp":
+        return attn_mlp_pool_forward(cfg, weights, hidden, obs1, obs2, prefix)
     obs1 = np.asarray(obs1, dtype=F32)
     obs2 = np.asarray(obs2, dtype=F32)
     B, N, _ = obs2.shape
@@ -511,7 +570,16 @@ NN_SPECS = {
 }
 
 
+# AttentionMLPPooling(hidden_dim, out_dim=args.pool_dim, mlp_dim_spatial=args.spatial_dim (32), mlp_dim_vel=args.vel_dim (32))
+ATTN_SPECS = {
+    "attentionmlp": dict(hidden_dim=128, mlp_dim=128, mlp_dim_spatial=32, mlp_dim_vel=32, out_dim=256),
+    "attentionmlp_small": dict(hidden_dim=128, mlp_dim=48, mlp_dim_spatial=16, mlp_dim_vel=8, out_dim=40),
+}
+
+
 def pool_config(kind):
+    if kind in ATTN_SPECS:
+        return AttnPoolConfig(**ATTN_SPECS[kind])
     if kind in NONGRID_SPECS:
         return MlpPoolConfig(**NONGRID_SPECS[kind])
     if kind in NN_SPECS:
@@ -536,6 +604,21 @@ def random_weights(kind, seed=0, scale=1.0, embedding_dim=64, hidden_dim=128):
     pool_dim = 0
     if cfg is not None and cfg.type_ == "nn":
         lin("pool.embedding.0.weight", "pool.embedding.0.bias", cfg.out_dim // cfg.n, cfg.input_dim)
+        pool_dim = cfg.out_dim
+    elif cfg is not None and cfg.type_ == "attentionmlp":
+        lin("pool.spatial_embedding.0.weight", "pool.spatial_embedding.0.bias", cfg.mlp_dim_spatial, 2)
+        if cfg.mlp_dim_vel:
+            lin("pool.vel_embedding.0.weight", "pool.vel_embedding.0.bias", cfg.mlp_dim_vel, 2)
+        if cfg.mlp_dim_hidden:
+            lin("pool.hidden_embedding.0.weight", "pool.hidden_embedding.0.bias", cfg.mlp_dim_hidden, H)
+        Ea = cfg.mlp_dim
+        ka = scale / math.sqrt(Ea)
+        for nm in ("wq", "wk", "wv"):
+            W["pool.%s.weight" % nm] = rng.uniform(-ka, ka, size=(Ea, Ea)).astype(F32)
+        W["pool.multihead_attn.in_proj_weight"] = rng.uniform(-ka, ka, size=(3 * Ea, Ea)).astype(F32)
+        W["pool.multihead_attn.in_proj_bias"] = rng.uniform(-ka, ka, size=(3 * Ea,)).astype(F32)
+        lin("pool.multihead_attn.out_proj.weight", "pool.multihead_attn.out_proj.bias", Ea, Ea)
+        lin("pool.out_projection.weight", "pool.out_projection.bias", cfg.out_dim, Ea)
         pool_dim = cfg.out_dim
     elif cfg is not None and cfg.type_ == "hiddenstatemlp":
         lin("pool.spatial_embedding.0.weight", "pool.spatial_embedding.0.bias", cfg.mlp_dim_spatial, 2)

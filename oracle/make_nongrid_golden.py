@@ -1,5 +1,5 @@
-"""Golden vectors of the non-grid interaction modules HiddenStateMLPPooling and NearestNeighborMLP, produced by the
-UNMODIFIED reference (trajnetbaselines/lstm/non_gridbased_pooling.py:64-147,150-239 inside trajnetbaselines.lstm.LSTM).
+"""Golden vectors of the non-grid interaction modules HiddenStateMLPPooling, NearestNeighborMLP and AttentionMLPPooling, produced
+by the UNMODIFIED reference (trajnetbaselines/lstm/non_gridbased_pooling.py:64-147,150-239,242-351 inside trajnetbaselines.lstm.LSTM).
 
 TEST INFRASTRUCTURE.  Run in the build container (needs the reference): python -m oracle.make_nongrid_golden
 -> tests/golden/nongrid_golden.npz.  Cases: the stand-alone plug on padded scenes with NaN tracks, and
@@ -14,6 +14,7 @@ from oracle.ref_shim import import_reference
 
 KINDS = ["hiddenstatemlp", "hiddenstatemlp_small"]
 NN_KINDS = ["nn", "nn_small"]
+ATTN_KINDS = ["attentionmlp", "attentionmlp_small"]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -37,8 +38,13 @@ def scene_inputs():
 
 def build_reference_model(kind, W):
     from trajnetbaselines.lstm import LSTM
-    from trajnetbaselines.lstm.non_gridbased_pooling import HiddenStateMLPPooling, NearestNeighborMLP
-    pool = NearestNeighborMLP(**O.NN_SPECS[kind]) if kind in O.NN_SPECS else HiddenStateMLPPooling(**O.NONGRID_SPECS[kind])
+    from trajnetbaselines.lstm.non_gridbased_pooling import AttentionMLPPooling, HiddenStateMLPPooling, NearestNeighborMLP
+    if kind in O.NN_SPECS:
+        pool = NearestNeighborMLP(**O.NN_SPECS[kind])
+    elif kind in O.ATTN_SPECS:
+        pool = AttentionMLPPooling(**O.ATTN_SPECS[kind])
+    else:
+        pool = HiddenStateMLPPooling(**O.NONGRID_SPECS[kind])
     model = LSTM(pool=pool)
     model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in W.items()}, strict=True)
     return model.eval()
@@ -50,7 +56,7 @@ def main():
     hid, obs1, obs2 = plug_inputs()
     xy, bs = scene_inputs()
     M = xy.shape[1]
-    for kind in KINDS + NN_KINDS:
+    for kind in KINDS + NN_KINDS + ATTN_KINDS:
         W = O.random_weights(kind, seed=13)
         model = build_reference_model(kind, W)
         with torch.no_grad():

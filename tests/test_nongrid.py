@@ -1,5 +1,5 @@
-"""Non-grid interaction modules HiddenStateMLPPooling and NearestNeighborMLP (reference
-lstm/non_gridbased_pooling.py:150-239 and :64-147) against vectors the unmodified reference produced
+"""Non-grid interaction modules HiddenStateMLPPooling, NearestNeighborMLP and AttentionMLPPooling (SURVEY.md 8f rank 4;
+reference lstm/non_gridbased_pooling.py:150-239, :64-147 and :242-351) against vectors the unmodified reference produced
 (oracle/make_nongrid_golden.py): the numpy oracle on CPU, the CUDA kernel behind the plug and inside
 LSTM.forward on the GPU."""
 import os
@@ -9,17 +9,24 @@ import pytest
 import torch
 
 from oracle import lstm_oracle as O
-from oracle.make_nongrid_golden import KINDS, NN_KINDS, plug_inputs, scene_inputs
+from oracle.make_nongrid_golden import ATTN_KINDS, KINDS, NN_KINDS, plug_inputs, scene_inputs
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "nongrid_golden.npz"))
 
 
+ALL_KINDS = KINDS + NN_KINDS + ATTN_KINDS
+
+
 def _pool(kind):
-    from trajnetplusplusbaselines_b200.lstm import HiddenStateMLPPooling, NearestNeighborMLP
-    return NearestNeighborMLP(**O.NN_SPECS[kind]) if kind in O.NN_SPECS else HiddenStateMLPPooling(**O.NONGRID_SPECS[kind])
+    from trajnetplusplusbaselines_b200.lstm import AttentionMLPPooling, HiddenStateMLPPooling, NearestNeighborMLP
+    if kind in O.NN_SPECS:
+        return NearestNeighborMLP(**O.NN_SPECS[kind])
+    if kind in O.ATTN_SPECS:
+        return AttentionMLPPooling(**O.ATTN_SPECS[kind])
+    return HiddenStateMLPPooling(**O.NONGRID_SPECS[kind])
 
 
-@pytest.mark.parametrize("kind", KINDS + NN_KINDS)
+@pytest.mark.parametrize("kind", ALL_KINDS)
 def test_oracle_matches_reference_vectors(kind):
     W = O.random_weights(kind, seed=13)
     cfg = O.pool_config(kind)
@@ -36,7 +43,7 @@ def test_oracle_matches_reference_vectors(kind):
 
 def test_state_dict_keys_match_reference_layout():
     from trajnetplusplusbaselines_b200.lstm import LSTM
-    for kind in KINDS + NN_KINDS:
+    for kind in ALL_KINDS:
         model = LSTM(pool=_pool(kind))
         W = O.random_weights(kind, seed=13)           # keys / shapes checked against the reference by the generator
         sd = model.state_dict()
@@ -47,7 +54,7 @@ def test_state_dict_keys_match_reference_layout():
 
 def test_unbuilt_modules_raise():
     from trajnetplusplusbaselines_b200.lstm import non_gridbased_pooling as ngp
-    for name in ("AttentionMLPPooling", "NearestNeighborLSTM", "TrajectronPooling"):
+    for name in ("NearestNeighborLSTM", "TrajectronPooling"):
         with pytest.raises(NotImplementedError):
             getattr(ngp, name)()
 
@@ -60,7 +67,7 @@ def _model(kind):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", KINDS + NN_KINDS)
+@pytest.mark.parametrize("kind", ALL_KINDS)
 def test_cuda_plug_matches_reference_vectors(kind):
     from trajnetplusplusbaselines_b200 import _lib
     model = _model(kind)
@@ -74,7 +81,7 @@ def test_cuda_plug_matches_reference_vectors(kind):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", KINDS + NN_KINDS)
+@pytest.mark.parametrize("kind", ALL_KINDS)
 def test_cuda_forward_matches_reference_vectors(kind):
     model = _model(kind)
     xy, bs = scene_inputs()
@@ -91,7 +98,7 @@ def test_cuda_forward_matches_reference_vectors(kind):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", ["hiddenstatemlp", "nn"])
+@pytest.mark.parametrize("kind", ["hiddenstatemlp", "nn", "attentionmlp"])
 def test_cuda_baseline_shape_vs_oracle_and_training_raises(kind):
     """256-d pooling at N = 20, T = 9 + 12 on 48 scenes vs the oracle; training is inference-only."""
     model = _model(kind)

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtrajnet_b200.so")
 
-POOL_NONE, POOL_OCCUPANCY, POOL_DIRECTIONAL, POOL_SOCIAL, POOL_HIDDEN_MLP, POOL_NN_MLP = 0, 1, 2, 3, 4, 5
+POOL_NONE, POOL_OCCUPANCY, POOL_DIRECTIONAL, POOL_SOCIAL, POOL_HIDDEN_MLP, POOL_NN_MLP, POOL_ATTN_MLP = 0, 1, 2, 3, 4, 5, 6
 PHASE_ENCODER, PHASE_DECODER = 0, 1
 
 _c_float_p = ctypes.c_void_p   # device pointers travel as integers
@@ -35,6 +35,7 @@ class LstmConfig(ctypes.Structure):
         ("mlp_dim_spatial", ctypes.c_int32),
         ("mlp_dim_vel", ctypes.c_int32),
         ("mlp_dim_hidden", ctypes.c_int32),
+        ("attn_fill", ctypes.c_float),
     ]
 
 
@@ -64,6 +65,13 @@ class LstmWeights(ctypes.Structure):
         ("pool_hidden_bias", ctypes.c_void_p),
         ("pool_out_weight", ctypes.c_void_p),
         ("pool_out_bias", ctypes.c_void_p),
+        ("pool_attn_wq", ctypes.c_void_p),
+        ("pool_attn_wk", ctypes.c_void_p),
+        ("pool_attn_wv", ctypes.c_void_p),
+        ("pool_attn_in_proj_weight", ctypes.c_void_p),
+        ("pool_attn_in_proj_bias", ctypes.c_void_p),
+        ("pool_attn_out_proj_weight", ctypes.c_void_p),
+        ("pool_attn_out_proj_bias", ctypes.c_void_p),
     ]
 
 

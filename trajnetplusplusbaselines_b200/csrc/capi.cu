@@ -198,7 +198,7 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
     *out = nullptr;
     TB2_REQUIRE(cfg->hidden_dim == 128, "hidden_dim must be 128 (kernel specialisation)");
     TB2_REQUIRE(cfg->embedding_dim >= 4 && cfg->embedding_dim <= 1024, "embedding_dim out of range");
-    TB2_REQUIRE(cfg->pool_type >= TB2_POOL_NONE && cfg->pool_type <= TB2_POOL_NN_MLP, "bad pool_type");
+    TB2_REQUIRE(cfg->pool_type >= TB2_POOL_NONE && cfg->pool_type <= TB2_POOL_ATTN_MLP, "bad pool_type");
     tb2_lstm* m = new (std::nothrow) tb2_lstm();
     TB2_REQUIRE(m, "out of host memory");
     m->cfg = *cfg;
@@ -212,10 +212,21 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
     for (int i = 0; i < 2; ++i) { m->WgT[i] = m->bg[i] = nullptr; m->Wg_hi[i] = m->Wg_lo[i] = nullptr; }
     for (int i = 0; i < kMaxMlpLayers; ++i) { m->WT[i] = m->bl[i] = nullptr; m->W_hi[i] = m->W_lo[i] = nullptr; }
     m->mp_Ws = m->mp_bs = m->mp_Wv = m->mp_bv = m->mp_WhT = m->mp_bh = m->mp_WoT = m->mp_bo = nullptr;
+    m->at_AqT = m->at_AkT = m->at_AvT = m->at_bqkv = m->at_WoT = m->at_bo = nullptr;
     auto fail = [&](int rc) { tb2_lstm_destroy(m); return rc; };
     if (cfg->pool_type == TB2_POOL_NN_MLP) {
         if (!(cfg->n >= 1 && cfg->n <= 32 && cfg->mlp_dim_spatial >= 1 && cfg->out_dim == cfg->n * cfg->mlp_dim_spatial)) {
             set_error("invalid argument: nearest-neighbour pooling needs 1 <= n <= 32 and out_dim == n * mlp_dim_spatial");
+            return fail(TB2_ERR_INVALID);
+        }
+        m->pool_out = cfg->out_dim;
+        if (cfg->pool_to_input) m->P = m->pool_out;
+        else if (m->pool_out != m->H) { set_error("invalid argument: pool_to_input=0 needs out_dim == hidden_dim"); return fail(TB2_ERR_INVALID); }
+    } else
+    if (cfg->pool_type == TB2_POOL_ATTN_MLP) {
+        const int Ea = cfg->mlp_dim_spatial + cfg->mlp_dim_vel + cfg->mlp_dim_hidden;
+        if (!(cfg->mlp_dim_spatial >= 1 && cfg->mlp_dim_vel >= 0 && cfg->mlp_dim_hidden >= 0 && cfg->out_dim >= 1 && Ea <= 128)) {
+            set_error("invalid argument: attention pooling needs mlp_dim <= 128 (kernel specialisation)");
             return fail(TB2_ERR_INVALID);
         }
         m->pool_out = cfg->out_dim;
@@ -288,7 +299,16 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
         ALLOC(m->mp_Ws, cfg->mlp_dim_spatial * 4);
         ALLOC(m->mp_bs, cfg->mlp_dim_spatial);
     } else
-    if (cfg->pool_type == TB2_POOL_HIDDEN_MLP) {
+    if (cfg->pool_type == TB2_POOL_ATTN_MLP) {
+        const size_t Ea = (size_t)(cfg->mlp_dim_spatial + cfg->mlp_dim_vel + cfg->mlp_dim_hidden);
+        ALLOC(m->at_AqT, Ea * Ea);
+        ALLOC(m->at_AkT, Ea * Ea);
+        ALLOC(m->at_AvT, Ea * Ea);
+        ALLOC(m->at_bqkv, 3 * Ea);
+        ALLOC(m->at_WoT, Ea * Ea);
+        ALLOC(m->at_bo, Ea);
+    }
+    if (cfg->pool_type == TB2_POOL_HIDDEN_MLP || cfg->pool_type == TB2_POOL_ATTN_MLP) {
         const int D = cfg->mlp_dim_spatial + cfg->mlp_dim_vel + cfg->mlp_dim_hidden;
         ALLOC(m->mp_Ws, cfg->mlp_dim_spatial * 2);
         ALLOC(m->mp_bs, cfg->mlp_dim_spatial);
@@ -478,13 +498,15 @@ int tb2_pool_forward(const tb2_lstm* m, const tb2_layout* l, const float* hidden
     if (rc) return rc;
     TB2_REQUIRE(m->cfg.pool_type != TB2_POOL_NONE, "model has no interaction pooling");
     TB2_REQUIRE(obs1 && obs2 && pooled_out, "null argument");
-    TB2_REQUIRE((m->cfg.pool_type != TB2_POOL_SOCIAL && m->cfg.pool_type != TB2_POOL_HIDDEN_MLP) || hidden,
+    TB2_REQUIRE((m->cfg.pool_type != TB2_POOL_SOCIAL && m->cfg.pool_type != TB2_POOL_HIDDEN_MLP &&
+                 m->cfg.pool_type != TB2_POOL_ATTN_MLP) || hidden,
                 "this pooling needs hidden states");
     Workspace ws;
     carve_workspace(m, l, workspace, &ws);
     cudaStream_t st = (cudaStream_t)stream;
     if (m->cfg.pool_type == TB2_POOL_HIDDEN_MLP) return launch_hidden_mlp_pool(m, l, hidden, obs1, obs2, pooled_out, st);
     if (m->cfg.pool_type == TB2_POOL_NN_MLP) return launch_nn_mlp_pool(m, l, obs1, obs2, pooled_out, st);
+    if (m->cfg.pool_type == TB2_POOL_ATTN_MLP) return launch_attn_mlp_pool(m, l, hidden, obs1, obs2, pooled_out, st);
     if ((rc = launch_pool_prepare(m, l, hidden, obs1, obs2, 0, 0, 0, &ws, st))) return rc;
     return launch_pool_mlp(m, l, &ws, pooled_out, nullptr, nullptr, st);
 }
@@ -497,9 +519,10 @@ static int step_impl(const tb2_lstm* m, const tb2_layout* l, int phase, const fl
     int rc;
     const bool tc = m->Wg_hi[0] != nullptr;
     const float* pooled = nullptr;
-    if (m->cfg.pool_type == TB2_POOL_HIDDEN_MLP || m->cfg.pool_type == TB2_POOL_NN_MLP) {
+    if (m->cfg.pool_type == TB2_POOL_HIDDEN_MLP || m->cfg.pool_type == TB2_POOL_NN_MLP || m->cfg.pool_type == TB2_POOL_ATTN_MLP) {
         // non-grid interaction module: one kernel per scene -> pooled fp32, split for the tensor-core gate kernel
         if (m->cfg.pool_type == TB2_POOL_NN_MLP) rc = launch_nn_mlp_pool(m, l, obs1, obs2, ws->pooled, st);
+        else if (m->cfg.pool_type == TB2_POOL_ATTN_MLP) rc = launch_attn_mlp_pool(m, l, h_in, obs1, obs2, ws->pooled, st);
         else rc = launch_hidden_mlp_pool(m, l, h_in, obs1, obs2, ws->pooled, st);
         if (rc) return rc;
         if (tc && (rc = launch_split_rows(ws->pooled, ws->pool_hi, ws->pool_lo, (size_t)l->M * m->P, st))) return rc;
@@ -513,7 +536,7 @@ static int step_impl(const tb2_lstm* m, const tb2_layout* l, int phase, const fl
         pooled = ws->pooled;
     }
     if (tc) {
-        if ((m->cfg.pool_type == TB2_POOL_NONE || m->cfg.pool_type == TB2_POOL_HIDDEN_MLP || m->cfg.pool_type == TB2_POOL_NN_MLP) &&     // grid pools: pool_prepare already wrote emb
+        if ((m->cfg.pool_type == TB2_POOL_NONE || m->cfg.pool_type >= TB2_POOL_HIDDEN_MLP) &&     // grid pools: pool_prepare already wrote emb
             (rc = launch_embed_split(m, l->M, obs1, obs2, ws->emb_hi, ws->emb_lo, st)))
             return rc;
         return launch_gates_tc(m, l, phase, obs1, obs2, ws->emb_hi, ws->emb_lo, ws->pool_hi, ws->pool_lo,

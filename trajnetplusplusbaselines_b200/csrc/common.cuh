@@ -138,6 +138,9 @@ struct tb2_lstm {
     std::vector<cudaEvent_t> step_events;     // tb2_lstm_forward_sequence_host: one event per recurrence step
     // HiddenStateMLPPooling (TB2_POOL_HIDDEN_MLP)
     float *mp_Ws, *mp_bs, *mp_Wv, *mp_bv, *mp_WhT, *mp_bh, *mp_WoT, *mp_bo;
+    // AttentionMLPPooling (TB2_POOL_ATTN_MLP): in-projection . wq / wk / wv combined and transposed [E in][E out], biases,
+    // out-projection transposed
+    float *at_AqT, *at_AkT, *at_AvT, *at_bqkv, *at_WoT, *at_bo;
     void* Wg_hi[2];        // gate weights [4H (rank, gate, unit), K_gate] bf16 split (null: FFMA gates)
     void* Wg_lo[2];
     std::vector<void*> owned;
@@ -232,6 +235,8 @@ int launch_repack_layer2_sw(const float* W2, void* dst, int N2, int K, cudaStrea
 int launch_repack_layer1_sw(const float* W1, void* hi, void* lo, int OUT, int cells, cudaStream_t st);
 int launch_hidden_mlp_pool(const tb2_lstm* m, const tb2_layout* l, const float* hidden, const float* obs1,
                            const float* obs2, float* out, cudaStream_t st);
+int launch_attn_mlp_pool(const tb2_lstm* m, const tb2_layout* l, const float* hidden, const float* obs1, const float* obs2,
+                         float* out, cudaStream_t st);
 int launch_nn_mlp_pool(const tb2_lstm* m, const tb2_layout* l, const float* obs1, const float* obs2, float* out,
                        cudaStream_t st);
 bool dense_tc_supported(int K, int N);

@@ -282,6 +282,16 @@ __global__ void repack_gates_kernel(const float* __restrict__ w_ih, const float*
     }
 }
 
+// outT[c][o] = sum_m Win[o][m] * w[m][c]   (E x E matrices; AttentionMLPPooling: in-projection after wq / wk / wv)
+__global__ void combine_proj_kernel(const float* __restrict__ Win, const float* __restrict__ w, float* __restrict__ outT, int E) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= E * E) return;
+    const int c = idx / E, o = idx - c * E;
+    float acc = 0.f;
+    for (int mm = 0; mm < E; ++mm) acc = fmaf(Win[(size_t)o * E + mm], w[(size_t)mm * E + c], acc);
+    outT[idx] = acc;
+}
+
 __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ WT, int N, int K) {
     // W [N, K] -> WT [K, N]
     size_t total = (size_t)N * K;
@@ -357,7 +367,25 @@ int launch_repack(tb2_lstm* m, const tb2_lstm_weights* w, cudaStream_t st) {
         if ((rc = copy_dev(w->pool_spatial_weight, m->mp_Ws, (size_t)c.mlp_dim_spatial * (c.mlp_dim_vel ? 4 : 2), st))) return rc;
         if ((rc = copy_dev(w->pool_spatial_bias, m->mp_bs, (size_t)c.mlp_dim_spatial, st))) return rc;
     }
-    if (m->cfg.pool_type == TB2_POOL_HIDDEN_MLP) {
+    if (m->cfg.pool_type == TB2_POOL_ATTN_MLP) {
+        const int Ea = m->cfg.mlp_dim_spatial + m->cfg.mlp_dim_vel + m->cfg.mlp_dim_hidden;
+        TB2_REQUIRE(w->pool_attn_wq && w->pool_attn_wk && w->pool_attn_wv && w->pool_attn_in_proj_weight &&
+                    w->pool_attn_in_proj_bias && w->pool_attn_out_proj_weight && w->pool_attn_out_proj_bias,
+                    "pool.wq / wk / wv / multihead_attn parameters missing");
+        // in-projection . w{q,k,v}: A[o][c] = sum_m Win[o][m] w[m][c], stored transposed [c][o]
+        const float* wqkv[3] = {w->pool_attn_wq, w->pool_attn_wk, w->pool_attn_wv};
+        float* outT[3] = {m->at_AqT, m->at_AkT, m->at_AvT};
+        for (int i = 0; i < 3; ++i) {
+            combine_proj_kernel<<<(Ea * Ea + 255) / 256, 256, 0, st>>>(w->pool_attn_in_proj_weight + (size_t)i * Ea * Ea, wqkv[i],
+                                                                     outT[i], Ea);
+            TB2_LAUNCH_CHECK();
+        }
+        if ((rc = copy_dev(w->pool_attn_in_proj_bias, m->at_bqkv, (size_t)3 * Ea, st))) return rc;
+        transpose_kernel<<<64, 256, 0, st>>>(w->pool_attn_out_proj_weight, m->at_WoT, Ea, Ea);
+        TB2_LAUNCH_CHECK();
+        if ((rc = copy_dev(w->pool_attn_out_proj_bias, m->at_bo, (size_t)Ea, st))) return rc;
+    }
+    if (m->cfg.pool_type == TB2_POOL_HIDDEN_MLP || m->cfg.pool_type == TB2_POOL_ATTN_MLP) {
         const tb2_lstm_config& c = m->cfg;
         const int D = c.mlp_dim_spatial + c.mlp_dim_vel + c.mlp_dim_hidden;
         TB2_REQUIRE(w->pool_spatial_weight && w->pool_spatial_bias && w->pool_out_weight && w->pool_out_bias,
@@ -385,8 +413,7 @@ int launch_repack(tb2_lstm* m, const tb2_lstm_weights* w, cudaStream_t st) {
         TB2_LAUNCH_CHECK();
         if ((rc = copy_dev(w->pool_encoding_bias, m->benc, (size_t)m->C, st))) return rc;
     }
-    if (m->cfg.pool_type != TB2_POOL_NONE && m->cfg.pool_type != TB2_POOL_HIDDEN_MLP && m->cfg.pool_type != TB2_POOL_NN_MLP &&
-        m->n_mlp >= 1) {
+    if (m->cfg.pool_type != TB2_POOL_NONE && m->cfg.pool_type < TB2_POOL_HIDDEN_MLP && m->n_mlp >= 1) {
         TB2_REQUIRE(w->pool_embedding_weight[0] && w->pool_embedding_bias[0], "pool.embedding.0 missing");
         repack_layer1_kernel<<<1024, 256, 0, st>>>(w->pool_embedding_weight[0], w->pool_embedding_bias[0],
                                                    m->Wt1, m->base1, m->mlp_dims[1], m->C, m->cells,

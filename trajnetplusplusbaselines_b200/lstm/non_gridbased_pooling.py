@@ -10,8 +10,10 @@ projection.  One kernel per step (csrc/mlp_pool.cu); same plug contract as GridB
 NearestNeighborMLP (:64-147, `--type nn`): relative position (and velocity) of the n nearest tracks, each through a
 shared Linear + ReLU, concatenated.  One kernel per step (nn_mlp_pool_kernel in csrc/mlp_pool.cu).
 
-AttentionMLPPooling (:242-351), NearestNeighborLSTM, TrajectronPooling and NMMP are not built (their constructors
-raise).
+AttentionMLPPooling (:242-351, `--type attentionmlp`): the embeddings of HiddenStateMLPPooling, wq / wk / wv and a
+one-head torch.nn.MultiheadAttention over all slots of the scene, out_projection (attn_mlp_pool_kernel).
+
+NearestNeighborLSTM, TrajectronPooling and NMMP are not built (their constructors raise).
 """
 import torch
 
@@ -180,6 +182,80 @@ class NearestNeighborMLP(torch.nn.Module, _StandalonePlug):
         return out.to(obs2.device) if obs2.device != device else out
 
 
+class AttentionMLPPooling(torch.nn.Module, _StandalonePlug):
+    def __init__(self, hidden_dim=128, mlp_dim=128, mlp_dim_spatial=32, mlp_dim_vel=32, out_dim=None, fill_value=-10):
+        """Same arguments, sub-module names and parameters as the reference (non_gridbased_pooling.py:257-292)."""
+        super().__init__()
+        self.out_dim = out_dim or hidden_dim
+        self.hidden_dim = hidden_dim
+        self.fill_value = fill_value
+        self.mlp_dim = mlp_dim
+        self.mlp_dim_spatial = mlp_dim_spatial
+        self.mlp_dim_vel = mlp_dim_vel
+        self.mlp_dim_hidden = mlp_dim - mlp_dim_spatial - mlp_dim_vel
+        if self.mlp_dim_spatial < 1 or self.mlp_dim_vel < 0 or self.mlp_dim_hidden < 0 or mlp_dim > 128:
+            raise ValueError("mlp_dim (<= 128) must cover mlp_dim_spatial (>= 1) + mlp_dim_vel")
+        self.spatial_embedding = torch.nn.Sequential(torch.nn.Linear(2, self.mlp_dim_spatial), torch.nn.ReLU())
+        if self.mlp_dim_vel:
+            self.vel_embedding = torch.nn.Sequential(torch.nn.Linear(2, self.mlp_dim_vel), torch.nn.ReLU())
+        if self.mlp_dim_hidden:
+            self.hidden_embedding = torch.nn.Sequential(torch.nn.Linear(self.hidden_dim, self.mlp_dim_hidden), torch.nn.ReLU())
+        self.wq = torch.nn.Linear(self.mlp_dim, self.mlp_dim, bias=False)
+        self.wk = torch.nn.Linear(self.mlp_dim, self.mlp_dim, bias=False)
+        self.wv = torch.nn.Linear(self.mlp_dim, self.mlp_dim, bias=False)
+        self.multihead_attn = torch.nn.MultiheadAttention(embed_dim=self.mlp_dim, num_heads=1)
+        self.out_projection = torch.nn.Linear(self.mlp_dim, self.out_dim)
+        self._handle = None
+        self._layouts = LayoutCache()
+
+    def fill_config(self, cfg):
+        cfg.pool_type = _lib.POOL_ATTN_MLP
+        cfg.out_dim = int(self.out_dim)
+        cfg.mlp_dim_spatial = int(self.mlp_dim_spatial)
+        cfg.mlp_dim_vel = int(self.mlp_dim_vel)
+        cfg.mlp_dim_hidden = int(self.mlp_dim_hidden)
+        cfg.attn_fill = float(self.fill_value)
+        cfg.pool_size = cfg.blur_size = 1
+
+    def weight_fields(self):
+        fields = dict(pool_spatial_weight=self.spatial_embedding[0].weight, pool_spatial_bias=self.spatial_embedding[0].bias,
+                      pool_out_weight=self.out_projection.weight, pool_out_bias=self.out_projection.bias,
+                      pool_attn_wq=self.wq.weight, pool_attn_wk=self.wk.weight, pool_attn_wv=self.wv.weight,
+                      pool_attn_in_proj_weight=self.multihead_attn.in_proj_weight,
+                      pool_attn_in_proj_bias=self.multihead_attn.in_proj_bias,
+                      pool_attn_out_proj_weight=self.multihead_attn.out_proj.weight,
+                      pool_attn_out_proj_bias=self.multihead_attn.out_proj.bias)
+        if self.mlp_dim_vel:
+            fields.update(pool_vel_weight=self.vel_embedding[0].weight, pool_vel_bias=self.vel_embedding[0].bias)
+        if self.mlp_dim_hidden:
+            fields.update(pool_hidden_weight=self.hidden_embedding[0].weight, pool_hidden_bias=self.hidden_embedding[0].bias)
+        return fields
+
+    def weights_version(self):
+        return weights_key(self)
+
+    def reset(self, num_tracks, max_num_neigh, device):
+        self.track_mask = None
+
+    def forward(self, hidden_states, obs1, obs2):
+        """[B, N, H], [B, N, 2], [B, N, 2] -> [B * N, out_dim] (non_gridbased_pooling.py:297-351)."""
+        _lib.require_cuda()
+        batch_size, num_tracks = obs2.size(0), obs2.size(1)
+        device = self.out_projection.weight.device
+        if device.type != 'cuda':
+            raise RuntimeError("AttentionMLPPooling runs on CUDA only: move the module to a B200 (module.cuda())")
+        if hidden_states.size(-1) != self.hidden_dim:
+            raise ValueError("hidden_states width != hidden_dim")
+        handle = self._plug_handle(device)
+        layout = self._layouts.get(range(0, batch_size * num_tracks + 1, num_tracks), device=device)
+        f32 = dict(device=device, dtype=torch.float32)
+        o1 = obs1.detach().to(**f32).reshape(-1, 2).contiguous()
+        o2 = obs2.detach().to(**f32).reshape(-1, 2).contiguous()
+        hid = hidden_states.detach().to(**f32).reshape(batch_size * num_tracks, -1).contiguous()
+        out = handle.pool_forward(layout, hid, o1, o2, self.out_dim)
+        return out.to(obs2.device) if obs2.device != device else out
+
+
 def _not_built(name, lines):
     class _NotBuilt(torch.nn.Module):
         def __init__(self, *args, **kwargs):
@@ -189,6 +265,5 @@ def _not_built(name, lines):
     return _NotBuilt
 
 
-AttentionMLPPooling = _not_built("AttentionMLPPooling", "242-351")
 NearestNeighborLSTM = _not_built("NearestNeighborLSTM", "354-")
 TrajectronPooling = _not_built("TrajectronPooling", "")
