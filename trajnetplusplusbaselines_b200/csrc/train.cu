@@ -884,6 +884,88 @@ __global__ void __launch_bounds__(256) social_scene_reduce_kernel(
     }
 }
 
+
+// dWt1 on the tensor cores (warp-level mma.sync, 3-pass bf16 split): per cell
+//   dWt1[cell][16 ch][d1] += lat^T [16 ch x pairs] . dz1[rows of the pairs][d1]
+// M = the 16 latent channels, K = the pairs of the cell (16 per k-step), N = 32 output columns per warp (4 n-tiles).
+// The A fragments (latent vectors of the winning pairs, zero for overwritten ones) come from shared memory, the B
+// fragments straight from the gathered dz1 rows (lane (g, t) reads column o0 + g of the rows of pairs 2t, 2t+1, 2t+8,
+// 2t+9); one CTA = (cell, 256 columns).  The FFMA kernel below it is kept for C != 16.
+__global__ void __launch_bounds__(256) social_dw1_mma_kernel(const unsigned* __restrict__ sorted, const int* __restrict__ start,
+                                                             int nm1, const int* __restrict__ row_scene,
+                                                             const int* __restrict__ scene_off, const float* __restrict__ lat,
+                                                             const float* __restrict__ dz1, int d1, float* __restrict__ dWt1) {
+    __shared__ float lat_s[32][17];          // [pair][channel], +1: conflict-free column reads
+    __shared__ int row_s[32];
+    const int cell = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int p0 = start[cell], p1 = start[cell + 1];
+    if (p0 >= p1) return;
+    const int obase = blockIdx.y * 256 + warp * 32;
+    const bool active = obase < d1;          // d1 % 32 == 0: a warp is entirely inside or outside
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[nt][k] = 0.f;
+    for (int pb = p0; pb < p1; pb += 32) {
+        const int nb = min(32, p1 - pb);
+        __syncthreads();
+        for (int idx = tid; idx < 32 * 16; idx += 256) {
+            const int tt = idx >> 4, ch = idx & 15;
+            float v = 0.f;
+            int rowi = 0;
+            if (tt < nb) {
+                const unsigned sv = sorted[pb + tt];
+                const int slot = (int)(sv & 0x3fffffffu);
+                const int i = slot / nm1, jj = slot - i * nm1;
+                const int s0 = scene_off[row_scene[i]];
+                const int j = jj + (jj >= i - s0);
+                // overwritten pairs are not in the grid: they contribute to d lat only
+                v = (sv & 0x80000000u) ? 0.f : lat[(size_t)(s0 + j) * 16 + ch];
+                rowi = i;
+            }
+            lat_s[tt][ch] = v;
+            if (ch == 0) row_s[tt] = rowi;       // padded pairs read row 0 with a zero latent vector
+        }
+        __syncthreads();
+        if (!active) continue;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            if (ks * 16 >= nb) break;
+            const int kb = ks * 16;
+            uint32_t ah[4], al[4];
+            split2(make_float2(lat_s[kb + 2 * t][g], lat_s[kb + 2 * t + 1][g]), ah[0], al[0]);
+            split2(make_float2(lat_s[kb + 2 * t][g + 8], lat_s[kb + 2 * t + 1][g + 8]), ah[1], al[1]);
+            split2(make_float2(lat_s[kb + 2 * t + 8][g], lat_s[kb + 2 * t + 9][g]), ah[2], al[2]);
+            split2(make_float2(lat_s[kb + 2 * t + 8][g + 8], lat_s[kb + 2 * t + 9][g + 8]), ah[3], al[3]);
+            const float* r0 = dz1 + (size_t)row_s[kb + 2 * t] * d1 + obase + g;
+            const float* r1 = dz1 + (size_t)row_s[kb + 2 * t + 1] * d1 + obase + g;
+            const float* r2 = dz1 + (size_t)row_s[kb + 2 * t + 8] * d1 + obase + g;
+            const float* r3 = dz1 + (size_t)row_s[kb + 2 * t + 9] * d1 + obase + g;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                uint32_t bh0, bl0, bh1, bl1;
+                split2(make_float2(__ldg(r0 + nt * 8), __ldg(r1 + nt * 8)), bh0, bl0);
+                split2(make_float2(__ldg(r2 + nt * 8), __ldg(r3 + nt * 8)), bh1, bl1);
+                mma_bf16_16816(acc[nt], ah, bh0, bh1);
+                mma_bf16_16816(acc[nt], al, bh0, bh1);
+                mma_bf16_16816(acc[nt], ah, bl0, bl1);
+            }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            float* d0 = dWt1 + ((size_t)cell * 16 + g) * d1 + obase + nt * 8 + 2 * t;
+            float* d8 = dWt1 + ((size_t)cell * 16 + g + 8) * d1 + obase + nt * 8 + 2 * t;
+            float2 v0 = *reinterpret_cast<float2*>(d0), v8 = *reinterpret_cast<float2*>(d8);
+            v0.x += acc[nt][0]; v0.y += acc[nt][1]; v8.x += acc[nt][2]; v8.y += acc[nt][3];
+            *reinterpret_cast<float2*>(d0) = v0;
+            *reinterpret_cast<float2*>(d8) = v8;
+        }
+    }
+}
+
 // dWt1[cell][ch][o] += sum over the cell's pairs (sorted order) of dz1[i][o] * lat_j[ch]
 template <int C>
 __global__ void __launch_bounds__(256) social_dw1_kernel(const unsigned* __restrict__ sorted,
@@ -1334,7 +1416,11 @@ static int social_pair_kernels(const tb2_lstm* m, const tb2_layout* l, const Soc
             b.sorted, b.start, b.DH1, d1, m->Wt1, nm1, b.DGRID);
     }
     TB2_LAUNCH_CHECK();
-    {
+    if (C == 16 && d1 % 32 == 0 && !(nomma && nomma[0] == '1')) {
+        KernelTimer kt("social_dw1_mma", st);
+        social_dw1_mma_kernel<<<dim3(m->cells, (d1 + 255) / 256), 256, 0, st>>>(
+            b.sorted, b.start, nm1, l->row_scene, l->scene_off, lat, b.DH1, d1, b.dWt1);
+    } else {
         KernelTimer kt("social_dw1", st);
         social_dw1_kernel<C><<<dim3(m->cells, (d1 + 255) / 256), 256, 0, st>>>(
             b.sorted, b.start, nm1, l->row_scene, l->scene_off, lat, b.DH1, d1, b.dWt1);
@@ -1519,11 +1605,7 @@ static int social_backward(const tb2_lstm* m, const tb2_layout* l, const tb2_lst
             } else if ((rc = gemm_nn(DXs + E, EP, w->pool_embedding_weight[1], d1, b.DH1, d1, Mi, d1, P, nullptr, st))) return rc;
             masked_copy_kernel<<<eb, 256, 0, st>>>(H1s, d1, b.DH1, d1, b.DH1, d1, Mi, d1);
             TB2_LAUNCH_CHECK();
-            if ((rc = gemm_tn(DXs + E, EP, H1s, d1, g->pool_embedding_weight1, d1, Mi, P, d1, b.scratch,
-                              b.scratch_floats, st)))
-                return rc;
-            if ((rc = colsum(DXs + E, EP, Mi, P, g->pool_embedding_bias1, nullptr, b.scratch, b.scratch_floats, st)))
-                return rc;
+            // dW2 / db2: one reduction over the rows of ALL steps after the loop (dz2 stays in DXIN, hidden1 in H1)
         } else {
             masked_copy_kernel<<<eb, 256, 0, st>>>(Xs + E, K, DXs + E, EP, b.DH1, d1, Mi, d1);
             TB2_LAUNCH_CHECK();
@@ -1559,6 +1641,11 @@ static int social_backward(const tb2_lstm* m, const tb2_layout* l, const tb2_lst
                 s > 0 ? b.pass[cur] : nullptr);
         }
         TB2_LAUNCH_CHECK();
+    }
+    if (two) {
+        if ((rc = gemm_tn(b.DXIN + E, EP, b.H1, d1, g->pool_embedding_weight1, d1, S * Mi, P, d1, b.scratch, b.scratch_floats, st)))
+            return rc;
+        if ((rc = colsum(b.DXIN + E, EP, S * Mi, P, g->pool_embedding_bias1, nullptr, b.scratch, b.scratch_floats, st))) return rc;
     }
     // (D) parameter gradients: one reduction over all (step, row) records per tensor
     for (int phase = 0; phase < 2; ++phase) {
