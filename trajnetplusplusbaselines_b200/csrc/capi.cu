@@ -348,6 +348,21 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
                 }
             }
         }
+        {
+            // occupancy / directional: first Linear as a dense 3-pass tcgen05 GEMM over an explicit (sparse, zero-padded)
+            // grid row per pedestrian: weights [d1][K padded to 64] in (cell, channel) order as bf16 (hi, lo)
+            const char* no_tc = getenv("TB2_DISABLE_TC");
+            const int k0p = (m->C * m->cells + 63) / 64 * 64;
+            if (cfg->pool_type != TB2_POOL_SOCIAL && m->n_mlp >= 1 && !(no_tc && no_tc[0] == '1') &&
+                dense_tc_supported(k0p, m->mlp_dims[1])) {
+                const size_t half = ((size_t)k0p * m->mlp_dims[1] + 1) / 2;
+                float *hi, *lo;
+                ALLOC(hi, half);
+                ALLOC(lo, half);
+                m->W_hi[0] = hi;
+                m->W_lo[0] = lo;
+            }
+        }
         for (int layer = 1; layer < m->n_mlp; ++layer) {
             ALLOC(m->WT[layer], (size_t)m->mlp_dims[layer] * m->mlp_dims[layer + 1]);
             ALLOC(m->bl[layer], m->mlp_dims[layer + 1]);
