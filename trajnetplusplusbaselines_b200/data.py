@@ -22,16 +22,28 @@ def paths_to_xy(paths):
     primary pedestrian's frames, and a pedestrian without a single row in those frames is dropped (it
     would be an all-NaN column that the writer later emits as NaN track rows).
     """
-    frames = sorted(set(r.frame for r in paths[0]))
+    if paths and paths[0] and not isinstance(paths[0][0], tuple):     # rows with attributes only: normalise to tuples
+        paths = [[(r.frame, r.pedestrian, r.x, r.y) for r in path] for path in paths]
+    frames = sorted({r[0] for r in paths[0]})              # TrackRow is a tuple: (frame, pedestrian, x, y, ...)
     frame_index = {f: i for i, f in enumerate(frames)}
-    paths = [path for path in paths if any(r.frame in frame_index for r in path)]
-    xy = np.full((len(frames), len(paths), 2), np.nan)
-    for p, path in enumerate(paths):
+    n_frames = len(frames)
+    nan = float('nan')
+    columns = []                                            # one flat [x0, y0, x1, y1, ...] list per kept pedestrian
+    for path in paths:
+        col = None
         for r in path:
-            i = frame_index.get(r.frame)
+            i = frame_index.get(r[0])
             if i is not None:
-                xy[i, p] = (r.x, r.y)
-    return xy
+                if col is None:
+                    col = [nan] * (2 * n_frames)
+                col[2 * i] = r[2]
+                col[2 * i + 1] = r[3]
+        if col is not None:
+            columns.append(col)
+    if not columns:
+        return np.full((n_frames, 0, 2), np.nan)
+    xy = np.array(columns, dtype=np.float64).reshape(len(columns), n_frames, 2)
+    return np.ascontiguousarray(xy.transpose(1, 0, 2))
 
 
 def read_ndjson_scenes(filename):
