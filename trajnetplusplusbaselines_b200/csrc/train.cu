@@ -1070,19 +1070,17 @@ struct CublasApi {
 };
 static const CublasApi& cublas_api() {
     static CublasApi api;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static std::once_flag once;
+    std::call_once(once, [] {
         void* lib = dlopen("libcublas.so.12", RTLD_NOW | RTLD_GLOBAL);
         if (!lib) lib = dlopen("libcublas.so", RTLD_NOW | RTLD_GLOBAL);
-        if (lib) {
-            api.create = reinterpret_cast<decltype(api.create)>(dlsym(lib, "cublasCreate_v2"));
-            api.set_stream = reinterpret_cast<decltype(api.set_stream)>(dlsym(lib, "cublasSetStream_v2"));
-            api.gemm_ex = reinterpret_cast<decltype(api.gemm_ex)>(dlsym(lib, "cublasGemmEx"));
-            api.set_emulation = reinterpret_cast<decltype(api.set_emulation)>(dlsym(lib, "cublasSetEmulationStrategy"));
-            api.ok = api.create && api.set_stream && api.gemm_ex;
-        }
-    }
+        if (!lib) return;
+        api.create = reinterpret_cast<decltype(api.create)>(dlsym(lib, "cublasCreate_v2"));
+        api.set_stream = reinterpret_cast<decltype(api.set_stream)>(dlsym(lib, "cublasSetStream_v2"));
+        api.gemm_ex = reinterpret_cast<decltype(api.gemm_ex)>(dlsym(lib, "cublasGemmEx"));
+        api.set_emulation = reinterpret_cast<decltype(api.set_emulation)>(dlsym(lib, "cublasSetEmulationStrategy"));
+        api.ok = api.create && api.set_stream && api.gemm_ex;
+    });
     return api;
 }
 
