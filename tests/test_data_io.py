@@ -146,3 +146,20 @@ def test_fast_writer_is_byte_identical_to_the_line_writer(tmp_path):
         want += [trajnet_line(TrackRow(first + 10 * j, scenes[0][2][n + 1][0].pedestrian, neigh[j, n, 0], neigh[j, n, 1], 0, 3))
                  for j in range(12)]
     assert lines == want
+
+
+def test_paths_to_xy_contract():
+    """trajnetplusplustools.Reader.paths_to_xy semantics: frames = sorted set of the primary's frames, pedestrians
+    without a row in those frames are dropped, rows outside them ignored; rows may be plain objects with attributes."""
+    import types
+    from trajnetplusplusbaselines_b200.data import TrackRow, paths_to_xy
+    primary = [TrackRow(30, 1, 3.0, 3.5), TrackRow(10, 1, 1.0, 1.5), TrackRow(20, 1, 2.0, 2.5)]     # unsorted on purpose
+    other = [TrackRow(20, 2, 7.0, 7.5), TrackRow(40, 2, 9.0, 9.5)]                                  # frame 40 is outside
+    ghost = [TrackRow(50, 3, 0.0, 0.0)]                                                            # never inside: dropped
+    xy = paths_to_xy([primary, other, ghost])
+    assert xy.shape == (3, 2, 2) and xy.dtype == np.float64 and xy.flags["C_CONTIGUOUS"]
+    assert xy[:, 0].tolist() == [[1.0, 1.5], [2.0, 2.5], [3.0, 3.5]]
+    assert np.isnan(xy[0, 1]).all() and xy[1, 1].tolist() == [7.0, 7.5] and np.isnan(xy[2, 1]).all()
+    rows = [[types.SimpleNamespace(frame=r.frame, pedestrian=r.pedestrian, x=r.x, y=r.y) for r in path]
+            for path in (primary, other, ghost)]
+    assert np.array_equal(np.isnan(paths_to_xy(rows)), np.isnan(xy)) and np.nanmax(np.abs(paths_to_xy(rows) - xy)) == 0.0
