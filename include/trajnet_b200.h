@@ -45,6 +45,11 @@ extern "C" {
                                    * embeddings of TB2_POOL_HIDDEN_MLP (fill value attn_fill instead of -100, 0 for the
                                    * hidden part), wq / wk / wv, a one-head torch.nn.MultiheadAttention, out_projection */
 
+#define TB2_POOL_NN_LSTM 7        /* NearestNeighborLSTM (--type nn_lstm) non_gridbased_pooling.py:354-451: the features of
+                                   * TB2_POOL_NN_MLP (always with velocities) drive a per-track LSTMCell (mlp_dim_hidden =
+                                   * its hidden_dim) whose state lives in the caller's workspace over the steps of a
+                                   * sequence; interaction vector = hidden2pool(h') */
+
 #define TB2_PHASE_ENCODER 0
 #define TB2_PHASE_DECODER 1
 
@@ -122,6 +127,11 @@ typedef struct tb2_lstm_weights {
     const float* pool_attn_in_proj_bias;    /* pool.multihead_attn.in_proj_bias [3E] */
     const float* pool_attn_out_proj_weight; /* pool.multihead_attn.out_proj.weight [E, E] */
     const float* pool_attn_out_proj_bias;   /* pool.multihead_attn.out_proj.bias [E] */
+    /* TB2_POOL_NN_LSTM (NULL otherwise), Hp = mlp_dim_hidden; hidden2pool = pool_out_weight / pool_out_bias */
+    const float* pool_lstm_weight_ih;     /* pool.pool_lstm.weight_ih [4 Hp, out_dim] */
+    const float* pool_lstm_weight_hh;     /* pool.pool_lstm.weight_hh [4 Hp, Hp] */
+    const float* pool_lstm_bias_ih;       /* [4 Hp] */
+    const float* pool_lstm_bias_hh;       /* [4 Hp] */
 } tb2_lstm_weights;
 
 typedef struct tb2_lstm tb2_lstm;          /* opaque: config + repacked weights on the device */
@@ -287,6 +297,13 @@ int tb2_lstm_sequence_backward(const tb2_lstm* model, const tb2_layout* layout, 
                                const float* d_normals_dev, const int32_t* active_rows_dev, int32_t num_active,
                                const tb2_lstm_grads* grads, void* workspace_dev, size_t workspace_bytes,
                                void* bwd_workspace_dev, size_t bwd_workspace_bytes, void* stream);
+
+/* TB2_POOL_NN_LSTM: zero the interaction-encoder LSTM state kept in `workspace` (NearestNeighborLSTM.reset,
+ * non_gridbased_pooling.py:385-389).  tb2_lstm_forward_sequence / _steps(first_step = 0) do this themselves; the
+ * stand-alone plug (tb2_pool_forward) advances the state on every call and needs it after a reset().  No-op for the
+ * other pool types. */
+int tb2_pool_state_reset(const tb2_lstm* model, const tb2_layout* layout, void* workspace_dev, size_t workspace_bytes,
+                         void* stream);
 
 /* Training forward that keeps, per step, what the social backward would otherwise recompute (winners, latent vectors,
  * hidden1 and the pooled vector of the grid embedding; reference: everything autograd saves inside

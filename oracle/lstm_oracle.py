@@ -77,6 +77,18 @@ class AttnPoolConfig:
         self.fill_value = fill_value
 
 
+class NnLstmPoolConfig:
+    """Constructor arguments of NearestNeighborLSTM (non_gridbased_pooling.py:371-383)."""
+
+    def __init__(self, n=4, hidden_dim=256, out_dim=32):
+        self.type_ = "nn_lstm"
+        self.n = n
+        self.hidden_dim = hidden_dim
+        self.out_dim = out_dim
+        self.no_vel = False
+        self.input_dim = 4
+
+
 class NnPoolConfig:
     """Constructor arguments of NearestNeighborMLP (non_gridbased_pooling.py:78-91)."""
 
@@ -312,8 +324,21 @@ def nn_mlp_pool_forward(cfg, weights, obs1, obs2, prefix="pool."):
     return out.reshape(B * N, -1)
 
 
-def pool_forward(cfg, weights, hidden, obs1, obs2, prefix="pool."):
+def nn_lstm_pool_forward(cfg, weights, obs1, obs2, state, prefix="pool."):
+    """NearestNeighborLSTM.forward (non_gridbased_pooling.py:391-451): the NearestNeighborMLP features of every slot
+    (absent ones included: zero features) drive a per-slot LSTMCell whose state persists over the steps of a forward
+    (reset at its start, lstm.py:213-216); the interaction vector is hidden2pool(h').  `state` = {"h", "c"} [B*N, Hp],
+    updated in place."""
+    feats = nn_mlp_pool_forward(cfg, weights, obs1, obs2, prefix)
+    h2, c2 = lstm_cell(weights, prefix + "pool_lstm.", feats, state["h"], state["c"])
+    state["h"], state["c"] = h2, c2
+    return _linear(h2, weights[prefix + "hidden2pool.weight"], weights[prefix + "hidden2pool.bias"])
+
+
+def pool_forward(cfg, weights, hidden, obs1, obs2, prefix="pool.", state=None):
     """GridBasedPooling.forward (gridbased_pooling.py:94-110) -> [B*N, out_dim]."""
+    if getattr(cfg, "type_", None) == "nn_lstm":
+        return nn_lstm_pool_forward(cfg, weights, obs1, obs2, state, prefix)
     if getattr(cfg, "type_", None) == "hiddenstatemlp":
         return hidden_mlp_pool_forward(cfg, weights, hidden, obs1, obs2, prefix)
     if getattr(cfg, "type_", None) == "nn":
@@ -376,7 +401,7 @@ def _pad_scenes(x, batch_split, n_max, fill):
 
 
 def step(weights, pool_cfg, phase, h, c, obs1, obs2, batch_split, pool_to_input=True,
-         return_pooled=False):
+         return_pooled=False, pool_state=None):
     """LSTM.step (lstm.py:91-168).  h, c [M, H] are updated functionally.
 
     phase = 'encoder' | 'decoder'.  Returns (h', c', normal [M, 5]); rows whose track is
@@ -397,7 +422,11 @@ def step(weights, pool_cfg, phase, h, c, obs1, obs2, batch_split, pool_to_input=
         prev = _pad_scenes(obs1, bs, n_max, F32(NAN))
         hid = _pad_scenes(h.astype(F32), bs, n_max, F32(NAN))               # :26,39 (ALL tracks)
         mpos = _pad_scenes(mask, bs, n_max, False)
-        pooled_all = pool_forward(pool_cfg, weights, hid, prev, cur)        # :145
+        if getattr(pool_cfg, "type_", None) == "nn_lstm" and pool_state is not None and "h" not in pool_state:
+            Hp = pool_cfg.hidden_dim                                        # pool.reset(B * Nmax, ...) lstm.py:213-216
+            pool_state["h"] = np.zeros((cur.shape[0] * cur.shape[1], Hp), dtype=F32)
+            pool_state["c"] = np.zeros((cur.shape[0] * cur.shape[1], Hp), dtype=F32)
+        pooled_all = pool_forward(pool_cfg, weights, hid, prev, cur, state=pool_state)        # :145
         pooled = pooled_all[mpos.reshape(-1)]                               # :146
         if pool_to_input:
             x = np.concatenate([x, pooled], axis=1)                         # :149
@@ -434,10 +463,11 @@ def forward(weights, pool_cfg, observed, batch_split, prediction_truth=None, n_p
     bs = np.asarray(batch_split, dtype=np.int64)
     primaries = bs[:-1]
     normals, positions, states = [], [], []
+    pool_state = {}                                                         # interaction-encoder LSTM state (nn_lstm)
     if len(observed) == 2:                                                  # :222-223
         positions = [observed[-1]]
     for obs1, obs2 in zip(observed[:-1], observed[1:]):                     # :226-232
-        h, c, normal = step(weights, pool_cfg, "encoder", h, c, obs1, obs2, bs, pool_to_input)
+        h, c, normal = step(weights, pool_cfg, "encoder", h, c, obs1, obs2, bs, pool_to_input, pool_state=pool_state)
         normals.append(normal)
         positions.append((obs2 + normal[:, :2]).astype(F32))
         states.append((h, c))
@@ -454,7 +484,7 @@ def forward(weights, pool_cfg, observed, batch_split, prediction_truth=None, n_p
             obs2 = positions[-1]
         else:
             obs2[primaries] = positions[-1][primaries]
-        h, c, normal = step(weights, pool_cfg, "decoder", h, c, obs1, obs2, bs, pool_to_input)
+        h, c, normal = step(weights, pool_cfg, "decoder", h, c, obs1, obs2, bs, pool_to_input, pool_state=pool_state)
         normals.append(normal)
         positions.append((obs2 + normal[:, :2]).astype(F32))
         states.append((h, c))
@@ -577,7 +607,16 @@ ATTN_SPECS = {
 }
 
 
+# NearestNeighborLSTM(n=args.neigh (4), hidden_dim=args.hidden_dim (128), out_dim=args.pool_dim) (lstm/trainer.py:478-479)
+NN_LSTM_SPECS = {
+    "nn_lstm": dict(n=4, hidden_dim=128, out_dim=256),
+    "nn_lstm_small": dict(n=3, hidden_dim=40, out_dim=24),
+}
+
+
 def pool_config(kind):
+    if kind in NN_LSTM_SPECS:
+        return NnLstmPoolConfig(**NN_LSTM_SPECS[kind])
     if kind in ATTN_SPECS:
         return AttnPoolConfig(**ATTN_SPECS[kind])
     if kind in NONGRID_SPECS:
@@ -602,7 +641,16 @@ def random_weights(kind, seed=0, scale=1.0, embedding_dim=64, hidden_dim=128):
 
     E, H = embedding_dim, hidden_dim
     pool_dim = 0
-    if cfg is not None and cfg.type_ == "nn":
+    if cfg is not None and cfg.type_ == "nn_lstm":
+        lin("pool.embedding.0.weight", "pool.embedding.0.bias", cfg.out_dim // cfg.n, cfg.input_dim)
+        kp = scale / math.sqrt(cfg.hidden_dim)
+        W["pool.pool_lstm.weight_ih"] = rng.uniform(-kp, kp, size=(4 * cfg.hidden_dim, cfg.out_dim)).astype(F32)
+        W["pool.pool_lstm.weight_hh"] = rng.uniform(-kp, kp, size=(4 * cfg.hidden_dim, cfg.hidden_dim)).astype(F32)
+        W["pool.pool_lstm.bias_ih"] = rng.uniform(-kp, kp, size=(4 * cfg.hidden_dim,)).astype(F32)
+        W["pool.pool_lstm.bias_hh"] = rng.uniform(-kp, kp, size=(4 * cfg.hidden_dim,)).astype(F32)
+        lin("pool.hidden2pool.weight", "pool.hidden2pool.bias", cfg.out_dim, cfg.hidden_dim)
+        pool_dim = cfg.out_dim
+    elif cfg is not None and cfg.type_ == "nn":
         lin("pool.embedding.0.weight", "pool.embedding.0.bias", cfg.out_dim // cfg.n, cfg.input_dim)
         pool_dim = cfg.out_dim
     elif cfg is not None and cfg.type_ == "attentionmlp":

@@ -15,6 +15,7 @@ from oracle.ref_shim import import_reference
 KINDS = ["hiddenstatemlp", "hiddenstatemlp_small"]
 NN_KINDS = ["nn", "nn_small"]
 ATTN_KINDS = ["attentionmlp", "attentionmlp_small"]
+NN_LSTM_KINDS = ["nn_lstm", "nn_lstm_small"]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -38,8 +39,11 @@ def scene_inputs():
 
 def build_reference_model(kind, W):
     from trajnetbaselines.lstm import LSTM
-    from trajnetbaselines.lstm.non_gridbased_pooling import AttentionMLPPooling, HiddenStateMLPPooling, NearestNeighborMLP
-    if kind in O.NN_SPECS:
+    from trajnetbaselines.lstm.non_gridbased_pooling import (AttentionMLPPooling, HiddenStateMLPPooling, NearestNeighborLSTM,
+                                                              NearestNeighborMLP)
+    if kind in O.NN_LSTM_SPECS:
+        pool = NearestNeighborLSTM(**O.NN_LSTM_SPECS[kind])
+    elif kind in O.NN_SPECS:
         pool = NearestNeighborMLP(**O.NN_SPECS[kind])
     elif kind in O.ATTN_SPECS:
         pool = AttentionMLPPooling(**O.ATTN_SPECS[kind])
@@ -56,11 +60,18 @@ def main():
     hid, obs1, obs2 = plug_inputs()
     xy, bs = scene_inputs()
     M = xy.shape[1]
-    for kind in KINDS + NN_KINDS + ATTN_KINDS:
+    for kind in KINDS + NN_KINDS + ATTN_KINDS + NN_LSTM_KINDS:
         W = O.random_weights(kind, seed=13)
         model = build_reference_model(kind, W)
         with torch.no_grad():
-            out[kind + "/plug"] = model.pool(torch.from_numpy(hid), torch.from_numpy(obs1), torch.from_numpy(obs2)).numpy()
+            if kind in NN_LSTM_KINDS:     # stateful plug: two consecutive calls after a reset
+                model.pool.reset(obs2.shape[0] * obs2.shape[1], obs2.shape[1] - 1, device=torch.device("cpu"))
+                first = model.pool(torch.from_numpy(hid), torch.from_numpy(obs1), torch.from_numpy(obs2)).numpy()
+                second = model.pool(torch.from_numpy(hid), torch.from_numpy(obs2), torch.from_numpy(obs2 + (obs2 - obs1))).numpy()
+                out[kind + "/plug"] = first
+                out[kind + "/plug2"] = second
+            else:
+                out[kind + "/plug"] = model.pool(torch.from_numpy(hid), torch.from_numpy(obs1), torch.from_numpy(obs2)).numpy()
             rel, pred = model(torch.from_numpy(xy[:9]), torch.zeros(M, 2), torch.from_numpy(bs), n_predict=12)
             rel_t, pred_t = model(torch.from_numpy(xy[:9]), torch.zeros(M, 2), torch.from_numpy(bs),
                                   prediction_truth=torch.from_numpy(xy[9:20]).clone())

@@ -9,16 +9,18 @@ import pytest
 import torch
 
 from oracle import lstm_oracle as O
-from oracle.make_nongrid_golden import ATTN_KINDS, KINDS, NN_KINDS, plug_inputs, scene_inputs
+from oracle.make_nongrid_golden import ATTN_KINDS, KINDS, NN_KINDS, NN_LSTM_KINDS, plug_inputs, scene_inputs
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "nongrid_golden.npz"))
 
 
-ALL_KINDS = KINDS + NN_KINDS + ATTN_KINDS
+ALL_KINDS = KINDS + NN_KINDS + ATTN_KINDS + NN_LSTM_KINDS
 
 
 def _pool(kind):
-    from trajnetplusplusbaselines_b200.lstm import AttentionMLPPooling, HiddenStateMLPPooling, NearestNeighborMLP
+    from trajnetplusplusbaselines_b200.lstm import AttentionMLPPooling, HiddenStateMLPPooling, NearestNeighborLSTM, NearestNeighborMLP
+    if kind in O.NN_LSTM_SPECS:
+        return NearestNeighborLSTM(**O.NN_LSTM_SPECS[kind])
     if kind in O.NN_SPECS:
         return NearestNeighborMLP(**O.NN_SPECS[kind])
     if kind in O.ATTN_SPECS:
@@ -31,7 +33,13 @@ def test_oracle_matches_reference_vectors(kind):
     W = O.random_weights(kind, seed=13)
     cfg = O.pool_config(kind)
     hid, obs1, obs2 = plug_inputs()
-    assert np.abs(O.pool_forward(cfg, W, hid, obs1, obs2) - GOLD[kind + "/plug"]).max() < 1e-5
+    if kind in NN_LSTM_KINDS:      # stateful plug: two calls after a reset
+        n = obs2.shape[0] * obs2.shape[1]
+        st = {"h": np.zeros((n, cfg.hidden_dim), np.float32), "c": np.zeros((n, cfg.hidden_dim), np.float32)}
+        assert np.abs(O.pool_forward(cfg, W, hid, obs1, obs2, state=st) - GOLD[kind + "/plug"]).max() < 1e-5
+        assert np.abs(O.pool_forward(cfg, W, hid, obs2, obs2 + (obs2 - obs1), state=st) - GOLD[kind + "/plug2"]).max() < 1e-5
+    else:
+        assert np.abs(O.pool_forward(cfg, W, hid, obs1, obs2) - GOLD[kind + "/plug"]).max() < 1e-5
     xy, bs = scene_inputs()
     rel, pred = O.forward(W, cfg, xy[:9], bs, n_predict=12)
     _, pred_t = O.forward(W, cfg, xy[:9], bs, prediction_truth=xy[9:20])
@@ -54,7 +62,7 @@ def test_state_dict_keys_match_reference_layout():
 
 def test_unbuilt_modules_raise():
     from trajnetplusplusbaselines_b200.lstm import non_gridbased_pooling as ngp
-    for name in ("NearestNeighborLSTM", "TrajectronPooling"):
+    for name in ("TrajectronPooling",):
         with pytest.raises(NotImplementedError):
             getattr(ngp, name)()
 
@@ -78,6 +86,15 @@ def test_cuda_plug_matches_reference_vectors(kind):
     ref = GOLD[kind + "/plug"]
     assert out.shape == ref.shape
     assert np.abs(out.cpu().numpy() - ref).max() < 1e-4 * max(1.0, float(np.abs(ref).max()))      # fp32 order of the 128-term sums
+    if kind in NN_LSTM_KINDS:      # the state advanced: second call, then the same pair again after a reset
+        o2 = torch.from_numpy(obs2).cuda()
+        o3 = torch.from_numpy(obs2 + (obs2 - obs1)).cuda()
+        out2 = model.pool(torch.from_numpy(hid).cuda(), o2, o3)
+        ref2 = GOLD[kind + "/plug2"]
+        assert np.abs(out2.cpu().numpy() - ref2).max() < 1e-4 * max(1.0, float(np.abs(ref2).max()))
+        model.pool.reset(obs2.shape[0] * obs2.shape[1], obs2.shape[1] - 1, device=o2.device)
+        again = model.pool(torch.from_numpy(hid).cuda(), torch.from_numpy(obs1).cuda(), o2)
+        assert np.abs(again.cpu().numpy() - ref).max() < 1e-4 * max(1.0, float(np.abs(ref).max()))
 
 
 @pytest.mark.gpu
@@ -98,7 +115,7 @@ def test_cuda_forward_matches_reference_vectors(kind):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", ["hiddenstatemlp", "nn", "attentionmlp"])
+@pytest.mark.parametrize("kind", ["hiddenstatemlp", "nn", "attentionmlp", "nn_lstm"])
 def test_cuda_baseline_shape_vs_oracle_and_training_raises(kind):
     """256-d pooling at N = 20, T = 9 + 12 on 48 scenes vs the oracle; training is inference-only."""
     model = _model(kind)

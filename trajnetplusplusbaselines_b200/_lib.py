@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtrajnet_b200.so")
 
-POOL_NONE, POOL_OCCUPANCY, POOL_DIRECTIONAL, POOL_SOCIAL, POOL_HIDDEN_MLP, POOL_NN_MLP, POOL_ATTN_MLP = 0, 1, 2, 3, 4, 5, 6
+POOL_NONE, POOL_OCCUPANCY, POOL_DIRECTIONAL, POOL_SOCIAL, POOL_HIDDEN_MLP, POOL_NN_MLP, POOL_ATTN_MLP, POOL_NN_LSTM = 0, 1, 2, 3, 4, 5, 6, 7
 PHASE_ENCODER, PHASE_DECODER = 0, 1
 
 _c_float_p = ctypes.c_void_p   # device pointers travel as integers
@@ -72,6 +72,10 @@ class LstmWeights(ctypes.Structure):
         ("pool_attn_in_proj_bias", ctypes.c_void_p),
         ("pool_attn_out_proj_weight", ctypes.c_void_p),
         ("pool_attn_out_proj_bias", ctypes.c_void_p),
+        ("pool_lstm_weight_ih", ctypes.c_void_p),
+        ("pool_lstm_weight_hh", ctypes.c_void_p),
+        ("pool_lstm_bias_ih", ctypes.c_void_p),
+        ("pool_lstm_bias_hh", ctypes.c_void_p),
     ]
 
 
@@ -139,6 +143,7 @@ PROTOTYPES = {
     "tb2_lstm_sequence_backward": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(LstmWeights), _vp, _i32, _vp, _i32,
                                                   _vp, _vp, _vp, _vp, _i32, ctypes.POINTER(LstmGrads),
                                                   _vp, _sz, _vp, _sz, _vp]),
+    "tb2_pool_state_reset": (ctypes.c_int, [_vp, _vp, _vp, _sz, _vp]),
     "tb2_lstm_train_cache_bytes": (_sz, [_vp, _vp, _i32]),
     "tb2_lstm_forward_sequence_train": (ctypes.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "tb2_lstm_sequence_backward_cached": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(LstmWeights), _vp, _i32, _vp, _i32,

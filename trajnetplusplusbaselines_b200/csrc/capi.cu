@@ -76,6 +76,12 @@ size_t carve_workspace(const tb2_lstm* m, const tb2_layout* l, void* base, Works
         w.hs_hi[i] = take(M * 128 * 2);
         w.hs_lo[i] = take(M * 128 * 2);
     }
+    w.pool_feat = w.pool_h = w.pool_c = nullptr;
+    if (m->cfg.pool_type == TB2_POOL_NN_LSTM) {
+        w.pool_feat = (float*)take(M * (size_t)m->cfg.out_dim * sizeof(float));
+        w.pool_h = (float*)take(M * (size_t)m->cfg.mlp_dim_hidden * sizeof(float));
+        w.pool_c = (float*)take(M * (size_t)m->cfg.mlp_dim_hidden * sizeof(float));
+    }
     w.bytes = off;
     w.write_pairs = 0;
     if (ws) *ws = w;
@@ -198,7 +204,7 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
     *out = nullptr;
     TB2_REQUIRE(cfg->hidden_dim == 128, "hidden_dim must be 128 (kernel specialisation)");
     TB2_REQUIRE(cfg->embedding_dim >= 4 && cfg->embedding_dim <= 1024, "embedding_dim out of range");
-    TB2_REQUIRE(cfg->pool_type >= TB2_POOL_NONE && cfg->pool_type <= TB2_POOL_ATTN_MLP, "bad pool_type");
+    TB2_REQUIRE(cfg->pool_type >= TB2_POOL_NONE && cfg->pool_type <= TB2_POOL_NN_LSTM, "bad pool_type");
     tb2_lstm* m = new (std::nothrow) tb2_lstm();
     TB2_REQUIRE(m, "out of host memory");
     m->cfg = *cfg;
@@ -213,8 +219,14 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
     for (int i = 0; i < kMaxMlpLayers; ++i) { m->WT[i] = m->bl[i] = nullptr; m->W_hi[i] = m->W_lo[i] = nullptr; }
     m->mp_Ws = m->mp_bs = m->mp_Wv = m->mp_bv = m->mp_WhT = m->mp_bh = m->mp_WoT = m->mp_bo = nullptr;
     m->at_AqT = m->at_AkT = m->at_AvT = m->at_bqkv = m->at_WoT = m->at_bo = nullptr;
+    m->pl_WihT = m->pl_WhhT = m->pl_b = nullptr;
     auto fail = [&](int rc) { tb2_lstm_destroy(m); return rc; };
-    if (cfg->pool_type == TB2_POOL_NN_MLP) {
+    if (cfg->pool_type == TB2_POOL_NN_LSTM &&
+        !(cfg->mlp_dim_hidden >= 1 && cfg->mlp_dim_hidden <= 512 && cfg->out_dim <= 1024 && cfg->mlp_dim_vel != 0)) {
+        set_error("invalid argument: nearest-neighbour LSTM pooling needs 1 <= hidden_dim <= 512, out_dim <= 1024 and velocities");
+        return fail(TB2_ERR_INVALID);
+    }
+    if (cfg->pool_type == TB2_POOL_NN_MLP || cfg->pool_type == TB2_POOL_NN_LSTM) {
         if (!(cfg->n >= 1 && cfg->n <= 32 && cfg->mlp_dim_spatial >= 1 && cfg->out_dim == cfg->n * cfg->mlp_dim_spatial)) {
             set_error("invalid argument: nearest-neighbour pooling needs 1 <= n <= 32 and out_dim == n * mlp_dim_spatial");
             return fail(TB2_ERR_INVALID);
@@ -295,7 +307,15 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
         ALLOC(m->WencT, m->H * m->C);
         ALLOC(m->benc, m->C);
     }
-    if (cfg->pool_type == TB2_POOL_NN_MLP) {
+    if (cfg->pool_type == TB2_POOL_NN_LSTM) {
+        const size_t Hp = (size_t)cfg->mlp_dim_hidden;
+        ALLOC(m->pl_WihT, (size_t)cfg->out_dim * 4 * Hp);
+        ALLOC(m->pl_WhhT, Hp * 4 * Hp);
+        ALLOC(m->pl_b, 4 * Hp);
+        ALLOC(m->mp_WoT, Hp * (size_t)cfg->out_dim);
+        ALLOC(m->mp_bo, cfg->out_dim);
+    }
+    if (cfg->pool_type == TB2_POOL_NN_MLP || cfg->pool_type == TB2_POOL_NN_LSTM) {
         ALLOC(m->mp_Ws, cfg->mlp_dim_spatial * 4);
         ALLOC(m->mp_bs, cfg->mlp_dim_spatial);
     } else
@@ -521,6 +541,10 @@ int tb2_pool_forward(const tb2_lstm* m, const tb2_layout* l, const float* hidden
     cudaStream_t st = (cudaStream_t)stream;
     if (m->cfg.pool_type == TB2_POOL_HIDDEN_MLP) return launch_hidden_mlp_pool(m, l, hidden, obs1, obs2, pooled_out, st);
     if (m->cfg.pool_type == TB2_POOL_NN_MLP) return launch_nn_mlp_pool(m, l, obs1, obs2, pooled_out, st);
+    if (m->cfg.pool_type == TB2_POOL_NN_LSTM) {      // stateful: advances the LSTM state kept in the workspace
+        if ((rc = launch_nn_mlp_pool(m, l, obs1, obs2, ws.pool_feat, st))) return rc;
+        return launch_pool_lstm_cell(m, l, ws.pool_feat, ws.pool_h, ws.pool_c, pooled_out, st);
+    }
     if (m->cfg.pool_type == TB2_POOL_ATTN_MLP) return launch_attn_mlp_pool(m, l, hidden, obs1, obs2, pooled_out, st);
     if ((rc = launch_pool_prepare(m, l, hidden, obs1, obs2, 0, 0, 0, &ws, st))) return rc;
     return launch_pool_mlp(m, l, &ws, pooled_out, nullptr, nullptr, st);
@@ -534,9 +558,13 @@ static int step_impl(const tb2_lstm* m, const tb2_layout* l, int phase, const fl
     int rc;
     const bool tc = m->Wg_hi[0] != nullptr;
     const float* pooled = nullptr;
-    if (m->cfg.pool_type == TB2_POOL_HIDDEN_MLP || m->cfg.pool_type == TB2_POOL_NN_MLP || m->cfg.pool_type == TB2_POOL_ATTN_MLP) {
+    if (m->cfg.pool_type >= TB2_POOL_HIDDEN_MLP) {
         // non-grid interaction module: one kernel per scene -> pooled fp32, split for the tensor-core gate kernel
         if (m->cfg.pool_type == TB2_POOL_NN_MLP) rc = launch_nn_mlp_pool(m, l, obs1, obs2, ws->pooled, st);
+        else if (m->cfg.pool_type == TB2_POOL_NN_LSTM) {
+            rc = launch_nn_mlp_pool(m, l, obs1, obs2, ws->pool_feat, st);
+            if (!rc) rc = launch_pool_lstm_cell(m, l, ws->pool_feat, ws->pool_h, ws->pool_c, ws->pooled, st);
+        }
         else if (m->cfg.pool_type == TB2_POOL_ATTN_MLP) rc = launch_attn_mlp_pool(m, l, h_in, obs1, obs2, ws->pooled, st);
         else rc = launch_hidden_mlp_pool(m, l, h_in, obs1, obs2, ws->pooled, st);
         if (rc) return rc;
@@ -605,6 +633,10 @@ static int forward_steps_impl(const tb2_lstm* m, const tb2_layout* l, const floa
     cudaStream_t st = (cudaStream_t)stream;
     const size_t M = (size_t)l->M, H = (size_t)m->H;
     const size_t frame = M * 2;
+    if (first_step == 0 && ws.pool_h) {       // pool.reset(...) lstm.py:213-216
+        TB2_CHECK_CUDA(cudaMemsetAsync(ws.pool_h, 0, M * (size_t)m->cfg.mlp_dim_hidden * sizeof(float), st));
+        TB2_CHECK_CUDA(cudaMemsetAsync(ws.pool_c, 0, M * (size_t)m->cfg.mlp_dim_hidden * sizeof(float), st));
+    }
     if (first_step == 0) {
         TB2_CHECK_CUDA(cudaMemsetAsync(h, 0, M * H * sizeof(float), st));     // lstm.py:207-210
         TB2_CHECK_CUDA(cudaMemsetAsync(c, 0, M * H * sizeof(float), st));
@@ -686,6 +718,19 @@ int tb2_lstm_forward_sequence_host(tb2_lstm* m, const tb2_layout* l, const float
     HostSink sink{normals_host, positions_host, (cudaStream_t)copy_stream, &m->step_events};
     return forward_steps_impl(m, l, observed, obs_length, truth, n_decode, 0, S, normals_out, positions_out, h, c,
                               nullptr, workspace, workspace_bytes, stream, &sink);
+}
+
+int tb2_pool_state_reset(const tb2_lstm* m, const tb2_layout* l, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_ready(m, l, workspace, workspace_bytes);
+    if (rc) return rc;
+    Workspace ws;
+    carve_workspace(m, l, workspace, &ws);
+    if (ws.pool_h) {
+        const size_t n = (size_t)l->M * (size_t)m->cfg.mlp_dim_hidden * sizeof(float);
+        TB2_CHECK_CUDA(cudaMemsetAsync(ws.pool_h, 0, n, (cudaStream_t)stream));
+        TB2_CHECK_CUDA(cudaMemsetAsync(ws.pool_c, 0, n, (cudaStream_t)stream));
+    }
+    return TB2_OK;
 }
 
 size_t tb2_lstm_train_cache_bytes(const tb2_lstm* m, const tb2_layout* l, int32_t num_steps) {

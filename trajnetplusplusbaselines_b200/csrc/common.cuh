@@ -141,6 +141,8 @@ struct tb2_lstm {
     // AttentionMLPPooling (TB2_POOL_ATTN_MLP): in-projection . wq / wk / wv combined and transposed [E in][E out], biases,
     // out-projection transposed
     float *at_AqT, *at_AkT, *at_AvT, *at_bqkv, *at_WoT, *at_bo;
+    // NearestNeighborLSTM (TB2_POOL_NN_LSTM): interaction-encoder LSTMCell, weights transposed [in][4 Hp], fused bias
+    float *pl_WihT, *pl_WhhT, *pl_b;
     void* Wg_hi[2];        // gate weights [4H (rank, gate, unit), K_gate] bf16 split (null: FFMA gates)
     void* Wg_lo[2];
     std::vector<void*> owned;
@@ -187,6 +189,9 @@ struct Workspace {
     void* hs_lo[2];
     size_t bytes;
     int write_pairs;       // pool_prepare also exports the pair tables (training forward with a cache)
+    float* pool_feat;      // [M, out_dim] neighbour features of NearestNeighborLSTM (null otherwise)
+    float* pool_h;         // [M, Hp] state of its interaction-encoder LSTM, kept over the steps of a sequence
+    float* pool_c;
 };
 
 // Per-step forward quantities a training forward keeps for the social backward (tb2_lstm_forward_sequence_train):
@@ -237,6 +242,8 @@ int launch_hidden_mlp_pool(const tb2_lstm* m, const tb2_layout* l, const float* 
                            const float* obs2, float* out, cudaStream_t st);
 int launch_attn_mlp_pool(const tb2_lstm* m, const tb2_layout* l, const float* hidden, const float* obs1, const float* obs2,
                          float* out, cudaStream_t st);
+int launch_pool_lstm_cell(const tb2_lstm* m, const tb2_layout* l, const float* feat, float* h, float* c, float* out,
+                          cudaStream_t st);
 int launch_nn_mlp_pool(const tb2_lstm* m, const tb2_layout* l, const float* obs1, const float* obs2, float* out,
                        cudaStream_t st);
 bool dense_tc_supported(int K, int N);

@@ -284,6 +284,11 @@ __global__ void repack_gates_kernel(const float* __restrict__ w_ih, const float*
     }
 }
 
+__global__ void add_bias_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i];
+}
+
 // pool.embedding.0.weight [d1][C * cells] (channel-major columns) -> bf16 (hi, lo) [d1][Kp] with columns in
 // (cell, channel) order, zero-padded to Kp: the B operand of the dense grid GEMM (occupancy / directional)
 __global__ void grid_weight_split_kernel(const float* __restrict__ W1, __nv_bfloat16* __restrict__ hi,
@@ -381,7 +386,22 @@ int launch_repack(tb2_lstm* m, const tb2_lstm_weights* w, cudaStream_t st) {
             (rc = launch_repack_gates_tc(wih[ph], whh[ph], m->Wg_hi[ph], m->Wg_lo[ph], m->E + m->P, m->H, st)))
             return rc;
     }
-    if (m->cfg.pool_type == TB2_POOL_NN_MLP) {
+    if (m->cfg.pool_type == TB2_POOL_NN_LSTM) {
+        const tb2_lstm_config& c = m->cfg;
+        const int Hp = c.mlp_dim_hidden;
+        TB2_REQUIRE(w->pool_lstm_weight_ih && w->pool_lstm_weight_hh && w->pool_lstm_bias_ih && w->pool_lstm_bias_hh &&
+                    w->pool_out_weight && w->pool_out_bias, "pool.pool_lstm / pool.hidden2pool parameters missing");
+        transpose_kernel<<<256, 256, 0, st>>>(w->pool_lstm_weight_ih, m->pl_WihT, 4 * Hp, c.out_dim);
+        TB2_LAUNCH_CHECK();
+        transpose_kernel<<<256, 256, 0, st>>>(w->pool_lstm_weight_hh, m->pl_WhhT, 4 * Hp, Hp);
+        TB2_LAUNCH_CHECK();
+        add_bias_kernel<<<(4 * Hp + 255) / 256, 256, 0, st>>>(w->pool_lstm_bias_ih, w->pool_lstm_bias_hh, m->pl_b, 4 * Hp);
+        TB2_LAUNCH_CHECK();
+        transpose_kernel<<<128, 256, 0, st>>>(w->pool_out_weight, m->mp_WoT, c.out_dim, Hp);
+        TB2_LAUNCH_CHECK();
+        if ((rc = copy_dev(w->pool_out_bias, m->mp_bo, (size_t)c.out_dim, st))) return rc;
+    }
+    if (m->cfg.pool_type == TB2_POOL_NN_MLP || m->cfg.pool_type == TB2_POOL_NN_LSTM) {
         const tb2_lstm_config& c = m->cfg;
         TB2_REQUIRE(w->pool_spatial_weight && w->pool_spatial_bias, "pool.embedding.0 (nearest-neighbour pooling) missing");
         if ((rc = copy_dev(w->pool_spatial_weight, m->mp_Ws, (size_t)c.mlp_dim_spatial * (c.mlp_dim_vel ? 4 : 2), st))) return rc;

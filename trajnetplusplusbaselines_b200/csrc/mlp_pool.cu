@@ -349,6 +349,109 @@ int launch_attn_mlp_pool(const tb2_lstm* m, const tb2_layout* l, const float* hi
 }
 
 // ------------------------------------------------------------------------------------------
+// Interaction-encoder LSTMCell of NearestNeighborLSTM (--type nn_lstm, reference non_gridbased_pooling.py:445-451):
+//   gates = W_ih feat + b_ih + W_hh h + b_hh (order i, f, g, o); c' = sigma(f) c + sigma(i) tanh(g); h' = sigma(o) tanh(c');
+//   out = hidden2pool(h').   Every track is updated every step (absent ones with zero features).
+// One CTA per 16 tracks: the inputs [feat | h] of its rows sit in shared memory, thread = gate column(s), the transposed
+// weights stream coalesced from L2 with 16 accumulators per column; FP32 FFMA, accurate expf / tanhf.
+// ------------------------------------------------------------------------------------------
+constexpr int kPlRows = 16;
+
+struct PoolLstmParams {
+    const float* feat;     // [M, D]
+    float* h;              // [M, Hp] state, updated in place
+    float* c;
+    const float* WihT;     // [D][4 Hp]
+    const float* WhhT;     // [Hp][4 Hp]
+    const float* b;        // [4 Hp]
+    const float* WoT;      // [Hp][D]
+    const float* bo;       // [D]
+    float* out;            // [M, D]
+    int M, D, Hp;
+};
+
+__global__ void __launch_bounds__(256) pool_lstm_cell_kernel(PoolLstmParams p) {
+    extern __shared__ __align__(16) float smem_pl[];
+    const int K = p.D + p.Hp, G = 4 * p.Hp;
+    float* x = smem_pl;                        // [K][kPlRows]  (input-major: one k at a time is a broadcast row)
+    float* gates = x + (size_t)K * kPlRows;    // [kPlRows][G]
+    float* hn = gates + (size_t)kPlRows * G;   // [kPlRows][Hp]
+    const int tid = threadIdx.x, r0 = blockIdx.x * kPlRows;
+    const int nr = min(kPlRows, p.M - r0);
+    grid_dep_wait();
+    grid_dep_launch();
+    for (int idx = tid; idx < kPlRows * K; idx += blockDim.x) {
+        const int r = idx / K, k = idx - r * K;
+        float v = 0.f;
+        if (r < nr) v = k < p.D ? p.feat[(size_t)(r0 + r) * p.D + k] : p.h[(size_t)(r0 + r) * p.Hp + (k - p.D)];
+        x[(size_t)k * kPlRows + r] = v;
+    }
+    __syncthreads();
+    for (int col = tid; col < G; col += blockDim.x) {
+        float acc[kPlRows];
+        const float b = p.b[col];
+#pragma unroll
+        for (int r = 0; r < kPlRows; ++r) acc[r] = b;
+        for (int k = 0; k < K; ++k) {
+            const float w = k < p.D ? __ldg(p.WihT + (size_t)k * G + col) : __ldg(p.WhhT + (size_t)(k - p.D) * G + col);
+            const float4* xr = reinterpret_cast<const float4*>(x + (size_t)k * kPlRows);
+#pragma unroll
+            for (int q = 0; q < kPlRows / 4; ++q) {
+                const float4 xv = xr[q];
+                acc[4 * q] = fmaf(xv.x, w, acc[4 * q]); acc[4 * q + 1] = fmaf(xv.y, w, acc[4 * q + 1]);
+                acc[4 * q + 2] = fmaf(xv.z, w, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(xv.w, w, acc[4 * q + 3]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kPlRows; ++r) gates[(size_t)r * G + col] = acc[r];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < kPlRows * p.Hp; idx += blockDim.x) {
+        const int r = idx / p.Hp, u = idx - r * p.Hp;
+        float hv = 0.f;
+        if (r < nr) {
+            const float* g = gates + (size_t)r * G;
+            const float ig = 1.f / (1.f + expf(-g[u]));
+            const float fg = 1.f / (1.f + expf(-g[p.Hp + u]));
+            const float gt = tanhf(g[2 * p.Hp + u]);
+            const float og = 1.f / (1.f + expf(-g[3 * p.Hp + u]));
+            const size_t o = (size_t)(r0 + r) * p.Hp + u;
+            const float cn = fg * p.c[o] + ig * gt;
+            hv = og * tanhf(cn);
+            p.c[o] = cn;
+            p.h[o] = hv;
+        }
+        hn[idx] = hv;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nr * p.D; idx += blockDim.x) {
+        const int r = idx / p.D, o = idx - r * p.D;
+        float acc = p.bo[o];
+        for (int k = 0; k < p.Hp; ++k) acc = fmaf(hn[(size_t)r * p.Hp + k], __ldg(p.WoT + (size_t)k * p.D + o), acc);
+        p.out[(size_t)(r0 + r) * p.D + o] = acc;
+    }
+}
+
+int launch_pool_lstm_cell(const tb2_lstm* m, const tb2_layout* l, const float* feat, float* h, float* c, float* out,
+                          cudaStream_t st) {
+    PoolLstmParams p;
+    p.feat = feat; p.h = h; p.c = c;
+    p.WihT = m->pl_WihT; p.WhhT = m->pl_WhhT; p.b = m->pl_b; p.WoT = m->mp_WoT; p.bo = m->mp_bo;
+    p.out = out;
+    p.M = l->M; p.D = m->cfg.out_dim; p.Hp = m->cfg.mlp_dim_hidden;
+    const size_t smem = ((size_t)(p.D + p.Hp) * kPlRows + (size_t)kPlRows * 4 * p.Hp + (size_t)kPlRows * p.Hp) * sizeof(float);
+    TB2_REQUIRE(smem <= 200 * 1024, "interaction-encoder LSTM too wide for the kernel");
+    static DynSmemConfig configured;
+    TB2_CHECK_CUDA(configured.ensure(pool_lstm_cell_kernel, smem, 48 * 1024));
+    {
+        KernelTimer kt("pool_lstm_cell", st);
+        launch_pdl(pool_lstm_cell_kernel, dim3((l->M + kPlRows - 1) / kPlRows), dim3(256), smem, st, p);
+    }
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // NearestNeighborMLP on the device (--type nn, reference non_gridbased_pooling.py:64-147).
 //
 //   for every track i: the n nearest other tracks of its scene by ||pos_j - pos_i|| (absent tracks count as 1000 m,

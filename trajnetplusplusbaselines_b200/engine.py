@@ -189,6 +189,13 @@ class ModelHandle:
                                             _ptr(obs2), _ptr(out), _ptr(ws), need, _stream(self.device)))
         return out
 
+    def pool_state_reset(self, layout):
+        """tb2_pool_state_reset: zero the interaction-encoder LSTM state of a stateful pool in this handle's workspace."""
+        lib = _lib.load()
+        ws, need = self.workspace(layout)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.tb2_pool_state_reset(self.handle, layout.handle, _ptr(ws), need, _stream(self.device)))
+
     def step_forward(self, layout, phase, obs1, obs2, h, c):
         """One step; h, c updated in place.  Returns (normal [M,5], pos [M,2])."""
         lib = _lib.load()

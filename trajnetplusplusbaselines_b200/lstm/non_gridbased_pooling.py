@@ -13,7 +13,11 @@ shared Linear + ReLU, concatenated.  One kernel per step (nn_mlp_pool_kernel in 
 AttentionMLPPooling (:242-351, `--type attentionmlp`): the embeddings of HiddenStateMLPPooling, wq / wk / wv and a
 one-head torch.nn.MultiheadAttention over all slots of the scene, out_projection (attn_mlp_pool_kernel).
 
-NearestNeighborLSTM, TrajectronPooling and NMMP are not built (their constructors raise).
+NearestNeighborLSTM (:354-451, `--type nn_lstm`): the NearestNeighborMLP features drive a per-track LSTMCell whose state
+persists over the steps of a forward (nn_mlp_pool_kernel + pool_lstm_cell_kernel); the state lives in the model handle's
+workspace, `reset()` zeroes it.
+
+TrajectronPooling and NMMP are not built (their constructors raise).
 """
 import torch
 
@@ -256,6 +260,65 @@ class AttentionMLPPooling(torch.nn.Module, _StandalonePlug):
         return out.to(obs2.device) if obs2.device != device else out
 
 
+class NearestNeighborLSTM(torch.nn.Module, _StandalonePlug):
+    def __init__(self, n=4, hidden_dim=256, out_dim=32):
+        """Same arguments and sub-module names as the reference (non_gridbased_pooling.py:371-383)."""
+        super().__init__()
+        if n < 1 or n > 32 or out_dim % n != 0 or hidden_dim > 512 or out_dim > 1024:
+            raise ValueError("NearestNeighborLSTM needs 1 <= n <= 32, n dividing out_dim, hidden_dim <= 512, out_dim <= 1024")
+        self.n = n
+        self.out_dim = out_dim
+        self.input_dim = 4
+        self.embedding = torch.nn.Sequential(torch.nn.Linear(self.input_dim, int(out_dim / self.n)), torch.nn.ReLU())
+        self.hidden_dim = hidden_dim
+        self.pool_lstm = torch.nn.LSTMCell(out_dim, hidden_dim)
+        self.hidden2pool = torch.nn.Linear(hidden_dim, out_dim)
+        self._handle = None
+        self._layouts = LayoutCache()
+        self._reset_pending = True
+
+    def fill_config(self, cfg):
+        cfg.pool_type = _lib.POOL_NN_LSTM
+        cfg.n = int(self.n)
+        cfg.out_dim = int(self.out_dim)
+        cfg.mlp_dim_spatial = int(self.out_dim // self.n)
+        cfg.mlp_dim_vel = 1
+        cfg.mlp_dim_hidden = int(self.hidden_dim)
+        cfg.pool_size = cfg.blur_size = 1
+
+    def weight_fields(self):
+        return dict(pool_spatial_weight=self.embedding[0].weight, pool_spatial_bias=self.embedding[0].bias,
+                    pool_lstm_weight_ih=self.pool_lstm.weight_ih, pool_lstm_weight_hh=self.pool_lstm.weight_hh,
+                    pool_lstm_bias_ih=self.pool_lstm.bias_ih, pool_lstm_bias_hh=self.pool_lstm.bias_hh,
+                    pool_out_weight=self.hidden2pool.weight, pool_out_bias=self.hidden2pool.bias)
+
+    def weights_version(self):
+        return weights_key(self)
+
+    def reset(self, num_tracks, max_num_neigh, device):
+        """Reference: fresh zero state per track (non_gridbased_pooling.py:385-389); here the state of the stand-alone plug
+        lives in the handle's workspace and is zeroed before the next call (LSTM.forward zeroes its own)."""
+        self._reset_pending = True
+
+    def forward(self, _, obs1, obs2):
+        """_, [B, N, 2], [B, N, 2] -> [B * N, out_dim]; advances the interaction-encoder state (non_gridbased_pooling.py:391-451)."""
+        _lib.require_cuda()
+        batch_size, num_tracks = obs2.size(0), obs2.size(1)
+        device = self.hidden2pool.weight.device
+        if device.type != 'cuda':
+            raise RuntimeError("NearestNeighborLSTM runs on CUDA only: move the module to a B200 (module.cuda())")
+        handle = self._plug_handle(device)
+        layout = self._layouts.get(range(0, batch_size * num_tracks + 1, num_tracks), device=device)
+        if self._reset_pending:
+            handle.pool_state_reset(layout)
+            self._reset_pending = False
+        f32 = dict(device=device, dtype=torch.float32)
+        o1 = obs1.detach().to(**f32).reshape(-1, 2).contiguous()
+        o2 = obs2.detach().to(**f32).reshape(-1, 2).contiguous()
+        out = handle.pool_forward(layout, None, o1, o2, self.out_dim)
+        return out.to(obs2.device) if obs2.device != device else out
+
+
 def _not_built(name, lines):
     class _NotBuilt(torch.nn.Module):
         def __init__(self, *args, **kwargs):
@@ -265,5 +328,4 @@ def _not_built(name, lines):
     return _NotBuilt
 
 
-NearestNeighborLSTM = _not_built("NearestNeighborLSTM", "354-")
 TrajectronPooling = _not_built("TrajectronPooling", "")
