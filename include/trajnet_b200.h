@@ -50,6 +50,11 @@ extern "C" {
                                    * its hidden_dim) whose state lives in the caller's workspace over the steps of a
                                    * sequence; interaction vector = hidden2pool(h') */
 
+#define TB2_POOL_TRAJECTRON 8     /* TrajectronPooling (--type traj_pool) non_gridbased_pooling.py:454-537: every visible track
+                                   * embeds [own (pos, vel) | sum over the other visible tracks] with pool_spatial_weight
+                                   * [out_dim, 8]; the sum runs over the whole batch in the padded (trainer) layout and over
+                                   * the scene in the per-scene layout; then the LSTMCell / hidden2pool of TB2_POOL_NN_LSTM */
+
 #define TB2_PHASE_ENCODER 0
 #define TB2_PHASE_DECODER 1
 
@@ -111,7 +116,8 @@ typedef struct tb2_lstm_weights {
     const float* pool_embedding_weight[3];/* pool.embedding.{0,2,4}.weight */
     const float* pool_embedding_bias[3];  /* pool.embedding.{0,2,4}.bias   */
     /* TB2_POOL_HIDDEN_MLP (NULL otherwise) */
-    const float* pool_spatial_weight;     /* pool.spatial_embedding.0.weight [mlp_dim_spatial, 2] */
+    const float* pool_spatial_weight;     /* pool.spatial_embedding.0.weight [mlp_dim_spatial, 2]; TB2_POOL_NN_MLP / _NN_LSTM:
+                                           * pool.embedding.0.weight [out_dim / n, 2 or 4]; TB2_POOL_TRAJECTRON: [out_dim, 8] */
     const float* pool_spatial_bias;
     const float* pool_vel_weight;         /* pool.vel_embedding.0.weight [mlp_dim_vel, 2] */
     const float* pool_vel_bias;
@@ -127,7 +133,7 @@ typedef struct tb2_lstm_weights {
     const float* pool_attn_in_proj_bias;    /* pool.multihead_attn.in_proj_bias [3E] */
     const float* pool_attn_out_proj_weight; /* pool.multihead_attn.out_proj.weight [E, E] */
     const float* pool_attn_out_proj_bias;   /* pool.multihead_attn.out_proj.bias [E] */
-    /* TB2_POOL_NN_LSTM (NULL otherwise), Hp = mlp_dim_hidden; hidden2pool = pool_out_weight / pool_out_bias */
+    /* TB2_POOL_NN_LSTM / TB2_POOL_TRAJECTRON (NULL otherwise), Hp = mlp_dim_hidden; hidden2pool = pool_out_weight / pool_out_bias */
     const float* pool_lstm_weight_ih;     /* pool.pool_lstm.weight_ih [4 Hp, out_dim] */
     const float* pool_lstm_weight_hh;     /* pool.pool_lstm.weight_hh [4 Hp, Hp] */
     const float* pool_lstm_bias_ih;       /* [4 Hp] */
@@ -298,8 +304,8 @@ int tb2_lstm_sequence_backward(const tb2_lstm* model, const tb2_layout* layout, 
                                const tb2_lstm_grads* grads, void* workspace_dev, size_t workspace_bytes,
                                void* bwd_workspace_dev, size_t bwd_workspace_bytes, void* stream);
 
-/* TB2_POOL_NN_LSTM: zero the interaction-encoder LSTM state kept in `workspace` (NearestNeighborLSTM.reset,
- * non_gridbased_pooling.py:385-389).  tb2_lstm_forward_sequence / _steps(first_step = 0) do this themselves; the
+/* TB2_POOL_NN_LSTM / TB2_POOL_TRAJECTRON: zero the interaction-encoder LSTM state kept in `workspace`
+ * (NearestNeighborLSTM.reset, non_gridbased_pooling.py:385-389; TrajectronPooling.reset, :481-485).  tb2_lstm_forward_sequence / _steps(first_step = 0) do this themselves; the
  * stand-alone plug (tb2_pool_forward) advances the state on every call and needs it after a reset().  No-op for the
  * other pool types. */
 int tb2_pool_state_reset(const tb2_lstm* model, const tb2_layout* layout, void* workspace_dev, size_t workspace_bytes,

@@ -89,6 +89,16 @@ class NnLstmPoolConfig:
         self.input_dim = 4
 
 
+class TrajectronPoolConfig:
+    """Constructor arguments of TrajectronPooling (non_gridbased_pooling.py:468-479; `n` is unused there)."""
+
+    def __init__(self, n=4, hidden_dim=256, out_dim=32):
+        self.type_ = "traj_pool"
+        self.n = n
+        self.hidden_dim = hidden_dim
+        self.out_dim = out_dim
+
+
 class NnPoolConfig:
     """Constructor arguments of NearestNeighborMLP (non_gridbased_pooling.py:78-91)."""
 
@@ -335,8 +345,34 @@ def nn_lstm_pool_forward(cfg, weights, obs1, obs2, state, prefix="pool."):
     return _linear(h2, weights[prefix + "hidden2pool.weight"], weights[prefix + "hidden2pool.bias"])
 
 
+def trajectron_pool_forward(cfg, weights, obs1, obs2, state, prefix="pool."):
+    """TrajectronPooling.forward (non_gridbased_pooling.py:487-537): every VISIBLE slot of the flattened batch embeds
+    [own (pos, vel) | sum of the (pos, vel) of all OTHER visible slots of the batch] (Linear(8, out_dim) + ReLU; the sum
+    runs over the whole [B * N] batch, :516-527), invisible slots get zeros; then the per-slot LSTMCell and hidden2pool
+    like NearestNeighborLSTM."""
+    obs1 = np.asarray(obs1, dtype=F32)
+    obs2 = np.asarray(obs2, dtype=F32)
+    B, N, _ = obs2.shape
+    states = np.concatenate([obs2, obs2 - obs1], axis=-1).reshape(B * N, 4).astype(F32)
+    vis = ~np.isnan(states).any(axis=-1)
+    feats = np.zeros((B * N, cfg.out_dim), dtype=F32)
+    sv = states[vis]
+    if len(sv):
+        rows = []
+        for i in range(len(sv)):
+            others = np.delete(sv, i, axis=0)
+            rows.append(np.concatenate([sv[i], others.sum(axis=0, dtype=F32) if len(others) else np.zeros(4, F32)]))
+        x = np.stack(rows).astype(F32)
+        feats[vis] = np.maximum(_linear(x, weights[prefix + "embedding.0.weight"], weights[prefix + "embedding.0.bias"]), F32(0.0))
+    h2, c2 = lstm_cell(weights, prefix + "pool_lstm.", feats, state["h"], state["c"])
+    state["h"], state["c"] = h2, c2
+    return _linear(h2, weights[prefix + "hidden2pool.weight"], weights[prefix + "hidden2pool.bias"])
+
+
 def pool_forward(cfg, weights, hidden, obs1, obs2, prefix="pool.", state=None):
     """GridBasedPooling.forward (gridbased_pooling.py:94-110) -> [B*N, out_dim]."""
+    if getattr(cfg, "type_", None) == "traj_pool":
+        return trajectron_pool_forward(cfg, weights, obs1, obs2, state, prefix)
     if getattr(cfg, "type_", None) == "nn_lstm":
         return nn_lstm_pool_forward(cfg, weights, obs1, obs2, state, prefix)
     if getattr(cfg, "type_", None) == "hiddenstatemlp":
@@ -422,7 +458,7 @@ def step(weights, pool_cfg, phase, h, c, obs1, obs2, batch_split, pool_to_input=
         prev = _pad_scenes(obs1, bs, n_max, F32(NAN))
         hid = _pad_scenes(h.astype(F32), bs, n_max, F32(NAN))               # :26,39 (ALL tracks)
         mpos = _pad_scenes(mask, bs, n_max, False)
-        if getattr(pool_cfg, "type_", None) == "nn_lstm" and pool_state is not None and "h" not in pool_state:
+        if getattr(pool_cfg, "type_", None) in ("nn_lstm", "traj_pool") and pool_state is not None and "h" not in pool_state:
             Hp = pool_cfg.hidden_dim                                        # pool.reset(B * Nmax, ...) lstm.py:213-216
             pool_state["h"] = np.zeros((cur.shape[0] * cur.shape[1], Hp), dtype=F32)
             pool_state["c"] = np.zeros((cur.shape[0] * cur.shape[1], Hp), dtype=F32)
@@ -614,7 +650,16 @@ NN_LSTM_SPECS = {
 }
 
 
+# TrajectronPooling(hidden_dim=args.hidden_dim (128), out_dim=args.pool_dim) (lstm/trainer.py:480-481)
+TRAJ_SPECS = {
+    "traj_pool": dict(hidden_dim=128, out_dim=256),
+    "traj_pool_small": dict(hidden_dim=40, out_dim=24),
+}
+
+
 def pool_config(kind):
+    if kind in TRAJ_SPECS:
+        return TrajectronPoolConfig(**TRAJ_SPECS[kind])
     if kind in NN_LSTM_SPECS:
         return NnLstmPoolConfig(**NN_LSTM_SPECS[kind])
     if kind in ATTN_SPECS:
@@ -641,8 +686,11 @@ def random_weights(kind, seed=0, scale=1.0, embedding_dim=64, hidden_dim=128):
 
     E, H = embedding_dim, hidden_dim
     pool_dim = 0
-    if cfg is not None and cfg.type_ == "nn_lstm":
-        lin("pool.embedding.0.weight", "pool.embedding.0.bias", cfg.out_dim // cfg.n, cfg.input_dim)
+    if cfg is not None and cfg.type_ in ("nn_lstm", "traj_pool"):
+        if cfg.type_ == "traj_pool":
+            lin("pool.embedding.0.weight", "pool.embedding.0.bias", cfg.out_dim, 8)
+        else:
+            lin("pool.embedding.0.weight", "pool.embedding.0.bias", cfg.out_dim // cfg.n, cfg.input_dim)
         kp = scale / math.sqrt(cfg.hidden_dim)
         W["pool.pool_lstm.weight_ih"] = rng.uniform(-kp, kp, size=(4 * cfg.hidden_dim, cfg.out_dim)).astype(F32)
         W["pool.pool_lstm.weight_hh"] = rng.uniform(-kp, kp, size=(4 * cfg.hidden_dim, cfg.hidden_dim)).astype(F32)

@@ -16,6 +16,7 @@ KINDS = ["hiddenstatemlp", "hiddenstatemlp_small"]
 NN_KINDS = ["nn", "nn_small"]
 ATTN_KINDS = ["attentionmlp", "attentionmlp_small"]
 NN_LSTM_KINDS = ["nn_lstm", "nn_lstm_small"]
+TRAJ_KINDS = ["traj_pool", "traj_pool_small"]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -40,8 +41,10 @@ def scene_inputs():
 def build_reference_model(kind, W):
     from trajnetbaselines.lstm import LSTM
     from trajnetbaselines.lstm.non_gridbased_pooling import (AttentionMLPPooling, HiddenStateMLPPooling, NearestNeighborLSTM,
-                                                              NearestNeighborMLP)
-    if kind in O.NN_LSTM_SPECS:
+                                                              NearestNeighborMLP, TrajectronPooling)
+    if kind in O.TRAJ_SPECS:
+        pool = TrajectronPooling(**O.TRAJ_SPECS[kind])
+    elif kind in O.NN_LSTM_SPECS:
         pool = NearestNeighborLSTM(**O.NN_LSTM_SPECS[kind])
     elif kind in O.NN_SPECS:
         pool = NearestNeighborMLP(**O.NN_SPECS[kind])
@@ -60,11 +63,11 @@ def main():
     hid, obs1, obs2 = plug_inputs()
     xy, bs = scene_inputs()
     M = xy.shape[1]
-    for kind in KINDS + NN_KINDS + ATTN_KINDS + NN_LSTM_KINDS:
+    for kind in KINDS + NN_KINDS + ATTN_KINDS + NN_LSTM_KINDS + TRAJ_KINDS:
         W = O.random_weights(kind, seed=13)
         model = build_reference_model(kind, W)
         with torch.no_grad():
-            if kind in NN_LSTM_KINDS:     # stateful plug: two consecutive calls after a reset
+            if kind in NN_LSTM_KINDS + TRAJ_KINDS:     # stateful plug: two consecutive calls after a reset
                 model.pool.reset(obs2.shape[0] * obs2.shape[1], obs2.shape[1] - 1, device=torch.device("cpu"))
                 first = model.pool(torch.from_numpy(hid), torch.from_numpy(obs1), torch.from_numpy(obs2)).numpy()
                 second = model.pool(torch.from_numpy(hid), torch.from_numpy(obs2), torch.from_numpy(obs2 + (obs2 - obs1))).numpy()

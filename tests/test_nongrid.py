@@ -9,16 +9,20 @@ import pytest
 import torch
 
 from oracle import lstm_oracle as O
-from oracle.make_nongrid_golden import ATTN_KINDS, KINDS, NN_KINDS, NN_LSTM_KINDS, plug_inputs, scene_inputs
+from oracle.make_nongrid_golden import ATTN_KINDS, KINDS, NN_KINDS, NN_LSTM_KINDS, TRAJ_KINDS, plug_inputs, scene_inputs
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "nongrid_golden.npz"))
 
 
-ALL_KINDS = KINDS + NN_KINDS + ATTN_KINDS + NN_LSTM_KINDS
+ALL_KINDS = KINDS + NN_KINDS + ATTN_KINDS + NN_LSTM_KINDS + TRAJ_KINDS
+STATEFUL_KINDS = NN_LSTM_KINDS + TRAJ_KINDS
 
 
 def _pool(kind):
-    from trajnetplusplusbaselines_b200.lstm import AttentionMLPPooling, HiddenStateMLPPooling, NearestNeighborLSTM, NearestNeighborMLP
+    from trajnetplusplusbaselines_b200.lstm import (AttentionMLPPooling, HiddenStateMLPPooling, NearestNeighborLSTM, NearestNeighborMLP,
+                                                    TrajectronPooling)
+    if kind in O.TRAJ_SPECS:
+        return TrajectronPooling(**O.TRAJ_SPECS[kind])
     if kind in O.NN_LSTM_SPECS:
         return NearestNeighborLSTM(**O.NN_LSTM_SPECS[kind])
     if kind in O.NN_SPECS:
@@ -33,7 +37,7 @@ def test_oracle_matches_reference_vectors(kind):
     W = O.random_weights(kind, seed=13)
     cfg = O.pool_config(kind)
     hid, obs1, obs2 = plug_inputs()
-    if kind in NN_LSTM_KINDS:      # stateful plug: two calls after a reset
+    if kind in STATEFUL_KINDS:      # stateful plug: two calls after a reset
         n = obs2.shape[0] * obs2.shape[1]
         st = {"h": np.zeros((n, cfg.hidden_dim), np.float32), "c": np.zeros((n, cfg.hidden_dim), np.float32)}
         assert np.abs(O.pool_forward(cfg, W, hid, obs1, obs2, state=st) - GOLD[kind + "/plug"]).max() < 1e-5
@@ -60,13 +64,6 @@ def test_state_dict_keys_match_reference_layout():
             assert tuple(sd[k].shape) == v.shape, k
 
 
-def test_unbuilt_modules_raise():
-    from trajnetplusplusbaselines_b200.lstm import non_gridbased_pooling as ngp
-    for name in ("TrajectronPooling",):
-        with pytest.raises(NotImplementedError):
-            getattr(ngp, name)()
-
-
 def _model(kind):
     from trajnetplusplusbaselines_b200.lstm import LSTM
     model = LSTM(pool=_pool(kind))
@@ -86,7 +83,7 @@ def test_cuda_plug_matches_reference_vectors(kind):
     ref = GOLD[kind + "/plug"]
     assert out.shape == ref.shape
     assert np.abs(out.cpu().numpy() - ref).max() < 1e-4 * max(1.0, float(np.abs(ref).max()))      # fp32 order of the 128-term sums
-    if kind in NN_LSTM_KINDS:      # the state advanced: second call, then the same pair again after a reset
+    if kind in STATEFUL_KINDS:      # the state advanced: second call, then the same pair again after a reset
         o2 = torch.from_numpy(obs2).cuda()
         o3 = torch.from_numpy(obs2 + (obs2 - obs1)).cuda()
         out2 = model.pool(torch.from_numpy(hid).cuda(), o2, o3)
@@ -115,7 +112,7 @@ def test_cuda_forward_matches_reference_vectors(kind):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", ["hiddenstatemlp", "nn", "attentionmlp", "nn_lstm"])
+@pytest.mark.parametrize("kind", ["hiddenstatemlp", "nn", "attentionmlp", "nn_lstm", "traj_pool"])
 def test_cuda_baseline_shape_vs_oracle_and_training_raises(kind):
     """256-d pooling at N = 20, T = 9 + 12 on 48 scenes vs the oracle; training is inference-only."""
     model = _model(kind)

@@ -76,8 +76,9 @@ size_t carve_workspace(const tb2_lstm* m, const tb2_layout* l, void* base, Works
         w.hs_hi[i] = take(M * 128 * 2);
         w.hs_lo[i] = take(M * 128 * 2);
     }
-    w.pool_feat = w.pool_h = w.pool_c = nullptr;
-    if (m->cfg.pool_type == TB2_POOL_NN_LSTM) {
+    w.pool_feat = w.pool_h = w.pool_c = w.scene_sum = nullptr;
+    if (m->cfg.pool_type == TB2_POOL_TRAJECTRON) w.scene_sum = (float*)take((size_t)l->B * 4 * sizeof(float));
+    if (m->cfg.pool_type == TB2_POOL_NN_LSTM || m->cfg.pool_type == TB2_POOL_TRAJECTRON) {
         w.pool_feat = (float*)take(M * (size_t)m->cfg.out_dim * sizeof(float));
         w.pool_h = (float*)take(M * (size_t)m->cfg.mlp_dim_hidden * sizeof(float));
         w.pool_c = (float*)take(M * (size_t)m->cfg.mlp_dim_hidden * sizeof(float));
@@ -204,7 +205,7 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
     *out = nullptr;
     TB2_REQUIRE(cfg->hidden_dim == 128, "hidden_dim must be 128 (kernel specialisation)");
     TB2_REQUIRE(cfg->embedding_dim >= 4 && cfg->embedding_dim <= 1024, "embedding_dim out of range");
-    TB2_REQUIRE(cfg->pool_type >= TB2_POOL_NONE && cfg->pool_type <= TB2_POOL_NN_LSTM, "bad pool_type");
+    TB2_REQUIRE(cfg->pool_type >= TB2_POOL_NONE && cfg->pool_type <= TB2_POOL_TRAJECTRON, "bad pool_type");
     tb2_lstm* m = new (std::nothrow) tb2_lstm();
     TB2_REQUIRE(m, "out of host memory");
     m->cfg = *cfg;
@@ -221,6 +222,15 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
     m->at_AqT = m->at_AkT = m->at_AvT = m->at_bqkv = m->at_WoT = m->at_bo = nullptr;
     m->pl_WihT = m->pl_WhhT = m->pl_b = nullptr;
     auto fail = [&](int rc) { tb2_lstm_destroy(m); return rc; };
+    if (cfg->pool_type == TB2_POOL_TRAJECTRON) {
+        if (!(cfg->mlp_dim_hidden >= 1 && cfg->mlp_dim_hidden <= 512 && cfg->out_dim >= 1 && cfg->out_dim <= 1024)) {
+            set_error("invalid argument: Trajectron pooling needs 1 <= hidden_dim <= 512 and out_dim <= 1024");
+            return fail(TB2_ERR_INVALID);
+        }
+        m->pool_out = cfg->out_dim;
+        if (cfg->pool_to_input) m->P = m->pool_out;
+        else if (m->pool_out != m->H) { set_error("invalid argument: pool_to_input=0 needs out_dim == hidden_dim"); return fail(TB2_ERR_INVALID); }
+    }
     if (cfg->pool_type == TB2_POOL_NN_LSTM &&
         !(cfg->mlp_dim_hidden >= 1 && cfg->mlp_dim_hidden <= 512 && cfg->out_dim <= 1024 && cfg->mlp_dim_vel != 0)) {
         set_error("invalid argument: nearest-neighbour LSTM pooling needs 1 <= hidden_dim <= 512, out_dim <= 1024 and velocities");
@@ -307,7 +317,11 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
         ALLOC(m->WencT, m->H * m->C);
         ALLOC(m->benc, m->C);
     }
-    if (cfg->pool_type == TB2_POOL_NN_LSTM) {
+    if (cfg->pool_type == TB2_POOL_TRAJECTRON) {
+        ALLOC(m->mp_Ws, (size_t)cfg->out_dim * 8);
+        ALLOC(m->mp_bs, cfg->out_dim);
+    }
+    if (cfg->pool_type == TB2_POOL_NN_LSTM || cfg->pool_type == TB2_POOL_TRAJECTRON) {
         const size_t Hp = (size_t)cfg->mlp_dim_hidden;
         ALLOC(m->pl_WihT, (size_t)cfg->out_dim * 4 * Hp);
         ALLOC(m->pl_WhhT, Hp * 4 * Hp);
@@ -541,8 +555,10 @@ int tb2_pool_forward(const tb2_lstm* m, const tb2_layout* l, const float* hidden
     cudaStream_t st = (cudaStream_t)stream;
     if (m->cfg.pool_type == TB2_POOL_HIDDEN_MLP) return launch_hidden_mlp_pool(m, l, hidden, obs1, obs2, pooled_out, st);
     if (m->cfg.pool_type == TB2_POOL_NN_MLP) return launch_nn_mlp_pool(m, l, obs1, obs2, pooled_out, st);
-    if (m->cfg.pool_type == TB2_POOL_NN_LSTM) {      // stateful: advances the LSTM state kept in the workspace
-        if ((rc = launch_nn_mlp_pool(m, l, obs1, obs2, ws.pool_feat, st))) return rc;
+    if (m->cfg.pool_type == TB2_POOL_NN_LSTM || m->cfg.pool_type == TB2_POOL_TRAJECTRON) {      // stateful: advances the LSTM state kept in the workspace
+        if (m->cfg.pool_type == TB2_POOL_NN_LSTM) rc = launch_nn_mlp_pool(m, l, obs1, obs2, ws.pool_feat, st);
+        else rc = launch_trajectron_feat(m, l, obs1, obs2, ws.scene_sum, ws.pool_feat, st);
+        if (rc) return rc;
         return launch_pool_lstm_cell(m, l, ws.pool_feat, ws.pool_h, ws.pool_c, pooled_out, st);
     }
     if (m->cfg.pool_type == TB2_POOL_ATTN_MLP) return launch_attn_mlp_pool(m, l, hidden, obs1, obs2, pooled_out, st);
@@ -561,8 +577,9 @@ static int step_impl(const tb2_lstm* m, const tb2_layout* l, int phase, const fl
     if (m->cfg.pool_type >= TB2_POOL_HIDDEN_MLP) {
         // non-grid interaction module: one kernel per scene -> pooled fp32, split for the tensor-core gate kernel
         if (m->cfg.pool_type == TB2_POOL_NN_MLP) rc = launch_nn_mlp_pool(m, l, obs1, obs2, ws->pooled, st);
-        else if (m->cfg.pool_type == TB2_POOL_NN_LSTM) {
-            rc = launch_nn_mlp_pool(m, l, obs1, obs2, ws->pool_feat, st);
+        else if (m->cfg.pool_type == TB2_POOL_NN_LSTM || m->cfg.pool_type == TB2_POOL_TRAJECTRON) {
+            if (m->cfg.pool_type == TB2_POOL_NN_LSTM) rc = launch_nn_mlp_pool(m, l, obs1, obs2, ws->pool_feat, st);
+            else rc = launch_trajectron_feat(m, l, obs1, obs2, ws->scene_sum, ws->pool_feat, st);
             if (!rc) rc = launch_pool_lstm_cell(m, l, ws->pool_feat, ws->pool_h, ws->pool_c, ws->pooled, st);
         }
         else if (m->cfg.pool_type == TB2_POOL_ATTN_MLP) rc = launch_attn_mlp_pool(m, l, h_in, obs1, obs2, ws->pooled, st);

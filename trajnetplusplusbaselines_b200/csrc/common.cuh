@@ -192,6 +192,7 @@ struct Workspace {
     float* pool_feat;      // [M, out_dim] neighbour features of NearestNeighborLSTM (null otherwise)
     float* pool_h;         // [M, Hp] state of its interaction-encoder LSTM, kept over the steps of a sequence
     float* pool_c;
+    float* scene_sum;      // [B, 4] TrajectronPooling: sum of (pos, vel) over the visible tracks of every scene
 };
 
 // Per-step forward quantities a training forward keeps for the social backward (tb2_lstm_forward_sequence_train):
@@ -242,6 +243,8 @@ int launch_hidden_mlp_pool(const tb2_lstm* m, const tb2_layout* l, const float* 
                            const float* obs2, float* out, cudaStream_t st);
 int launch_attn_mlp_pool(const tb2_lstm* m, const tb2_layout* l, const float* hidden, const float* obs1, const float* obs2,
                          float* out, cudaStream_t st);
+int launch_trajectron_feat(const tb2_lstm* m, const tb2_layout* l, const float* obs1, const float* obs2, float* scene_sum,
+                           float* feat, cudaStream_t st);
 int launch_pool_lstm_cell(const tb2_lstm* m, const tb2_layout* l, const float* feat, float* h, float* c, float* out,
                           cudaStream_t st);
 int launch_nn_mlp_pool(const tb2_lstm* m, const tb2_layout* l, const float* obs1, const float* obs2, float* out,

@@ -386,7 +386,12 @@ int launch_repack(tb2_lstm* m, const tb2_lstm_weights* w, cudaStream_t st) {
             (rc = launch_repack_gates_tc(wih[ph], whh[ph], m->Wg_hi[ph], m->Wg_lo[ph], m->E + m->P, m->H, st)))
             return rc;
     }
-    if (m->cfg.pool_type == TB2_POOL_NN_LSTM) {
+    if (m->cfg.pool_type == TB2_POOL_TRAJECTRON) {
+        TB2_REQUIRE(w->pool_spatial_weight && w->pool_spatial_bias, "pool.embedding.0 (Trajectron pooling) missing");
+        if ((rc = copy_dev(w->pool_spatial_weight, m->mp_Ws, (size_t)m->cfg.out_dim * 8, st))) return rc;
+        if ((rc = copy_dev(w->pool_spatial_bias, m->mp_bs, (size_t)m->cfg.out_dim, st))) return rc;
+    }
+    if (m->cfg.pool_type == TB2_POOL_NN_LSTM || m->cfg.pool_type == TB2_POOL_TRAJECTRON) {
         const tb2_lstm_config& c = m->cfg;
         const int Hp = c.mlp_dim_hidden;
         TB2_REQUIRE(w->pool_lstm_weight_ih && w->pool_lstm_weight_hh && w->pool_lstm_bias_ih && w->pool_lstm_bias_hh &&

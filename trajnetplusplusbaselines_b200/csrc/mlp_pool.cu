@@ -349,6 +349,116 @@ int launch_attn_mlp_pool(const tb2_lstm* m, const tb2_layout* l, const float* hi
 }
 
 // ------------------------------------------------------------------------------------------
+// TrajectronPooling features (--type traj_pool, reference non_gridbased_pooling.py:509-529): a visible track embeds
+// [own (pos, vel) | sum of (pos, vel) over the OTHER visible tracks]; the reference sums over the whole flattened
+// batch, so with the padded (trainer) layout the other scenes' sums are included, with the per-scene layout they are not.
+// Kernel 1: one warp per scene sums its visible tracks in index order.  Kernel 2: one CTA per scene; "others" = the
+// other scenes' sums (fixed order) + the own scene's other tracks, then Linear(8, out_dim) + ReLU; invisible tracks: 0.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) traj_scene_sum_kernel(const float2* __restrict__ obs1, const float2* __restrict__ obs2,
+                                                             const int* __restrict__ scene_off, int B, float* __restrict__ scene_sum) {
+    grid_dep_wait();
+    grid_dep_launch();
+    const int scene = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (scene >= B) return;
+    const int row0 = scene_off[scene], n = scene_off[scene + 1] - row0;
+    if (lane == 0) {         // sequential over the scene's tracks: a few dozen additions, fixed order
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        for (int j = 0; j < n; ++j) {
+            const float2 a = obs1[row0 + j], b = obs2[row0 + j];
+            const float vx = b.x - a.x, vy = b.y - a.y;
+            if (isnan(b.x) || isnan(b.y) || isnan(vx) || isnan(vy)) continue;
+            s0 += b.x; s1 += b.y; s2 += vx; s3 += vy;
+        }
+        scene_sum[scene * 4 + 0] = s0; scene_sum[scene * 4 + 1] = s1; scene_sum[scene * 4 + 2] = s2; scene_sum[scene * 4 + 3] = s3;
+    }
+}
+
+struct TrajFeatParams {
+    const float2* obs1;
+    const float2* obs2;
+    const int* scene_off;
+    const float* scene_sum;    // [B, 4]
+    const float* W;            // [D, 8]
+    const float* b;            // [D]
+    float* feat;               // [M, D]
+    int B, D, whole_batch;
+};
+
+__global__ void __launch_bounds__(256) traj_feat_kernel(TrajFeatParams p) {
+    extern __shared__ __align__(16) float smem_tj[];
+    const int scene = blockIdx.x;
+    const int row0 = p.scene_off[scene], n = p.scene_off[scene + 1] - row0;
+    float4* st = reinterpret_cast<float4*>(smem_tj);              // [n] (pos, vel), NaN kept
+    float* in8 = reinterpret_cast<float*>(st + n);                // [n][8]
+    __shared__ float other_scenes[4];
+    const int tid = threadIdx.x;
+    grid_dep_wait();
+    grid_dep_launch();
+    for (int j = tid; j < n; j += blockDim.x) {
+        const float2 a = p.obs1[row0 + j], b = p.obs2[row0 + j];
+        st[j] = make_float4(b.x, b.y, b.x - a.x, b.y - a.y);
+    }
+    if (tid < 4) {
+        float s = 0.f;
+        if (p.whole_batch)
+            for (int b = 0; b < p.B; ++b)
+                if (b != scene) s += p.scene_sum[b * 4 + tid];
+        other_scenes[tid] = s;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float4 me = st[i];
+        const bool vis = !(isnan(me.x) || isnan(me.y) || isnan(me.z) || isnan(me.w));
+        float s0 = other_scenes[0], s1 = other_scenes[1], s2 = other_scenes[2], s3 = other_scenes[3];
+        if (vis)
+            for (int j = 0; j < n; ++j) {
+                if (j == i) continue;
+                const float4 o = st[j];
+                if (isnan(o.x) || isnan(o.y) || isnan(o.z) || isnan(o.w)) continue;
+                s0 += o.x; s1 += o.y; s2 += o.z; s3 += o.w;
+            }
+        float* x = in8 + (size_t)i * 8;
+        x[0] = vis ? me.x : CUDART_NAN_F; x[1] = me.y; x[2] = me.z; x[3] = me.w;
+        x[4] = s0; x[5] = s1; x[6] = s2; x[7] = s3;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * p.D; idx += blockDim.x) {
+        const int i = idx / p.D, o = idx - i * p.D;
+        const float* x = in8 + (size_t)i * 8;
+        float v = 0.f;
+        if (!isnan(x[0])) {
+            float acc = p.b[o];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc = fmaf(x[c], __ldg(p.W + (size_t)o * 8 + c), acc);
+            v = fmaxf(acc, 0.f);
+        }
+        p.feat[(size_t)(row0 + i) * p.D + o] = v;
+    }
+}
+
+int launch_trajectron_feat(const tb2_lstm* m, const tb2_layout* l, const float* obs1, const float* obs2, float* scene_sum,
+                           float* feat, cudaStream_t st) {
+    {
+        KernelTimer kt("traj_scene_sum", st);
+        launch_pdl(traj_scene_sum_kernel, dim3((l->B + 3) / 4), dim3(128), 0, st, (const float2*)obs1, (const float2*)obs2,
+                   (const int*)l->scene_off, l->B, scene_sum);
+    }
+    TB2_LAUNCH_CHECK();
+    TrajFeatParams p;
+    p.obs1 = (const float2*)obs1; p.obs2 = (const float2*)obs2; p.scene_off = l->scene_off; p.scene_sum = scene_sum;
+    p.W = m->mp_Ws; p.b = m->mp_bs; p.feat = feat; p.B = l->B; p.D = m->cfg.out_dim; p.whole_batch = l->pad_to_max;
+    const size_t smem = (size_t)l->n_max * 12 * sizeof(float) + 16;
+    TB2_REQUIRE(smem <= 48 * 1024, "scene too large for the Trajectron pooling kernel");
+    {
+        KernelTimer kt("traj_feat", st);
+        launch_pdl(traj_feat_kernel, dim3(l->B), dim3(256), smem, st, p);
+    }
+    TB2_LAUNCH_CHECK();
+    return TB2_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // Interaction-encoder LSTMCell of NearestNeighborLSTM (--type nn_lstm, reference non_gridbased_pooling.py:445-451):
 //   gates = W_ih feat + b_ih + W_hh h + b_hh (order i, f, g, o); c' = sigma(f) c + sigma(i) tanh(g); h' = sigma(o) tanh(c');
 //   out = hidden2pool(h').   Every track is updated every step (absent ones with zero features).

@@ -110,7 +110,7 @@ class LSTM(torch.nn.Module):
             cfg.pool_size = cfg.blur_size = 1
             if self.pool is not None:
                 if not hasattr(self.pool, 'fill_config'):
-                    raise NotImplementedError("only GridBasedPooling and the HiddenStateMLPPooling / NearestNeighborMLP / AttentionMLPPooling / NearestNeighborLSTM interaction modules are built")
+                    raise NotImplementedError("only GridBasedPooling and the HiddenStateMLPPooling / NearestNeighborMLP / AttentionMLPPooling / NearestNeighborLSTM / TrajectronPooling interaction modules are built")
                 self.pool.fill_config(cfg)
             self._handle = ModelHandle(cfg, device)
         key = weights_key(self)

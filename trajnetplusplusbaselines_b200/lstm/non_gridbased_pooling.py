@@ -17,7 +17,9 @@ NearestNeighborLSTM (:354-451, `--type nn_lstm`): the NearestNeighborMLP feature
 persists over the steps of a forward (nn_mlp_pool_kernel + pool_lstm_cell_kernel); the state lives in the model handle's
 workspace, `reset()` zeroes it.
 
-TrajectronPooling and NMMP are not built (their constructors raise).
+TrajectronPooling (:454-537, `--type traj_pool`): own (pos, vel) and the sum over the other visible tracks, embedded, then
+the same per-track LSTMCell / hidden2pool (traj_scene_sum_kernel + traj_feat_kernel + pool_lstm_cell_kernel).
+
 """
 import torch
 
@@ -319,13 +321,28 @@ class NearestNeighborLSTM(torch.nn.Module, _StandalonePlug):
         return out.to(obs2.device) if obs2.device != device else out
 
 
-def _not_built(name, lines):
-    class _NotBuilt(torch.nn.Module):
-        def __init__(self, *args, **kwargs):
-            raise NotImplementedError("%s (reference non_gridbased_pooling.py:%s) is not built; HiddenStateMLPPooling "
-                                      "and GridBasedPooling are" % (name, lines))
-    _NotBuilt.__name__ = name
-    return _NotBuilt
+class TrajectronPooling(NearestNeighborLSTM):
+    def __init__(self, n=4, hidden_dim=256, out_dim=32, track_mask=None):
+        """Same arguments and sub-module names as the reference (non_gridbased_pooling.py:468-479; `n` is unused there)."""
+        torch.nn.Module.__init__(self)
+        if hidden_dim > 512 or out_dim > 1024:
+            raise ValueError("TrajectronPooling needs hidden_dim <= 512 and out_dim <= 1024")
+        self.n = n
+        self.out_dim = out_dim
+        self.embedding = torch.nn.Sequential(torch.nn.Linear(8, out_dim), torch.nn.ReLU())
+        self.hidden_dim = hidden_dim
+        self.pool_lstm = torch.nn.LSTMCell(out_dim, hidden_dim)
+        self.hidden2pool = torch.nn.Linear(hidden_dim, out_dim)
+        self.track_mask = track_mask
+        self._handle = None
+        self._layouts = LayoutCache()
+        self._reset_pending = True
 
-
-TrajectronPooling = _not_built("TrajectronPooling", "")
+    def fill_config(self, cfg):
+        cfg.pool_type = _lib.POOL_TRAJECTRON
+        cfg.n = int(self.n)
+        cfg.out_dim = int(self.out_dim)
+        cfg.mlp_dim_spatial = int(self.out_dim)
+        cfg.mlp_dim_vel = 1
+        cfg.mlp_dim_hidden = int(self.hidden_dim)
+        cfg.pool_size = cfg.blur_size = 1
