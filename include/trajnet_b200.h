@@ -353,6 +353,31 @@ int tb2_collision_loss(const tb2_layout* layout, const float* positions_dev, int
                        float col_distance, float* loss_out_dev, float* dprimary_out_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Scene preprocessing on the device: the O(T * M) NumPy passes the reference runs scene by scene
+ * before a batch reaches the model, for a whole ragged batch per launch.  xy is float64 [T, M, 2] (the dtype
+ * Reader.paths_to_xy produces), scene_off int32 [B + 1] row offsets ON THE DEVICE; the primary of a scene is its first
+ * row.  All arithmetic is float64 in the reference's operation order with unfused multiplies / adds; the float32 batch is
+ * rounded once at the end (torch.Tensor(ndarray), lstm/trainer.py:124), so it equals the host path bit for bit.
+ *
+ * tb2_scenes_drop_distant -- drop_distant (lstm/lstm.py:16-22): keep_out [M] = 1 where the track comes within r of its
+ *   scene's primary in some frame (nanmin over frames of the squared distance < r_squared; the caller passes r ** 2),
+ *   kept_count_out [B] = kept tracks per scene (the caller's cumulative sum is the new batch_split).
+ * tb2_scenes_transform -- compaction by `keep` (NULL: keep all, then M_out == M and out_off == scene_off) into out_off
+ *   [B + 1], then center_scene (lstm/utils.py:32-51; frame [B, 4] = centre x, centre y, cos(rotation), sin(rotation); NULL: skip)
+ *   = shift by the centre and einsum('ptc,ci->pti', xy, [[ct, st], [-st, ct]]), then random_rotation (lstm/utils.py:10-17;
+ *   aug [B, 2] = cos(theta), sin(theta); NULL: skip); xy_out float32 [T, M_out, 2].  The O(B) scalars of `frame` / `aug` come
+ *   from the caller (the reference's own libm calls on the primary's last two observed positions).
+ * tb2_scenes_inverse -- inverse_scene (augmentation.py:65-68) of float32 predictions [S, M, 2]: rotation by
+ *   frame [B, 4] = centre x, centre y, cos(-rotation), sin(-rotation), then + centre; xy_out float64 [S, M, 2]. */
+int tb2_scenes_drop_distant(const double* xy_dev, const int32_t* scene_off_dev, int32_t T, int32_t M, int32_t B,
+                            double r_squared, uint8_t* keep_out_dev, int32_t* kept_count_out_dev, void* stream);
+int tb2_scenes_transform(const double* xy_dev, const int32_t* scene_off_dev, const uint8_t* keep_dev,
+                         const int32_t* out_off_dev, int32_t T, int32_t M, int32_t M_out, int32_t B,
+                         const double* frame_dev, const double* aug_dev, float* xy_out_dev, void* stream);
+int tb2_scenes_inverse(const float* xy_dev, const int32_t* scene_off_dev, int32_t S, int32_t M, int32_t B,
+                       const double* frame_dev, double* xy_out_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Classical crowd simulators (classical/socialforce.py, classical/orca.py).  One simulator
  * per scene, all scenes stepped in lockstep by one persistent kernel; no collective.
  * State is SoA-free AoS fp32: scenes are contiguous ranges of agents (layout handle).

@@ -7,6 +7,8 @@ LSTMCell / Gaussian head and the decoder feedback rule all run on the GPU throug
 tb2_lstm_forward_sequence (csrc/capi.cu).  There is no torch or CPU implementation of the
 step in this package: without the CUDA library the calls raise.
 """
+import math
+
 import numpy as np
 import torch
 
@@ -26,7 +28,8 @@ def drop_distant(xy, r=6.0):
 
 
 def theta_rotation(xy, theta):
-    ct, st = np.cos(theta), np.sin(theta)
+    """Reference lstm/utils.py:24-30 (math.cos / math.sin of the scalar angle, like the reference)."""
+    ct, st = math.cos(theta), math.sin(theta)
     r = np.array([[ct, st], [-st, ct]])
     return np.einsum('ptc,ci->pti', xy, r)
 
@@ -338,24 +341,26 @@ class LSTMPredictor(object):
         the reference would add (those clobber grid cell 0, gridbased_pooling.py:281-293)."""
         self.model.eval()
         normalize = bool(getattr(args, 'normalize_scene', False))
-        xys, frames, split = [], [], [0]
-        for i, paths in enumerate(scenes):
-            xy = paths_to_xy(paths)
-            if normalize:
-                xy, rotation, center = center_scene(xy, obs_length)
-                frames.append((rotation, center))
-            xys.append(xy[start_length:obs_length])
-            split.append(split[-1] + xy.shape[1])
+        xys = [paths_to_xy(paths) for paths in scenes]
+        split = np.zeros(len(scenes) + 1, dtype=np.int64)
+        split[1:] = np.cumsum([xy.shape[1] for xy in xys])
         with torch.no_grad():
-            observed = torch.Tensor(np.concatenate(xys, axis=1))
-            goals = torch.zeros(observed.shape[1], 2)
-            _, output_scenes = self.model._forward_nograd(observed, torch.tensor(split).long(), None, n_predict,
+            if normalize:
+                # center_scene / inverse_scene of every scene on the device (lstm/scene_ops.py, SURVEY.md 8f rank 3)
+                from .scene_ops import inverse_scenes, preprocess_scenes
+                observed, _, _, rotation, center = preprocess_scenes([xy[:obs_length] for xy in xys], device=self.model._device(),
+                                                                     normalize_scene=True, obs_length=obs_length)
+                observed = observed[start_length:]
+            else:
+                observed = torch.Tensor(np.concatenate([xy[start_length:obs_length] for xy in xys], axis=1))
+            _, output_scenes = self.model._forward_nograd(observed, torch.from_numpy(split), None, n_predict,
                                                           pad_to_batch_max=False)
-            output_scenes = output_scenes.cpu().numpy()
+            if normalize:
+                output_scenes = inverse_scenes(output_scenes, split, rotation, center)
+            else:
+                output_scenes = output_scenes.cpu().numpy()
         results = []
         for i in range(len(scenes)):
             out = output_scenes[:, split[i]:split[i + 1]]
-            if normalize:
-                out = inverse_scene(out, *frames[i])
             results.append({0: [np.array(out[-n_predict:, 0]), np.array(out[-n_predict:, 1:])]})
         return results
