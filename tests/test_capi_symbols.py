@@ -101,3 +101,50 @@ def test_weight_key_follows_optimizer_steps():
     with torch.no_grad():
         lin.weight.add_(1.0)            # plain in-place update: version counter
     assert weights_key(lin) != k1
+
+
+def _all_model_kinds():
+    from oracle import lstm_oracle as O
+    kinds = [k for k in O.MODEL_SPECS]
+    for table in (O.NONGRID_SPECS, O.NN_SPECS, O.ATTN_SPECS, O.NN_LSTM_SPECS, O.TRAJ_SPECS):
+        kinds += list(table)
+    return kinds
+
+
+def _build_pool(kind):
+    from oracle import lstm_oracle as O
+    from trajnetplusplusbaselines_b200 import lstm as L
+    if kind in O.TRAJ_SPECS:
+        return L.TrajectronPooling(**O.TRAJ_SPECS[kind])
+    if kind in O.NN_LSTM_SPECS:
+        return L.NearestNeighborLSTM(**O.NN_LSTM_SPECS[kind])
+    if kind in O.NN_SPECS:
+        return L.NearestNeighborMLP(**O.NN_SPECS[kind])
+    if kind in O.ATTN_SPECS:
+        return L.AttentionMLPPooling(**O.ATTN_SPECS[kind])
+    if kind in O.NONGRID_SPECS:
+        return L.HiddenStateMLPPooling(**O.NONGRID_SPECS[kind])
+    spec = O.MODEL_SPECS[kind]
+    return L.GridBasedPooling(**spec) if spec is not None else None
+
+
+@pytest.mark.parametrize("kind", _all_model_kinds())
+def test_create_accepts_every_model_configuration(kind):
+    """tb2_lstm_create validates the configuration before its first CUDA call: on a box without a GPU every model kind
+    must get PAST the validation (TB2_ERR_CUDA from the first allocation), never TB2_ERR_INVALID / _UNSUPPORTED."""
+    import ctypes
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-side check of the argument validation")
+    from trajnetplusplusbaselines_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.LstmConfig()
+    cfg.hidden_dim, cfg.embedding_dim, cfg.pool_to_input = 128, 64, 1
+    cfg.pool_type = _lib.POOL_NONE
+    cfg.pool_size = cfg.blur_size = 1
+    pool = _build_pool(kind)
+    if pool is not None:
+        pool.fill_config(cfg)
+    handle = ctypes.c_void_p()
+    rc = lib.tb2_lstm_create(ctypes.byref(cfg), ctypes.byref(handle))
+    assert rc == -2, (kind, rc, lib.tb2_last_error())

@@ -236,6 +236,9 @@ int tb2_lstm_create(const tb2_lstm_config* cfg, tb2_lstm** out) {
         set_error("invalid argument: nearest-neighbour LSTM pooling needs 1 <= hidden_dim <= 512, out_dim <= 1024 and velocities");
         return fail(TB2_ERR_INVALID);
     }
+    if (cfg->pool_type == TB2_POOL_TRAJECTRON) {
+        // validated above
+    } else
     if (cfg->pool_type == TB2_POOL_NN_MLP || cfg->pool_type == TB2_POOL_NN_LSTM) {
         if (!(cfg->n >= 1 && cfg->n <= 32 && cfg->mlp_dim_spatial >= 1 && cfg->out_dim == cfg->n * cfg->mlp_dim_spatial)) {
             set_error("invalid argument: nearest-neighbour pooling needs 1 <= n <= 32 and out_dim == n * mlp_dim_spatial");
