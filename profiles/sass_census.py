@@ -7,9 +7,9 @@ import sys
 
 LIB = "trajnetplusplusbaselines_b200/libtrajnet_b200.so"
 KEEP = ("pool_prepare", "sparse_layer1_pair", "sparse_layer1_tc", "dense_layer_tc", "lstm_gates_tc", "social_dgrid_mma",
-        "hidden_mlp_pool", "sf_simulate", "orca_simulate")
+        "hidden_mlp_pool", "sf_simulate", "orca_simulate", "scenes_", "traj_", "pool_lstm_cell")
 OPS = ("UTCHMMA", "UTCQMMA", "UTCBAR", "UTCATOMSWS", "LDTM", "STTM", "UTMALDG", "UBLKCP", "SYNCS", "UCGABAR_ARV", "UCGABAR_WAIT",
-       "HMMA", "LDGSTS", "MATCH", "FFMA", "DFMA", "MUFU", "MEMBAR", "CCTL", "ACQBULK", "UTCCP")
+       "HMMA", "LDGSTS", "MATCH", "FFMA", "DFMA", "DMUL", "DADD", "F2F", "MUFU", "MEMBAR", "CCTL", "ACQBULK", "UTCCP")
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 print("SASS opcode census of the step kernels in libtrajnet_b200.so (cuobjdump -sass, sm_100a), round 2 final")
 print("tcgen05.mma -> UTC*MMA, tcgen05.ld/st -> LDTM/STTM, TMA tensor loads -> UTMALDG, cp.async.bulk -> UBLKCP, tcgen05.commit -> UTCBAR,")
