@@ -148,3 +148,31 @@ def test_create_accepts_every_model_configuration(kind):
     handle = ctypes.c_void_p()
     rc = lib.tb2_lstm_create(ctypes.byref(cfg), ctypes.byref(handle))
     assert rc == -2, (kind, rc, lib.tb2_last_error())
+
+
+@pytest.mark.parametrize("kind", ["social_small", "hiddenstatemlp_small", "nn_small", "attentionmlp_small", "nn_lstm_small",
+                                  "traj_pool_small"])
+def test_predictor_pickle_drops_device_handles(kind, tmp_path):
+    """LSTMPredictor.save pickles the whole model (lstm.py:270-277): the per-process handles a pooling module holds after its
+    stand-alone plug was used (ctypes pointers, layouts) must not reach the pickle."""
+    import torch
+    from oracle import lstm_oracle as O
+    from trajnetplusplusbaselines_b200.lstm import LSTM, LSTMPredictor
+    model = LSTM(pool=_build_pool(kind))
+    model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in O.random_weights(kind, seed=3).items()})
+    unpicklable = lambda: None                       # stands for a ModelHandle / ctypes pointer
+    model.pool._handle = unpicklable
+    model.pool._layouts._items[("fake",)] = unpicklable
+    model.pool._standalone_dummy = {"x": unpicklable}
+    model.pool._state_tracks = 5
+    if hasattr(model.pool, "_reset_pending"):
+        model.pool._reset_pending = False
+    fn = str(tmp_path / "m.pkl")
+    LSTMPredictor(model).save({"epoch": 0}, fn)
+    again = LSTMPredictor.load(fn)
+    assert again.model.pool._handle is None and len(again.model.pool._layouts._items) == 0
+    assert getattr(again.model.pool, "_standalone_dummy", None) is None
+    if hasattr(model.pool, "_reset_pending"):
+        assert again.model.pool._reset_pending is True
+    for k, v in model.state_dict().items():
+        assert torch.equal(v, again.model.state_dict()[k]), k

@@ -96,6 +96,23 @@ class LayoutCache:
         return item
 
 
+def plug_getstate(module):
+    """`__getstate__` of the pooling modules: the per-process device handles of the stand-alone plug path (model
+    handle, layouts, zero LSTM-cell weights, interaction-encoder state bookkeeping) are never pickled
+    (LSTMPredictor.save pickles the whole model, lstm.py:270-277); they are rebuilt lazily after loading."""
+    state = module.__dict__.copy()
+    state.pop('_compiled_call_impl', None)         # like torch.nn.Module.__getstate__
+    if '_handle' in state:
+        state['_handle'] = None
+    if '_layouts' in state:
+        state['_layouts'] = LayoutCache()
+    state.pop('_standalone_dummy', None)
+    state.pop('_state_tracks', None)
+    if '_reset_pending' in state:
+        state['_reset_pending'] = True
+    return state
+
+
 class ModelHandle:
     """tb2_lstm wrapper: configuration + repacked weights on one device."""
 

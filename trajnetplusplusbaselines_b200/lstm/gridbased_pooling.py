@@ -9,7 +9,7 @@ pool is not even called -- the fused sequence entry point consumes its parameter
 import torch
 
 from .. import _lib
-from ..engine import LayoutCache, ModelHandle, weights_key
+from ..engine import LayoutCache, ModelHandle, plug_getstate, weights_key
 
 _TYPES = {'occupancy': _lib.POOL_OCCUPANCY, 'directional': _lib.POOL_DIRECTIONAL,
           'social': _lib.POOL_SOCIAL}
@@ -78,6 +78,9 @@ class GridBasedPooling(torch.nn.Module):
         self._layouts = LayoutCache()
 
     # -- configuration shared with LSTM ---------------------------------------------------------
+    def __getstate__(self):
+        return plug_getstate(self)
+
     def fill_config(self, cfg):
         """Write the pooling fields of a tb2_lstm_config."""
         cfg.pool_type = _TYPES[self.type_]

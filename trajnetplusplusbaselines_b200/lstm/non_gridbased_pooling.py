@@ -24,7 +24,7 @@ the same per-track LSTMCell / hidden2pool (traj_scene_sum_kernel + traj_feat_ker
 import torch
 
 from .. import _lib
-from ..engine import LayoutCache, ModelHandle, weights_key
+from ..engine import LayoutCache, ModelHandle, plug_getstate, weights_key
 
 
 class HiddenStateMLPPooling(torch.nn.Module):
@@ -49,6 +49,9 @@ class HiddenStateMLPPooling(torch.nn.Module):
         self._layouts = LayoutCache()
 
     # -- configuration shared with LSTM ---------------------------------------------------------
+    def __getstate__(self):
+        return plug_getstate(self)
+
     def fill_config(self, cfg):
         cfg.pool_type = _lib.POOL_HIDDEN_MLP
         cfg.out_dim = int(self.out_dim)
@@ -154,6 +157,9 @@ class NearestNeighborMLP(torch.nn.Module, _StandalonePlug):
         self._handle = None
         self._layouts = LayoutCache()
 
+    def __getstate__(self):
+        return plug_getstate(self)
+
     def fill_config(self, cfg):
         cfg.pool_type = _lib.POOL_NN_MLP
         cfg.n = int(self.n)
@@ -213,6 +219,9 @@ class AttentionMLPPooling(torch.nn.Module, _StandalonePlug):
         self.out_projection = torch.nn.Linear(self.mlp_dim, self.out_dim)
         self._handle = None
         self._layouts = LayoutCache()
+
+    def __getstate__(self):
+        return plug_getstate(self)
 
     def fill_config(self, cfg):
         cfg.pool_type = _lib.POOL_ATTN_MLP
@@ -279,6 +288,9 @@ class NearestNeighborLSTM(torch.nn.Module, _StandalonePlug):
         self._layouts = LayoutCache()
         self._reset_pending = True
 
+    def __getstate__(self):
+        return plug_getstate(self)
+
     def fill_config(self, cfg):
         cfg.pool_type = _lib.POOL_NN_LSTM
         cfg.n = int(self.n)
@@ -314,6 +326,11 @@ class NearestNeighborLSTM(torch.nn.Module, _StandalonePlug):
         if self._reset_pending:
             handle.pool_state_reset(layout)
             self._reset_pending = False
+            self._state_tracks = batch_size * num_tracks
+        elif getattr(self, '_state_tracks', None) != batch_size * num_tracks:
+            # the reference stacks `num_tracks` state rows from reset() against B * N feature rows and fails the same way
+            raise RuntimeError("the interaction-encoder state holds %s tracks, this call has %d: call reset(num_tracks, ...)"
+                               % (getattr(self, '_state_tracks', None), batch_size * num_tracks))
         f32 = dict(device=device, dtype=torch.float32)
         o1 = obs1.detach().to(**f32).reshape(-1, 2).contiguous()
         o2 = obs2.detach().to(**f32).reshape(-1, 2).contiguous()
