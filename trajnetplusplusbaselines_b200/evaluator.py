@@ -3,8 +3,13 @@ evaluator/write_utils.py do around the predictor -- read the test scenes of an n
 preprocess_test, predict, write_predictions -- with the per-scene joblib fan-out
 (`Parallel(n_jobs=12)(delayed(predict_scene)...)`, trajnet_evaluator.py:61) replaced by chunks of
 scenes going through ONE batched forward each (LSTMPredictor.predict_batch).
+
+Multi-GPU (scenes are independent, no data-path collective): under `torchrun` every rank takes a contiguous
+range of the file's scenes (balanced by sum N^2, parallel.shard_scenes), writes its records to `<outfile>.part<rank>`, and
+rank 0 concatenates the parts in rank order after a barrier -- the file is byte-identical to the single-process one.
 """
 import os
+import shutil
 
 from .data import preprocess_test, read_ndjson_scenes, write_predictions
 
@@ -33,14 +38,63 @@ def predict_scenes(predictor, scenes, obs_length=9, pred_length=12, modes=1, chu
     return out
 
 
-def evaluate_file(predictor, infile, outfile, obs_length=9, pred_length=12, modes=1, chunk=1024, args=None):
+def _rank_world(rank=None, world_size=None):
+    """(rank, world_size): explicit arguments, else the initialised torch.distributed group, else (0, 1)."""
+    if rank is not None and world_size is not None:
+        return int(rank), int(world_size)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def _barrier():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.barrier()
+    except ImportError:
+        pass
+
+
+def evaluate_file(predictor, infile, outfile, obs_length=9, pred_length=12, modes=1, chunk=1024, args=None,
+                  rank=None, world_size=None):
     """ndjson in -> ndjson out (the records evaluator/write_utils.write_predictions appends).
-    Returns the number of scenes written."""
+    Returns the number of scenes of the file.  With world_size > 1 (arguments or the initialised process group) the
+    scenes are sharded over the ranks; rank 0 assembles `outfile` from the per-rank parts."""
     scenes = load_test_scenes(infile, obs_length)
-    preds = predict_scenes(predictor, scenes, obs_length, pred_length, modes, chunk, args)
-    if os.path.exists(outfile):
-        os.remove(outfile)
-    write_predictions(preds, scenes, outfile, obs_length=obs_length, pred_length=pred_length)
+    rank, world = _rank_world(rank, world_size)
+    if world == 1:
+        preds = predict_scenes(predictor, scenes, obs_length, pred_length, modes, chunk, args)
+        if os.path.exists(outfile):
+            os.remove(outfile)
+        write_predictions(preds, scenes, outfile, obs_length=obs_length, pred_length=pred_length)
+        return len(scenes)
+    from .parallel import shard_scenes
+    split = [0]
+    for _, _, paths in scenes:
+        split.append(split[-1] + len(paths))
+    lo, hi = shard_scenes(split, world, rank)[:2]
+    mine = scenes[lo:hi]
+    part = "%s.part%d" % (outfile, rank)
+    if os.path.exists(part):
+        os.remove(part)
+    open(part, "w").close()                                # an empty shard still leaves its (empty) part
+    if mine:
+        preds = predict_scenes(predictor, mine, obs_length, pred_length, modes, chunk, args)
+        write_predictions(preds, mine, part, obs_length=obs_length, pred_length=pred_length)
+    _barrier()                                              # every part is complete
+    if rank == 0:
+        with open(outfile, "wb") as out:
+            for r in range(world):
+                with open("%s.part%d" % (outfile, r), "rb") as f:
+                    shutil.copyfileobj(f, out)
+        for r in range(world):
+            os.remove("%s.part%d" % (outfile, r))
+    _barrier()                                              # outfile is complete before any rank returns
     return len(scenes)
 
 
@@ -54,6 +108,7 @@ def get_predictions(args, load_predictor=None):
             predictor = LSTMPredictor.load(filename)
             predictor.model.to('cuda')
             return predictor
+    rank = _rank_world()[0]
     pred_dir = args.path.rstrip(os.sep)       # .../test_pred -> the scenes are in .../test (trajnet_evaluator.py:31)
     test_dir = pred_dir[:-len('_pred')] if pred_dir.endswith('_pred') else pred_dir
     datasets = sorted(f for f in os.listdir(test_dir) if not f.startswith('.') and f.endswith('.ndjson'))
@@ -61,10 +116,15 @@ def get_predictions(args, load_predictor=None):
     for model in args.output:
         model_name = os.path.basename(model).replace('.pkl', '') + '_modes' + str(args.modes)
         out_dir = os.path.join(args.path, model_name)
-        if os.path.exists(out_dir):
-            print('Predictions corresponding to {} already exist.'.format(model_name))
+        exists = os.path.exists(out_dir)
+        _barrier()                                          # every rank has looked before rank 0 creates the folder
+        if exists:
+            if rank == 0:
+                print('Predictions corresponding to {} already exist.'.format(model_name))
             continue
-        os.makedirs(out_dir)
+        if rank == 0:
+            os.makedirs(out_dir)
+        _barrier()
         predictor = load_predictor(model)
         written[model_name] = sum(
             evaluate_file(predictor, os.path.join(test_dir, dataset), os.path.join(out_dir, dataset),
@@ -95,8 +155,20 @@ def main(argv=None):
     args = parser.parse_args(argv)
     args.output = args.output if args.output is not None else []
     args.path = os.path.join('DATA_BLOCK', args.path, 'test_pred') + os.sep
-    for name, n in get_predictions(args).items():
-        print('{}: {} scenes written'.format(name, n))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world > 1:                                            # torchrun: one process per GPU, scenes sharded over the ranks
+        import torch
+        import torch.distributed as dist
+        if torch.cuda.is_available():
+            torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+        dist.init_process_group('nccl' if torch.cuda.is_available() else 'gloo')
+    written = get_predictions(args)
+    if _rank_world()[0] == 0:
+        for name, n in written.items():
+            print('{}: {} scenes written'.format(name, n))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':
