@@ -378,6 +378,28 @@ int tb2_scenes_inverse(const float* xy_dev, const int32_t* scene_off_dev, int32_
                        const double* frame_dev, double* xy_out_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Host-side ndjson codec of the batched evaluator path (no CUDA).  The TrajNet++ on-disk format as the
+ * reference reads / writes it through trajnetplusplustools (evaluator/write_utils.py:42-81, DATA_BLOCK files): one JSON
+ * object per line, {"track": {"f", "p", "x", "y"[, "prediction_number", "scene_id"]}} or {"scene": {"id", "p", "s", "e", "fps", "tag"}}.
+ *
+ * tb2_ndjson_parse -- text -> column arrays (caller-allocated, max_rows = number of lines): track rows in file order and
+ *   scene rows in file order.  Numbers are read as json.loads reads them (integer literals for f / p / id / s / e, float(str)
+ *   = correctly rounded strtod for x / y, NaN / Infinity accepted).  A line the parser is not certain about (string
+ *   escapes, a missing or non-integer field, an unknown record type) stops it: refused_line_out = its 0-based index
+ *   (else -1) and the caller takes its json.loads path for the whole file.
+ * tb2_ndjson_format -- prediction records -> text: per scene one scene line then rows_per_scene[i] track lines, in the
+ *   caller's row order, byte-identical to json.dumps of the reference writer's dictionaries with coordinates round(v, 2).
+ *   Returns the byte count needed (writes only when `capacity` suffices; <= 160 bytes per line), or a negative error
+ *   (TB2_ERR_UNSUPPORTED for finite |coordinate| >= 1e15, where repr() would need an exponent). */
+int tb2_ndjson_parse(const char* text, size_t len, int64_t max_rows, int64_t* track_frame, int64_t* track_ped,
+                     double* track_x, double* track_y, int64_t* num_tracks_out, int64_t* scene_id, int64_t* scene_ped,
+                     int64_t* scene_start, int64_t* scene_end, int64_t* num_scenes_out, int64_t* refused_line_out);
+int64_t tb2_ndjson_format(int64_t num_scenes, const int64_t* scene_id, const int64_t* scene_ped, const int64_t* scene_start,
+                          const int64_t* scene_end, const int64_t* rows_per_scene, const int64_t* row_frame,
+                          const int64_t* row_ped, const double* row_x, const double* row_y, const int64_t* row_mode,
+                          char* out, int64_t capacity);
+
+/* ---------------------------------------------------------------------------------------
  * Classical crowd simulators (classical/socialforce.py, classical/orca.py).  One simulator
  * per scene, all scenes stepped in lockstep by one persistent kernel; no collective.
  * State is SoA-free AoS fp32: scenes are contiguous ranges of agents (layout handle).

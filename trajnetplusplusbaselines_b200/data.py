@@ -131,3 +131,149 @@ def write_predictions(pred_list, scenes, filename, obs_length=9, pred_length=12)
                         rows.extend(track_line(first_frame + j * frame_diff, neigh_ids[n], neigh[j][n][0], neigh[j][n][1],
                                                m, scene_id) for j in range(len(neigh)))
                 out.write(''.join(rows))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Column pipeline of the batched evaluator.  Same results as the row pipeline above
+# (read_ndjson_scenes -> preprocess_test -> paths_to_xy ... write_predictions), without one Python object per track row:
+# the text passes are native (csrc/ndjson.cu: tb2_ndjson_parse / tb2_ndjson_format), the per-scene assembly is NumPy.
+# The row pipeline stays the definition: a file the native parser refuses goes through it, and tests/test_data_io.py
+# holds the two against each other (arrays equal, output files byte-identical).
+# ------------------------------------------------------------------------------------------------------------------
+SceneMeta = namedtuple('SceneMeta', ['scene_id', 'pedestrian', 'first_frame', 'frame_diff', 'last_obs_frame', 'neigh_ids'])
+
+
+def parse_ndjson_columns(filename):
+    """Track / scene columns of an ndjson file through the native parser, or None when it refuses a line.
+
+    Returns dict(frame, ped, x, y: track rows in file order; scene_id, scene_ped, scene_start, scene_end)."""
+    import ctypes
+    from . import _lib
+    with open(filename, 'rb') as f:
+        text = f.read()
+    max_rows = text.count(b'\n') + 1
+    i64 = lambda: np.empty(max_rows, dtype=np.int64)
+    cols = dict(frame=i64(), ped=i64(), x=np.empty(max_rows), y=np.empty(max_rows),
+                scene_id=i64(), scene_ped=i64(), scene_start=i64(), scene_end=i64())
+    counts = np.zeros(3, dtype=np.int64)                    # tracks, scenes, refused line
+    ptr = lambda a: ctypes.c_void_p(a.ctypes.data)
+    _lib.check(_lib.load().tb2_ndjson_parse(
+        ctypes.cast(ctypes.c_char_p(text), ctypes.c_void_p), len(text), max_rows,            # the bytes object's own buffer
+        ptr(cols['frame']), ptr(cols['ped']), ptr(cols['x']), ptr(cols['y']),
+        ptr(counts[0:1]), ptr(cols['scene_id']), ptr(cols['scene_ped']), ptr(cols['scene_start']), ptr(cols['scene_end']),
+        ptr(counts[1:2]), ptr(counts[2:3])))
+    if counts[2] >= 0:
+        return None
+    nt, ns = int(counts[0]), int(counts[1])
+    return {k: (v[:ns] if k.startswith('scene_') else v[:nt]) for k, v in cols.items()}
+
+
+def _scene_meta_from_paths(scene_id, paths, obs_length):
+    observed_path = paths[0]
+    return SceneMeta(scene_id, observed_path[0].pedestrian, observed_path[0].frame,
+                     observed_path[1].frame - observed_path[0].frame, observed_path[obs_length - 1].frame,
+                     [p[0].pedestrian for p in paths[1:]])
+
+
+def load_test_scenes_xy(filename, obs_length=9):
+    """[(xy float64 [n_frames, n_peds, 2], SceneMeta)] of the test scenes of an ndjson file: per scene exactly
+    paths_to_xy(preprocess_test(paths, obs_length)) and what write_predictions reads off those paths."""
+    cols = parse_ndjson_columns(filename)
+    if cols is None:                                        # the row pipeline is the definition
+        out = []
+        for scene_id, paths in read_ndjson_scenes(filename):
+            paths = preprocess_test(paths, obs_length)
+            out.append((paths_to_xy(paths), _scene_meta_from_paths(scene_id, paths, obs_length)))
+        return out
+    order = np.argsort(cols['frame'], kind='stable')        # by frame, file order within a frame (tracks_by_frame)
+    f, p, x, y = cols['frame'][order], cols['ped'][order], cols['x'][order], cols['y'][order]
+    los = np.searchsorted(f, cols['scene_start'], side='left')
+    his = np.searchsorted(f, cols['scene_end'], side='right')
+    out = []
+    for i in range(len(los)):
+        lo, hi = int(los[i]), int(his[i])
+        fs, ps = f[lo:hi], p[lo:hi]
+        primary = int(cols['scene_ped'][i])
+        pf = fs[ps == primary]                              # the primary's rows, ascending frames
+        if len(pf) == 0:
+            continue                                        # read_ndjson_scenes skips a scene without its primary
+        last = pf[:obs_length][-1]                          # preprocess_test: last frame of the observation
+        cut = int(np.searchsorted(fs, last, side='right'))
+        fs, ps, xs, ys = fs[:cut], ps[:cut], x[lo:lo + cut], y[lo:lo + cut]
+        observed = pf[pf <= last]
+        if len(observed) < max(obs_length, 2):
+            raise IndexError("scene %d: the primary has %d observed rows, %d needed" % (int(cols['scene_id'][i]), len(observed), obs_length))
+        uniq, first, inv = np.unique(ps, return_index=True, return_inverse=True)
+        by_first = np.argsort(first, kind='stable')         # pedestrians in order of first appearance
+        peds = uniq[by_first]
+        k = int(np.nonzero(peds == primary)[0][0])
+        peds = np.concatenate([peds[k:k + 1], peds[:k], peds[k + 1:]])           # primary first
+        rank = np.empty(len(uniq), dtype=np.int64)
+        rank[np.searchsorted(uniq, peds)] = np.arange(len(peds))
+        col = rank[inv]
+        frames = np.unique(observed)                        # paths_to_xy: sorted set of the primary's frames
+        fi = np.minimum(np.searchsorted(frames, fs), len(frames) - 1)
+        valid = frames[fi] == fs
+        present = np.zeros(len(peds), dtype=bool)
+        present[col[valid]] = True                          # a pedestrian without a row in those frames is dropped
+        newcol = np.cumsum(present) - 1
+        xy = np.full((len(frames), int(present.sum()), 2), np.nan)
+        xy[fi[valid], newcol[col[valid]], 0] = xs[valid]
+        xy[fi[valid], newcol[col[valid]], 1] = ys[valid]
+        meta = SceneMeta(int(cols['scene_id'][i]), primary, int(observed[0]), int(observed[1] - observed[0]),
+                         int(observed[obs_length - 1]), peds[1:].tolist())
+        out.append((xy, meta))
+    return out
+
+
+def write_predictions_xy(pred_list, metas, filename, obs_length=9, pred_length=12):
+    """write_predictions for the column pipeline: same records, same bytes (one native formatting pass per call)."""
+    import ctypes
+    from . import _lib
+    seq_length = obs_length + pred_length
+    n = len(metas)
+    sid = np.empty(n, dtype=np.int64)
+    sped, sstart, send, nrows = (np.empty(n, dtype=np.int64) for _ in range(4))
+    frames, peds, xs, ys, modes = [], [], [], [], []
+    for i, (predictions, m) in enumerate(zip(pred_list, metas)):
+        first_frame = m.last_obs_frame + m.frame_diff
+        sid[i], sped[i], sstart[i], send[i] = m.scene_id, m.pedestrian, m.first_frame, m.first_frame + (seq_length - 1) * m.frame_diff
+        rows = 0
+        for mode in range(len(predictions)):
+            prediction, neigh = predictions[mode]
+            prediction = np.asarray(prediction, dtype=np.float64)
+            T = len(prediction)
+            f_prim = first_frame + np.arange(T, dtype=np.int64) * m.frame_diff
+            frames.append(f_prim)
+            peds.append(np.full(T, m.pedestrian, dtype=np.int64))
+            xs.append(prediction[:, 0])
+            ys.append(prediction[:, 1])
+            count = T
+            if len(neigh):
+                neigh = np.asarray(neigh, dtype=np.float64)                    # [T', K, 2]
+                Tn, K = neigh.shape[0], neigh.shape[1]
+                ids = np.asarray(m.neigh_ids[:K], dtype=np.int64)
+                if len(ids) != K:
+                    raise IndexError("scene %d: %d neighbour predictions, %d neighbour ids" % (m.scene_id, K, len(ids)))
+                frames.append(np.tile(first_frame + np.arange(Tn, dtype=np.int64) * m.frame_diff, K))
+                peds.append(np.repeat(ids, Tn))
+                xs.append(neigh[:, :, 0].T.reshape(-1))
+                ys.append(neigh[:, :, 1].T.reshape(-1))
+                count += Tn * K
+            modes.append(np.full(count, mode, dtype=np.int64))
+            rows += count
+        nrows[i] = rows
+    cat = lambda parts, dt: np.ascontiguousarray(np.concatenate(parts)) if parts else np.empty(0, dtype=dt)
+    frames, peds, modes = cat(frames, np.int64), cat(peds, np.int64), cat(modes, np.int64)
+    xs, ys = cat(xs, np.float64), cat(ys, np.float64)
+    capacity = 160 * (n + len(frames)) + 16
+    buf = ctypes.create_string_buffer(capacity)
+    ptr = lambda a: ctypes.c_void_p(a.ctypes.data)
+    used = _lib.load().tb2_ndjson_format(n, ptr(sid), ptr(sped), ptr(sstart), ptr(send), ptr(nrows), ptr(frames), ptr(peds),
+                                         ptr(xs), ptr(ys), ptr(modes), ctypes.cast(buf, ctypes.c_void_p), capacity)
+    if used < 0:
+        _lib.check(int(used))
+    if used > capacity:
+        raise RuntimeError("tb2_ndjson_format needs %d bytes, %d provided" % (used, capacity))
+    with open(filename, "ab") as out:
+        out.write(memoryview(buf)[:used])

@@ -11,7 +11,7 @@ rank 0 concatenates the parts in rank order after a barrier -- the file is byte-
 import os
 import shutil
 
-from .data import preprocess_test, read_ndjson_scenes, write_predictions
+from .data import load_test_scenes_xy, preprocess_test, read_ndjson_scenes, write_predictions, write_predictions_xy
 
 
 def load_test_scenes(filename, obs_length=9):
@@ -60,23 +60,47 @@ def _barrier():
         pass
 
 
+def _column_pipeline(predictor, modes):
+    """The column pipeline (data.load_test_scenes_xy -> predict_batch_xy -> data.write_predictions_xy: native text passes,
+    no Python object per track row) serves predictors that take arrays; it writes the same bytes as the row pipeline."""
+    return hasattr(predictor, 'predict_batch_xy') and modes == 1
+
+
 def evaluate_file(predictor, infile, outfile, obs_length=9, pred_length=12, modes=1, chunk=1024, args=None,
                   rank=None, world_size=None):
     """ndjson in -> ndjson out (the records evaluator/write_utils.write_predictions appends).
     Returns the number of scenes of the file.  With world_size > 1 (arguments or the initialised process group) the
     scenes are sharded over the ranks; rank 0 assembles `outfile` from the per-rank parts."""
-    scenes = load_test_scenes(infile, obs_length)
+    columns = _column_pipeline(predictor, modes)
+    if columns:
+        scenes = load_test_scenes_xy(infile, obs_length)                 # [(xy, SceneMeta)]
+        sizes = [xy.shape[1] for xy, _ in scenes]
+
+        def run(part, filename):
+            preds = []
+            for i in range(0, len(part), chunk):
+                preds.extend(predictor.predict_batch_xy([xy for xy, _ in part[i:i + chunk]], n_predict=pred_length,
+                                                        obs_length=obs_length, args=args))
+            write_predictions_xy(preds, [meta for _, meta in part], filename, obs_length=obs_length, pred_length=pred_length)
+    else:
+        scenes = load_test_scenes(infile, obs_length)                    # [(filename, scene_id, paths)]
+        sizes = [len(paths) for _, _, paths in scenes]
+
+        def run(part, filename):
+            preds = predict_scenes(predictor, part, obs_length, pred_length, modes, chunk, args)
+            write_predictions(preds, part, filename, obs_length=obs_length, pred_length=pred_length)
     rank, world = _rank_world(rank, world_size)
     if world == 1:
-        preds = predict_scenes(predictor, scenes, obs_length, pred_length, modes, chunk, args)
         if os.path.exists(outfile):
             os.remove(outfile)
-        write_predictions(preds, scenes, outfile, obs_length=obs_length, pred_length=pred_length)
+        open(outfile, "w").close()
+        if scenes:
+            run(scenes, outfile)
         return len(scenes)
     from .parallel import shard_scenes
     split = [0]
-    for _, _, paths in scenes:
-        split.append(split[-1] + len(paths))
+    for n in sizes:
+        split.append(split[-1] + n)
     lo, hi = shard_scenes(split, world, rank)[:2]
     mine = scenes[lo:hi]
     part = "%s.part%d" % (outfile, rank)
@@ -84,8 +108,7 @@ def evaluate_file(predictor, infile, outfile, obs_length=9, pred_length=12, mode
         os.remove(part)
     open(part, "w").close()                                # an empty shard still leaves its (empty) part
     if mine:
-        preds = predict_scenes(predictor, mine, obs_length, pred_length, modes, chunk, args)
-        write_predictions(preds, mine, part, obs_length=obs_length, pred_length=pred_length)
+        run(mine, part)
     _barrier()                                              # every part is complete
     if rank == 0:
         with open(outfile, "wb") as out:

@@ -339,10 +339,15 @@ class LSTMPredictor(object):
         in the same order, equal to calling the predictor scene by scene: the scene layout is created
         with tb2_layout_set_padding(0), so a scene does not see the padding slots a batched call of
         the reference would add (those clobber grid cell 0, gridbased_pooling.py:281-293)."""
+        return self.predict_batch_xy([paths_to_xy(paths) for paths in scenes], scene_goals, n_predict, obs_length,
+                                     start_length, args)
+
+    def predict_batch_xy(self, xys, scene_goals=None, n_predict=12, obs_length=9, start_length=0, args=None):
+        """predict_batch on arrays: xys = list of float64 [n_frames, N_i, 2] as paths_to_xy returns them (the column
+        pipeline of the evaluator, data.load_test_scenes_xy, builds them without TrackRow objects)."""
         self.model.eval()
         normalize = bool(getattr(args, 'normalize_scene', False))
-        xys = [paths_to_xy(paths) for paths in scenes]
-        split = np.zeros(len(scenes) + 1, dtype=np.int64)
+        split = np.zeros(len(xys) + 1, dtype=np.int64)
         split[1:] = np.cumsum([xy.shape[1] for xy in xys])
         with torch.no_grad():
             if normalize:
@@ -360,7 +365,7 @@ class LSTMPredictor(object):
             else:
                 output_scenes = output_scenes.cpu().numpy()
         results = []
-        for i in range(len(scenes)):
+        for i in range(len(xys)):
             out = output_scenes[:, split[i]:split[i + 1]]
             results.append({0: [np.array(out[-n_predict:, 0]), np.array(out[-n_predict:, 1:])]})
         return results
