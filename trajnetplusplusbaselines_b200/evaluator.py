@@ -16,7 +16,14 @@ from .data import load_test_scenes_xy, preprocess_test, read_ndjson_scenes, writ
 
 def load_test_scenes(filename, obs_length=9):
     """[(filename, scene_id, paths)] like evaluator/write_utils.load_test_datasets, already through
-    preprocess_test (tracks that start after the observation period are dropped)."""
+    preprocess_test (tracks that start after the observation period are dropped).
+
+    Deliberate deviation in the written neighbour ids: the reference keeps the UN-preprocessed paths for
+    write_predictions (lstm/trajnet_evaluator.py:57-64) while predict_scene drops the late tracks (:15-17), so the
+    n-th predicted neighbour is labelled with the id of the n-th neighbour of the full scene
+    (evaluator/write_utils.py:51-53,74-79) -- shifted whenever a dropped track precedes a kept one.  Here the ids
+    come from the same preprocessed paths the predictions were made from, i.e. every trajectory carries its own id;
+    primary rows, frames and scene rows are identical, and files without late tracks are identical throughout."""
     name = os.path.basename(filename)
     return [(name, scene_id, preprocess_test(paths, obs_length)) for scene_id, paths in read_ndjson_scenes(filename)]
 
