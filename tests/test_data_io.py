@@ -372,3 +372,34 @@ def test_column_pipeline_on_the_reference_data_block():
             continue                        # training files hold scenes shorter than the test protocol assumes
         _assert_pipelines_agree(fn)
         assert rows
+
+
+def test_native_parser_reads_numbers_like_float(tmp_path):
+    """Coordinates bit for bit as json.loads reads them: the exact-division fast path (short decimals) and the strtod path
+    (long mantissas, exponents, subnormals) against float(str)."""
+    import random
+    from trajnetplusplusbaselines_b200.data import parse_ndjson_columns
+    rng = random.Random(5)
+    lits = []
+    for _ in range(60000):
+        k = rng.randint(0, 22)
+        digits = str(rng.randint(0, 10 ** rng.randint(1, 15)))
+        sign = '-' if rng.random() < 0.3 else ''
+        if k == 0:
+            lits.append(sign + digits + '.0')
+        else:
+            digits = digits.rjust(k + 1, '0')
+            lits.append(sign + digits[:-k] + '.' + digits[-k:])
+    lits += [repr(rng.gauss(0, 1) * 10 ** rng.randint(-8, 8)) for _ in range(40000)]
+    lits += ['0.0', '-0.0', '0.10', '0.000000000000000000001', '123456789012345.67', '1234567890123456.7', '0.30000000000000004',
+             '1e5', '1.5e-7', '-2.5E+3', '5e-324', '1.7976931348623157e308', '0.000', '100000000000000.0', '99999999999999.99', '7']
+    fn = os.path.join(tmp_path, "numbers.ndjson")
+    with open(fn, "w") as f:
+        for i in range(0, len(lits) - 1, 2):
+            f.write('{"track": {"f": %d, "p": 1, "x": %s, "y": %s}}\n' % (i, lits[i], lits[i + 1]))
+    cols = parse_ndjson_columns(fn)
+    assert cols is not None and len(cols['x']) == len(lits) // 2
+    want_x = np.array([float(lits[2 * i]) for i in range(len(cols['x']))])
+    want_y = np.array([float(lits[2 * i + 1]) for i in range(len(cols['y']))])
+    assert np.array_equal(cols['x'].view(np.int64), want_x.view(np.int64))
+    assert np.array_equal(cols['y'].view(np.int64), want_y.view(np.int64))

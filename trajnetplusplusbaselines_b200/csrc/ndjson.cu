@@ -115,6 +115,33 @@ inline ValueKind parse_value(Cursor& c, long long* iv, double* dv) {
     }
     const size_t n = (size_t)(q - b);
     if (n == 0 || n >= 64) return V_BAD;            // longer literals go to the json.loads path
+    if (is_float) {
+        // Clinger's exact case: a decimal d x 10^-k with d < 2^53 and k <= 22 is ONE correctly rounded division of two
+        // exactly representable doubles -- the same double strtod returns.  Covers the "%.2f"-style coordinates of
+        // the DATA_BLOCK files; exponents, long mantissas and everything else go through strtod below.
+        static const double kPow10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
+                                          1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+        const char* t = b;
+        const bool neg = *t == '-';
+        if (neg) ++t;
+        unsigned long long mant = 0;
+        int digits = 0, frac = 0;
+        bool seen_point = false, simple = true;
+        for (; t < q; ++t) {
+            if (*t == '.') { seen_point = true; continue; }
+            if (*t < '0' || *t > '9') { simple = false; break; }          // an exponent part
+            if (digits >= 15 && mant != 0) { simple = false; break; }    // keep the mantissa below 10^15 < 2^53
+            mant = mant * 10 + (unsigned)(*t - '0');
+            if (mant != 0) ++digits;
+            if (seen_point) ++frac;
+        }
+        if (simple && frac <= 22) {
+            const double v = (double)mant / kPow10[frac];
+            *dv = neg ? -v : v;
+            c.p = q;
+            return V_FLOAT;
+        }
+    }
     char tok[64];
     memcpy(tok, b, n);
     tok[n] = 0;
