@@ -34,6 +34,22 @@ def test_kalman_matches_numpy_restatement():
         assert np.abs(p - ref).max() < 1e-8          # float64 both sides; pinv vs Gauss-Jordan
 
 
+def test_kalman_host_threads_do_not_change_results(monkeypatch):
+    """Tracks are independent: the host-thread fan-out of tb2_kalman_predict (>= 64 tracks per thread) returns the
+    single-thread result bit for bit, and a bad track is reported whichever thread meets it."""
+    from trajnetplusplusbaselines_b200.classical import kalman
+    rng = np.random.RandomState(7)
+    tracks = [np.cumsum(rng.randn(rng.randint(2, 10), 2) * 0.3, axis=0) + rng.randn(2) * 5 for _ in range(700)]
+    monkeypatch.setenv("TB2_KALMAN_THREADS", "1")
+    one = kalman.predict_tracks(tracks, n_predict=12, n_samples=0)
+    monkeypatch.setenv("TB2_KALMAN_THREADS", "5")
+    many = kalman.predict_tracks(tracks, n_predict=12, n_samples=0)
+    assert all(np.array_equal(a, b) for a, b in zip(one, many))
+    tracks[650] = tracks[650][:1]                       # a single observation (kalman.py:28-29)
+    with pytest.raises(RuntimeError):
+        kalman.predict_tracks(tracks, n_predict=12, n_samples=0)
+
+
 def test_kalman_config0_64_scenes_of_5_peds():
     """BASELINE configs[0]: 64 synthetic 5-ped scenes, obs=9 pred=12, through `predict`."""
     from trajnetplusplusbaselines_b200.classical import kalman

@@ -9,8 +9,11 @@
 //                       Q, R so the caller can add the reference's sampled noise.
 // pykalman is not vendored (parity unpinned, see oracle/classical_oracle.py); the EM follows
 // Shumway & Stoffer as pykalman documents it.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -100,6 +103,66 @@ bool smooth(const M4& A, Track& t) {
     return true;
 }
 
+// One track: EM (Q, R, mu0, Sigma0), smoother, expected rollout.  Returns nullptr or a static error message; tracks are
+// independent, so the caller may run them on several host threads (results do not depend on the thread count).
+const char* kalman_track(int tr_i, const M4& A, const M4& At, const double* obs, const int64_t* track_offsets, int32_t n_predict,
+                         int32_t em_iterations, double* pred_out, double* q_out, double* r_out, double* last_state_out) {
+    const int64_t o0 = track_offsets[tr_i];
+    const int T = (int)(track_offsets[tr_i + 1] - o0);
+    if (T < 2) return "invalid argument: a track needs at least 2 observations (kalman.py:28-29)";
+    const double* Z = obs + 2 * o0;
+    Track t;
+    t.T = T;
+    t.pm.resize(T); t.fm.resize(T); t.sm.resize(T);
+    t.pc.resize(T); t.fc.resize(T); t.sc.resize(T); t.G.resize(T);
+    M4 Q = eye4(1e-5);
+    double R[2][2] = {{0.05 * 0.05, 0.0}, {0.0, 0.05 * 0.05}};
+    V4 mu0 = {{Z[0], 0.0, Z[1], 0.0}};
+    M4 S0 = eye4(1.0);
+    for (int it = 0; it < em_iterations; ++it) {
+        filter(A, Q, R, mu0, S0, Z, t);
+        if (!smooth(A, t)) return "kalman: singular predicted covariance";
+        // M-step (pykalman _em_observation_covariance / _em_transition_covariance / initial state)
+        double Rn[2][2] = {{0, 0}, {0, 0}};
+        for (int k = 0; k < T; ++k) {
+            const double e0 = Z[2 * k] - t.sm[k].a[0], e1 = Z[2 * k + 1] - t.sm[k].a[2];
+            Rn[0][0] += e0 * e0 + t.sc[k].a[0][0];
+            Rn[0][1] += e0 * e1 + t.sc[k].a[0][2];
+            Rn[1][0] += e1 * e0 + t.sc[k].a[2][0];
+            Rn[1][1] += e1 * e1 + t.sc[k].a[2][2];
+        }
+        for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) R[i][j] = Rn[i][j] / T;
+        M4 Qn = zero4();
+        for (int k = 0; k < T - 1; ++k) {
+            const V4 ax = mulv(A, t.sm[k]);
+            V4 err;
+            for (int i = 0; i < 4; ++i) err.a[i] = t.sm[k + 1].a[i] - ax.a[i];
+            const M4 pair = mul(t.sc[k + 1], tr(t.G[k]));      // Cov(x_{k+1}, x_k | Z)
+            const M4 pa = mul(pair, At);
+            M4 term = add(outer(err, err), mul(mul(A, t.sc[k]), At));
+            term = add(term, t.sc[k + 1]);
+            term = sub(term, pa);
+            term = sub(term, tr(pa));
+            Qn = add(Qn, term);
+        }
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) Q.a[i][j] = Qn.a[i][j] / (T - 1);
+        mu0 = t.sm[0];
+        S0 = t.sc[0];
+    }
+    filter(A, Q, R, mu0, S0, Z, t);
+    if (!smooth(A, t)) return "kalman: singular predicted covariance";
+    V4 x = t.sm[T - 1];
+    if (last_state_out) for (int i = 0; i < 4; ++i) last_state_out[(size_t)tr_i * 4 + i] = x.a[i];
+    for (int k = 0; k < n_predict; ++k) {
+        x = mulv(A, x);
+        pred_out[((size_t)tr_i * n_predict + k) * 2 + 0] = x.a[0];
+        pred_out[((size_t)tr_i * n_predict + k) * 2 + 1] = x.a[2];
+    }
+    if (q_out) for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) q_out[(size_t)tr_i * 16 + i * 4 + j] = Q.a[i][j];
+    if (r_out) for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) r_out[(size_t)tr_i * 4 + i * 2 + j] = R[i][j];
+    return nullptr;
+}
+
 }  // namespace
 
 extern "C" int tb2_kalman_predict(const double* obs, const int64_t* track_offsets, int32_t n_tracks,
@@ -111,60 +174,24 @@ extern "C" int tb2_kalman_predict(const double* obs, const int64_t* track_offset
     A.a[0][1] = 1.0;
     A.a[2][3] = 1.0;
     const M4 At = tr(A);
-    for (int tr_i = 0; tr_i < n_tracks; ++tr_i) {
-        const int64_t o0 = track_offsets[tr_i];
-        const int T = (int)(track_offsets[tr_i + 1] - o0);
-        TB2_REQUIRE(T >= 2, "a track needs at least 2 observations (kalman.py:28-29)");
-        const double* Z = obs + 2 * o0;
-        Track t;
-        t.T = T;
-        t.pm.resize(T); t.fm.resize(T); t.sm.resize(T);
-        t.pc.resize(T); t.fc.resize(T); t.sc.resize(T); t.G.resize(T);
-        M4 Q = eye4(1e-5);
-        double R[2][2] = {{0.05 * 0.05, 0.0}, {0.0, 0.05 * 0.05}};
-        V4 mu0 = {{Z[0], 0.0, Z[1], 0.0}};
-        M4 S0 = eye4(1.0);
-        for (int it = 0; it < em_iterations; ++it) {
-            filter(A, Q, R, mu0, S0, Z, t);
-            if (!smooth(A, t)) { tb2::set_error("kalman: singular predicted covariance"); return TB2_ERR_INVALID; }
-            // M-step (pykalman _em_observation_covariance / _em_transition_covariance / initial state)
-            double Rn[2][2] = {{0, 0}, {0, 0}};
-            for (int k = 0; k < T; ++k) {
-                const double e0 = Z[2 * k] - t.sm[k].a[0], e1 = Z[2 * k + 1] - t.sm[k].a[2];
-                Rn[0][0] += e0 * e0 + t.sc[k].a[0][0];
-                Rn[0][1] += e0 * e1 + t.sc[k].a[0][2];
-                Rn[1][0] += e1 * e0 + t.sc[k].a[2][0];
-                Rn[1][1] += e1 * e1 + t.sc[k].a[2][2];
-            }
-            for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) R[i][j] = Rn[i][j] / T;
-            M4 Qn = zero4();
-            for (int k = 0; k < T - 1; ++k) {
-                const V4 ax = mulv(A, t.sm[k]);
-                V4 err;
-                for (int i = 0; i < 4; ++i) err.a[i] = t.sm[k + 1].a[i] - ax.a[i];
-                const M4 pair = mul(t.sc[k + 1], tr(t.G[k]));      // Cov(x_{k+1}, x_k | Z)
-                const M4 pa = mul(pair, At);
-                M4 term = add(outer(err, err), mul(mul(A, t.sc[k]), At));
-                term = add(term, t.sc[k + 1]);
-                term = sub(term, pa);
-                term = sub(term, tr(pa));
-                Qn = add(Qn, term);
-            }
-            for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) Q.a[i][j] = Qn.a[i][j] / (T - 1);
-            mu0 = t.sm[0];
-            S0 = t.sc[0];
-        }
-        filter(A, Q, R, mu0, S0, Z, t);
-        if (!smooth(A, t)) { tb2::set_error("kalman: singular predicted covariance"); return TB2_ERR_INVALID; }
-        V4 x = t.sm[T - 1];
-        if (last_state_out) for (int i = 0; i < 4; ++i) last_state_out[(size_t)tr_i * 4 + i] = x.a[i];
-        for (int k = 0; k < n_predict; ++k) {
-            x = mulv(A, x);
-            pred_out[((size_t)tr_i * n_predict + k) * 2 + 0] = x.a[0];
-            pred_out[((size_t)tr_i * n_predict + k) * 2 + 1] = x.a[2];
-        }
-        if (q_out) for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) q_out[(size_t)tr_i * 16 + i * 4 + j] = Q.a[i][j];
-        if (r_out) for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) r_out[(size_t)tr_i * 4 + i * 2 + j] = R[i][j];
+    // host threads over contiguous track ranges (TB2_KALMAN_THREADS overrides; small jobs stay on the calling thread)
+    int threads = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("TB2_KALMAN_THREADS")) threads = atoi(e);
+    threads = std::max(1, std::min(threads, n_tracks / 64));
+    std::vector<const char*> errors((size_t)threads, nullptr);
+    auto run = [&](int w) {
+        const int lo = (int)((int64_t)n_tracks * w / threads), hi = (int)((int64_t)n_tracks * (w + 1) / threads);
+        for (int i = lo; i < hi && !errors[w]; ++i)
+            errors[w] = kalman_track(i, A, At, obs, track_offsets, n_predict, em_iterations, pred_out, q_out, r_out, last_state_out);
+    };
+    if (threads == 1) run(0);
+    else {
+        std::vector<std::thread> pool;
+        for (int w = 1; w < threads; ++w) pool.emplace_back(run, w);
+        run(0);
+        for (auto& th : pool) th.join();
     }
+    for (const char* e : errors)
+        if (e) { tb2::set_error(e); return TB2_ERR_INVALID; }
     return TB2_OK;
 }
