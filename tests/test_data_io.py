@@ -403,3 +403,30 @@ def test_native_parser_reads_numbers_like_float(tmp_path):
     want_y = np.array([float(lits[2 * i + 1]) for i in range(len(cols['y']))])
     assert np.array_equal(cols['x'].view(np.int64), want_x.view(np.int64))
     assert np.array_equal(cols['y'].view(np.int64), want_y.view(np.int64))
+
+
+def _assert_whole_scenes_agree(filename):
+    from trajnetplusplusbaselines_b200.data import load_scenes_xy
+    cols = load_scenes_xy(filename)
+    rows = [(sid, paths_to_xy(paths)) for sid, paths in read_ndjson_scenes(filename)]
+    assert len(cols) == len(rows)
+    for (sid_c, xy_c), (sid_r, xy_r) in zip(cols, rows):
+        assert sid_c == sid_r and xy_c.shape == xy_r.shape and np.array_equal(xy_c, xy_r, equal_nan=True)
+    return len(cols)
+
+
+def test_whole_scene_loader_equals_paths_to_xy(tmp_path):
+    """load_scenes_xy (training files: every scene over its whole frame range) == paths_to_xy of the row reader."""
+    fn = os.path.join(tmp_path, "tricky.ndjson")
+    for seed in range(3):
+        _tricky_file(fn, seed)
+        assert _assert_whole_scenes_agree(fn) >= 30
+
+
+@pytest.mark.needs_reference
+def test_whole_scene_loader_on_the_reference_training_files():
+    import glob
+    from oracle.ref_shim import reference_root
+    files = sorted(glob.glob(os.path.join(reference_root(), "DATA_BLOCK", "trajdata", "train", "*.ndjson")))
+    assert files
+    assert sum(_assert_whole_scenes_agree(fn) for fn in files) > 10000

@@ -175,6 +175,16 @@ def _scene_meta_from_paths(scene_id, paths, obs_length):
                      [p[0].pedestrian for p in paths[1:]])
 
 
+def load_scenes_xy(filename):
+    """[(scene_id, xy float64 [n_frames, n_peds, 2])] of EVERY scene of an ndjson file over its whole frame range: per scene
+    exactly paths_to_xy(paths) of read_ndjson_scenes (what the reference's trainer loop starts from,
+    lstm/trainer.py:98-99) -- the input of lstm.scene_ops.preprocess_scenes."""
+    cols = parse_ndjson_columns(filename)
+    if cols is None:
+        return [(scene_id, paths_to_xy(paths)) for scene_id, paths in read_ndjson_scenes(filename)]
+    return [(meta.scene_id, xy) for xy, meta in _assemble_scenes(cols, None)]
+
+
 def load_test_scenes_xy(filename, obs_length=9):
     """[(xy float64 [n_frames, n_peds, 2], SceneMeta)] of the test scenes of an ndjson file: per scene exactly
     paths_to_xy(preprocess_test(paths, obs_length)) and what write_predictions reads off those paths."""
@@ -185,6 +195,12 @@ def load_test_scenes_xy(filename, obs_length=9):
             paths = preprocess_test(paths, obs_length)
             out.append((paths_to_xy(paths), _scene_meta_from_paths(scene_id, paths, obs_length)))
         return out
+    return _assemble_scenes(cols, obs_length)
+
+
+def _assemble_scenes(cols, obs_length):
+    """Per scene the xy array and SceneMeta from the parsed columns; obs_length None = the whole scene (no preprocess_test,
+    the frame fields of the SceneMeta then describe the primary's first two frames and its last one)."""
     order = np.argsort(cols['frame'], kind='stable')        # by frame, file order within a frame (tracks_by_frame)
     f, p, x, y = cols['frame'][order], cols['ped'][order], cols['x'][order], cols['y'][order]
     los = np.searchsorted(f, cols['scene_start'], side='left')
@@ -197,12 +213,13 @@ def load_test_scenes_xy(filename, obs_length=9):
         pf = fs[ps == primary]                              # the primary's rows, ascending frames
         if len(pf) == 0:
             continue                                        # read_ndjson_scenes skips a scene without its primary
-        last = pf[:obs_length][-1]                          # preprocess_test: last frame of the observation
+        last = pf[:obs_length][-1] if obs_length is not None else fs[-1]      # preprocess_test: last frame of the observation
         cut = int(np.searchsorted(fs, last, side='right'))
         fs, ps, xs, ys = fs[:cut], ps[:cut], x[lo:lo + cut], y[lo:lo + cut]
         observed = pf[pf <= last]
-        if len(observed) < max(obs_length, 2):
-            raise IndexError("scene %d: the primary has %d observed rows, %d needed" % (int(cols['scene_id'][i]), len(observed), obs_length))
+        need = 1 if obs_length is None else max(obs_length, 2)
+        if len(observed) < need:
+            raise IndexError("scene %d: the primary has %d observed rows, %d needed" % (int(cols['scene_id'][i]), len(observed), need))
         uniq, first, inv = np.unique(ps, return_index=True, return_inverse=True)
         by_first = np.argsort(first, kind='stable')         # pedestrians in order of first appearance
         peds = uniq[by_first]
@@ -220,8 +237,8 @@ def load_test_scenes_xy(filename, obs_length=9):
         xy = np.full((len(frames), int(present.sum()), 2), np.nan)
         xy[fi[valid], newcol[col[valid]], 0] = xs[valid]
         xy[fi[valid], newcol[col[valid]], 1] = ys[valid]
-        meta = SceneMeta(int(cols['scene_id'][i]), primary, int(observed[0]), int(observed[1] - observed[0]),
-                         int(observed[obs_length - 1]), peds[1:].tolist())
+        meta = SceneMeta(int(cols['scene_id'][i]), primary, int(observed[0]), int(observed[1] - observed[0]) if len(observed) > 1 else 0,
+                         int(observed[obs_length - 1] if obs_length is not None else observed[-1]), peds[1:].tolist())
         out.append((xy, meta))
     return out
 
