@@ -49,8 +49,25 @@ with tempfile.TemporaryDirectory() as d:
     t0 = time.perf_counter()
     write_predictions(batched, scenes, os.path.join(d, "pred.ndjson"))
     t_write = time.perf_counter() - t0
+# file -> file through evaluate_file (column pipeline: native ndjson parse, predict_batch_xy, native formatting)
+from trajnetplusplusbaselines_b200.data import SceneRow, trajnet_line
+from trajnetplusplusbaselines_b200.evaluator import evaluate_file
+with tempfile.TemporaryDirectory() as d:
+    infile, outfile = os.path.join(d, "in.ndjson"), os.path.join(d, "out.ndjson")
+    with open(infile, "w") as f:
+        for _, b, paths in scenes:
+            f.write(trajnet_line(SceneRow(b, paths[0][0].pedestrian, 20000 * b, 20000 * b + 200, 2.5, 0)) + "\n")
+            for path in paths:
+                for r in path:
+                    f.write(trajnet_line(TrackRow(20000 * b + r.frame, r.pedestrian, r.x, r.y)) + "\n")
+    evaluate_file(predictor, infile, outfile, args=args)          # warm-up (layout / pinned pools)
+    t0 = time.perf_counter()
+    n_file = evaluate_file(predictor, infile, outfile, args=args)
+    torch.cuda.synchronize()
+    t_file = time.perf_counter() - t0
 dev = max(float(np.abs(single[i][0][0] - batched[i][0][0]).max()) for i in range(n_single))
 print(json.dumps({"workload": "%s evaluator path, %d scenes x %d peds, obs 9 -> pred 12" % (kind, B, N),
                   "per_scene_call_scenes_per_s": 1.0 / t_single, "predict_batch_scenes_per_s": B / t_batch,
                   "speedup": t_single * B / t_batch, "ndjson_write_scenes_per_s": B / t_write,
+                  "evaluate_file_scenes_per_s": n_file / t_file,
                   "max_abs_dev_single_vs_batched_m": dev}))
