@@ -389,7 +389,8 @@ int tb2_scenes_inverse(const float* xy_dev, const int32_t* scene_off_dev, int32_
  *   (else -1) and the caller takes its json.loads path for the whole file.
  * tb2_ndjson_format -- prediction records -> text: per scene one scene line then rows_per_scene[i] track lines, in the
  *   caller's row order, byte-identical to json.dumps of the reference writer's dictionaries with coordinates round(v, 2).
- *   Returns the byte count needed (writes only when `capacity` suffices; <= 160 bytes per line), or a negative error
+ *   Returns the byte count needed (whole lines are written while they fit into `capacity`, nothing past it;
+ *   <= 160 bytes per line), or a negative error
  *   (TB2_ERR_UNSUPPORTED for finite |coordinate| >= 1e15, where repr() would need an exponent). */
 int tb2_ndjson_parse(const char* text, size_t len, int64_t max_rows, int64_t* track_frame, int64_t* track_ped,
                      double* track_x, double* track_y, int64_t* num_tracks_out, int64_t* scene_id, int64_t* scene_ped,

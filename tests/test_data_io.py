@@ -430,3 +430,28 @@ def test_whole_scene_loader_on_the_reference_training_files():
     files = sorted(glob.glob(os.path.join(reference_root(), "DATA_BLOCK", "trajdata", "train", "*.ndjson")))
     assert files
     assert sum(_assert_whole_scenes_agree(fn) for fn in files) > 10000
+
+
+def test_native_format_reports_the_size_it_needs():
+    """tb2_ndjson_format: the byte count is returned whatever the capacity; nothing is written past it."""
+    import ctypes
+    from trajnetplusplusbaselines_b200 import _lib
+    lib = _lib.load()
+    i64 = lambda *v: np.array(v, dtype=np.int64)
+    sid, sped, ss, se, nrows = i64(3), i64(12), i64(100), i64(300), i64(2)
+    fr, pd, md = i64(190, 200), i64(12, 12), i64(0, 0)
+    x, y = np.array([1.005, -0.0]), np.array([np.nan, 2.5])
+    ptr = lambda a: ctypes.c_void_p(a.ctypes.data)
+    args = (1, ptr(sid), ptr(sped), ptr(ss), ptr(se), ptr(nrows), ptr(fr), ptr(pd), ptr(x), ptr(y), ptr(md))
+    need = lib.tb2_ndjson_format(*args, ctypes.c_void_p(0), 0)
+    want = ('{"scene": {"id": 3, "p": 12, "s": 100, "e": 300, "fps": 2.5, "tag": 0}}\n'
+            '{"track": {"f": 190, "p": 12, "x": 1.0, "y": NaN, "prediction_number": 0, "scene_id": 3}}\n'
+            '{"track": {"f": 200, "p": 12, "x": -0.0, "y": 2.5, "prediction_number": 0, "scene_id": 3}}\n')
+    assert need == len(want)
+    buf = ctypes.create_string_buffer(need + 8)
+    buf.raw = b"#" * (need + 8)
+    assert lib.tb2_ndjson_format(*args, ctypes.cast(buf, ctypes.c_void_p), need) == need
+    assert buf.raw[:need].decode() == want and buf.raw[need:] == b"#" * 8
+    small = ctypes.create_string_buffer(b"#" * 40, 40)
+    assert lib.tb2_ndjson_format(*args, ctypes.cast(small, ctypes.c_void_p), 40) == need      # too small: size only
+    assert small.raw == b"#" * 40
